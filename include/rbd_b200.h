@@ -1,0 +1,139 @@
+/* rbd_b200.h - C ABI of the B200-native batched rigid-body-dynamics library (librbd_b200.so).
+ *
+ * Drop-in boundary for the hot path of A2R-Lab/RBDReference: rnea, rnea_grad, minv and their
+ * eight per-pass helpers, evaluated over B knot points per call on one CUDA device.
+ * The reference has no FFI of its own (one pure-Python class); each entry point below names
+ * the reference method (RBDReference.py:line) it replaces.  INTEGRATION.md shows the ctypes
+ * binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - All tensors are dense, contiguous, row-major DEVICE pointers with the batch axis first;
+ *    out[k] equals the reference's result for (q[k], qd[k], qdd[k]).
+ *      q, qd, qdd, c        (B, n)
+ *      v, a, f              (B, 6, NB)          spatial vectors are [angular; linear]
+ *      dv, da, df           (B, 6, n, NB)
+ *      dc_dq, dc_dqd        (B, n, n)           dc_du (B, n, 2n) = [dc_dq | dc_dqd]
+ *      Minv                 (B, n, n)           F (B, n, 6, n)   U (B, n, 6)   Dinv (B, n)
+ *    n = NB = number of 1-DoF joints (fixed base), 1 <= n <= RBD_MAX_DOF.
+ *  - `_f64` entry points take double*, `_f32` take float*; both compute in that type.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only
+ *    enqueue work; they never synchronise.  A model handle is immutable after creation, so any
+ *    number of host threads may call with the same handle on different streams.
+ *  - Every function returns 0 on success, a positive cudaError_t value for CUDA failures, or a
+ *    negative RBD_E_* code for argument errors; rbd_last_error_string() describes the last
+ *    failure on the calling thread.  No exceptions cross the ABI, nothing is printed.
+ *  - There is no CPU fallback: without a CUDA device the compute entry points fail.
+ */
+#ifndef RBD_B200_H_
+#define RBD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBD_MAX_DOF 32
+#define RBD_ABI_VERSION 1
+
+#define RBD_E_INVALID_ARGUMENT (-1)
+#define RBD_E_UNSUPPORTED      (-2)
+#define RBD_E_NO_DEVICE        (-3)
+
+/* Host-side description of a compiled robot (rbdreference_b200/model.py builds it by probing
+ * the robot object handed to RBDReference.__init__, RBDReference.py:6-7).  All pointers are
+ * HOST pointers, copied during rbd_model_create. */
+typedef struct RbdModelDesc {
+  int32_t n;                /* bodies == DoF                                                  */
+  const int32_t* parent;    /* [n]   get_parent_id, -1 = fixed base; parent[i] < i            */
+  const int32_t* kind;      /* [n]   0: X(q)=A+B cos q+C sin q (revolute), 1: X(q)=A+B q      */
+  const double* S;          /* [n*6] get_S_by_id                                              */
+  const double* XA;         /* [n*18] E (3x3 row-major) then L (3x3), X = [[E,0],[L,E]]       */
+  const double* XB;         /* [n*18]                                                         */
+  const double* XC;         /* [n*18]                                                         */
+  const double* I;          /* [n*36] get_Imat_by_id, row-major 6x6                           */
+  const double* damping;    /* [n]   get_damping_by_id                                        */
+} RbdModelDesc;
+
+typedef struct rbd_model rbd_model_t;
+
+int rbd_abi_version(void);
+const char* rbd_last_error_string(void);
+
+/* RBDReference.__init__ (RBDReference.py:6-7): compile-once model handle (host memory only;
+ * the model travels to the device as a kernel parameter, so one handle serves every device). */
+int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out);
+int rbd_model_destroy(rbd_model_t* m);
+int rbd_model_num_dof(const rbd_model_t* m);
+
+/* ---- fused drivers ------------------------------------------------------------------------ */
+/* rnea (RBDReference.py:623-628).  qdd may be NULL (skips the S*qdd term, :589).  v, a, f may
+ * each be NULL when the caller only wants c; f is the ACCUMULATED force (:619,:628). */
+int rbd_rnea_f64(const rbd_model_t* m, int64_t B, const double* q, const double* qd, const double* qdd,
+                 double gravity, double* c, double* v, double* a, double* f, void* stream);
+int rbd_rnea_f32(const rbd_model_t* m, int64_t B, const float* q, const float* qd, const float* qdd,
+                 float gravity, float* c, float* v, float* a, float* f, void* stream);
+
+/* rnea_grad (RBDReference.py:1345-1368): dc_du (B,n,2n).  c_out (B,n) optional. */
+int rbd_rnea_grad_f64(const rbd_model_t* m, int64_t B, const double* q, const double* qd, const double* qdd,
+                      double gravity, int use_velocity_damping, double* dc_du, double* c_out, void* stream);
+int rbd_rnea_grad_f32(const rbd_model_t* m, int64_t B, const float* q, const float* qd, const float* qdd,
+                      float gravity, int use_velocity_damping, float* dc_du, float* c_out, void* stream);
+
+/* minv (RBDReference.py:785-806).  output_dense=0 keeps the rows as the forward pass leaves them
+ * (the reference updates whole rows at :771, so the matrix is still full). */
+int rbd_minv_f64(const rbd_model_t* m, int64_t B, const double* q, int output_dense, double* Minv, void* stream);
+int rbd_minv_f32(const rbd_model_t* m, int64_t B, const float* q, int output_dense, float* Minv, void* stream);
+
+/* ---- per-pass helpers (same in-place contracts as the reference) ----------------------------- */
+/* rnea_fpass (RBDReference.py:559-598) */
+int rbd_rnea_fpass_f64(const rbd_model_t* m, int64_t B, const double* q, const double* qd, const double* qdd,
+                       double gravity, double* v, double* a, double* f, void* stream);
+int rbd_rnea_fpass_f32(const rbd_model_t* m, int64_t B, const float* q, const float* qd, const float* qdd,
+                       float gravity, float* v, float* a, float* f, void* stream);
+/* rnea_bpass (RBDReference.py:600-621): f is accumulated IN PLACE. */
+int rbd_rnea_bpass_f64(const rbd_model_t* m, int64_t B, const double* q, double* f, double* c, void* stream);
+int rbd_rnea_bpass_f32(const rbd_model_t* m, int64_t B, const float* q, float* f, float* c, void* stream);
+/* rnea_grad_fpass_dq (RBDReference.py:1127-1187) */
+int rbd_rnea_grad_fpass_dq_f64(const rbd_model_t* m, int64_t B, const double* q, const double* qd, const double* v,
+                               const double* a, double gravity, double* dv, double* da, double* df, void* stream);
+int rbd_rnea_grad_fpass_dq_f32(const rbd_model_t* m, int64_t B, const float* q, const float* qd, const float* v,
+                               const float* a, float gravity, float* dv, float* da, float* df, void* stream);
+/* rnea_grad_fpass_dqd (RBDReference.py:1189-1255) */
+int rbd_rnea_grad_fpass_dqd_f64(const rbd_model_t* m, int64_t B, const double* q, const double* qd, const double* v,
+                                double* dv, double* da, double* df, void* stream);
+int rbd_rnea_grad_fpass_dqd_f32(const rbd_model_t* m, int64_t B, const float* q, const float* qd, const float* v,
+                                float* dv, float* da, float* df, void* stream);
+/* rnea_grad_bpass_dq (RBDReference.py:1257-1297): df_dq is accumulated IN PLACE. */
+int rbd_rnea_grad_bpass_dq_f64(const rbd_model_t* m, int64_t B, const double* q, const double* f, double* df_dq,
+                               double* dc_dq, void* stream);
+int rbd_rnea_grad_bpass_dq_f32(const rbd_model_t* m, int64_t B, const float* q, const float* f, float* df_dq,
+                               float* dc_dq, void* stream);
+/* rnea_grad_bpass_dqd (RBDReference.py:1299-1343): df_dqd is accumulated IN PLACE. */
+int rbd_rnea_grad_bpass_dqd_f64(const rbd_model_t* m, int64_t B, const double* q, double* df_dqd,
+                                int use_velocity_damping, double* dc_dqd, void* stream);
+int rbd_rnea_grad_bpass_dqd_f32(const rbd_model_t* m, int64_t B, const float* q, float* df_dqd,
+                                int use_velocity_damping, float* dc_dqd, void* stream);
+/* minv_bpass (RBDReference.py:630-735): Dinv receives D = S^T U (not its reciprocal, :698). */
+int rbd_minv_bpass_f64(const rbd_model_t* m, int64_t B, const double* q, double* Minv, double* F, double* U,
+                       double* Dinv, void* stream);
+int rbd_minv_bpass_f32(const rbd_model_t* m, int64_t B, const float* q, float* Minv, float* F, float* U,
+                       float* Dinv, void* stream);
+/* minv_fpass (RBDReference.py:737-783): Minv and F are updated IN PLACE. */
+int rbd_minv_fpass_f64(const rbd_model_t* m, int64_t B, const double* q, double* Minv, double* F, const double* U,
+                       const double* Dinv, void* stream);
+int rbd_minv_fpass_f32(const rbd_model_t* m, int64_t B, const float* q, float* Minv, float* F, const float* U,
+                       const float* Dinv, void* stream);
+
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
+/* Runs a dependent-chain FMA micro-benchmark on `stream`'s device and returns the achieved
+ * FLOP/s (2 per FMA) in *flops_per_s; is_f64 selects DFMA or FFMA.  Used only to put a measured
+ * denominator under the FP64/FP32 roofline fraction. */
+int rbd_measure_fma_peak(int is_f64, double* flops_per_s, double* elapsed_ms, void* stream);
+/* Number of kernel launches issued through this library by the calling process so far. */
+int64_t rbd_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBD_B200_H_ */

@@ -1,0 +1,86 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container).
+
+    python oracle/make_golden.py            # needs /root/reference/RBDReference.py
+
+The reference ships no golden vectors, so parity is pinned on the
+outputs of the reference itself: for each robot a handful of seeded states is pushed
+through every hot-path function of /root/reference/RBDReference.py and the results are
+stored.  The GPU box has no /root/reference; tests there read only these files.
+TEST INFRASTRUCTURE - not imported by the product package.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root")
+
+from reference.RBDReference import RBDReference  # noqa: E402  (the live, unmodified reference)
+from rbdreference_b200 import robots  # noqa: E402
+
+CASES = [
+    ("iiwa14", lambda: robots.iiwa14(), 8),
+    ("hyq", lambda: robots.hyq(), 6),
+    ("atlas", lambda: robots.atlas(), 3),
+    ("tree9", lambda: robots.random_tree(9, seed=1), 6),
+    ("tree13", lambda: robots.random_tree(13, seed=2, branching=0.5, prismatic=0.3), 4),
+]
+
+
+def run_case(name, make, B, seed):
+    rb = make()
+    ref = RBDReference(rb)
+    n = rb.get_num_vel()
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(-np.pi, np.pi, (B, n))
+    qd = rng.uniform(-1.0, 1.0, (B, n))
+    qdd = rng.uniform(-1.0, 1.0, (B, n))
+    out = dict(q=q, qd=qd, qdd=qdd, gravity_alt=np.array(-3.7))
+    keys = ["c", "v", "a", "f", "c_noqdd", "a_noqdd", "f_noqdd", "c_galt", "f_fpass", "dc_du", "dc_du_damped",
+            "dc_du_noqdd", "dv_dq", "da_dq", "df_dq", "dv_dqd", "da_dqd", "df_dqd", "dc_dq", "dc_dqd",
+            "df_dq_acc", "df_dqd_acc", "Minv", "Minv_sparse", "Minv_b", "F_b", "U", "Dinv", "F_f", "H"]
+    acc = {k: [] for k in keys}
+    for k in range(B):
+        v, a, f = ref.rnea_fpass(q[k], qd[k], qdd[k])
+        acc["f_fpass"].append(f.copy())
+        c, v, a, f = ref.rnea(q[k], qd[k], qdd[k])
+        for key, val in (("c", c), ("v", v), ("a", a), ("f", f)):
+            acc[key].append(val.copy())
+        c0, _, a0, f0 = ref.rnea(q[k], qd[k])
+        acc["c_noqdd"].append(c0); acc["a_noqdd"].append(a0); acc["f_noqdd"].append(f0)
+        acc["c_galt"].append(ref.rnea(q[k], qd[k], qdd[k], GRAVITY=-3.7)[0])
+        acc["dc_du"].append(ref.rnea_grad(q[k], qd[k], qdd[k]))
+        acc["dc_du_damped"].append(ref.rnea_grad(q[k], qd[k], qdd[k], USE_VELOCITY_DAMPING=True))
+        acc["dc_du_noqdd"].append(ref.rnea_grad(q[k], qd[k]))
+        dv, da, df = ref.rnea_grad_fpass_dq(q[k], qd[k], v, a)
+        acc["dv_dq"].append(dv.copy()); acc["da_dq"].append(da.copy()); acc["df_dq"].append(df.copy())
+        dv2, da2, df2 = ref.rnea_grad_fpass_dqd(q[k], qd[k], v)
+        acc["dv_dqd"].append(dv2.copy()); acc["da_dqd"].append(da2.copy()); acc["df_dqd"].append(df2.copy())
+        acc["dc_dq"].append(ref.rnea_grad_bpass_dq(q[k], f, df))      # mutates df
+        acc["dc_dqd"].append(ref.rnea_grad_bpass_dqd(q[k], df2))      # mutates df2
+        acc["df_dq_acc"].append(df.copy()); acc["df_dqd_acc"].append(df2.copy())
+        acc["Minv"].append(ref.minv(q[k]))
+        acc["Minv_sparse"].append(ref.minv(q[k], output_dense=False))
+        Mb, Fb, U, D = ref.minv_bpass(q[k])
+        acc["Minv_b"].append(Mb.copy()); acc["F_b"].append(Fb.copy()); acc["U"].append(U.copy()); acc["Dinv"].append(D.copy())
+        ref.minv_fpass(q[k], Mb, Fb, U, D)
+        acc["F_f"].append(Fb.copy())
+        acc["H"].append(ref.crba(q[k]))
+    for key in keys:
+        out[key] = np.stack(acc[key])
+    # model tables, to detect drift of rbdreference_b200/robots.py against the fixture
+    out["parent"] = np.array([rb.get_parent_id(i) for i in range(n)])
+    out["S"] = np.stack([np.asarray(rb.get_S_by_id(i), float).reshape(-1) for i in range(n)])
+    out["I"] = np.stack([rb.get_Imat_by_id(i) for i in range(n)])
+    out["X_at_0p3"] = np.stack([rb.get_Xmat_Func_by_id(i)(0.3) for i in range(n)])
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s (%d states, %.1f KB)" % (path, B, os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    for idx, (name, make, B) in enumerate(CASES):
+        run_case(name, make, B, seed=1000 + idx)

@@ -1,0 +1,136 @@
+// rbd_common.cuh - device model layout and spatial-algebra primitives (sm_100a).
+//
+// The robot is compiled once on the host (rbdreference_b200/model.py) and travels to every
+// kernel as a __grid_constant__ parameter, i.e. it lives in the constant bank: warp-uniform
+// reads cost no shared memory or L1 bandwidth and there is no per-device upload to race on.
+//
+// Spatial vectors are [angular(3); linear(3)] (RBDReference.py:566).  A joint transform is the
+// Pluecker matrix X = [[E,0],[L,E]]; only E and L (9 + 9 values) are ever formed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define RBD_MAX_DOF 32
+
+namespace rbd {
+
+template <typename T>
+struct DevModel {
+  int n;
+  int parent[RBD_MAX_DOF];
+  int kind[RBD_MAX_DOF];            // 0 revolute (cos/sin), 1 prismatic (affine)
+  unsigned anc_mask[RBD_MAX_DOF];   // bit c set iff c is an ancestor of i or c == i
+  unsigned sub_mask[RBD_MAX_DOF];   // bit j set iff j is in subtree(i) (including i)
+  T damping[RBD_MAX_DOF];
+  T S[RBD_MAX_DOF][6];
+  T XA[RBD_MAX_DOF][18];
+  T XB[RBD_MAX_DOF][18];
+  T XC[RBD_MAX_DOF][18];
+  T I[RBD_MAX_DOF][36];
+};
+
+// ---- scalar helpers ---------------------------------------------------------------------
+__device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+
+// ---- joint transform X(q) = A + B*f1 + C*f2 ------------------------------------------------
+// X[0..8] = E row-major, X[9..17] = L row-major.
+template <typename T>
+__device__ __forceinline__ void joint_basis(const DevModel<T>& m, int i, T q, T& f1, T& f2) {
+  if (m.kind[i] == 0) {
+    sincos_t(q, &f2, &f1);
+  } else {
+    f1 = q;
+    f2 = T(0);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void build_X(const DevModel<T>& m, int i, T f1, T f2, T (&X)[18]) {
+#pragma unroll
+  for (int k = 0; k < 18; ++k) X[k] = fma_t(m.XC[i][k], f2, fma_t(m.XB[i][k], f1, m.XA[i][k]));
+}
+
+template <typename T>
+__device__ __forceinline__ void build_X_from_q(const DevModel<T>& m, int i, T q, T (&X)[18]) {
+  T f1, f2;
+  joint_basis(m, i, q, f1, f2);
+  build_X(m, i, f1, f2, X);
+}
+
+// y = X x   (motion vector parent -> child)
+template <typename T>
+__device__ __forceinline__ void X_apply(const T (&X)[18], const T (&x)[6], T (&y)[6]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    y[r] = X[3 * r] * x[0] + X[3 * r + 1] * x[1] + X[3 * r + 2] * x[2];
+    y[3 + r] = X[9 + 3 * r] * x[0] + X[9 + 3 * r + 1] * x[1] + X[9 + 3 * r + 2] * x[2] +
+               X[3 * r] * x[3] + X[3 * r + 1] * x[4] + X[3 * r + 2] * x[5];
+  }
+}
+
+// y = X^T f   (force vector child -> parent)
+template <typename T>
+__device__ __forceinline__ void XT_apply(const T (&X)[18], const T (&f)[6], T (&y)[6]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    y[c] = X[c] * f[0] + X[3 + c] * f[1] + X[6 + c] * f[2] +
+           X[9 + c] * f[3] + X[12 + c] * f[4] + X[15 + c] * f[5];
+    y[3 + c] = X[c] * f[3] + X[3 + c] * f[4] + X[6 + c] * f[5];
+  }
+}
+
+// y += X^T f
+template <typename T>
+__device__ __forceinline__ void XT_apply_add(const T (&X)[18], const T (&f)[6], T (&y)[6]) {
+  T t[6];
+  XT_apply(X, f, t);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) y[k] += t[k];
+}
+
+// y = M x for a dense row-major 6x6 held in the model (constant bank)
+template <typename T>
+__device__ __forceinline__ void mat6_apply(const T* __restrict__ M, const T (&x)[6], T (&y)[6]) {
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    T acc = M[6 * r] * x[0];
+#pragma unroll
+    for (int k = 1; k < 6; ++k) acc = fma_t(M[6 * r + k], x[k], acc);
+    y[r] = acc;
+  }
+}
+
+// y = crm(v) s  : motion cross product  v x s            (RBDReference.py:9-21, :56-59)
+template <typename T>
+__device__ __forceinline__ void crm_mul(const T (&v)[6], const T (&s)[6], T (&y)[6]) {
+  y[0] = v[1] * s[2] - v[2] * s[1];
+  y[1] = v[2] * s[0] - v[0] * s[2];
+  y[2] = v[0] * s[1] - v[1] * s[0];
+  y[3] = v[4] * s[2] - v[5] * s[1] + v[1] * s[5] - v[2] * s[4];
+  y[4] = v[5] * s[0] - v[3] * s[2] + v[2] * s[3] - v[0] * s[5];
+  y[5] = v[3] * s[1] - v[4] * s[0] + v[0] * s[4] - v[1] * s[3];
+}
+
+// y = crf(v) f  : force cross product  v x* f = -crm(v)^T f   (RBDReference.py:149-164)
+template <typename T>
+__device__ __forceinline__ void crf_mul(const T (&v)[6], const T (&f)[6], T (&y)[6]) {
+  y[0] = v[1] * f[2] - v[2] * f[1] + v[4] * f[5] - v[5] * f[4];
+  y[1] = v[2] * f[0] - v[0] * f[2] + v[5] * f[3] - v[3] * f[5];
+  y[2] = v[0] * f[1] - v[1] * f[0] + v[3] * f[4] - v[4] * f[3];
+  y[3] = v[1] * f[5] - v[2] * f[4];
+  y[4] = v[2] * f[3] - v[0] * f[5];
+  y[5] = v[0] * f[4] - v[1] * f[3];
+}
+
+template <typename T>
+__device__ __forceinline__ T dot6(const T* __restrict__ s, const T (&x)[6]) {
+  T acc = s[0] * x[0];
+#pragma unroll
+  for (int k = 1; k < 6; ++k) acc = fma_t(s[k], x[k], acc);
+  return acc;
+}
+
+}  // namespace rbd

@@ -1,0 +1,73 @@
+"""Multi-GPU sharding of the batch axis (one process per GPU, torch.distributed).
+
+Every knot point is independent - there is no exchange step anywhere in rnea / rnea_grad /
+minv (no reduction over the batch in /root/reference/RBDReference.py) - so the batch is cut
+into contiguous slices, one per rank, each rank evaluates its slice with the same kernels,
+and results stay sharded.  A collective (NCCL all-gather / gather over NVLink) runs only when
+the caller asks for the full result on one or all devices.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["shard_bounds", "gather_to_all", "gather_to_rank"]
+
+
+def shard_bounds(B: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of a batch of B knot points owned by `rank`.
+
+    The first B % world_size ranks get one extra point; concatenating the slices in rank order
+    reproduces the unsharded batch, so sharded and unsharded results are bit-identical.
+    """
+    if not (0 <= rank < world_size):
+        raise ValueError("rank %d outside world of size %d" % (rank, world_size))
+    base, extra = divmod(int(B), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _world(group) -> Tuple[int, int]:
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def gather_to_all(local: torch.Tensor, B: int, group=None) -> torch.Tensor:
+    """All-gather per-rank result slices (first axis) into the full (B, ...) tensor on every rank."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    sizes = [shard_bounds(B, r, world)[1] - shard_bounds(B, r, world)[0] for r in range(world)]
+    if local.shape[0] != sizes[rank]:
+        raise ValueError("local slice has %d rows, expected %d" % (local.shape[0], sizes[rank]))
+    if len(set(sizes)) == 1:
+        out = torch.empty((B,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    # ragged slices: pad every rank to the largest slice, gather, then drop the padding
+    smax = max(sizes)
+    padded = torch.zeros((smax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: sizes[rank]] = local
+    buf = torch.empty((world * smax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, padded, group=group)
+    return torch.cat([buf[r * smax: r * smax + sizes[r]] for r in range(world)], dim=0)
+
+
+def gather_to_rank(local: torch.Tensor, B: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
+    """Gather result slices onto rank `dst` only (other ranks get None)."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    sizes = [shard_bounds(B, r, world)[1] - shard_bounds(B, r, world)[0] for r in range(world)]
+    if rank == dst:
+        parts = [torch.empty((s,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for s in sizes]
+        parts[dst] = local.contiguous()
+        reqs = [dist.irecv(parts[r], src=r, group=group) for r in range(world) if r != dst]
+        for r in reqs:
+            r.wait()
+        return torch.cat(parts, dim=0)
+    dist.send(local.contiguous(), dst=dst, group=group)
+    return None

@@ -1,0 +1,318 @@
+"""`RBDReference(robot).ALGORITHM(...)` - drop-in host API over the sm_100a kernels.
+
+Same method names, positional order and defaults as /root/reference/RBDReference.py
+(README.md:9-17), for the hot path: rnea, rnea_grad, minv and their eight per-pass helpers.
+
+Accepted inputs (every array argument of one call must be of the same kind):
+
+* reference shapes - numpy `(n,)` vectors (and `(6,NB)`, `(6,n,NB)`, ... intermediates):
+  one knot point, results returned as fresh numpy arrays of the reference's shapes, except the
+  documented in-place cases which update and return the caller's array (`rnea_bpass` f,
+  `minv_fpass` Minv/F, `rnea_grad_bpass_*` df), exactly like the reference;
+* batched - a leading batch axis `B` on every argument: numpy arrays (copied to the device and
+  back) or torch tensors (CUDA tensors are used in place, outputs stay on the device).
+  `out[k]` equals the reference called on element k.
+
+All arithmetic runs in hand-written CUDA kernels through the C ABI in include/rbd_b200.h;
+PyTorch only owns device memory and streams.  There is no CPU fallback: without the built
+library or without a CUDA device the calls raise.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _capi
+from .model import RobotModel, compile_model
+
+__all__ = ["RBDReference"]
+
+_SUFFIX = {torch.float64: "f64", torch.float32: "f32"}
+
+
+class RBDReference:
+    """B200-native counterpart of the reference class (RBDReference.py:5-7)."""
+
+    def __init__(self, robotObj, dtype=torch.float64, device=None):
+        if isinstance(dtype, str):
+            dtype = {"float64": torch.float64, "f64": torch.float64, "fp64": torch.float64,
+                     "float32": torch.float32, "f32": torch.float32, "fp32": torch.float32}[dtype]
+        if dtype not in _SUFFIX:
+            raise ValueError("dtype must be torch.float64 or torch.float32")
+        self.robot = robotObj
+        self.dtype = dtype
+        self._suffix = _SUFFIX[dtype]
+        self._np_dtype = np.float64 if dtype == torch.float64 else np.float32
+        self.model: RobotModel = robotObj if isinstance(robotObj, RobotModel) else compile_model(robotObj)
+        self.n = self.model.n
+        self.NB = self.model.n
+        self._lib = _capi.load_library()            # raises if the CUDA library is missing
+        self._handle = _capi.ModelHandle(self.model)
+        self._device = torch.device(device) if device is not None else None
+
+    # ------------------------------------------------------------------------------------
+    # plumbing
+    # ------------------------------------------------------------------------------------
+    def _default_device(self) -> torch.device:
+        if self._device is not None:
+            return self._device
+        if not torch.cuda.is_available():
+            raise RuntimeError("rbdreference_b200: no CUDA device available - the hot path has no CPU fallback")
+        return torch.device("cuda", torch.cuda.current_device())
+
+    class _Ctx:
+        """Normalises one call's arguments to contiguous device tensors with a batch axis."""
+
+        def __init__(self, eng: "RBDReference", lead, base_ndim: int):
+            self.eng = eng
+            self.kind = "torch" if isinstance(lead, torch.Tensor) else "numpy"
+            arr_ndim = lead.dim() if self.kind == "torch" else np.ndim(lead)
+            if arr_ndim == base_ndim:
+                self.batched = False
+            elif arr_ndim == base_ndim + 1:
+                self.batched = True
+            else:
+                raise ValueError("expected an array with %d or %d dimensions" % (base_ndim, base_ndim + 1))
+            if self.kind == "torch" and lead.is_cuda:
+                self.device = lead.device
+            else:
+                self.device = eng._default_device()
+            self.in_device = lead.device if self.kind == "torch" else None
+            self.B: Optional[int] = None
+
+        def dev(self, x, shape_tail, name):
+            """-> contiguous (B, *shape_tail) tensor of the engine dtype on the compute device."""
+            if x is None:
+                return None
+            eng = self.eng
+            if isinstance(x, torch.Tensor):
+                t = x
+            else:
+                t = torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=eng._np_dtype))
+            if not self.batched:
+                t = t.unsqueeze(0)
+            if tuple(t.shape[1:]) != tuple(shape_tail):
+                raise ValueError("%s: expected trailing shape %s, got %s" % (name, tuple(shape_tail), tuple(t.shape[1:])))
+            if self.B is None:
+                self.B = int(t.shape[0])
+            elif int(t.shape[0]) != self.B:
+                raise ValueError("%s: batch size %d does not match %d" % (name, t.shape[0], self.B))
+            return t.to(device=self.device, dtype=eng.dtype).contiguous()
+
+        def empty(self, *shape_tail):
+            return torch.empty((self.B,) + tuple(shape_tail), dtype=self.eng.dtype, device=self.device)
+
+        def ret(self, t):
+            """device tensor -> what the caller expects (numpy / torch, batched or not)."""
+            if t is None:
+                return None
+            if not self.batched:
+                t = t[0]
+            if self.kind == "numpy":
+                return t.cpu().numpy()
+            if self.in_device is not None and self.in_device != t.device:
+                return t.to(self.in_device)
+            return t
+
+        def write_back(self, target, t):
+            """In-place contract: put device result `t` into the caller's array and return it."""
+            if not self.batched:
+                t = t[0]
+            if isinstance(target, torch.Tensor):
+                if target.data_ptr() != t.data_ptr():
+                    target.copy_(t)
+                return target
+            np.copyto(target, t.cpu().numpy().astype(target.dtype, copy=False))
+            return target
+
+    def _call(self, name: str, ctx: "_Ctx", *args):
+        fn = getattr(self._lib, "rbd_%s_%s" % (name, self._suffix))
+        conv = []
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                conv.append(a.data_ptr())
+            else:
+                conv.append(a)
+        with torch.cuda.device(ctx.device):
+            stream = torch.cuda.current_stream(ctx.device).cuda_stream
+            rc = fn(self._handle.ptr, ctx.B, *conv, stream)
+        _capi.check(rc, "rbd_%s_%s" % (name, self._suffix))
+
+    # ------------------------------------------------------------------------------------
+    # RNEA
+    # ------------------------------------------------------------------------------------
+    def rnea_fpass(self, q, qd, qdd=None, GRAVITY=-9.81):
+        """RBDReference.py:559-598 -> (v, a, f), each (6, NB)."""
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq, dqd, dqdd = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(qdd, (n,), "qdd")
+        v, a, f = ctx.empty(6, n), ctx.empty(6, n), ctx.empty(6, n)
+        self._call("rnea_fpass", ctx, dq, dqd, dqdd, float(GRAVITY), v, a, f)
+        return ctx.ret(v), ctx.ret(a), ctx.ret(f)
+
+    def rnea_bpass(self, q, f):
+        """RBDReference.py:600-621 -> (c, f); `f` is accumulated in place and returned."""
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq, df = ctx.dev(q, (n,), "q"), ctx.dev(f, (6, n), "f")
+        c = ctx.empty(n)
+        self._call("rnea_bpass", ctx, dq, df, c)
+        return ctx.ret(c), ctx.write_back(f, df)
+
+    def rnea(self, q, qd, qdd=None, GRAVITY=-9.81, f_ext=None, outputs="all"):
+        """RBDReference.py:623-628 -> (c, v, a, f).  `f_ext` is accepted and ignored as upstream.
+
+        `outputs="c"` (extension) skips writing v, a, f and returns only c.
+        """
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq, dqd, dqdd = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(qdd, (n,), "qdd")
+        c = ctx.empty(n)
+        if outputs == "c":
+            self._call("rnea", ctx, dq, dqd, dqdd, float(GRAVITY), c, None, None, None)
+            return ctx.ret(c)
+        v, a, f = ctx.empty(6, n), ctx.empty(6, n), ctx.empty(6, n)
+        self._call("rnea", ctx, dq, dqd, dqdd, float(GRAVITY), c, v, a, f)
+        return ctx.ret(c), ctx.ret(v), ctx.ret(a), ctx.ret(f)
+
+    # ------------------------------------------------------------------------------------
+    # Minv
+    # ------------------------------------------------------------------------------------
+    def minv_bpass(self, q):
+        """RBDReference.py:630-735 -> (Minv, F, U, Dinv) with Dinv = D (:698)."""
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq = ctx.dev(q, (n,), "q")
+        Minv, F, U, D = ctx.empty(n, n), ctx.empty(n, 6, n), ctx.empty(n, 6), ctx.empty(n)
+        self._call("minv_bpass", ctx, dq, Minv, F, U, D)
+        return ctx.ret(Minv), ctx.ret(F), ctx.ret(U), ctx.ret(D)
+
+    def minv_fpass(self, q, Minv, F, U, Dinv):
+        """RBDReference.py:737-783 -> Minv (the caller's array, updated in place; F is rewritten)."""
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq = ctx.dev(q, (n,), "q")
+        dM, dF = ctx.dev(Minv, (n, n), "Minv"), ctx.dev(F, (n, 6, n), "F")
+        dU, dD = ctx.dev(U, (n, 6), "U"), ctx.dev(Dinv, (n,), "Dinv")
+        self._call("minv_fpass", ctx, dq, dM, dF, dU, dD)
+        ctx.write_back(F, dF)
+        return ctx.write_back(Minv, dM)
+
+    def minv(self, q, output_dense=True, out=None):
+        """RBDReference.py:785-806 -> Minv (n, n)."""
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq = ctx.dev(q, (n,), "q")
+        Minv = out if (out is not None and ctx.kind == "torch" and ctx.batched) else ctx.empty(n, n)
+        self._call("minv", ctx, dq, 1 if output_dense else 0, Minv)
+        return ctx.ret(Minv)
+
+    # ------------------------------------------------------------------------------------
+    # RNEA gradient
+    # ------------------------------------------------------------------------------------
+    def rnea_grad_fpass_dq(self, q, qd, v, a, GRAVITY=-9.81):
+        """RBDReference.py:1127-1187 -> (dv_dq, da_dq, df_dq), each (6, n, NB)."""
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq, dqd = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd")
+        dv_, da_ = ctx.dev(v, (6, n), "v"), ctx.dev(a, (6, n), "a")
+        dv, da, df = ctx.empty(6, n, n), ctx.empty(6, n, n), ctx.empty(6, n, n)
+        self._call("rnea_grad_fpass_dq", ctx, dq, dqd, dv_, da_, float(GRAVITY), dv, da, df)
+        return ctx.ret(dv), ctx.ret(da), ctx.ret(df)
+
+    def rnea_grad_fpass_dqd(self, q, qd, v):
+        """RBDReference.py:1189-1255 -> (dv_dqd, da_dqd, df_dqd)."""
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq, dqd, dv_ = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(v, (6, n), "v")
+        dv, da, df = ctx.empty(6, n, n), ctx.empty(6, n, n), ctx.empty(6, n, n)
+        self._call("rnea_grad_fpass_dqd", ctx, dq, dqd, dv_, dv, da, df)
+        return ctx.ret(dv), ctx.ret(da), ctx.ret(df)
+
+    def rnea_grad_bpass_dq(self, q, f, df_dq):
+        """RBDReference.py:1257-1297 -> dc_dq (n, n); `df_dq` is accumulated in place."""
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq, df_, ddf = ctx.dev(q, (n,), "q"), ctx.dev(f, (6, n), "f"), ctx.dev(df_dq, (6, n, n), "df_dq")
+        dc = ctx.empty(n, n)
+        self._call("rnea_grad_bpass_dq", ctx, dq, df_, ddf, dc)
+        ctx.write_back(df_dq, ddf)
+        return ctx.ret(dc)
+
+    def rnea_grad_bpass_dqd(self, q, df_dqd, USE_VELOCITY_DAMPING=False):
+        """RBDReference.py:1299-1343 -> dc_dqd (n, n); `df_dqd` is accumulated in place."""
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq, ddf = ctx.dev(q, (n,), "q"), ctx.dev(df_dqd, (6, n, n), "df_dqd")
+        dc = ctx.empty(n, n)
+        self._call("rnea_grad_bpass_dqd", ctx, dq, ddf, 1 if USE_VELOCITY_DAMPING else 0, dc)
+        ctx.write_back(df_dqd, ddf)
+        return ctx.ret(dc)
+
+    def rnea_grad(self, q, qd, qdd=None, GRAVITY=-9.81, USE_VELOCITY_DAMPING=False, out=None, c_out=None):
+        """RBDReference.py:1345-1368 -> dc_du (n, 2n) = [dc_dq | dc_dqd], one fused launch.
+
+        `out` / `c_out` (extension, batched CUDA tensors only) receive dc_du (B,n,2n) / c (B,n).
+        """
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq, dqd, dqdd = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(qdd, (n,), "qdd")
+        use_out = out is not None and ctx.kind == "torch" and ctx.batched
+        dc_du = out if use_out else ctx.empty(n, 2 * n)
+        if use_out and (tuple(out.shape) != (ctx.B, n, 2 * n) or out.dtype != self.dtype or not out.is_contiguous()):
+            raise ValueError("out must be a contiguous (B, n, 2n) tensor of the engine dtype")
+        self._call("rnea_grad", ctx, dq, dqd, dqdd, float(GRAVITY), 1 if USE_VELOCITY_DAMPING else 0, dc_du, c_out)
+        return ctx.ret(dc_du)
+
+    def rnea_grad_passes(self, q, qd, qdd=None, GRAVITY=-9.81, USE_VELOCITY_DAMPING=False):
+        """rnea_grad composed from the per-pass entry points (the reference's own call sequence,
+        RBDReference.py:1353-1367).  Debug path: materialises every (6,n,NB) intermediate."""
+        c, v, a, f = self.rnea(q, qd, qdd, GRAVITY)
+        _, _, df_dq = self.rnea_grad_fpass_dq(q, qd, v, a, GRAVITY)
+        _, _, df_dqd = self.rnea_grad_fpass_dqd(q, qd, v)
+        dc_dq = self.rnea_grad_bpass_dq(q, f, df_dq)
+        dc_dqd = self.rnea_grad_bpass_dqd(q, df_dqd, USE_VELOCITY_DAMPING)
+        if isinstance(dc_dq, torch.Tensor):
+            return torch.cat((dc_dq, dc_dqd), dim=-1)
+        return np.concatenate((dc_dq, dc_dqd), axis=-1)
+
+    def minv_passes(self, q, output_dense=True):
+        """minv composed from minv_bpass + minv_fpass (+ mirror), RBDReference.py:793-804."""
+        Minv, F, U, D = self.minv_bpass(q)
+        Minv = self.minv_fpass(q, Minv, F, U, D)
+        if output_dense:
+            n = self.n
+            iu = np.triu_indices(n, 1)
+            if isinstance(Minv, torch.Tensor):
+                Minv[..., iu[1], iu[0]] = Minv[..., iu[0], iu[1]]
+            else:
+                Minv[..., iu[1], iu[0]] = Minv[..., iu[0], iu[1]]
+        return Minv
+
+    # ------------------------------------------------------------------------------------
+    # compositions of the hot-path kernels
+    # ------------------------------------------------------------------------------------
+    def forward_dynamics(self, q, qd, u):
+        """RBDReference.py:1371-1374: Minv @ (u - c) with c = rnea(q, qd) (qdd omitted upstream)."""
+        c = self.rnea(q, qd, outputs="c")
+        Minv = self.minv(q)
+        if isinstance(Minv, torch.Tensor):
+            u_t = u if isinstance(u, torch.Tensor) else torch.as_tensor(u)
+            return torch.matmul(Minv, (u_t.to(Minv) - c).unsqueeze(-1)).squeeze(-1)
+        return np.matmul(Minv, (np.asarray(u) - c)[..., None])[..., 0]
+
+    def forward_dynamics_grad(self, q, qd, u):
+        """RBDReference.py:1376-1384 -> (qdd_dq, qdd_dqd)."""
+        qdd = self.forward_dynamics(q, qd, u)
+        dc_du = self.rnea_grad(q, qd, qdd)
+        Minv = self.minv(q)
+        n = self.n
+        if isinstance(Minv, torch.Tensor):
+            return -torch.matmul(Minv, dc_du[..., :n]), -torch.matmul(Minv, dc_du[..., n:])
+        return -np.matmul(Minv, dc_du[..., :n]), -np.matmul(Minv, dc_du[..., n:])
+
+    # ------------------------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self._lib.rbd_launch_count())

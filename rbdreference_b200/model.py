@@ -1,0 +1,177 @@
+"""Model compiler: URDFParser-style robot object -> flat, device-ready tables.
+
+The reference re-queries the robot object per body per call
+(/root/reference/RBDReference.py:570-574, :595, :662, :666).  Here the robot is
+compiled ONCE into plain arrays that the CUDA library turns into a kernel-parameter
+(constant-bank) model:
+
+* topology: parent[], ancestor bit masks, subtree lists, level schedule;
+* per joint: motion subspace S (6), spatial inertia I (6x6), damping;
+* per joint transform coefficients: every 1-DoF joint satisfies
+      X(q) = A + B*cos(q) + C*sin(q)   (revolute)      X(q) = A + B*q   (prismatic)
+  so A, B, C are recovered by PROBING the robot's own `get_Xmat_Func_by_id(i)` callable at
+  q = 0, pi/2, pi (or 0, 1) and verified on random angles.  This reproduces whatever
+  convention the parser used without re-deriving URDF semantics.
+
+Only the 18 structurally non-zero entries of a Pluecker transform are kept:
+X = [[E, 0], [L, E]]  ->  E (3x3 row-major) followed by L (3x3 row-major).
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import List
+
+import numpy as np
+
+MAX_DOF = 32  # kernel-parameter model limit (include/rbd_b200.h: RBD_MAX_DOF)
+
+__all__ = ["RobotModel", "compile_model", "MAX_DOF"]
+
+
+@dataclasses.dataclass
+class RobotModel:
+    name: str
+    n: int
+    parent: np.ndarray        # (n,) int32, -1 = fixed base
+    kind: np.ndarray          # (n,) int32, 0 = revolute (cos/sin), 1 = prismatic (affine)
+    S: np.ndarray             # (n,6) float64
+    XA: np.ndarray            # (n,18) float64  [E | L]
+    XB: np.ndarray            # (n,18)
+    XC: np.ndarray            # (n,18)
+    I: np.ndarray             # (n,36) float64 row-major 6x6
+    damping: np.ndarray       # (n,) float64
+    anc_mask: np.ndarray      # (n,) uint32: bit c set iff c is an ancestor of i or c == i
+    subtree: List[List[int]]  # subtree(i) including i
+    depth: np.ndarray         # (n,) int32, roots have depth 0
+    levels: List[List[int]]   # bodies per depth
+
+    # ---- derived counts used by bench.py / DESIGN.md (SURVEY.md 8d formulae) -------------
+    def flops(self, op: str) -> int:
+        """Algorithmic flop count per evaluation (ancestor-sparse, block-dense)."""
+        n = self.n
+        P = self.depth.astype(np.int64)                  # number of ancestors
+        A = P + 1
+        ST = np.array([len(s) for s in self.subtree], dtype=np.int64)
+        Bi = A + ST - 1
+        nr = self.parent >= 0
+        root_of = np.arange(n)
+        for i in range(n):
+            root_of[i] = i if self.parent[i] < 0 else root_of[self.parent[i]]
+        C = np.array([np.sum((root_of == root_of[i]) & (np.arange(n) >= i)) for i in range(n)], dtype=np.int64)
+        rnea = int(np.sum(54 + np.where(nr, 132, 6) + 10 + 168) + 72 * np.sum(nr))
+        if op == "rnea":
+            return rnea
+        if op == "rnea_grad":
+            return int(rnea + 2 * np.sum(132 * P + 212 * A + 4) + 2 * 72 * np.sum(Bi[nr]) + 72 * np.sum(nr))
+        if op == "minv":
+            return int(np.sum(55 + 2 * ST) + np.sum(906 + 84 * ST[nr]) + np.sum(66 + 81 * C[nr]))
+        raise KeyError(op)
+
+    def io_bytes(self, op: str, itemsize: int = 8, full_rnea: bool = False) -> int:
+        """Compulsory HBM bytes per evaluation: dense inputs + outputs."""
+        n = self.n
+        if op == "rnea":
+            return (3 * n + n + (18 * n if full_rnea else 0)) * itemsize
+        if op == "rnea_grad":
+            return (3 * n + 2 * n * n) * itemsize
+        if op == "minv":
+            return (n + n * n) * itemsize
+        raise KeyError(op)
+
+
+def _as_matrix(x) -> np.ndarray:
+    return np.asarray(x, dtype=np.float64).reshape(6, 6)
+
+
+def _pack18(X: np.ndarray, tol: float, what: str) -> np.ndarray:
+    """Keep [E | L] of a Pluecker-structured 6x6 and check the structure."""
+    if np.max(np.abs(X[:3, 3:])) > tol:
+        raise ValueError("%s: upper-right 3x3 block is not zero - not a Pluecker motion transform" % what)
+    if np.max(np.abs(X[:3, :3] - X[3:, 3:])) > tol:
+        raise ValueError("%s: rotation blocks differ - not a Pluecker motion transform" % what)
+    return np.concatenate((X[:3, :3].reshape(-1), X[3:, :3].reshape(-1)))
+
+
+def compile_model(robot, name: str | None = None, check_points: int = 6) -> RobotModel:
+    """Compile a URDFParser-style fixed-base robot into flat tables (see module docstring)."""
+    if getattr(robot, "floating_base", False):
+        raise NotImplementedError(
+            "floating-base robots are outside the accelerated hot path (SURVEY.md 8f rank 3)")
+    n = int(robot.get_num_bodies())
+    if int(robot.get_num_vel()) != n:
+        raise ValueError("hot path expects one 1-DoF joint per body (num_vel == num_bodies)")
+    if not (1 <= n <= MAX_DOF):
+        raise ValueError("robot has %d DoF; supported range is 1..%d" % (n, MAX_DOF))
+
+    parent = np.array([int(robot.get_parent_id(i)) for i in range(n)], dtype=np.int32)
+    for i in range(n):
+        if not (-1 <= parent[i] < i):
+            raise ValueError("body ids must be topologically ordered (parent id < child id)")
+        for getter in ("get_joint_index_q", "get_joint_index_v", "get_joint_index_f"):
+            fn = getattr(robot, getter, None)
+            if fn is not None and int(fn(i)) != i:
+                raise ValueError("%s(%d) != %d: only identity joint indexing is supported" % (getter, i, i))
+
+    S = np.zeros((n, 6))
+    kind = np.zeros(n, dtype=np.int32)
+    XA = np.zeros((n, 18)); XB = np.zeros((n, 18)); XC = np.zeros((n, 18))
+    I = np.zeros((n, 36))
+    damping = np.zeros(n)
+    rng = np.random.default_rng(20261018)
+    for i in range(n):
+        Si = np.asarray(robot.get_S_by_id(i), dtype=np.float64).reshape(-1)   # (6,), (6,1) or np.matrix
+        if Si.shape != (6,):
+            raise ValueError("S of joint %d must have 6 entries" % i)
+        S[i] = Si
+        ang, lin = np.any(Si[:3] != 0), np.any(Si[3:] != 0)
+        if ang and lin:
+            raise ValueError("joint %d: helical/compound motion subspaces are not supported" % i)
+        kind[i] = 0 if ang else 1
+        fn = robot.get_Xmat_Func_by_id(i)
+        X0 = _as_matrix(fn(0.0))
+        scale = max(1.0, float(np.max(np.abs(X0))))
+        tol = 1e-11 * scale
+        if kind[i] == 0:
+            Xh, Xp = _as_matrix(fn(np.pi / 2)), _as_matrix(fn(np.pi))
+            A, Bm = 0.5 * (X0 + Xp), 0.5 * (X0 - Xp)
+            C = Xh - A
+        else:
+            A, Bm, C = X0, _as_matrix(fn(1.0)) - X0, np.zeros((6, 6))
+        for t in rng.uniform(-3.0, 3.0, size=check_points):
+            f1, f2 = (np.cos(t), np.sin(t)) if kind[i] == 0 else (t, 0.0)
+            if np.max(np.abs(A + f1 * Bm + f2 * C - _as_matrix(fn(t)))) > tol:
+                raise ValueError("joint %d: Xmat(q) is not A + B*cos(q) + C*sin(q) / A + B*q" % i)
+        XA[i] = _pack18(A, tol, "joint %d (A)" % i)
+        XB[i] = _pack18(Bm, tol, "joint %d (B)" % i)
+        XC[i] = _pack18(C, tol, "joint %d (C)" % i)
+        # snap numerical dust (|x| < 1e-15) so structural zeros are exact zeros
+        for arr in (XA, XB, XC):
+            arr[i][np.abs(arr[i]) < 1e-15 * scale] = 0.0
+        I[i] = np.asarray(robot.get_Imat_by_id(i), dtype=np.float64).reshape(36)
+        dget = getattr(robot, "get_damping_by_id", None)
+        damping[i] = float(dget(i)) if dget is not None else 0.0
+
+    # subtree(i) includes i (RBDReference.py:720-723); cross-check with the robot's own answer
+    subtree: List[List[int]] = [[i] for i in range(n)]
+    for i in range(n - 1, -1, -1):
+        if parent[i] >= 0:
+            subtree[parent[i]].extend(subtree[i])
+    subtree = [sorted(s) for s in subtree]
+    sget = getattr(robot, "get_subtree_by_id", None)
+    if sget is not None:
+        for i in range(n):
+            if sorted(int(x) for x in sget(i)) != subtree[i]:
+                raise ValueError("get_subtree_by_id(%d) disagrees with the parent array" % i)
+
+    depth = np.zeros(n, dtype=np.int32)
+    anc_mask = np.zeros(n, dtype=np.uint32)
+    for i in range(n):
+        if parent[i] >= 0:
+            depth[i] = depth[parent[i]] + 1
+            anc_mask[i] = anc_mask[parent[i]]
+        anc_mask[i] |= np.uint32(1) << np.uint32(i)
+    levels = [[int(i) for i in range(n) if depth[i] == d] for d in range(int(depth.max()) + 1)]
+
+    return RobotModel(name=name or getattr(robot, "name", "robot"), n=n, parent=parent, kind=kind, S=S,
+                      XA=XA, XB=XB, XC=XC, I=I, damping=damping, anc_mask=anc_mask, subtree=subtree,
+                      depth=depth, levels=levels)

@@ -1,0 +1,53 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# parity bars from BASELINE.json north_star: rel = max|x - ref| / max|ref| per tensor
+TOL_F64 = 1e-10
+TOL_F32 = 1e-4
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def rel_err(x, ref):
+    x = np.asarray(x, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert x.shape == ref.shape, "shape %s vs reference %s" % (x.shape, ref.shape)
+    scale = float(np.max(np.abs(ref))) if ref.size else 0.0
+    if scale == 0.0:
+        return float(np.max(np.abs(x))) if x.size else 0.0
+    return float(np.max(np.abs(x - ref))) / scale
+
+
+def make_robot(name):
+    from rbdreference_b200 import robots
+    if name == "tree9":
+        return robots.random_tree(9, seed=1)
+    if name == "tree13":
+        return robots.random_tree(13, seed=2, branching=0.5, prismatic=0.3)
+    return robots.by_name(name)
+
+
+GOLDEN_CASES = ["iiwa14", "hyq", "atlas", "tree9", "tree13"]
+
+
+@pytest.fixture(scope="session", params=GOLDEN_CASES)
+def golden(request):
+    name = request.param
+    data = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    return name, make_robot(name), data
+
+
+def random_states(n, B, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.uniform(-np.pi, np.pi, (B, n)), rng.uniform(-1, 1, (B, n)), rng.uniform(-1, 1, (B, n)))

@@ -1,0 +1,252 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): every C-ABI entry point, called
+through the `RBDReference` host API, against the reference's golden outputs and the oracle.
+
+Bars (BASELINE.json north_star): rel = max|x - ref| / max|ref| per tensor,
+FP64 <= 1e-10, FP32 <= 1e-4.  Nothing here reads /root/reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TOL_F32, TOL_F64, make_robot, random_states, rel_err
+from oracle.rbd_oracle import BatchOracle
+
+pytestmark = pytest.mark.gpu
+
+requires_cuda = pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")
+
+
+def _engine(rb, dtype=torch.float64):
+    from rbdreference_b200 import RBDReference
+    return RBDReference(rb, dtype=dtype)
+
+
+def _t(x, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype, device="cuda")
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors produced by the unmodified reference
+# ---------------------------------------------------------------------------------------------
+@requires_cuda
+def test_fused_drivers_vs_reference_golden(golden):
+    name, rb, g = golden
+    eng = _engine(rb)
+    q, qd, qdd = g["q"], g["qd"], g["qdd"]
+    c, v, a, f = eng.rnea(q, qd, qdd)
+    for got, key in ((c, "c"), (v, "v"), (a, "a"), (f, "f")):
+        assert rel_err(got, g[key]) < TOL_F64, key
+    c0, _, a0, f0 = eng.rnea(q, qd)
+    assert rel_err(c0, g["c_noqdd"]) < TOL_F64 and rel_err(a0, g["a_noqdd"]) < TOL_F64
+    assert rel_err(f0, g["f_noqdd"]) < TOL_F64
+    assert rel_err(eng.rnea(q, qd, qdd, GRAVITY=-3.7)[0], g["c_galt"]) < TOL_F64
+    assert rel_err(eng.rnea(q, qd, qdd, outputs="c"), g["c"]) < TOL_F64
+    assert rel_err(eng.rnea_grad(q, qd, qdd), g["dc_du"]) < TOL_F64
+    assert rel_err(eng.rnea_grad(q, qd, qdd, USE_VELOCITY_DAMPING=True), g["dc_du_damped"]) < TOL_F64
+    assert rel_err(eng.rnea_grad(q, qd), g["dc_du_noqdd"]) < TOL_F64
+    assert rel_err(eng.minv(q), g["Minv"]) < TOL_F64
+    assert rel_err(eng.minv(q, output_dense=False), g["Minv_sparse"]) < TOL_F64
+
+
+@requires_cuda
+def test_pass_helpers_vs_reference_golden(golden):
+    name, rb, g = golden
+    eng = _engine(rb)
+    q, qd, qdd = g["q"], g["qd"], g["qdd"]
+    v, a, f = eng.rnea_fpass(q, qd, qdd)
+    assert rel_err(v, g["v"]) < TOL_F64 and rel_err(a, g["a"]) < TOL_F64
+    assert rel_err(f, g["f_fpass"]) < TOL_F64
+    c, f_ret = eng.rnea_bpass(q, f)
+    assert f_ret is f                                            # in-place contract (:619,:621)
+    assert rel_err(c, g["c"]) < TOL_F64 and rel_err(f, g["f"]) < TOL_F64
+    dv, da, df = eng.rnea_grad_fpass_dq(q, qd, g["v"], g["a"])
+    for got, key in ((dv, "dv_dq"), (da, "da_dq"), (df, "df_dq")):
+        assert rel_err(got, g[key]) < TOL_F64, key
+    dv2, da2, df2 = eng.rnea_grad_fpass_dqd(q, qd, g["v"])
+    for got, key in ((dv2, "dv_dqd"), (da2, "da_dqd"), (df2, "df_dqd")):
+        assert rel_err(got, g[key]) < TOL_F64, key
+    dc_dq = eng.rnea_grad_bpass_dq(q, g["f"], df)
+    assert rel_err(dc_dq, g["dc_dq"]) < TOL_F64
+    assert rel_err(df, g["df_dq_acc"]) < TOL_F64                 # df_dq mutated in place (:1291)
+    dc_dqd = eng.rnea_grad_bpass_dqd(q, df2)
+    assert rel_err(dc_dqd, g["dc_dqd"]) < TOL_F64
+    assert rel_err(df2, g["df_dqd_acc"]) < TOL_F64
+    Mb, Fb, U, D = eng.minv_bpass(q)
+    for got, key in ((Mb, "Minv_b"), (Fb, "F_b"), (U, "U"), (D, "Dinv")):
+        assert rel_err(got, g[key]) < TOL_F64, key
+    M = eng.minv_fpass(q, Mb, Fb, U, D)
+    assert M is Mb                                               # returned object is the argument (:783)
+    assert rel_err(M, g["Minv_sparse"]) < TOL_F64
+    assert rel_err(Fb, g["F_f"]) < TOL_F64
+    assert rel_err(eng.rnea_grad_passes(q, qd, qdd), g["dc_du"]) < TOL_F64
+    assert rel_err(eng.minv_passes(q), g["Minv"]) < TOL_F64
+
+
+@requires_cuda
+def test_single_state_reference_shapes(golden):
+    """(n,) numpy in -> reference-shaped numpy out, one knot point (README.md:9-12)."""
+    name, rb, g = golden
+    eng = _engine(rb)
+    n = eng.n
+    q, qd, qdd = g["q"][0], g["qd"][0], g["qdd"][0]
+    c, v, a, f = eng.rnea(q, qd, qdd)
+    assert c.shape == (n,) and v.shape == (6, n) and a.shape == (6, n) and f.shape == (6, n)
+    assert isinstance(c, np.ndarray) and rel_err(c, g["c"][0]) < TOL_F64
+    dc = eng.rnea_grad(q, qd, qdd)
+    assert dc.shape == (n, 2 * n) and rel_err(dc, g["dc_du"][0]) < TOL_F64
+    M = eng.minv(q)
+    assert M.shape == (n, n) and rel_err(M, g["Minv"][0]) < TOL_F64
+    f_in = g["f_fpass"][0].copy()
+    c2, f_out = eng.rnea_bpass(q, f_in)
+    assert f_out is f_in and rel_err(f_in, g["f"][0]) < TOL_F64
+
+
+@requires_cuda
+def test_fp32_vs_reference_golden(golden):
+    name, rb, g = golden
+    eng = _engine(rb, torch.float32)
+    q, qd, qdd = g["q"], g["qd"], g["qdd"]
+    c, v, a, f = eng.rnea(q, qd, qdd)
+    assert c.dtype == np.float32
+    for got, key in ((c, "c"), (v, "v"), (a, "a"), (f, "f")):
+        assert rel_err(got, g[key]) < TOL_F32, key
+    assert rel_err(eng.rnea_grad(q, qd, qdd), g["dc_du"]) < TOL_F32
+    assert rel_err(eng.minv(q), g["Minv"]) < TOL_F32
+    assert rel_err(eng.rnea_grad_passes(q, qd, qdd), g["dc_du"]) < TOL_F32
+    assert rel_err(eng.minv_passes(q), g["Minv"]) < TOL_F32
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded batches against the oracle
+# ---------------------------------------------------------------------------------------------
+@requires_cuda
+@pytest.mark.parametrize("name,B", [("iiwa14", 4096), ("hyq", 2048), ("atlas", 1024), ("tree13", 777)])
+def test_batched_cuda_tensors_vs_oracle(name, B):
+    rb = make_robot(name)
+    eng, bo = _engine(rb), BatchOracle(rb)
+    n = eng.n
+    q, qd, qdd = random_states(n, B, seed=0xB200)
+    tq, tqd, tqdd = _t(q), _t(qd), _t(qdd)
+    c, v, a, f = eng.rnea(tq, tqd, tqdd)
+    assert c.is_cuda and c.shape == (B, n) and v.shape == (B, 6, n)
+    rc, rv, ra, rf = bo.rnea(q, qd, qdd)
+    for got, ref in ((c, rc), (v, rv), (a, ra), (f, rf)):
+        assert rel_err(got.cpu().numpy(), ref) < TOL_F64
+    dc = eng.rnea_grad(tq, tqd, tqdd)
+    assert dc.shape == (B, n, 2 * n)
+    assert rel_err(dc.cpu().numpy(), bo.rnea_grad(q, qd, qdd)) < TOL_F64
+    M = eng.minv(tq)
+    assert rel_err(M.cpu().numpy(), bo.minv(q)) < TOL_F64
+    out = torch.empty(B, n, 2 * n, dtype=torch.float64, device="cuda")
+    cbuf = torch.empty(B, n, dtype=torch.float64, device="cuda")
+    ret = eng.rnea_grad(tq, tqd, tqdd, out=out, c_out=cbuf)
+    assert ret.data_ptr() == out.data_ptr() and torch.equal(out, dc)
+    assert rel_err(cbuf.cpu().numpy(), rc) < TOL_F64
+
+
+@requires_cuda
+@pytest.mark.parametrize("B", [1, 2, 31, 32, 33, 127, 129, 1000])
+def test_ragged_batch_sizes(B):
+    rb = make_robot("hyq")
+    eng, bo = _engine(rb), BatchOracle(rb)
+    q, qd, qdd = random_states(eng.n, B, seed=B)
+    assert rel_err(eng.rnea_grad(q, qd, qdd), bo.rnea_grad(q, qd, qdd)) < TOL_F64
+    assert rel_err(eng.minv(q), bo.minv(q)) < TOL_F64
+    assert rel_err(eng.rnea(q, qd, qdd)[0], bo.rnea(q, qd, qdd)[0]) < TOL_F64
+
+
+@requires_cuda
+def test_empty_batch_and_bad_shapes():
+    eng = _engine(make_robot("iiwa14"))
+    z = torch.empty(0, 7, dtype=torch.float64, device="cuda")
+    assert eng.rnea_grad(z, z, z).shape == (0, 7, 14)
+    assert eng.minv(z).shape == (0, 7, 7)
+    with pytest.raises(ValueError):
+        eng.rnea(np.zeros(6), np.zeros(6))
+    with pytest.raises(ValueError):
+        eng.rnea_grad(np.zeros((3, 7)), np.zeros((4, 7)))
+
+
+@requires_cuda
+def test_fp32_batch_vs_fp64_oracle():
+    """FP32 kernels fed the FP64 draws cast down stay within 1e-4 on Atlas."""
+    rb = make_robot("atlas")
+    eng, bo = _engine(rb, torch.float32), BatchOracle(rb)
+    q, qd, qdd = random_states(30, 512, seed=5)
+    assert rel_err(eng.minv(q), bo.minv(q)) < TOL_F32
+    assert rel_err(eng.rnea_grad(q, qd, qdd), bo.rnea_grad(q, qd, qdd)) < TOL_F32
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size, size-independent properties (no oracle at 2^20 points)
+# ---------------------------------------------------------------------------------------------
+@requires_cuda
+def test_full_size_properties_iiwa_1m():
+    rb = make_robot("iiwa14")
+    eng, bo = _engine(rb), BatchOracle(rb)
+    n, B = 7, 1 << 20
+    gen = torch.Generator(device="cuda").manual_seed(0xB200)
+    q = (torch.rand(B, n, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1) * np.pi
+    qd = torch.rand(B, n, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1
+    qdd = torch.rand(B, n, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1
+    dc = eng.rnea_grad(q, qd, qdd)
+    M = eng.minv(q)
+    assert torch.isfinite(dc).all() and torch.isfinite(M).all()
+    assert torch.equal(M, M.transpose(1, 2))                      # mirror is exact (:799-804)
+    # linearity in qdd: c(q,qd,qdd) - c(q,qd,0) = H qdd  =>  Minv (c - c0) = qdd
+    c = eng.rnea(q, qd, qdd, outputs="c")
+    c0 = eng.rnea(q, qd, outputs="c")
+    back = torch.matmul(M, (c - c0).unsqueeze(-1)).squeeze(-1)
+    assert float((back - qdd).abs().max()) < 1e-9
+    # gravity-free, motion-free torque is exactly zero
+    zero = torch.zeros_like(q)
+    assert float(eng.rnea(q, zero, zero, GRAVITY=0.0, outputs="c").abs().max()) == 0.0
+    # dc/dqd does not depend on qdd; damping only touches its diagonal
+    dc2 = eng.rnea_grad(q, qd, None, USE_VELOCITY_DAMPING=True)
+    diff = dc2[:, :, n:] - dc[:, :, n:]
+    damp = torch.as_tensor(eng.model.damping, device="cuda")
+    assert float((diff - torch.diag(damp)).abs().max()) < 1e-12
+    # sharded evaluation (disjoint slices, same kernel) is bit-identical to the unsharded one
+    from rbdreference_b200.dist import shard_bounds
+    lo, hi = shard_bounds(B, 3, 8)
+    assert torch.equal(eng.rnea_grad(q[lo:hi], qd[lo:hi], qdd[lo:hi]), dc[lo:hi])
+    # spot-check 4096 strided points of the big batch against the oracle
+    idx = torch.arange(0, B, B // 4096, device="cuda")[:4096]
+    ref = bo.rnea_grad(q[idx].cpu().numpy(), qd[idx].cpu().numpy(), qdd[idx].cpu().numpy())
+    assert rel_err(dc[idx].cpu().numpy(), ref) < TOL_F64
+    assert rel_err(M[idx].cpu().numpy(), bo.minv(q[idx].cpu().numpy())) < TOL_F64
+
+
+@requires_cuda
+def test_full_size_properties_atlas_256k():
+    rb = make_robot("atlas")
+    n, B = 30, 1 << 18
+    bo = BatchOracle(rb)
+    gen = torch.Generator(device="cuda").manual_seed(0xA71A5)
+    q64 = (torch.rand(B, n, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1) * np.pi
+    for dtype, tol in ((torch.float64, TOL_F64), (torch.float32, TOL_F32)):
+        eng = _engine(rb, dtype)
+        M = eng.minv(q64.to(dtype))
+        assert torch.isfinite(M).all() and torch.equal(M, M.transpose(1, 2))
+        # block structure: pelvis-rooted components (torso+arms | l_leg | r_leg) do not couple
+        assert float(M[:, :18, 18:].abs().max()) == 0.0 and float(M[:, 18:24, 24:].abs().max()) == 0.0
+        idx = torch.arange(0, B, B // 512, device="cuda")[:512]
+        H = bo.crba(q64[idx].cpu().numpy())
+        MH = M[idx].double().cpu().numpy() @ H
+        assert np.max(np.abs(MH - np.eye(n))) < (1e-9 if dtype == torch.float64 else 2e-2)
+        assert rel_err(M[idx].cpu().numpy(), bo.minv(q64[idx].cpu().numpy())) < tol
+
+
+@requires_cuda
+def test_forward_dynamics_compositions():
+    """forward_dynamics / forward_dynamics_grad as compositions."""
+    from oracle.rbd_oracle import ScalarOracle
+    rb = make_robot("iiwa14")
+    eng, so = _engine(rb), ScalarOracle(rb)
+    q, qd, u = random_states(7, 4, seed=21)
+    qdd = eng.forward_dynamics(q, qd, u)
+    dq, dqd = eng.forward_dynamics_grad(q, qd, u)
+    for k in range(4):
+        assert rel_err(qdd[k], so.forward_dynamics(q[k], qd[k], u[k])) < 1e-9
+        r1, r2 = so.forward_dynamics_grad(q[k], qd[k], u[k])
+        assert rel_err(dq[k], r1) < 1e-9 and rel_err(dqd[k], r2) < 1e-9

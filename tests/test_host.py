@@ -1,0 +1,162 @@
+"""CPU tests of the host side: model compiler, C-ABI library surface, sharding, loud failures."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, make_robot
+from rbdreference_b200 import _capi, compile_model, robots
+from rbdreference_b200.dist import shard_bounds
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _capi.load_library()
+    header = open(os.path.join(ROOT, "include", "rbd_b200.h")).read()
+    declared = set(re.findall(r"\b(rbd_[a-z0-9_]+)\s*\(", header))
+    declared.discard("rbd_model")
+    assert declared == set(_capi.exported_symbols()), declared ^ set(_capi.exported_symbols())
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), "missing export " + sym
+    assert lib.rbd_abi_version() == 1
+
+
+def test_model_create_validates_arguments():
+    lib = _capi.load_library()
+    handle = ctypes.c_void_p()
+    assert lib.rbd_model_create(None, ctypes.byref(handle)) == -1
+    assert b"null" in lib.rbd_last_error_string()
+    m = compile_model(robots.iiwa14())
+    h = _capi.ModelHandle(m)
+    assert lib.rbd_model_num_dof(h.ptr) == 7
+    bad = compile_model(robots.iiwa14())
+    bad.parent = bad.parent.copy(); bad.parent[0] = 3
+    with pytest.raises(_capi.RbdError):
+        _capi.ModelHandle(bad)
+
+
+@pytest.mark.parametrize("name", ["iiwa14", "hyq", "atlas", "tree9", "tree13"])
+def test_model_compiler_reproduces_transforms(name):
+    rb = make_robot(name)
+    m = compile_model(rb)
+    n = m.n
+    rng = np.random.default_rng(3)
+    for i in range(n):
+        for t in rng.uniform(-3, 3, 3):
+            f1, f2 = (np.cos(t), np.sin(t)) if m.kind[i] == 0 else (t, 0.0)
+            x18 = m.XA[i] + f1 * m.XB[i] + f2 * m.XC[i]
+            X = np.zeros((6, 6))
+            X[:3, :3] = x18[:9].reshape(3, 3); X[3:, 3:] = X[:3, :3]; X[3:, :3] = x18[9:].reshape(3, 3)
+            assert np.max(np.abs(X - rb.get_Xmat_Func_by_id(i)(t))) < 1e-13
+    for i in range(n):
+        assert sorted(rb.get_subtree_by_id(i)) == m.subtree[i]
+        anc = set(rb.get_ancestors_by_id(i)) | {i}
+        assert anc == {c for c in range(n) if (int(m.anc_mask[i]) >> c) & 1}
+
+
+def test_model_compiler_flop_model_matches_survey_table():
+    """algorithmic flops / bytes per evaluation."""
+    expect = {"iiwa14": (2854, 26806, 9738), "hyq": (4440, 21912, 10464), "atlas": (12486, 144510, 53097)}
+    for name, (r, g, mi) in expect.items():
+        m = compile_model(make_robot(name))
+        assert (m.flops("rnea"), m.flops("rnea_grad"), m.flops("minv")) == (r, g, mi)
+    m = compile_model(make_robot("iiwa14"))
+    assert m.io_bytes("rnea_grad") == 952 and m.io_bytes("minv") == 448 and m.io_bytes("rnea") == 224
+    assert m.io_bytes("rnea", full_rnea=True) == 1232
+
+
+def test_model_compiler_rejects_unsupported_robots():
+    rb = robots.iiwa14()
+    rb.floating_base = True
+    with pytest.raises(NotImplementedError):
+        compile_model(rb)
+    big = robots.random_tree(40, seed=0)
+    with pytest.raises(ValueError):
+        compile_model(big)
+
+    class Weird(robots.Robot):
+        def get_Xmat_Func_by_id(self, i):
+            base = super().get_Xmat_Func_by_id(i)
+            return lambda q: base(q * q)        # not of 1-DoF A + B cos + C sin form
+    with pytest.raises(ValueError):
+        compile_model(Weird("weird", robots.iiwa14().joints))
+
+
+def test_S_shape_variants_are_normalised():
+    """The reference accepts S as (6,), (6,1) ndarray or (6,1) np.matrix."""
+    class ColS(robots.Robot):
+        def get_S_by_id(self, i):
+            return super().get_S_by_id(i).reshape(6, 1)
+    a = compile_model(robots.iiwa14())
+    b = compile_model(ColS("iiwa14", robots.iiwa14().joints))
+    assert np.array_equal(a.S, b.S)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_without_gpu_fails_loudly():
+    from rbdreference_b200 import RBDReference
+    eng = RBDReference(robots.iiwa14())
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        eng.rnea_grad(np.zeros(7), np.zeros(7), np.zeros(7))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        eng.minv(np.zeros((4, 7)))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "rbdreference_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|oracle[./]", src, re.M), fn + " uses the oracle"
+
+
+def test_shard_bounds_partition_the_batch():
+    for B in (0, 1, 7, 1000, 1 << 20):
+        for W in (1, 2, 3, 8):
+            spans = [shard_bounds(B, r, W) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0 and a0 <= a1
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["RBD_ROOT"])
+import torch, torch.distributed as dist
+from rbdreference_b200.dist import shard_bounds, gather_to_all, gather_to_rank
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+for B in (10, 7):
+    full = torch.arange(B * 3, dtype=torch.float64).reshape(B, 3)
+    lo, hi = shard_bounds(B, rank, world)
+    local = full[lo:hi].clone()
+    assert torch.equal(gather_to_all(local, B), full)
+    got = gather_to_rank(local, B, dst=0)
+    assert (got is None) == (rank != 0)
+    if rank == 0:
+        assert torch.equal(got, full)
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_gloo_gather(tmp_path):
+    """world_size-2 run of the sharding + gather plumbing on CPU (gloo)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, RBD_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o

@@ -1,0 +1,123 @@
+"""CPU tests: the oracle restatement against the reference's golden outputs and identities."""
+import numpy as np
+import pytest
+
+from conftest import rel_err, random_states, make_robot
+from oracle.rbd_oracle import BatchOracle, ScalarOracle
+from oracle import build_ref
+
+PIN = 1e-11   # oracle vs reference golden vectors (both float64, different summation order)
+
+
+def test_golden_matches_robot_tables(golden):
+    name, rb, g = golden
+    n = rb.get_num_vel()
+    assert np.array_equal(g["parent"], [rb.get_parent_id(i) for i in range(n)])
+    assert np.allclose(g["S"], np.stack([rb.get_S_by_id(i) for i in range(n)]), atol=0)
+    assert np.allclose(g["I"], np.stack([rb.get_Imat_by_id(i) for i in range(n)]), rtol=0, atol=1e-15)
+    assert np.allclose(g["X_at_0p3"], np.stack([rb.get_Xmat_Func_by_id(i)(0.3) for i in range(n)]), rtol=0, atol=1e-15)
+
+
+def test_scalar_oracle_vs_golden(golden):
+    name, rb, g = golden
+    so = ScalarOracle(rb)
+    q, qd, qdd = g["q"], g["qd"], g["qdd"]
+    for k in range(q.shape[0]):
+        v, a, f = so.rnea_fpass(q[k], qd[k], qdd[k])
+        assert rel_err(f, g["f_fpass"][k]) < PIN
+        c, f2 = so.rnea_bpass(q[k], f)
+        assert f2 is f                                   # in-place contract
+        for got, key in ((c, "c"), (v, "v"), (a, "a"), (f, "f")):
+            assert rel_err(got, g[key][k]) < PIN, key
+        assert rel_err(so.rnea(q[k], qd[k])[0], g["c_noqdd"][k]) < PIN
+        assert rel_err(so.rnea(q[k], qd[k], qdd[k], GRAVITY=-3.7)[0], g["c_galt"][k]) < PIN
+        assert rel_err(so.rnea_grad(q[k], qd[k], qdd[k]), g["dc_du"][k]) < PIN
+        assert rel_err(so.rnea_grad(q[k], qd[k], qdd[k], USE_VELOCITY_DAMPING=True), g["dc_du_damped"][k]) < PIN
+        assert rel_err(so.rnea_grad(q[k], qd[k]), g["dc_du_noqdd"][k]) < PIN
+        dv, da, df = so.rnea_grad_fpass_dq(q[k], qd[k], g["v"][k], g["a"][k])
+        for got, key in ((dv, "dv_dq"), (da, "da_dq"), (df, "df_dq")):
+            assert rel_err(got, g[key][k]) < PIN, key
+        dv2, da2, df2 = so.rnea_grad_fpass_dqd(q[k], qd[k], g["v"][k])
+        for got, key in ((dv2, "dv_dqd"), (da2, "da_dqd"), (df2, "df_dqd")):
+            assert rel_err(got, g[key][k]) < PIN, key
+        assert rel_err(so.rnea_grad_bpass_dq(q[k], g["f"][k], df), g["dc_dq"][k]) < PIN
+        assert rel_err(df, g["df_dq_acc"][k]) < PIN
+        assert rel_err(so.rnea_grad_bpass_dqd(q[k], df2), g["dc_dqd"][k]) < PIN
+        assert rel_err(df2, g["df_dqd_acc"][k]) < PIN
+        Mb, Fb, U, D = so.minv_bpass(q[k])
+        for got, key in ((Mb, "Minv_b"), (Fb, "F_b"), (U, "U"), (D, "Dinv")):
+            assert rel_err(got, g[key][k]) < PIN, key
+        M = so.minv_fpass(q[k], Mb, Fb, U, D)
+        assert M is Mb
+        assert rel_err(Fb, g["F_f"][k]) < PIN
+        assert rel_err(so.minv(q[k]), g["Minv"][k]) < PIN
+        assert rel_err(so.minv(q[k], output_dense=False), g["Minv_sparse"][k]) < PIN
+        assert rel_err(so.crba(q[k]), g["H"][k]) < PIN
+
+
+def test_batch_oracle_vs_golden(golden):
+    name, rb, g = golden
+    bo = BatchOracle(rb)
+    q, qd, qdd = g["q"], g["qd"], g["qdd"]
+    c, v, a, f = bo.rnea(q, qd, qdd)
+    for got, key in ((c, "c"), (v, "v"), (a, "a"), (f, "f")):
+        assert rel_err(got, g[key]) < PIN, key
+    assert rel_err(bo.rnea(q, qd)[0], g["c_noqdd"]) < PIN
+    dc, parts = bo.rnea_grad(q, qd, qdd, return_parts=True)
+    assert rel_err(dc, g["dc_du"]) < PIN
+    for key in ("dv_dq", "da_dq", "df_dq", "dv_dqd", "da_dqd", "df_dqd", "df_dq_acc", "df_dqd_acc"):
+        assert rel_err(parts[key], g[key]) < PIN, key
+    assert rel_err(bo.rnea_grad(q, qd, qdd, USE_VELOCITY_DAMPING=True), g["dc_du_damped"]) < PIN
+    M, mp = bo.minv(q, return_parts=True)
+    assert rel_err(M, g["Minv"]) < PIN
+    for key, gk in (("Minv_b", "Minv_b"), ("F_b", "F_b"), ("U", "U"), ("D", "Dinv"), ("F_f", "F_f")):
+        assert rel_err(mp[key], g[gk]) < PIN, key
+    assert rel_err(bo.minv(q, output_dense=False), g["Minv_sparse"]) < PIN
+    assert rel_err(bo.crba(q), g["H"]) < PIN
+
+
+@pytest.mark.parametrize("name", ["iiwa14", "hyq", "atlas"])
+def test_identities(name):
+    """SURVEY.md section 4 identity table, on the oracle alone."""
+    rb = make_robot(name)
+    bo = BatchOracle(rb)
+    n = rb.get_num_vel()
+    q, qd, qdd = random_states(n, 16, seed=7)
+    M, H = bo.minv(q), bo.crba(q)
+    assert np.max(np.abs(M @ H - np.eye(n))) < 1e-11
+    assert np.max(np.abs(M - np.swapaxes(M, 1, 2))) == 0.0
+    c = bo.rnea(q, qd, qdd)[0]
+    c0 = bo.rnea(q, qd, np.zeros_like(qdd))[0]
+    assert rel_err(np.einsum("bij,bj->bi", H, qdd) + c0, c) < 1e-12
+    assert np.array_equal(bo.rnea(q, qd)[0], c0)
+    assert np.max(np.abs(bo.rnea(q, 0 * qd, 0 * qdd, GRAVITY=0.0)[0])) == 0.0
+    # gradient vs central differences of rnea
+    dc = bo.rnea_grad(q[:4], qd[:4], qdd[:4])
+    eps = 1e-6
+    for j in range(n):
+        dq = np.zeros(n); dq[j] = eps
+        num_q = (bo.rnea(q[:4] + dq, qd[:4], qdd[:4])[0] - bo.rnea(q[:4] - dq, qd[:4], qdd[:4])[0]) / (2 * eps)
+        num_d = (bo.rnea(q[:4], qd[:4] + dq, qdd[:4])[0] - bo.rnea(q[:4], qd[:4] - dq, qdd[:4])[0]) / (2 * eps)
+        scale = max(1.0, np.max(np.abs(dc)))
+        assert np.max(np.abs(num_q - dc[:, :, j])) / scale < 1e-7
+        assert np.max(np.abs(num_d - dc[:, :, n + j])) / scale < 1e-7
+    # structural zeros: dc entries vanish unless i, j lie on one root-to-leaf branch
+    for i in range(n):
+        for j in range(n):
+            on_branch = (i in rb.get_subtree_by_id(j)) or (j in rb.get_subtree_by_id(i))
+            if not on_branch:
+                assert np.all(dc[:, i, j] == 0) and np.all(dc[:, i, n + j] == 0)
+
+
+def test_staged_reference_agrees_when_present():
+    """If oracle/_ref holds the byte-compiled reference, check the oracle against it live."""
+    Ref = build_ref.load_reference()
+    if Ref is None:
+        pytest.skip("oracle/_ref not staged (run `python oracle/build_ref.py` in the build container)")
+    rb = make_robot("hyq")
+    ref, so = Ref(rb), ScalarOracle(rb)
+    q, qd, qdd = random_states(12, 3, seed=11)
+    for k in range(3):
+        assert rel_err(so.rnea_grad(q[k], qd[k], qdd[k]), ref.rnea_grad(q[k], qd[k], qdd[k])) < PIN
+        assert rel_err(so.minv(q[k]), ref.minv(q[k])) < PIN
+        assert rel_err(so.rnea(q[k], qd[k], qdd[k])[0], ref.rnea(q[k], qd[k], qdd[k])[0]) < PIN
