@@ -128,6 +128,8 @@ class RBDReference:
             return target
 
     def _call(self, name: str, ctx: "_Ctx", *args):
+        if ctx.B == 0:
+            return                                   # empty batch: nothing to launch
         fn = getattr(self._lib, "rbd_%s_%s" % (name, self._suffix))
         conv = []
         for a in args:
