@@ -65,6 +65,12 @@ const char* rbd_last_error_string(void);
 int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out);
 int rbd_model_destroy(rbd_model_t* m);
 int rbd_model_num_dof(const rbd_model_t* m);
+/* 1 if the fused drivers run the world-frame kernels for this model (every spatial inertia has
+ * rigid-body structure), 0 if they run the generic body-frame kernels. */
+int rbd_model_uses_world_kernels(const rbd_model_t* m);
+/* Process-wide kernel selection for the fused drivers: 0 = automatic (default), 1 = always the
+ * generic body-frame kernels (the reference's own recursion; used to cross-check the two). */
+int rbd_set_kernel_variant(int variant);
 
 /* ---- fused drivers ------------------------------------------------------------------------ */
 /* rnea (RBDReference.py:623-628).  qdd may be NULL (skips the S*qdd term, :589).  v, a, f may

@@ -14,7 +14,8 @@ PASS_SYMBOLS = ["rnea_fpass", "rnea_bpass", "rnea_grad_fpass_dq", "rnea_grad_fpa
                 "rnea_grad_bpass_dq", "rnea_grad_bpass_dqd", "minv_bpass", "minv_fpass"]
 FUSED_SYMBOLS = ["rnea", "rnea_grad", "minv"]
 PLAIN_SYMBOLS = ["rbd_abi_version", "rbd_last_error_string", "rbd_model_create", "rbd_model_destroy",
-                 "rbd_model_num_dof", "rbd_measure_fma_peak", "rbd_launch_count"]
+                 "rbd_model_num_dof", "rbd_model_uses_world_kernels", "rbd_set_kernel_variant",
+                 "rbd_measure_fma_peak", "rbd_launch_count"]
 
 
 def exported_symbols():
@@ -54,6 +55,8 @@ def load_library():
     lib.rbd_model_create.argtypes = [POINTER(RbdModelDesc), POINTER(c_void_p)]
     lib.rbd_model_destroy.argtypes = [c_void_p]
     lib.rbd_model_num_dof.argtypes = [c_void_p]
+    lib.rbd_model_uses_world_kernels.argtypes = [c_void_p]
+    lib.rbd_set_kernel_variant.argtypes = [c_int]
     lib.rbd_measure_fma_peak.argtypes = [c_int, POINTER(c_double), POINTER(c_double), c_void_p]
     lib.rbd_launch_count.restype = c_int64
     P = c_void_p

@@ -1,5 +1,6 @@
 // rbd_capi.cu - C ABI of librbd_b200.so (declared in include/rbd_b200.h).
 // Plain pointers and sizes only; no torch types; never synchronises; no CPU fallback.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <atomic>
@@ -8,6 +9,7 @@
 #include "../../include/rbd_b200.h"
 #include "rbd_common.cuh"
 #include "rbd_fused_kernels.cuh"
+#include "rbd_grad_kernels.cuh"
 #include "rbd_pass_kernels.cuh"
 
 using namespace rbd;
@@ -15,12 +17,17 @@ using namespace rbd;
 struct rbd_model {
   DevModel<double> d;
   DevModel<float> f;
+  FastModel<double> fd;     // world-frame kernels (rigid-body inertias only)
+  FastModel<float> ff;
+  bool fast_ok;             // FastModel valid (rigid inertias, 1-DoF revolute/prismatic joints)
 };
 
 namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_variant{0};          // 0 auto, 1 force the generic body-frame kernels
+constexpr size_t kMaxDynSmem = 227 * 1024;
 
 int fail(int code, const char* msg) {
   std::snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -40,6 +47,14 @@ int cuda_status(const char* what) {
 template <typename T> const DevModel<T>& pick(const rbd_model* m);
 template <> const DevModel<double>& pick<double>(const rbd_model* m) { return m->d; }
 template <> const DevModel<float>& pick<float>(const rbd_model* m) { return m->f; }
+template <typename T> const FastModel<T>& pick_fast(const rbd_model* m);
+template <> const FastModel<double>& pick_fast<double>(const rbd_model* m) { return m->fd; }
+template <> const FastModel<float>& pick_fast<float>(const rbd_model* m) { return m->ff; }
+
+template <typename T>
+size_t grad_world_smem(const FastModel<T>& fm) {
+  return (size_t)(fm.n * kVecPerBody + fm.n_slot_a * 28 + fm.n_slot_b * 24) * 32 * sizeof(T);
+}
 
 inline unsigned blocks_for(int64_t B, int threads) { return (unsigned)((B + threads - 1) / threads); }
 
@@ -61,6 +76,20 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
                      T* dc_du, T* c_out, void* stream) {
   RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_rnea_grad: null model/q/qd/dc_du or negative B");
   if (B == 0) return 0;
+  const FastModel<T>& fm = pick_fast<T>(m);
+  const size_t smem = grad_world_smem(fm);
+  if (m->fast_ok && g_variant.load(std::memory_order_relaxed) == 0 && smem <= kMaxDynSmem) {
+    static thread_local size_t configured = 0;    // per (thread, T); attribute is per device context
+    if (smem > 48 * 1024 || configured < smem) {
+      cudaError_t e = cudaFuncSetAttribute(rnea_grad_world_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kMaxDynSmem);
+      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+      configured = smem;
+    }
+    rnea_grad_world_kernel<T><<<blocks_for(B, 32), 32, smem, (cudaStream_t)stream>>>(fm, B, q, qd, qdd, g, damp,
+                                                                                      dc_du, c_out);
+    return cuda_status("rbd_rnea_grad(world)");
+  }
   rnea_grad_fused_kernel<T><<<blocks_for(B, kFusedThreads), kFusedThreads, 0, (cudaStream_t)stream>>>(
       pick<T>(m), B, q, qd, qdd, g, damp, dc_du, c_out);
   return cuda_status("rbd_rnea_grad");
@@ -160,6 +189,93 @@ void fill_model(const RbdModelDesc* d, DevModel<T>& out) {
   }
 }
 
+// ---- FastModel: rigid-body parameters, r(q) coefficients, stash-slot plan ---------------------
+bool build_fast_model(const RbdModelDesc* d, FastModel<double>& out) {
+  std::memset(&out, 0, sizeof(out));
+  const int n = d->n;
+  out.n = n;
+  out.rigid = 1;
+  for (int i = 0; i < n; ++i) {
+    out.parent[i] = d->parent[i];
+    out.kind[i] = d->kind[i];
+    out.slot_a[i] = out.slot_b[i] = -1;
+    out.damping[i] = d->damping ? d->damping[i] : 0.0;
+    if (d->kind[i] == 1) out.has_prismatic = 1;
+    const double* S = d->S + 6 * i;
+    const bool ang = S[0] != 0 || S[1] != 0 || S[2] != 0, lin = S[3] != 0 || S[4] != 0 || S[5] != 0;
+    if ((ang && lin) || (!ang && !lin) || (ang != (d->kind[i] == 0))) return false;
+    for (int k = 0; k < 3; ++k) out.axis[i][k] = ang ? S[k] : S[3 + k];
+    const double* XA = d->XA + 18 * i; const double* XB = d->XB + 18 * i; const double* XC = d->XC + 18 * i;
+    for (int k = 0; k < 9; ++k) { out.EA[i][k] = XA[k]; out.EB[i][k] = XB[k]; out.EC[i][k] = XC[k]; }
+    // r(q) from r x = -E^T L, sampled where (f1, f2) is a valid basis value
+    auto r_of = [&](double f1, double f2, double* r) {
+      double E[9], L[9], R[9];
+      for (int k = 0; k < 9; ++k) { E[k] = XA[k] + f1 * XB[k] + f2 * XC[k]; L[k] = XA[9 + k] + f1 * XB[9 + k] + f2 * XC[9 + k]; }
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) R[3 * a + b] = -(E[a] * L[b] + E[3 + a] * L[3 + b] + E[6 + a] * L[6 + b]);
+      r[0] = 0.5 * (R[7] - R[5]); r[1] = 0.5 * (R[2] - R[6]); r[2] = 0.5 * (R[3] - R[1]);
+    };
+    double r0[3], r1[3], r2[3];
+    if (d->kind[i] == 0) {
+      r_of(1, 0, r0); r_of(-1, 0, r1); r_of(0, 1, r2);
+      for (int k = 0; k < 3; ++k) {
+        out.rA[i][k] = 0.5 * (r0[k] + r1[k]); out.rB[i][k] = 0.5 * (r0[k] - r1[k]); out.rC[i][k] = r2[k] - out.rA[i][k];
+      }
+    } else {
+      r_of(0, 0, r0); r_of(1, 0, r1);
+      for (int k = 0; k < 3; ++k) { out.rA[i][k] = r0[k]; out.rB[i][k] = r1[k] - r0[k]; out.rC[i][k] = 0; }
+    }
+    // rigid-body structure of the spatial inertia: [[Ibar, hx], [hx^T, m 1]]
+    const double* I = d->I + 36 * i;
+    const double mss = I[21];
+    const double h[3] = {I[2 * 6 + 4], I[0 * 6 + 5], I[1 * 6 + 3]};
+    double ref[36] = {0};
+    const double Ib[6] = {I[0], I[1], I[2], I[7], I[8], I[14]};
+    ref[0] = Ib[0]; ref[1] = Ib[1]; ref[2] = Ib[2]; ref[6] = Ib[1]; ref[7] = Ib[3]; ref[8] = Ib[4];
+    ref[12] = Ib[2]; ref[13] = Ib[4]; ref[14] = Ib[5];
+    const double hx[9] = {0, -h[2], h[1], h[2], 0, -h[0], -h[1], h[0], 0};
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) { ref[6 * a + 3 + b] = hx[3 * a + b]; ref[6 * (3 + b) + a] = hx[3 * a + b]; }
+    ref[21] = ref[28] = ref[35] = mss;
+    double scale = 0, err = 0;
+    for (int k = 0; k < 36; ++k) { scale = fmax(scale, fabs(I[k])); err = fmax(err, fabs(I[k] - ref[k])); }
+    if (err > 1e-12 * fmax(scale, 1e-300)) out.rigid = 0;
+    out.mass[i] = mss;
+    for (int k = 0; k < 3; ++k) out.h[i][k] = h[k];
+    for (int k = 0; k < 6; ++k) out.Ib[i][k] = Ib[k];
+    unsigned anc = 1u << i;
+    if (d->parent[i] >= 0) anc |= out.anc_mask[d->parent[i]];
+    out.anc_mask[i] = anc;
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    out.sub_mask[i] |= 1u << i;
+    if (d->parent[i] >= 0) out.sub_mask[d->parent[i]] |= out.sub_mask[i];
+  }
+  for (int c = 1; c < n; ++c) {
+    const int p = d->parent[c];
+    if (p >= 0 && p != c - 1 && out.slot_a[p] < 0) out.slot_a[p] = out.n_slot_a++;
+  }
+  for (int i = 0; i + 1 < n; ++i)
+    if (d->parent[i + 1] != i) out.slot_b[i] = out.n_slot_b++;
+  return out.rigid != 0;
+}
+
+void narrow_fast_model(const FastModel<double>& a, FastModel<float>& b) {
+  std::memset(&b, 0, sizeof(b));
+  b.n = a.n; b.n_slot_a = a.n_slot_a; b.n_slot_b = a.n_slot_b; b.rigid = a.rigid; b.has_prismatic = a.has_prismatic;
+  for (int i = 0; i < RBD_MAX_DOF; ++i) {
+    b.parent[i] = a.parent[i]; b.kind[i] = a.kind[i]; b.slot_a[i] = a.slot_a[i]; b.slot_b[i] = a.slot_b[i];
+    b.anc_mask[i] = a.anc_mask[i]; b.sub_mask[i] = a.sub_mask[i];
+    b.damping[i] = (float)a.damping[i]; b.mass[i] = (float)a.mass[i];
+    for (int k = 0; k < 9; ++k) { b.EA[i][k] = (float)a.EA[i][k]; b.EB[i][k] = (float)a.EB[i][k]; b.EC[i][k] = (float)a.EC[i][k]; }
+    for (int k = 0; k < 3; ++k) {
+      b.rA[i][k] = (float)a.rA[i][k]; b.rB[i][k] = (float)a.rB[i][k]; b.rC[i][k] = (float)a.rC[i][k];
+      b.axis[i][k] = (float)a.axis[i][k]; b.h[i][k] = (float)a.h[i][k];
+    }
+    for (int k = 0; k < 6; ++k) b.Ib[i][k] = (float)a.Ib[i][k];
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -184,6 +300,8 @@ int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out) {
   if (!m) return fail(RBD_E_INVALID_ARGUMENT, "rbd_model_create: out of host memory");
   fill_model<double>(desc, m->d);
   fill_model<float>(desc, m->f);
+  m->fast_ok = build_fast_model(desc, m->fd);
+  narrow_fast_model(m->fd, m->ff);
   *out = m;
   return 0;
 }
@@ -194,6 +312,13 @@ int rbd_model_destroy(rbd_model_t* m) {
 }
 
 int rbd_model_num_dof(const rbd_model_t* m) { return m ? m->d.n : RBD_E_INVALID_ARGUMENT; }
+
+int rbd_set_kernel_variant(int variant) {
+  if (variant != 0 && variant != 1) return fail(RBD_E_INVALID_ARGUMENT, "rbd_set_kernel_variant: 0 (auto) or 1 (generic)");
+  g_variant.store(variant, std::memory_order_relaxed);
+  return 0;
+}
+int rbd_model_uses_world_kernels(const rbd_model_t* m) { return (m && m->fast_ok) ? 1 : 0; }
 
 #define RBD_DEFINE(SUF, T)                                                                                           \
   int rbd_rnea_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* qd, const T* qdd, T gravity, T* c, T* v,  \

@@ -105,7 +105,7 @@ __device__ __forceinline__ void mat6_apply(const T* __restrict__ M, const T (&x)
 
 // y = crm(v) s  : motion cross product  v x s            (RBDReference.py:9-21, :56-59)
 template <typename T>
-__device__ __forceinline__ void crm_mul(const T (&v)[6], const T (&s)[6], T (&y)[6]) {
+__device__ __forceinline__ void crm_mul(const T* v, const T* s, T* y) {
   y[0] = v[1] * s[2] - v[2] * s[1];
   y[1] = v[2] * s[0] - v[0] * s[2];
   y[2] = v[0] * s[1] - v[1] * s[0];
@@ -116,7 +116,7 @@ __device__ __forceinline__ void crm_mul(const T (&v)[6], const T (&s)[6], T (&y)
 
 // y = crf(v) f  : force cross product  v x* f = -crm(v)^T f   (RBDReference.py:149-164)
 template <typename T>
-__device__ __forceinline__ void crf_mul(const T (&v)[6], const T (&f)[6], T (&y)[6]) {
+__device__ __forceinline__ void crf_mul(const T* v, const T* f, T* y) {
   y[0] = v[1] * f[2] - v[2] * f[1] + v[4] * f[5] - v[5] * f[4];
   y[1] = v[2] * f[0] - v[0] * f[2] + v[5] * f[3] - v[3] * f[5];
   y[2] = v[0] * f[1] - v[1] * f[0] + v[3] * f[4] - v[4] * f[3];
@@ -126,7 +126,7 @@ __device__ __forceinline__ void crf_mul(const T (&v)[6], const T (&f)[6], T (&y)
 }
 
 template <typename T>
-__device__ __forceinline__ T dot6(const T* __restrict__ s, const T (&x)[6]) {
+__device__ __forceinline__ T dot6(const T* s, const T* x) {
   T acc = s[0] * x[0];
 #pragma unroll
   for (int k = 1; k < 6; ++k) acc = fma_t(s[k], x[k], acc);

@@ -316,5 +316,15 @@ class RBDReference:
         return -np.matmul(Minv, dc_du[..., :n]), -np.matmul(Minv, dc_du[..., n:])
 
     # ------------------------------------------------------------------------------------
+    def uses_world_kernels(self) -> bool:
+        """True if the fused drivers run the world-frame kernels for this robot."""
+        return bool(self._lib.rbd_model_uses_world_kernels(self._handle.ptr))
+
+    @staticmethod
+    def set_kernel_variant(variant: int) -> None:
+        """0 = automatic kernel choice (default); 1 = force the generic body-frame kernels."""
+        lib = _capi.load_library()
+        _capi.check(lib.rbd_set_kernel_variant(int(variant)), "rbd_set_kernel_variant")
+
     def launch_count(self) -> int:
         return int(self._lib.rbd_launch_count())

@@ -49,6 +49,56 @@ def test_fused_drivers_vs_reference_golden(golden):
 
 
 @requires_cuda
+def test_generic_body_frame_kernels_vs_reference_golden(golden):
+    """The generic (reference-recursion) fused kernels stay reachable and correct."""
+    from rbdreference_b200 import RBDReference
+    name, rb, g = golden
+    eng = _engine(rb)
+    q, qd, qdd = g["q"], g["qd"], g["qdd"]
+    RBDReference.set_kernel_variant(1)
+    try:
+        assert rel_err(eng.rnea_grad(q, qd, qdd), g["dc_du"]) < TOL_F64
+        assert rel_err(eng.rnea_grad(q, qd, qdd, USE_VELOCITY_DAMPING=True), g["dc_du_damped"]) < TOL_F64
+        assert rel_err(eng.rnea_grad(q, qd), g["dc_du_noqdd"]) < TOL_F64
+        assert rel_err(eng.minv(q), g["Minv"]) < TOL_F64
+        assert rel_err(eng.minv(q, output_dense=False), g["Minv_sparse"]) < TOL_F64
+        e32 = _engine(rb, torch.float32)
+        assert rel_err(e32.rnea_grad(q, qd, qdd), g["dc_du"]) < TOL_F32
+        assert rel_err(e32.minv(q), g["Minv"]) < TOL_F32
+    finally:
+        RBDReference.set_kernel_variant(0)
+
+
+@requires_cuda
+def test_world_kernels_selected_for_rigid_robots(golden):
+    name, rb, g = golden
+    assert _engine(rb).uses_world_kernels()
+
+
+@requires_cuda
+def test_non_rigid_inertia_falls_back_to_generic_kernels():
+    """A spatial inertia without rigid-body structure is legal for the reference; the engine must
+    detect it and run the body-frame kernels."""
+    from rbdreference_b200 import robots
+
+    class Odd(robots.Robot):
+        def get_Imat_by_id(self, i):
+            I = super().get_Imat_by_id(i)
+            I[0, 4] += 0.01 * (i + 1); I[4, 0] += 0.01 * (i + 1)     # symmetric, but not [[Ibar, hx],[hx^T, m]]
+            return I
+
+        def get_Imats_dict_by_id(self):
+            return {i: self.get_Imat_by_id(i) for i in range(self.get_num_bodies())}
+
+    rb = Odd("odd", robots.hyq().joints)
+    eng, bo = _engine(rb), BatchOracle(rb)
+    assert not eng.uses_world_kernels()
+    q, qd, qdd = random_states(12, 64, seed=2)
+    assert rel_err(eng.rnea_grad(q, qd, qdd), bo.rnea_grad(q, qd, qdd)) < TOL_F64
+    assert rel_err(eng.minv(q), bo.minv(q)) < TOL_F64
+
+
+@requires_cuda
 def test_pass_helpers_vs_reference_golden(golden):
     name, rb, g = golden
     eng = _engine(rb)
