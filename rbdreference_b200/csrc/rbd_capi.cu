@@ -79,15 +79,12 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
   const FastModel<T>& fm = pick_fast<T>(m);
   const size_t smem = grad_world_smem(fm);
   if (m->fast_ok && g_variant.load(std::memory_order_relaxed) == 0 && smem <= kMaxDynSmem) {
-    static thread_local size_t configured = 0;    // per (thread, T); attribute is per device context
-    if (smem > 48 * 1024 || configured < smem) {
-      cudaError_t e = cudaFuncSetAttribute(rnea_grad_world_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)kMaxDynSmem);
-      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-      configured = smem;
-    }
-    rnea_grad_world_kernel<T><<<blocks_for(B, 32), 32, smem, (cudaStream_t)stream>>>(fm, B, q, qd, qdd, g, damp,
-                                                                                      dc_du, c_out);
+    // (a fully unrolled NC = 7 instantiation was measured 28 % slower on B200: the straight-line
+    //  code no longer fits the instruction cache with only ~5 resident warps per SM)
+    auto kern = rnea_grad_world_kernel<T, 0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    kern<<<blocks_for(B, 32), 32, smem, (cudaStream_t)stream>>>(fm, B, q, qd, qdd, g, damp, dc_du, c_out);
     return cuda_status("rbd_rnea_grad(world)");
   }
   rnea_grad_fused_kernel<T><<<blocks_for(B, kFusedThreads), kFusedThreads, 0, (cudaStream_t)stream>>>(

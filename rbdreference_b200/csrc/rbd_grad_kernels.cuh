@@ -55,6 +55,22 @@ struct FastModel {
 
 constexpr int kVecPerBody = 22;   // S(6) Psi_dot(6) Psi_ddot(6) f1 f2 qd qdd
 
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { typedef double2 type; };
+template <> struct Vec2<float> { typedef float2 type; };
+
+// two 3-term chains instead of one 6-term chain: halves the dependent-FMA depth
+template <typename T>
+__device__ __forceinline__ T dot6s(const T* s, const T* x) {
+  const T lo = fma_t(s[2], x[2], fma_t(s[1], x[1], s[0] * x[0]));
+  const T hi = fma_t(s[5], x[5], fma_t(s[4], x[4], s[3] * x[3]));
+  return lo + hi;
+}
+template <typename T>
+__device__ __forceinline__ T dot3s(const T* s, const T* x) {
+  return fma_t(s[2], x[2], fma_t(s[1], x[1], s[0] * x[0]));
+}
+
 // ---- small helpers -------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void cross3(const T* a, const T* b, T* y) {
@@ -88,7 +104,9 @@ __device__ __forceinline__ void rigid_mul(T m, const T* h, const T* Ib, const T*
 }
 
 // =============================================================================================
-template <typename T>
+// NC > 0: number of bodies known at compile time (body loops fully unrolled: static shared-memory
+// offsets, model constants become constant-bank immediates).  NC == 0: generic run-time n.
+template <typename T, int NC>
 __global__ void __launch_bounds__(32)
 rnea_grad_world_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const T* __restrict__ q,
                        const T* __restrict__ qd, const T* __restrict__ qdd, T gravity,
@@ -96,33 +114,57 @@ rnea_grad_world_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sm = reinterpret_cast<T*>(smem_raw);
   const int lane = threadIdx.x;
-  const int n = m.n;
+  const int n = NC > 0 ? NC : m.n;
   int64_t b = (int64_t)blockIdx.x * 32 + lane;
   const bool active = b < B;
   if (!active) b = B - 1;                      // keep the warp convergent; stores are masked
-#define VEC(i, k) sm[(((i) * kVecPerBody) + (k)) * 32 + lane]
+  // element k of body i lives at ((i*11 + k/2)*32 + lane)*2 + (k&1): each lane owns aligned
+  // pairs, so a 6-vector is three 16-byte shared-memory accesses (LDS.128 / STS.128 in FP64)
+#define VEC(i, k) sm[(((((i) * (kVecPerBody / 2)) + ((k) >> 1)) * 32 + lane) << 1) + ((k) & 1)]
+  typedef typename Vec2<T>::type V2;
+#define VEC2(i, k2) reinterpret_cast<V2*>(sm)[(((i) * (kVecPerBody / 2)) + (k2)) * 32 + lane]
   T* stash_a = sm + (size_t)n * kVecPerBody * 32;                 // [slot][28][32]
   T* stash_b = stash_a + (size_t)m.n_slot_a * 28 * 32;            // [slot][24][32]
 #define STA(s, k) stash_a[((s) * 28 + (k)) * 32 + lane]
 #define STB(s, k) stash_b[((s) * 24 + (k)) * 32 + lane]
 
-  const T* qb = q + b * n;
-  const T* qdb = qd + b * n;
-  const T* qddb = qdd ? qdd + b * n : nullptr;
+  // stage this warp's contiguous slab of (q, qd, qdd) with coalesced loads: element e of the
+  // slab belongs to knot point e / n, joint e % n and goes to that lane's slots 18 / 20 / 21
+  {
+    const int64_t base = (int64_t)blockIdx.x * 32 * n;
+    const int64_t limit = B * (int64_t)n;
+    int inst = lane / n, jnt = lane - inst * n;
+    const int dinst = 32 / n, djnt = 32 - dinst * n;
+    for (int e = lane; e < 32 * n; e += 32) {
+      const int64_t g = base + e;
+      const bool ok = g < limit;
+      const T vq = ok ? q[g] : T(0);
+      const T vqd = ok ? qd[g] : T(0);
+      const T vqdd = (ok && qdd) ? qdd[g] : T(0);
+      T* dst = sm + ((((jnt * (kVecPerBody / 2)) + 9) * 32 + inst) << 1);
+      dst[0] = vq;                      // slot 18 (converted to f1 in the forward sweep)
+      dst[64] = vqd;                    // slot 20
+      dst[65] = vqdd;                   // slot 21
+      inst += dinst; jnt += djnt;
+      if (jnt >= n) { jnt -= n; inst += 1; }
+    }
+    __syncwarp();
+  }
 
   // running state of the body processed last: E (world -> body), p (origin in world), v, a
   T E[9], p[3], v[6], a[6];
 
   // ------------------------------------------------------------------ forward sweep
+#pragma unroll 1
   for (int i = 0; i < n; ++i) {
     T f1, f2;
     {
-      const T qi = qb[i];
+      const T qi = VEC(i, 18);
       if (m.kind[i] == 0) sincos_t(qi, &f2, &f1);
       else { f1 = qi; f2 = T(0); }
     }
-    const T qdi = qdb[i];
-    const T qddi = qddb ? qddb[i] : T(0);
+    const T qdi = VEC(i, 20);
+    const T qddi = VEC(i, 21);
     const int par = m.parent[i];
     T Ep[9], pp[3], vp[6], ap[6];
     if (par < 0) {
@@ -184,11 +226,18 @@ rnea_grad_world_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
       Pdd[k] += t6[k];
       v[k] = fma_t(S[k], qdi, vp[k]);
       a[k] = fma_t(Pd[k], qdi, fma_t(S[k], qddi, ap[k]));
-      VEC(i, k) = S[k];
-      VEC(i, 6 + k) = Pd[k];
-      VEC(i, 12 + k) = Pdd[k];
     }
-    VEC(i, 18) = f1; VEC(i, 19) = f2; VEC(i, 20) = qdi; VEC(i, 21) = qddi;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      V2 t;
+      t.x = S[2 * k]; t.y = S[2 * k + 1]; VEC2(i, k) = t;
+      t.x = Pd[2 * k]; t.y = Pd[2 * k + 1]; VEC2(i, 3 + k) = t;
+      t.x = Pdd[2 * k]; t.y = Pdd[2 * k + 1]; VEC2(i, 6 + k) = t;
+    }
+    {
+      V2 t;
+      t.x = f1; t.y = f2; VEC2(i, 9) = t;
+    }
     const int sa = m.slot_a[i], sb = m.slot_b[i];
     if (sa >= 0) {
 #pragma unroll
@@ -217,6 +266,7 @@ rnea_grad_world_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
 #pragma unroll
     for (int k = 0; k < 28; ++k) STA(s, k) = T(0);
 
+#pragma unroll 1
   for (int i = n - 1; i >= 0; --i) {
     const bool chained = (i != n - 1) && (m.parent[i + 1] == i);   // running state/composites valid
     if (!chained && i != n - 1) {
@@ -309,7 +359,11 @@ rnea_grad_world_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
     // ---- per-body vectors and F vectors
     T S[6], Pd[6], Pdd[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { S[k] = VEC(i, k); Pd[k] = VEC(i, 6 + k); Pdd[k] = VEC(i, 12 + k); }
+    for (int k = 0; k < 3; ++k) {
+      V2 t = VEC2(i, k); S[2 * k] = t.x; S[2 * k + 1] = t.y;
+      t = VEC2(i, 3 + k); Pd[2 * k] = t.x; Pd[2 * k + 1] = t.y;
+      t = VEC2(i, 6 + k); Pdd[2 * k] = t.x; Pdd[2 * k + 1] = t.y;
+    }
     const T mC = acc[0];
     const T* hC = acc + 1;
     const T* IC = acc + 4;
@@ -370,11 +424,15 @@ rnea_grad_world_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
     for (int j = m.parent[i]; j >= 0; j = m.parent[j]) {
       T Sj[6], Pdj[6], Pddj[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { Sj[k] = VEC(j, k); Pdj[k] = VEC(j, 6 + k); Pddj[k] = VEC(j, 12 + k); }
-      const T dq_ji = dot6(Sj, F1);
-      const T dd_ji = dot6(Sj, F2);
-      const T dq_ij = T(2) * (F3[0] * Pdj[0] + F3[1] * Pdj[1] + F3[2] * Pdj[2]) + dot6(F4, Pddj);
-      const T dd_ij = T(2) * (dot6(F4, Pdj) + F3[0] * Sj[0] + F3[1] * Sj[1] + F3[2] * Sj[2]);
+      for (int k = 0; k < 3; ++k) {
+        V2 t = VEC2(j, k); Sj[2 * k] = t.x; Sj[2 * k + 1] = t.y;
+        t = VEC2(j, 3 + k); Pdj[2 * k] = t.x; Pdj[2 * k + 1] = t.y;
+        t = VEC2(j, 6 + k); Pddj[2 * k] = t.x; Pddj[2 * k + 1] = t.y;
+      }
+      const T dq_ji = dot6s(Sj, F1);
+      const T dd_ji = dot6s(Sj, F2);
+      const T dq_ij = fma_t(T(2), dot3s(F3, Pdj), dot6s(F4, Pddj));
+      const T dd_ij = T(2) * (dot6s(F4, Pdj) + dot3s(F3, Sj));
       if (active) {
         out[j * n2 + i] = dq_ji;
         out[j * n2 + n + i] = dd_ji;
@@ -397,7 +455,8 @@ rnea_grad_world_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
       for (int k = 0; k < 28; ++k) STA(s, k) += acc[k];
     }
     if (par >= 0 && par == i - 1) {
-      const T f1 = VEC(i, 18), f2 = VEC(i, 19), qdi = VEC(i, 20), qddi = VEC(i, 21);
+      const V2 bas = VEC2(i, 9), dd = VEC2(i, 10);
+      const T f1 = bas.x, f2 = bas.y, qdi = dd.x, qddi = dd.y;
       T Ej[9], r[3], Ep[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) Ej[k] = fma_t(m.EC[i][k], f2, fma_t(m.EB[i][k], f1, m.EA[i][k]));
@@ -421,6 +480,7 @@ rnea_grad_world_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
     }
   }
 #undef VEC
+#undef VEC2
 #undef STA
 #undef STB
 }
