@@ -3,6 +3,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <type_traits>
 #include <atomic>
 #include <new>
 
@@ -10,6 +12,7 @@
 #include "rbd_common.cuh"
 #include "rbd_fused_kernels.cuh"
 #include "rbd_grad_kernels.cuh"
+#include "rbd_minv_kernels.cuh"
 #include "rbd_pass_kernels.cuh"
 
 using namespace rbd;
@@ -20,6 +23,9 @@ struct rbd_model {
   FastModel<double> fd;     // world-frame kernels (rigid-body inertias only)
   FastModel<float> ff;
   bool fast_ok;             // FastModel valid (rigid inertias, 1-DoF revolute/prismatic joints)
+  FastModel<double> fd_dfs; // the same robot renumbered in depth-first preorder (minv kernel)
+  FastModel<float> ff_dfs;
+  DfsPlan plan;
 };
 
 namespace {
@@ -28,6 +34,16 @@ thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_variant{0};          // 0 auto, 1 force the generic body-frame kernels
 constexpr size_t kMaxDynSmem = 227 * 1024;
+// shared-memory budget per warp beyond which the local-memory variants are used
+// (RBD_SMEM_LIMIT_KB overrides it for experiments)
+size_t smem_limit() {
+  static size_t v = [] {
+    const char* e = std::getenv("RBD_SMEM_LIMIT_KB");
+    return (size_t)(e ? std::atoi(e) : 75) * 1024;
+  }();
+  return v;
+}
+#define kGradSmemLimit smem_limit()
 
 int fail(int code, const char* msg) {
   std::snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -47,14 +63,13 @@ int cuda_status(const char* what) {
 template <typename T> const DevModel<T>& pick(const rbd_model* m);
 template <> const DevModel<double>& pick<double>(const rbd_model* m) { return m->d; }
 template <> const DevModel<float>& pick<float>(const rbd_model* m) { return m->f; }
+template <typename T> const FastModel<T>& pick_dfs(const rbd_model* m);
+template <> const FastModel<double>& pick_dfs<double>(const rbd_model* m) { return m->fd_dfs; }
+template <> const FastModel<float>& pick_dfs<float>(const rbd_model* m) { return m->ff_dfs; }
 template <typename T> const FastModel<T>& pick_fast(const rbd_model* m);
 template <> const FastModel<double>& pick_fast<double>(const rbd_model* m) { return m->fd; }
 template <> const FastModel<float>& pick_fast<float>(const rbd_model* m) { return m->ff; }
 
-template <typename T>
-size_t grad_world_smem(const FastModel<T>& fm) {
-  return (size_t)(fm.n * kVecPerBody + fm.n_slot_a * 28 + fm.n_slot_b * 24) * 32 * sizeof(T);
-}
 
 inline unsigned blocks_for(int64_t B, int threads) { return (unsigned)((B + threads - 1) / threads); }
 
@@ -77,15 +92,22 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
   RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_rnea_grad: null model/q/qd/dc_du or negative B");
   if (B == 0) return 0;
   const FastModel<T>& fm = pick_fast<T>(m);
-  const size_t smem = grad_world_smem(fm);
-  if (m->fast_ok && g_variant.load(std::memory_order_relaxed) == 0 && smem <= kMaxDynSmem) {
-    // (a fully unrolled NC = 7 instantiation was measured 28 % slower on B200: the straight-line
-    //  code no longer fits the instruction cache with only ~5 resident warps per SM)
-    auto kern = rnea_grad_world_kernel<T, 0>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-    kern<<<blocks_for(B, 32), 32, smem, (cudaStream_t)stream>>>(fm, B, q, qd, qdd, g, damp, dc_du, c_out);
-    return cuda_status("rbd_rnea_grad(world)");
+  if (m->fast_ok && g_variant.load(std::memory_order_relaxed) == 0) {
+    // (a fully unrolled compile-time-n instantiation was measured 28 % slower on B200: the
+    //  straight-line code no longer fits the instruction cache with ~5 resident warps per SM)
+    const size_t stash = (size_t)(fm.n_slot_a * 28 + fm.n_slot_b * 24) * 32 * sizeof(T);
+    size_t smem = (size_t)fm.n * kVecPerBody * 32 * sizeof(T) + stash;
+    auto kern = rnea_grad_world_kernel<T, 0, 1>;
+    if (smem > kGradSmemLimit) {          // large trees: per-body vectors go to local memory
+      kern = rnea_grad_world_kernel<T, 1, 8>;   // (tighter register caps measured slower: spills)
+      smem = stash;
+    }
+    if (smem <= kMaxDynSmem) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+      kern<<<blocks_for(B, 32), 32, smem, (cudaStream_t)stream>>>(fm, B, q, qd, qdd, g, damp, dc_du, c_out);
+      return cuda_status("rbd_rnea_grad(world)");
+    }
   }
   rnea_grad_fused_kernel<T><<<blocks_for(B, kFusedThreads), kFusedThreads, 0, (cudaStream_t)stream>>>(
       pick<T>(m), B, q, qd, qdd, g, damp, dc_du, c_out);
@@ -96,6 +118,26 @@ template <typename T>
 int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && B >= 0, "rbd_minv: null model/q/Minv or negative B");
   if (B == 0) return 0;
+  // FP32: the world-frame recursion loses digits on light distal links far from the base (m |p|^2
+  // cancellation, measured 1.2e-4 on Atlas), so single precision keeps the body-frame kernel.
+  if (m->fast_ok && dense && std::is_same<T, double>::value && g_variant.load(std::memory_order_relaxed) == 0) {
+    const FastModel<T>& fm = pick_dfs<T>(m);
+    const int n = fm.n;
+    const size_t stash = (size_t)(fm.n_slot_a * kMinvSlotA + fm.n_slot_b * kMinvSlotB) * 32 * sizeof(T);
+    size_t smem = (size_t)(n * (kMinvPerBody + 6) + n * (n + 1) / 2) * 32 * sizeof(T) + stash;
+    // measured on B200 (iiwa14, 1M points): shared-memory variant 8.8e8 evals/s (4 warps/SM),
+    // local-memory variant 1.12e9 evals/s (12 warps/SM) -> local memory is the default for minv
+    auto kern = minv_world_kernel<T, 1, 12>;
+    static const bool force_smem = std::getenv("RBD_MINV_SMEM") != nullptr;
+    if (force_smem && smem <= kMaxDynSmem) kern = minv_world_kernel<T, 0, 1>;
+    else smem = stash;
+    if (smem <= kMaxDynSmem) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+      kern<<<blocks_for(B, 32), 32, smem, (cudaStream_t)stream>>>(fm, m->plan, B, q, Minv);
+      return cuda_status("rbd_minv(world)");
+    }
+  }
   minv_fused_kernel<T><<<blocks_for(B, kFusedThreads), kFusedThreads, 0, (cudaStream_t)stream>>>(
       pick<T>(m), B, q, dense, Minv);
   return cuda_status("rbd_minv");
@@ -257,6 +299,49 @@ bool build_fast_model(const RbdModelDesc* d, FastModel<double>& out) {
   return out.rigid != 0;
 }
 
+// Renumber the robot in depth-first preorder and build its FastModel + index tables.
+bool build_dfs_model(const RbdModelDesc* d, FastModel<double>& out, DfsPlan& plan) {
+  const int n = d->n;
+  std::memset(&plan, 0, sizeof(plan));
+  int order[RBD_MAX_DOF], cnt = 0, stack[RBD_MAX_DOF], sp = 0;
+  for (int r = n - 1; r >= 0; --r)
+    if (d->parent[r] < 0) stack[sp++] = r;              // roots, smallest id on top
+  while (sp > 0) {
+    const int i = stack[--sp];
+    order[cnt++] = i;
+    for (int c = n - 1; c > i; --c)
+      if (d->parent[c] == i) stack[sp++] = c;           // children, smallest id on top
+  }
+  if (cnt != n) return false;
+  int32_t parent[RBD_MAX_DOF], kind[RBD_MAX_DOF];
+  double S[RBD_MAX_DOF * 6], XA[RBD_MAX_DOF * 18], XB[RBD_MAX_DOF * 18], XC[RBD_MAX_DOF * 18], I[RBD_MAX_DOF * 36],
+      damping[RBD_MAX_DOF];
+  for (int k = 0; k < n; ++k) { plan.orig[k] = order[k]; plan.pos[order[k]] = k; }
+  for (int k = 0; k < n; ++k) {
+    const int o = order[k];
+    parent[k] = d->parent[o] < 0 ? -1 : plan.pos[d->parent[o]];
+    kind[k] = d->kind[o];
+    damping[k] = d->damping ? d->damping[o] : 0.0;
+    std::memcpy(S + 6 * k, d->S + 6 * o, 6 * sizeof(double));
+    std::memcpy(XA + 18 * k, d->XA + 18 * o, 18 * sizeof(double));
+    std::memcpy(XB + 18 * k, d->XB + 18 * o, 18 * sizeof(double));
+    std::memcpy(XC + 18 * k, d->XC + 18 * o, 18 * sizeof(double));
+    std::memcpy(I + 36 * k, d->I + 36 * o, 36 * sizeof(double));
+  }
+  RbdModelDesc pd = {n, parent, kind, S, XA, XB, XC, I, damping};
+  const bool ok = build_fast_model(&pd, out);
+  // subtree / component ranges (preorder => contiguous)
+  int size[RBD_MAX_DOF];
+  for (int k = 0; k < n; ++k) size[k] = 1;
+  for (int k = n - 1; k >= 0; --k)
+    if (parent[k] >= 0) size[parent[k]] += size[k];
+  for (int k = 0; k < n; ++k) {
+    plan.sub_end[k] = k + size[k];
+    plan.comp_end[k] = parent[k] < 0 ? k + size[k] : plan.comp_end[parent[k]];
+  }
+  return ok;
+}
+
 void narrow_fast_model(const FastModel<double>& a, FastModel<float>& b) {
   std::memset(&b, 0, sizeof(b));
   b.n = a.n; b.n_slot_a = a.n_slot_a; b.n_slot_b = a.n_slot_b; b.rigid = a.rigid; b.has_prismatic = a.has_prismatic;
@@ -299,6 +384,8 @@ int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out) {
   fill_model<float>(desc, m->f);
   m->fast_ok = build_fast_model(desc, m->fd);
   narrow_fast_model(m->fd, m->ff);
+  m->fast_ok = build_dfs_model(desc, m->fd_dfs, m->plan) && m->fast_ok;
+  narrow_fast_model(m->fd_dfs, m->ff_dfs);
   *out = m;
   return 0;
 }

@@ -104,33 +104,42 @@ __device__ __forceinline__ void rigid_mul(T m, const T* h, const T* Ib, const T*
 }
 
 // =============================================================================================
-// NC > 0: number of bodies known at compile time (body loops fully unrolled: static shared-memory
-// offsets, model constants become constant-bank immediates).  NC == 0: generic run-time n.
-template <typename T, int NC>
-__global__ void __launch_bounds__(32)
+// LOCAL == 0: per-body vectors in shared memory (robots whose working set fits: a warp's 32 knot
+// points need (22 n + stashes) * 32 values).  LOCAL == 1: the same vectors in per-thread local
+// memory (L1/L2-backed) for large trees, trading on-chip latency for 8 resident warps per SM.
+template <typename T, int LOCAL, int MINB>
+__global__ void __launch_bounds__(32, MINB)
 rnea_grad_world_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const T* __restrict__ q,
                        const T* __restrict__ qd, const T* __restrict__ qdd, T gravity,
                        int use_damping, T* __restrict__ dc_du, T* __restrict__ c_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sm = reinterpret_cast<T*>(smem_raw);
   const int lane = threadIdx.x;
-  const int n = NC > 0 ? NC : m.n;
+  const int n = m.n;
   int64_t b = (int64_t)blockIdx.x * 32 + lane;
   const bool active = b < B;
   if (!active) b = B - 1;                      // keep the warp convergent; stores are masked
   // element k of body i lives at ((i*11 + k/2)*32 + lane)*2 + (k&1): each lane owns aligned
   // pairs, so a 6-vector is three 16-byte shared-memory accesses (LDS.128 / STS.128 in FP64)
-#define VEC(i, k) sm[(((((i) * (kVecPerBody / 2)) + ((k) >> 1)) * 32 + lane) << 1) + ((k) & 1)]
   typedef typename Vec2<T>::type V2;
-#define VEC2(i, k2) reinterpret_cast<V2*>(sm)[(((i) * (kVecPerBody / 2)) + (k2)) * 32 + lane]
-  T* stash_a = sm + (size_t)n * kVecPerBody * 32;                 // [slot][28][32]
+  V2 lvec[LOCAL ? RBD_MAX_DOF * (kVecPerBody / 2) : 1];
+#define VEC2(i, k2) (*(LOCAL ? &lvec[(i) * (kVecPerBody / 2) + (k2)] \
+                             : &reinterpret_cast<V2*>(sm)[(((i) * (kVecPerBody / 2)) + (k2)) * 32 + lane]))
+#define VEC(i, k) (reinterpret_cast<T*>(&VEC2(i, (k) >> 1))[(k) & 1])
+  T* stash_a = sm + (LOCAL ? 0 : (size_t)n * kVecPerBody * 32);   // [slot][28][32]
   T* stash_b = stash_a + (size_t)m.n_slot_a * 28 * 32;            // [slot][24][32]
 #define STA(s, k) stash_a[((s) * 28 + (k)) * 32 + lane]
 #define STB(s, k) stash_b[((s) * 24 + (k)) * 32 + lane]
 
   // stage this warp's contiguous slab of (q, qd, qdd) with coalesced loads: element e of the
   // slab belongs to knot point e / n, joint e % n and goes to that lane's slots 18 / 20 / 21
-  {
+  if (LOCAL) {
+    for (int i = 0; i < n; ++i) {
+      VEC(i, 18) = q[b * n + i];
+      VEC(i, 20) = qd[b * n + i];
+      VEC(i, 21) = qdd ? qdd[b * n + i] : T(0);
+    }
+  } else {
     const int64_t base = (int64_t)blockIdx.x * 32 * n;
     const int64_t limit = B * (int64_t)n;
     int inst = lane / n, jnt = lane - inst * n;
