@@ -69,7 +69,9 @@ int rbd_model_num_dof(const rbd_model_t* m);
  * rigid-body structure), 0 if they run the generic body-frame kernels. */
 int rbd_model_uses_world_kernels(const rbd_model_t* m);
 /* Process-wide kernel selection for the fused drivers: 0 = automatic (default), 1 = always the
- * generic body-frame kernels (the reference's own recursion; used to cross-check the two). */
+ * generic body-frame kernels (the reference's own recursion), 2 = world-frame kernels with one
+ * knot point per thread, 3 = warp-cooperative world-frame kernels (one body per lane).  Used by
+ * the tests and the benchmark to cross-check / compare the implementations. */
 int rbd_set_kernel_variant(int variant);
 
 /* ---- fused drivers ------------------------------------------------------------------------ */

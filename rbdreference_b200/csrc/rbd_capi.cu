@@ -13,6 +13,7 @@
 #include "rbd_fused_kernels.cuh"
 #include "rbd_grad_kernels.cuh"
 #include "rbd_minv_kernels.cuh"
+#include "rbd_coop_kernels.cuh"
 #include "rbd_pass_kernels.cuh"
 
 using namespace rbd;
@@ -26,6 +27,7 @@ struct rbd_model {
   FastModel<double> fd_dfs; // the same robot renumbered in depth-first preorder (minv kernel)
   FastModel<float> ff_dfs;
   DfsPlan plan;
+  CoopPlan coop;
 };
 
 namespace {
@@ -91,8 +93,31 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
                      T* dc_du, T* c_out, void* stream) {
   RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_rnea_grad: null model/q/qd/dc_du or negative B");
   if (B == 0) return 0;
+  const int variant = g_variant.load(std::memory_order_relaxed);
+  if (m->fast_ok && (variant == 0 || variant == 3)) {
+    // warp-cooperative kernel: one body per lane, 32/G knot points per warp
+    const FastModel<T>& fm = pick_dfs<T>(m);
+    const int n = fm.n;
+    const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+    const int ipw = 32 / G;
+    const int tile_stride = (ipw * n * 2 * n + 1) & ~1;
+    const size_t smem = (size_t)(n * kCoopMdlStride + kCoopWarps * 32 * kCoopVecStride + kCoopWarps * tile_stride) * sizeof(T) +
+                        (size_t)n * kCoopIntStride * sizeof(int);
+    if (smem <= kMaxDynSmem) {
+      auto kern = G == 8 ? rnea_grad_coop_kernel<T, 8> : (G == 16 ? rnea_grad_coop_kernel<T, 16> : rnea_grad_coop_kernel<T, 32>);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+      const int64_t ngroups = (B + ipw - 1) / ipw;
+      int64_t blocks = (ngroups + kCoopWarps - 1) / kCoopWarps;
+      const int64_t cap = 148 * 16;
+      if (blocks > cap) blocks = cap;
+      kern<<<(unsigned)blocks, kCoopWarps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, B, q, qd, qdd, g, damp,
+                                                                              dc_du, c_out);
+      return cuda_status("rbd_rnea_grad(coop)");
+    }
+  }
   const FastModel<T>& fm = pick_fast<T>(m);
-  if (m->fast_ok && g_variant.load(std::memory_order_relaxed) == 0) {
+  if (m->fast_ok && (variant == 0 || variant == 2)) {
     // (a fully unrolled compile-time-n instantiation was measured 28 % slower on B200: the
     //  straight-line code no longer fits the instruction cache with ~5 resident warps per SM)
     const size_t stash = (size_t)(fm.n_slot_a * 28 + fm.n_slot_b * 24) * 32 * sizeof(T);
@@ -386,6 +411,21 @@ int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out) {
   narrow_fast_model(m->fd, m->ff);
   m->fast_ok = build_dfs_model(desc, m->fd_dfs, m->plan) && m->fast_ok;
   narrow_fast_model(m->fd_dfs, m->ff_dfs);
+  {
+    CoopPlan& cp = m->coop;
+    std::memset(&cp, 0, sizeof(cp));
+    const int n = desc->n;
+    int depth[RBD_MAX_DOF];
+    for (int i = 0; i < n; ++i) {
+      const int p = m->fd_dfs.parent[i];
+      cp.jump[0][i] = p;
+      depth[i] = p < 0 ? 0 : depth[p] + 1;
+      if (depth[i] > cp.maxdepth) cp.maxdepth = depth[i];
+    }
+    for (int s = 1; s < 5; ++s)
+      for (int i = 0; i < n; ++i) cp.jump[s][i] = cp.jump[s - 1][i] < 0 ? -1 : cp.jump[s - 1][cp.jump[s - 1][i]];
+    while ((1 << cp.nsteps) < cp.maxdepth + 1) ++cp.nsteps;
+  }
   *out = m;
   return 0;
 }
@@ -398,7 +438,8 @@ int rbd_model_destroy(rbd_model_t* m) {
 int rbd_model_num_dof(const rbd_model_t* m) { return m ? m->d.n : RBD_E_INVALID_ARGUMENT; }
 
 int rbd_set_kernel_variant(int variant) {
-  if (variant != 0 && variant != 1) return fail(RBD_E_INVALID_ARGUMENT, "rbd_set_kernel_variant: 0 (auto) or 1 (generic)");
+  if (variant < 0 || variant > 3)
+    return fail(RBD_E_INVALID_ARGUMENT, "rbd_set_kernel_variant: 0 auto, 1 generic, 2 world (thread per knot point), 3 cooperative");
   g_variant.store(variant, std::memory_order_relaxed);
   return 0;
 }

@@ -1,0 +1,387 @@
+// rbd_coop_kernels.cuh - warp-cooperative fused rnea_grad: one BODY per lane.
+//
+// Same world-frame composite formulation as rbd_grad_kernels.cuh, mapped the other way round:
+// a group of G = 8 / 16 / 32 lanes owns one knot point and lane i owns body i (bodies in
+// depth-first preorder), so a warp evaluates 32 / G knot points at a time.
+//
+//   * independent branches of the tree run concurrently by construction (every body is a lane);
+//   * the root-path recursions (pose, v, a) are pointer-jumping scans over the ancestor chain:
+//     ceil(log2(depth + 1)) rounds of warp shuffles instead of `depth` sequential steps;
+//   * subtree composites (inertia, momentum, Coriolis, force: 28 numbers) are a suffix scan over
+//     the contiguous preorder range of the subtree: comp_i = PS(i) - PS(subtree_end(i));
+//   * each lane walks its own ancestors for the four dot products per (body, ancestor) pair,
+//     reading the ancestor's S / Psi_dot / Psi_ddot from a per-warp shared-memory table;
+//   * dc_du of the warp's knot points is assembled in shared memory and written to HBM as one
+//     contiguous, fully coalesced slab.
+// Per-thread state is ~O(1) six-vectors, so residency is no longer limited by the O(n) working
+// set of a knot point (the limit of the thread-per-knot-point kernels on Atlas-sized trees).
+#pragma once
+#include "rbd_common.cuh"
+#include "rbd_grad_kernels.cuh"
+#include "rbd_minv_kernels.cuh"
+
+namespace rbd {
+
+constexpr int kCoopWarps = 4;          // warps per CTA
+constexpr int kCoopMdlStride = 51;     // per-body constants in shared memory (odd stride)
+constexpr int kCoopIntStride = 10;     // parent kind sub_end orig jump[0..4] pad
+constexpr int kCoopVecStride = 19;     // S(6) Psi_dot(6) Psi_ddot(6) + pad (odd stride)
+
+struct CoopPlan {
+  int nsteps;                          // pointer-jumping rounds
+  int maxdepth;                        // longest ancestor chain
+  int jump[5][RBD_MAX_DOF];            // jump[s][i] = ancestor of i at distance 2^s (DFS ids) or -1
+};
+
+template <typename T>
+__device__ __forceinline__ T shfl_t(T x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+
+template <typename T, int G>
+__global__ void __launch_bounds__(kCoopWarps * 32)
+rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__ DfsPlan plan,
+                      const __grid_constant__ CoopPlan cp, int64_t B, const T* __restrict__ q,
+                      const T* __restrict__ qd, const T* __restrict__ qdd, T gravity, int use_damping,
+                      T* __restrict__ dc_du, T* __restrict__ c_out) {
+  constexpr int IPW = 32 / G;                          // knot points per warp
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = m.n;
+  const int n2 = 2 * n;
+  const int tile_vals = IPW * n * n2;                  // dc_du values per warp
+  T* mdl = reinterpret_cast<T*>(smem_raw);                                   // [n][51]
+  T* vec_all = mdl + n * kCoopMdlStride;                                     // [warps][32][19]
+  T* tile_all = vec_all + kCoopWarps * 32 * kCoopVecStride;                  // [warps][tile_vals (+1)]
+  const int tile_stride = (tile_vals + 1) & ~1;
+  int* imdl = reinterpret_cast<int*>(tile_all + kCoopWarps * tile_stride);   // [n][10]
+
+  // ---- robot constants -> shared memory (once per CTA)
+  for (int idx = threadIdx.x; idx < n * kCoopMdlStride; idx += blockDim.x) {
+    const int i = idx / kCoopMdlStride, k = idx - i * kCoopMdlStride;
+    T val = T(0);
+    if (k < 9) val = m.EA[i][k];
+    else if (k < 18) val = m.EB[i][k - 9];
+    else if (k < 27) val = m.EC[i][k - 18];
+    else if (k < 30) val = m.rA[i][k - 27];
+    else if (k < 33) val = m.rB[i][k - 30];
+    else if (k < 36) val = m.rC[i][k - 33];
+    else if (k < 39) val = m.axis[i][k - 36];
+    else if (k == 39) val = m.mass[i];
+    else if (k < 43) val = m.h[i][k - 40];
+    else if (k < 49) val = m.Ib[i][k - 43];
+    else if (k == 49) val = m.damping[i];
+    mdl[idx] = val;
+  }
+  for (int idx = threadIdx.x; idx < n * kCoopIntStride; idx += blockDim.x) {
+    const int i = idx / kCoopIntStride, k = idx - i * kCoopIntStride;
+    int val = 0;
+    if (k == 0) val = m.parent[i];
+    else if (k == 1) val = m.kind[i];
+    else if (k == 2) val = plan.sub_end[i];
+    else if (k == 3) val = plan.orig[i];
+    else if (k < 9) val = cp.jump[k - 4][i];
+    imdl[idx] = val;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / G, i = lane - g * G;
+  const bool valid = i < n;
+  const int ib = valid ? i : 0;
+  const int gbase = g * G;
+  const T* mb = mdl + ib * kCoopMdlStride;
+  const int* ip = imdl + ib * kCoopIntStride;
+  const int par = valid ? ip[0] : -1;
+  const int kind = ip[1];
+  const int sub_end = ip[2];
+  const int oi = ip[3];
+  T* vec = vec_all + warp * 32 * kCoopVecStride;
+  T* tile = tile_all + warp * tile_stride;
+  T* myvec = vec + lane * kCoopVecStride;
+  T* mytile = tile + g * n * n2;
+  const int nsteps = cp.nsteps;
+
+  const int64_t ngroups = (B + IPW - 1) / IPW;
+  for (int64_t grp = (int64_t)blockIdx.x * kCoopWarps + warp; grp < ngroups; grp += (int64_t)gridDim.x * kCoopWarps) {
+    int64_t b = grp * IPW + g;
+    if (b >= B) b = B - 1;                                    // duplicate work, never stored
+
+    // ------------------------------------------------------------------ forward
+    T E[9], p[3], S[6], Pd[6], Pdd[6], v[6], a[6];
+    T qdi, qddi;
+    {
+      const T qi = q[b * n + oi];
+      qdi = qd[b * n + oi];
+      qddi = qdd ? qdd[b * n + oi] : T(0);
+      T f1, f2;
+      if (kind == 0) sincos_t(qi, &f2, &f1);
+      else { f1 = qi; f2 = T(0); }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) E[k] = fma_t(mb[18 + k], f2, fma_t(mb[9 + k], f1, mb[k]));
+#pragma unroll
+      for (int k = 0; k < 3; ++k) p[k] = fma_t(mb[33 + k], f2, fma_t(mb[30 + k], f1, mb[27 + k]));
+    }
+    // pose scan over the ancestor chain: (E, p) <- (E, p) o (E_anc, p_anc)
+    for (int s = 0; s < nsteps; ++s) {
+      const int src = valid ? ip[4 + s] : -1;
+      const int sl = gbase + (src >= 0 ? src : 0);
+      T E2[9], p2[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) E2[k] = shfl_t(E[k], sl);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) p2[k] = shfl_t(p[k], sl);
+      if (src >= 0) {
+        T En[9], pn[3];
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc)
+            En[3 * rr + cc] = E[3 * rr] * E2[cc] + E[3 * rr + 1] * E2[3 + cc] + E[3 * rr + 2] * E2[6 + cc];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) pn[cc] = p2[cc] + E2[cc] * p[0] + E2[3 + cc] * p[1] + E2[6 + cc] * p[2];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) E[k] = En[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p[k] = pn[k];
+      }
+    }
+    // world joint axis
+    {
+      T w[3];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) w[cc] = E[cc] * mb[36] + E[3 + cc] * mb[37] + E[6 + cc] * mb[38];
+      if (kind == 0) {
+        S[0] = w[0]; S[1] = w[1]; S[2] = w[2];
+        cross3(p, w, S + 3);
+      } else {
+        S[0] = S[1] = S[2] = T(0);
+        S[3] = w[0]; S[4] = w[1]; S[5] = w[2];
+      }
+      if (!valid) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) S[k] = T(0);
+      }
+    }
+    // v_i = sum over the root path of S_j qd_j
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = S[k] * qdi;
+    for (int s = 0; s < nsteps; ++s) {
+      const int src = valid ? ip[4 + s] : -1;
+      const int sl = gbase + (src >= 0 ? src : 0);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const T t = shfl_t(v[k], sl);
+        if (src >= 0) v[k] += t;
+      }
+    }
+    T vl[6], al[6];   // parent's velocity / acceleration
+#pragma unroll
+    for (int k = 0; k < 6; ++k) vl[k] = fma_t(-S[k], qdi, v[k]);
+    crm_mul(vl, S, Pd);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] = fma_t(Pd[k], qdi, S[k] * qddi);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) al[k] = a[k];           // own increment, subtracted back below
+    for (int s = 0; s < nsteps; ++s) {
+      const int src = valid ? ip[4 + s] : -1;
+      const int sl = gbase + (src >= 0 ? src : 0);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const T t = shfl_t(a[k], sl);
+        if (src >= 0) a[k] += t;
+      }
+    }
+    a[5] -= gravity;                                      // a_base = [0,0,0,0,0,-GRAVITY] (RBDReference.py:566)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) al[k] = a[k] - al[k];
+    {
+      T t6[6];
+      crm_mul(al, S, Pdd);
+      crm_mul(vl, Pd, t6);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Pdd[k] += t6[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { myvec[k] = S[k]; myvec[6 + k] = Pd[k]; myvec[12 + k] = Pdd[k]; }
+
+    // ------------------------------------------------------------------ own terms -> subtree composites
+    // 0 m | 1..3 h | 4..9 Ibar | 10..15 Sym | 16..18 n | 19..21 l | 22..27 f
+    T acc[28];
+    {
+      const T mi = valid ? mb[39] : T(0);
+      T hr[3], hw[3];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        hr[cc] = E[cc] * mb[40] + E[3 + cc] * mb[41] + E[6 + cc] * mb[42];
+        hw[cc] = fma_t(mi, p[cc], hr[cc]);
+      }
+      T IbE[9];
+      {
+        const T xx = mb[43], xy = mb[44], xz = mb[45], yy = mb[46], yz = mb[47], zz = mb[48];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          IbE[cc] = xx * E[cc] + xy * E[3 + cc] + xz * E[6 + cc];
+          IbE[3 + cc] = xy * E[cc] + yy * E[3 + cc] + yz * E[6 + cc];
+          IbE[6 + cc] = xz * E[cc] + yz * E[3 + cc] + zz * E[6 + cc];
+        }
+      }
+      T Iw[6];
+      {
+        const T tr = (hr[0] + hw[0]) * p[0] + (hr[1] + hw[1]) * p[1] + (hr[2] + hw[2]) * p[2];
+        int idx = 0;
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+          for (int cc = rr; cc < 3; ++cc) {
+            T val = E[rr] * IbE[cc] + E[3 + rr] * IbE[3 + cc] + E[6 + rr] * IbE[6 + cc];
+            val -= hr[rr] * p[cc] + p[rr] * hw[cc];
+            if (rr == cc) val += tr;
+            Iw[idx++] = val;
+          }
+      }
+      T mom[6], fo[6], t6[6];
+      rigid_mul(mi, hw, Iw, v, mom);
+      rigid_mul(mi, hw, Iw, a, fo);
+      crf_mul(v, mom, t6);
+      const T* wv = v;
+      const T* uv = v + 3;
+      T M[9];
+      {
+        const T Im[9] = {Iw[0], Iw[1], Iw[2], Iw[1], Iw[3], Iw[4], Iw[2], Iw[4], Iw[5]};
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          M[cc] = wv[1] * Im[6 + cc] - wv[2] * Im[3 + cc];
+          M[3 + cc] = wv[2] * Im[cc] - wv[0] * Im[6 + cc];
+          M[6 + cc] = wv[0] * Im[3 + cc] - wv[1] * Im[cc];
+        }
+      }
+      const T uh2 = T(2) * (uv[0] * hw[0] + uv[1] * hw[1] + uv[2] * hw[2]);
+      acc[0] = mi;
+      acc[1] = hw[0]; acc[2] = hw[1]; acc[3] = hw[2];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc[4 + k] = Iw[k];
+      acc[10] = T(2) * M[0] - T(2) * hw[0] * uv[0] + uh2;
+      acc[11] = M[1] + M[3] - (hw[0] * uv[1] + uv[0] * hw[1]);
+      acc[12] = M[2] + M[6] - (hw[0] * uv[2] + uv[0] * hw[2]);
+      acc[13] = T(2) * M[4] - T(2) * hw[1] * uv[1] + uh2;
+      acc[14] = M[5] + M[7] - (hw[1] * uv[2] + uv[1] * hw[2]);
+      acc[15] = T(2) * M[8] - T(2) * hw[2] * uv[2] + uh2;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { acc[16 + k] = mom[k]; acc[22 + k] = fo[k] + t6[k]; }
+      if (!valid) {
+#pragma unroll
+        for (int k = 0; k < 28; ++k) acc[k] = T(0);
+      }
+    }
+    // suffix scan inside the group, then remove what lies beyond the subtree
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+      const bool take = (i + d) < G;
+#pragma unroll
+      for (int k = 0; k < 28; ++k) {
+        const T t = __shfl_down_sync(0xffffffffu, acc[k], d, G);
+        if (take) acc[k] += t;
+      }
+    }
+    {
+      const bool cut = valid && sub_end < n;
+      const int sl = gbase + (cut ? sub_end : 0);
+#pragma unroll
+      for (int k = 0; k < 28; ++k) {
+        const T t = shfl_t(acc[k], sl);
+        if (cut) acc[k] -= t;
+      }
+    }
+
+    // ------------------------------------------------------------------ F vectors, diagonal, zero fill
+    const T mC = acc[0];
+    const T* hC = acc + 1;
+    const T* IC = acc + 4;
+    const T* SyC = acc + 10;
+    const T* nC = acc + 16;
+    const T* lC = acc + 19;
+    const T* fC = acc + 22;
+    T F1[6], F2[6], F3[3], F4[6];
+    rigid_mul(mC, hC, IC, S, F4);
+    {
+      T t3[3];
+      sym3_mul(SyC, S, F3);
+      cross3_add(nC, S, F3);
+      cross3(lC, S + 3, t3);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) F3[k] = fma_t(T(0.5), F3[k], t3[k]);
+    }
+    {
+      T t6[6], tb[3], tl[3];
+      rigid_mul(mC, hC, IC, Pdd, F1);
+      crf_mul(S, fC, t6);
+      sym3_mul(SyC, Pd, tb);
+      cross3(nC, Pd, tl);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) F1[k] += t6[k] + tb[k] - tl[k];
+      cross3(lC, Pd, tl);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) F1[3 + k] += t6[3 + k] - T(2) * tl[k];
+      rigid_mul(mC, hC, IC, Pd, F2);
+      sym3_mul(SyC, S, tb);
+      cross3(nC, S, tl);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) F2[k] = T(2) * F2[k] + tb[k] - tl[k];
+      cross3(lC, S, tl);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) F2[3 + k] = T(2) * (F2[3 + k] - tl[k]);
+    }
+    const bool store = valid && (grp * IPW + g) < B;
+    if (c_out && store) c_out[b * n + oi] = dot6s(S, fC);
+    if (valid) {
+      T* row = mytile + oi * n2;
+      for (int k = 0; k < n2; ++k) row[k] = T(0);            // structural zeros of row i
+    }
+    __syncwarp();
+    if (valid) {
+      T ddd = dot6s(S, F2);
+      if (use_damping) ddd += mb[49];                         // RBDReference.py:1341
+      mytile[oi * n2 + oi] = dot6s(S, F1);
+      mytile[oi * n2 + n + oi] = ddd;
+    }
+    if (kind == 1) {
+      // reference quirk for prismatic joints: X^T(-crm(f)S) instead of X^T(S x* f) (:1292)
+      T nrot[3], dl[3], da[3], t3[3];
+      cross3(p, fC + 3, t3);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) nrot[k] = fC[k] - t3[k];
+      cross3(S + 3, nrot, dl);
+      cross3(S + 3, fC + 3, da);
+      cross3(p, dl, t3);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { F1[k] += t3[k] - da[k]; F1[3 + k] += dl[k]; }
+    }
+    // ------------------------------------------------------------------ ancestors of i
+    {
+      int j = par;
+      for (int t = 0; t < cp.maxdepth; ++t) {
+        if (j >= 0) {
+          const T* vj = vec + (gbase + j) * kCoopVecStride;
+          T Sj[6], Pdj[6], Pddj[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { Sj[k] = vj[k]; Pdj[k] = vj[6 + k]; Pddj[k] = vj[12 + k]; }
+          const int oj = imdl[j * kCoopIntStride + 3];
+          mytile[oj * n2 + oi] = dot6s(Sj, F1);
+          mytile[oj * n2 + n + oi] = dot6s(Sj, F2);
+          mytile[oi * n2 + oj] = fma_t(T(2), dot3s(F3, Pdj), dot6s(F4, Pddj));
+          mytile[oi * n2 + n + oj] = T(2) * (dot6s(F4, Pdj) + dot3s(F3, Sj));
+          j = imdl[j * kCoopIntStride];
+        }
+      }
+    }
+    __syncwarp();
+    // ------------------------------------------------------------------ coalesced slab write
+    {
+      const int64_t first = grp * IPW;
+      const int count = (int)((B - first) < IPW ? (B - first) : IPW) * n * n2;
+      T* dst = dc_du + first * n * n2;
+      for (int k = lane; k < count; k += 32) dst[k] = tile[k];
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace rbd

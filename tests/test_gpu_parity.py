@@ -70,6 +70,33 @@ def test_generic_body_frame_kernels_vs_reference_golden(golden):
 
 
 @requires_cuda
+@pytest.mark.parametrize("variant", [2, 3])
+def test_world_kernel_variants_vs_reference_golden(golden, variant):
+    """Both world-frame mappings (2: knot point per thread, 3: body per lane) against the goldens."""
+    from rbdreference_b200 import RBDReference
+    name, rb, g = golden
+    q, qd, qdd = g["q"], g["qd"], g["qdd"]
+    RBDReference.set_kernel_variant(variant)
+    try:
+        for dtype, tol in ((torch.float64, TOL_F64), (torch.float32, TOL_F32)):
+            eng = _engine(rb, dtype)
+            assert rel_err(eng.rnea_grad(q, qd, qdd), g["dc_du"]) < tol
+            assert rel_err(eng.rnea_grad(q, qd, qdd, USE_VELOCITY_DAMPING=True), g["dc_du_damped"]) < tol
+            assert rel_err(eng.rnea_grad(q, qd), g["dc_du_noqdd"]) < tol
+            assert rel_err(eng.minv(q), g["Minv"]) < tol
+        eng = _engine(rb)
+        B = 333
+        bo = BatchOracle(rb)
+        qq, qqd, qqdd = random_states(eng.n, B, seed=variant)
+        cbuf = torch.empty(B, eng.n, dtype=torch.float64, device="cuda")
+        dc = eng.rnea_grad(_t(qq), _t(qqd), _t(qqdd), c_out=cbuf)
+        assert rel_err(dc.cpu().numpy(), bo.rnea_grad(qq, qqd, qqdd)) < TOL_F64
+        assert rel_err(cbuf.cpu().numpy(), bo.rnea(qq, qqd, qqdd)[0]) < TOL_F64
+    finally:
+        RBDReference.set_kernel_variant(0)
+
+
+@requires_cuda
 def test_world_kernels_selected_for_rigid_robots(golden):
     name, rb, g = golden
     assert _engine(rb).uses_world_kernels()
