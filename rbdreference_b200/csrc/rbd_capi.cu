@@ -14,6 +14,7 @@
 #include "rbd_grad_kernels.cuh"
 #include "rbd_minv_kernels.cuh"
 #include "rbd_coop_kernels.cuh"
+#include "rbd_coop_minv_kernels.cuh"
 #include "rbd_pass_kernels.cuh"
 
 using namespace rbd;
@@ -28,6 +29,7 @@ struct rbd_model {
   FastModel<float> ff_dfs;
   DfsPlan plan;
   CoopPlan coop;
+  CoopMinvPlan coop_minv;
 };
 
 namespace {
@@ -143,15 +145,46 @@ template <typename T>
 int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && B >= 0, "rbd_minv: null model/q/Minv or negative B");
   if (B == 0) return 0;
-  // FP32: the world-frame recursion loses digits on light distal links far from the base (m |p|^2
-  // cancellation, measured 1.2e-4 on Atlas), so single precision keeps the body-frame kernel.
-  if (m->fast_ok && dense && std::is_same<T, double>::value && g_variant.load(std::memory_order_relaxed) == 0) {
+  const int variant = g_variant.load(std::memory_order_relaxed);
+  if (m->fast_ok && dense && (variant == 0 || variant == 3)) {
+    // warp-cooperative kernel (local world-aligned frames: accurate in FP32 as well)
+    const FastModel<T>& fm = pick_dfs<T>(m);
+    const int n = fm.n;
+    const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+    // warps per CTA: the choice that keeps the most warps resident per SM (the model copy is
+    // shared by the CTA, the rest of the shared memory is per warp)
+    int warps = 0, best = 0;
+    size_t smem = 0;
+    for (int w = 4; w <= kCmMaxWarps; ++w) {
+      const size_t sz = coop_minv_smem_bytes(n, G, m->coop.maxdepth, fm.n_slot_a, w, sizeof(T));
+      if (sz > kMaxDynSmem) break;
+      const int ctas = (int)((size_t)(228 * 1024) / (sz + 1024));
+      const int resident = (ctas > 32 / w ? 32 / w : ctas) * w;
+      if (resident > best) { best = resident; warps = w; smem = sz; }
+    }
+    if (warps > 0) {
+      auto kern = G == 8 ? minv_coop_kernel<T, 8> : (G == 16 ? minv_coop_kernel<T, 16> : minv_coop_kernel<T, 32>);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+      const int ipw = 32 / G;
+      const int64_t ngroups = (B + ipw - 1) / ipw;
+      int64_t blocks = (ngroups + warps - 1) / warps;
+      const int64_t cap = 148 * 16;
+      if (blocks > cap) blocks = cap;
+      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, m->coop_minv, B, q, Minv);
+      return cuda_status("rbd_minv(coop)");
+    }
+  }
+  // thread-per-knot-point world-frame kernel.  FP32: coordinates about the world origin lose
+  // digits on light distal links far from the base (m |p|^2 cancellation, measured 1.2e-4 on
+  // Atlas), so in single precision this family is never selected.
+  if (m->fast_ok && dense && std::is_same<T, double>::value && (variant == 0 || variant == 2)) {
     const FastModel<T>& fm = pick_dfs<T>(m);
     const int n = fm.n;
     const size_t stash = (size_t)(fm.n_slot_a * kMinvSlotA + fm.n_slot_b * kMinvSlotB) * 32 * sizeof(T);
     size_t smem = (size_t)(n * (kMinvPerBody + 6) + n * (n + 1) / 2) * 32 * sizeof(T) + stash;
     // measured on B200 (iiwa14, 1M points): shared-memory variant 8.8e8 evals/s (4 warps/SM),
-    // local-memory variant 1.12e9 evals/s (12 warps/SM) -> local memory is the default for minv
+    // local-memory variant 1.12e9 evals/s (12 warps/SM) -> local memory is the default here
     auto kern = minv_world_kernel<T, 1, 12>;
     static const bool force_smem = std::getenv("RBD_MINV_SMEM") != nullptr;
     if (force_smem && smem <= kMaxDynSmem) kern = minv_world_kernel<T, 0, 1>;
@@ -425,6 +458,14 @@ int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out) {
     for (int s = 1; s < 5; ++s)
       for (int i = 0; i < n; ++i) cp.jump[s][i] = cp.jump[s - 1][i] < 0 ? -1 : cp.jump[s - 1][cp.jump[s - 1][i]];
     while ((1 << cp.nsteps) < cp.maxdepth + 1) ++cp.nsteps;
+    CoopMinvPlan& mp = m->coop_minv;
+    std::memset(&mp, 0, sizeof(mp));
+    for (int i = 0; i < n; ++i) {
+      const int p = m->fd_dfs.parent[i];
+      mp.depth[i] = depth[i];
+      mp.comp_root[i] = p < 0 ? i : mp.comp_root[p];
+      if (i - mp.comp_root[i] + 1 > mp.maxcomp) mp.maxcomp = i - mp.comp_root[i] + 1;
+    }
   }
   *out = m;
   return 0;
