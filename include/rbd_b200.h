@@ -70,8 +70,9 @@ int rbd_model_num_dof(const rbd_model_t* m);
 int rbd_model_uses_world_kernels(const rbd_model_t* m);
 /* Process-wide kernel selection for the fused drivers: 0 = automatic (default), 1 = always the
  * generic body-frame kernels (the reference's own recursion), 2 = world-frame kernels with one
- * knot point per thread, 3 = warp-cooperative world-frame kernels (one body per lane).  Used by
- * the tests and the benchmark to cross-check / compare the implementations. */
+ * knot point per thread, 3 = warp-cooperative kernels (one body per lane), 4 = hybrid minv kernel
+ * (knot point per lane for the articulated inertias, column per lane for the rows of Minv; other
+ * operations behave as 0).  Used by the tests and the benchmark to cross-check / compare. */
 int rbd_set_kernel_variant(int variant);
 
 /* ---- fused drivers ------------------------------------------------------------------------ */

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <type_traits>
 #include <atomic>
+#include <mutex>
 #include <new>
 
 #include "../../include/rbd_b200.h"
@@ -48,6 +49,29 @@ size_t smem_limit() {
   return v;
 }
 #define kGradSmemLimit smem_limit()
+
+// Stream-ordered scratch allocations come from one private pool per device that keeps its
+// memory between calls (release threshold = max), so steady-state calls never reach the driver's
+// allocator and the application's default pool is left alone.
+cudaMemPool_t scratch_pool(int dev) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  if (dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t p = nullptr;
+    if (cudaMemPoolCreate(&p, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep);
+    pools[dev] = p;
+  }
+  return pools[dev];
+}
 
 int fail(int code, const char* msg) {
   std::snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -95,7 +119,8 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
                      T* dc_du, T* c_out, void* stream) {
   RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_rnea_grad: null model/q/qd/dc_du or negative B");
   if (B == 0) return 0;
-  const int variant = g_variant.load(std::memory_order_relaxed);
+  int variant = g_variant.load(std::memory_order_relaxed);
+  if (variant == 4) variant = 0;                       // 4 only selects among the minv kernels
   if (m->fast_ok && (variant == 0 || variant == 3)) {
     // warp-cooperative kernel: one body per lane, 32/G knot points per warp
     const FastModel<T>& fm = pick_dfs<T>(m);
@@ -145,27 +170,76 @@ template <typename T>
 int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && B >= 0, "rbd_minv: null model/q/Minv or negative B");
   if (B == 0) return 0;
-  const int variant = g_variant.load(std::memory_order_relaxed);
-  if (m->fast_ok && dense && (variant == 0 || variant == 3)) {
+  int variant = g_variant.load(std::memory_order_relaxed);
+  if (variant == 0 && m->fast_ok && dense) {
+    // automatic choice, measured on B200 (evals/s FP64 | FP32 at the BASELINE batch sizes):
+    //   Atlas  n=30: hybrid 1.21e8 | 2.0e8   cooperative 1.19e8 | 1.8e8   thread 5.8e7 | 7.1e7
+    //   HyQ    n=12: hybrid 6.1e8 | 8.5e8    cooperative 8.8e8 | 1.2e9    thread 5.2e8
+    //   iiwa14 n=7 : hybrid 8.5e8 | 1.38e9   cooperative 7.8e8 | 1.2e9    thread 1.13e9 | 1.88e9 (body frame)
+    const int n = m->d.n;
+    variant = n > 16 ? 4 : (n > 8 ? 3 : (std::is_same<T, double>::value ? 2 : 1));
+  }
+  if (m->fast_ok && dense && variant == 4) {
+    // hybrid kernel: knot point per lane for the articulated inertias, column per lane for the
+    // rows of Minv, per-body table handed over through an L2-resident scratch buffer
+    const FastModel<T>& fm = pick_dfs<T>(m);
+    const int n = fm.n;
+    const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+    auto kern = fm.has_prismatic
+                    ? (G == 8 ? minv_hybrid_kernel<T, 8, true> : (G == 16 ? minv_hybrid_kernel<T, 16, true> : minv_hybrid_kernel<T, 32, true>))
+                    : (G == 8 ? minv_hybrid_kernel<T, 8, false> : (G == 16 ? minv_hybrid_kernel<T, 16, false> : minv_hybrid_kernel<T, 32, false>));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    int warps = 0, best = 0, ctas = 0;
+    size_t smem = 0;
+    for (int w = 4; w <= kCmMaxWarps; ++w) {
+      const size_t sz = hybrid_minv_smem_bytes<T>(n, G, m->coop.maxdepth, fm.n_slot_a, fm.n_slot_b, w);
+      if (sz > kMaxDynSmem) break;
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, sz) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (nb * w > best) { best = nb * w; warps = w; smem = sz; ctas = nb; }
+    }
+    int dev = 0, sms = 0;
+    if (warps > 0 && cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) {
+      const int64_t ntasks = (B + 31) / 32;
+      int64_t blocks = (ntasks + warps - 1) / warps;
+      if (blocks > (int64_t)sms * ctas) blocks = (int64_t)sms * ctas;
+      T* scratch = nullptr;
+      const size_t scratch_bytes = (size_t)blocks * warps * 32 * n * kHyScrStride * sizeof(T);
+      cudaMemPool_t pool = scratch_pool(dev);
+      if (!pool) return fail(RBD_E_NO_DEVICE, "rbd_minv: cannot create the scratch memory pool");
+      e = cudaMallocFromPoolAsync((void**)&scratch, scratch_bytes, pool, (cudaStream_t)stream);
+      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop_minv, m->coop.maxdepth, B, q, Minv,
+                                                                         scratch);
+      const int rc = cuda_status("rbd_minv(hybrid)");
+      cudaFreeAsync(scratch, (cudaStream_t)stream);
+      return rc;
+    }
+  }
+  if (m->fast_ok && dense && variant == 3) {
     // warp-cooperative kernel (local world-aligned frames: accurate in FP32 as well)
     const FastModel<T>& fm = pick_dfs<T>(m);
     const int n = fm.n;
     const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+    auto kern = fm.has_prismatic
+                    ? (G == 8 ? minv_coop_kernel<T, 8, true> : (G == 16 ? minv_coop_kernel<T, 16, true> : minv_coop_kernel<T, 32, true>))
+                    : (G == 8 ? minv_coop_kernel<T, 8, false> : (G == 16 ? minv_coop_kernel<T, 16, false> : minv_coop_kernel<T, 32, false>));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
     // warps per CTA: the choice that keeps the most warps resident per SM (the model copy is
     // shared by the CTA, the rest of the shared memory is per warp)
     int warps = 0, best = 0;
     size_t smem = 0;
     for (int w = 4; w <= kCmMaxWarps; ++w) {
-      const size_t sz = coop_minv_smem_bytes(n, G, m->coop.maxdepth, fm.n_slot_a, w, sizeof(T));
+      const size_t sz = coop_minv_smem_bytes<T>(n, G, m->coop.maxdepth, fm.n_slot_a, w);
       if (sz > kMaxDynSmem) break;
-      const int ctas = (int)((size_t)(228 * 1024) / (sz + 1024));
-      const int resident = (ctas > 32 / w ? 32 / w : ctas) * w;
-      if (resident > best) { best = resident; warps = w; smem = sz; }
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, sz) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (nb * w > best) { best = nb * w; warps = w; smem = sz; }
     }
     if (warps > 0) {
-      auto kern = G == 8 ? minv_coop_kernel<T, 8> : (G == 16 ? minv_coop_kernel<T, 16> : minv_coop_kernel<T, 32>);
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
       const int ipw = 32 / G;
       const int64_t ngroups = (B + ipw - 1) / ipw;
       int64_t blocks = (ngroups + warps - 1) / warps;
@@ -178,7 +252,7 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
   // thread-per-knot-point world-frame kernel.  FP32: coordinates about the world origin lose
   // digits on light distal links far from the base (m |p|^2 cancellation, measured 1.2e-4 on
   // Atlas), so in single precision this family is never selected.
-  if (m->fast_ok && dense && std::is_same<T, double>::value && (variant == 0 || variant == 2)) {
+  if (m->fast_ok && dense && std::is_same<T, double>::value && variant == 2) {
     const FastModel<T>& fm = pick_dfs<T>(m);
     const int n = fm.n;
     const size_t stash = (size_t)(fm.n_slot_a * kMinvSlotA + fm.n_slot_b * kMinvSlotB) * 32 * sizeof(T);
@@ -479,8 +553,9 @@ int rbd_model_destroy(rbd_model_t* m) {
 int rbd_model_num_dof(const rbd_model_t* m) { return m ? m->d.n : RBD_E_INVALID_ARGUMENT; }
 
 int rbd_set_kernel_variant(int variant) {
-  if (variant < 0 || variant > 3)
-    return fail(RBD_E_INVALID_ARGUMENT, "rbd_set_kernel_variant: 0 auto, 1 generic, 2 world (thread per knot point), 3 cooperative");
+  if (variant < 0 || variant > 4)
+    return fail(RBD_E_INVALID_ARGUMENT,
+                "rbd_set_kernel_variant: 0 auto, 1 generic, 2 world (thread per knot point), 3 cooperative, 4 hybrid (minv)");
   g_variant.store(variant, std::memory_order_relaxed);
   return 0;
 }

@@ -30,7 +30,10 @@
 
 namespace rbd {
 
-constexpr int kCmTabStride = 14;     // w(3) invD | U(6) | r(3) pad  (seven aligned pairs)
+// table row stride: 16-byte aligned and = 16 (mod 128) bytes, so rows of different bodies start in
+// different bank groups (lanes of one warp gather rows of up to eight different bodies at once)
+template <typename T> __host__ __device__ constexpr int cm_tab_stride() { return sizeof(T) == 8 ? 14 : 20; }
+#define kCmTabStride (cm_tab_stride<T>())
 constexpr int kCmIaStride = 22;      // articulated inertia handed to the parent (21, eleven pairs)
 constexpr int kCmMaxWarps = 8;       // warps per CTA is chosen at launch (blockDim.x / 32)
 
@@ -42,18 +45,149 @@ struct CoopMinvPlan {
 
 // per-warp shared memory, in values of T:  tab | mb | big, where `big` holds the children's
 // inertias in phase A and is re-used for the G stashes and the output tile in phase C
+template <typename T>
 __host__ __device__ inline int coop_minv_warp_vals(int n, int G, int maxdepth, int nslot) {
   const int ipw = 32 / G;
   const int a = 32 * kCmIaStride;
-  const int c = 6 * nslot * 32 + ((ipw * n * n + 1) & ~1);
+  const int c = 6 * nslot * 32 + ((ipw * n * n + 3) & ~3);
   return 32 * kCmTabStride + (maxdepth + 1) * 32 + (a > c ? a : c);
 }
-__host__ __device__ inline size_t coop_minv_smem_bytes(int n, int G, int maxdepth, int nslot, int warps, size_t tsize) {
-  return (size_t)(((n * kCoopMdlStride + 1) & ~1) + warps * coop_minv_warp_vals(n, G, maxdepth, nslot)) * tsize +
-         (size_t)n * 8 * sizeof(int);
+template <typename T>
+__host__ __device__ inline size_t coop_minv_smem_bytes(int n, int G, int maxdepth, int nslot, int warps) {
+  return (size_t)(((n * kCoopMdlStride + 3) & ~3) + warps * coop_minv_warp_vals<T>(n, G, maxdepth, nslot)) * sizeof(T) +
+         (size_t)n * 4 * sizeof(int);
 }
 
-template <typename T, int G>
+// ---- per-body table entry in shared memory: w(3) invD | U(6) | r(3), stride kCmTabStride ------
+template <typename T> struct TabEntry { T w[3], invD, U[6], r[3]; };
+__device__ __forceinline__ void tab_load(const double* p, TabEntry<double>& e) {
+  const double2* v = reinterpret_cast<const double2*>(p);
+  const double2 a = v[0], b = v[1], c = v[2], d = v[3], f = v[4], g = v[5], h = v[6];
+  e.w[0] = a.x; e.w[1] = a.y; e.w[2] = b.x; e.invD = b.y;
+  e.U[0] = c.x; e.U[1] = c.y; e.U[2] = d.x; e.U[3] = d.y; e.U[4] = f.x; e.U[5] = f.y;
+  e.r[0] = g.x; e.r[1] = g.y; e.r[2] = h.x;
+}
+__device__ __forceinline__ void tab_load(const float* p, TabEntry<float>& e) {
+  const float4* v = reinterpret_cast<const float4*>(p);
+  const float4 a = v[0], b = v[1], c = v[2];
+  const float d = p[12];
+  e.w[0] = a.x; e.w[1] = a.y; e.w[2] = a.z; e.invD = a.w;
+  e.U[0] = b.x; e.U[1] = b.y; e.U[2] = b.z; e.U[3] = b.w; e.U[4] = c.x; e.U[5] = c.y;
+  e.r[0] = c.z; e.r[1] = c.w; e.r[2] = d;
+}
+// packed topology word of a body: depth | (slot_a + 1) << 8 | (parent's slot_a + 1) << 16 | kind << 24
+__host__ __device__ inline int cm_pack(int depth, int slot, int pslot, int kind) {
+  return depth | ((slot + 1) << 8) | ((pslot + 1) << 16) | (kind << 24);
+}
+
+// Phases B and C of the header comment plus the mirrored, coalesced store, for the IPW knot points
+// whose per-body table is in `tab`.  Lane (g, i) is column i of knot point g.
+// imdl[a] = {parent, sub_end, orig, cm_pack(...)}.  PRISM = false: every joint is revolute.
+template <typename T, int G, bool PRISM>
+__device__ __forceinline__ void minv_column_phases(int n, int maxdepth, int maxcomp, int nslot, bool valid, int i, int gbase,
+                                                   int lane, int oi, int comp_root, const int4* imdl, const T* tab, T* mbw,
+                                                   T* big, T* __restrict__ dst, int nknots) {
+  constexpr int IPW = 32 / G;
+  typedef typename Vec2<T>::type V2;
+  const int nn = n * n;
+  const int g = lane / G;
+  T* tile = big + 6 * nslot * 32;                         // [IPW][n][n]
+  T* mytile = tile + g * nn;
+  const int tile_vals = IPW * nn;
+  const bool pair_ok = (tile_vals & 1) == 0;              // slab is a whole number of aligned pairs
+  // zero the output tile (entries between different root components stay zero)
+  if (pair_ok) {
+    V2 z; z.x = T(0); z.y = T(0);
+    for (int k = lane; k < (tile_vals >> 1); k += 32) reinterpret_cast<V2*>(tile)[k] = z;
+  } else {
+    for (int k = lane; k < tile_vals; k += 32) tile[k] = T(0);
+  }
+  // ------------------------------------------------------------------ phase B: walk to the root
+  {
+    T F[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+    int a = valid ? i : -1;
+    for (int t = 0; t <= maxdepth; ++t) {
+      if (a >= 0) {
+        TabEntry<T> e;
+        tab_load(tab + (gbase + a) * kCmTabStride, e);
+        const int4 ia = imdl[a];
+        const bool pris = PRISM && ((ia.w >> 24) != 0);
+        const T sF = pris ? dot3s(e.w, F + 3) : dot3s(e.w, F);
+        const T mij = (a == i ? e.invD : T(0)) - e.invD * sF;                  // :700-708
+        mbw[(ia.w & 0xff) * 32 + lane] = mij;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) F[k] = fma_t(e.U[k], mij, F[k]);           // :721-726
+        cross3_add(e.r, F + 3, F);                                             // moment about the parent's origin
+        a = ia.x;
+      }
+    }
+  }
+  __syncwarp();
+  // ------------------------------------------------------------------ phase C: preorder sweep
+  if (valid) {
+    T Gv[6];
+    const int oin = oi * n;
+    {
+      // the root of the component: no parent term (:778-781)
+      const int a = comp_root;
+      TabEntry<T> e;
+      tab_load(tab + (gbase + a) * kCmTabStride, e);
+      const int4 ia = imdl[a];
+      const T mij = mbw[lane];                            // depth 0; the root is an ancestor of (or is) i
+      const bool pris = PRISM && ((ia.w >> 24) != 0);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { Gv[k] = pris ? T(0) : e.w[k] * mij; Gv[3 + k] = pris ? e.w[k] * mij : T(0); }
+      const int sl = ((ia.w >> 8) & 0xff) - 1;
+      if (sl >= 0) {
+        T* gs = big + (sl * 6) * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gs[k * 32] = Gv[k];
+      }
+      mytile[ia.z * n + oi] = mij;
+      mytile[oin + ia.z] = mij;
+    }
+    for (int a = comp_root + 1; a <= i; ++a) {
+      TabEntry<T> e;
+      tab_load(tab + (gbase + a) * kCmTabStride, e);
+      const int4 ia = imdl[a];
+      T mij = (i < ia.y) ? mbw[(ia.w & 0xff) * 32 + lane] : T(0);
+      if (ia.x != a - 1) {                                // parent is a branch point: its G was stashed
+        const T* gs = big + ((((ia.w >> 16) & 0xff) - 1) * 6) * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Gv[k] = gs[k * 32];
+      }
+      cross3_add(Gv, e.r, Gv + 3);                                             // velocity at p_a: v += w x r
+      mij = fma_t(-e.invD, dot6s(e.U, Gv), mij);                               // :771-773
+      if (PRISM && ((ia.w >> 24) != 0)) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Gv[3 + k] = fma_t(e.w[k], mij, Gv[3 + k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Gv[k] = fma_t(e.w[k], mij, Gv[k]);         // :774-781
+      }
+      const int sl = ((ia.w >> 8) & 0xff) - 1;
+      if (sl >= 0) {
+        T* gs = big + (sl * 6) * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gs[k * 32] = Gv[k];
+      }
+      mytile[ia.z * n + oi] = mij;
+      mytile[oin + ia.z] = mij;                                                // :799-804
+    }
+  }
+  __syncwarp();
+  // ------------------------------------------------------------------ coalesced slab write
+  {
+    const int count = nknots * nn;
+    if (pair_ok && count == tile_vals) {
+      for (int k = lane; k < (tile_vals >> 1); k += 32) __stcs(reinterpret_cast<V2*>(dst) + k, reinterpret_cast<const V2*>(tile)[k]);
+    } else {
+      for (int k = lane; k < count; k += 32) __stcs(dst + k, tile[k]);
+    }
+  }
+}
+
+template <typename T, int G, bool PRISM>
 __global__ void __launch_bounds__(kCmMaxWarps * 32)
 minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__ DfsPlan plan,
                  const __grid_constant__ CoopPlan cp, const __grid_constant__ CoopMinvPlan mp, int64_t B,
@@ -65,10 +199,10 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
   const int nn = n * n;
   const int maxdepth = cp.maxdepth;
   const int nwarps = blockDim.x >> 5;
-  const int warp_vals = coop_minv_warp_vals(n, G, maxdepth, m.n_slot_a);
-  int4* imdl = reinterpret_cast<int4*>(smem_raw);                            // [n][2]
-  T* mdl = reinterpret_cast<T*>(smem_raw + (size_t)n * 2 * sizeof(int4));    // [n][51]
-  T* warp_all = mdl + ((n * kCoopMdlStride + 1) & ~1);                       // [nwarps][warp_vals]
+  const int warp_vals = coop_minv_warp_vals<T>(n, G, maxdepth, m.n_slot_a);
+  int4* imdl = reinterpret_cast<int4*>(smem_raw);                            // [n]
+  T* mdl = reinterpret_cast<T*>(smem_raw + (size_t)n * sizeof(int4));        // [n][51]
+  T* warp_all = mdl + ((n * kCoopMdlStride + 3) & ~3);                       // [nwarps][warp_vals]
 
   for (int idx = threadIdx.x; idx < n * kCoopMdlStride; idx += blockDim.x) {
     const int i = idx / kCoopMdlStride, k = idx - i * kCoopMdlStride;
@@ -87,9 +221,8 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int p = m.parent[i];
-    imdl[2 * i] = make_int4(p, m.kind[i], plan.sub_end[i], plan.orig[i]);
-    // slot of this body's G (kept for a later, non-first child) and of the parent's
-    imdl[2 * i + 1] = make_int4(mp.depth[i], mp.comp_root[i], m.slot_a[i], p >= 0 ? m.slot_a[p] : -1);
+    // slot_a: this body's G is kept for a later (non-first) child
+    imdl[i] = make_int4(p, plan.sub_end[i], plan.orig[i], cm_pack(mp.depth[i], m.slot_a[i], p >= 0 ? m.slot_a[p] : -1, m.kind[i]));
   }
   __syncthreads();
 
@@ -99,25 +232,21 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
   const int ib = valid ? i : 0;
   const int gbase = g * G;
   const T* mb = mdl + ib * kCoopMdlStride;
-  const int4 myA = imdl[2 * ib], myB = imdl[2 * ib + 1];
+  const int4 myA = imdl[ib];
   const int par = valid ? myA.x : -1;
-  const int kind = myA.y;
-  const int sub_end = myA.z;
-  const int oi = myA.w;
-  const int depth = valid ? myB.x : -1;
-  const int comp_root = myB.y;
+  const int kind = PRISM ? (myA.w >> 24) : 0;
+  const int sub_end = myA.y;
+  const int oi = myA.z;
+  const int depth = valid ? (myA.w & 0xff) : -1;
+  const int comp_root = mp.comp_root[ib];
   int jump[5];
 #pragma unroll
   for (int s = 0; s < 5; ++s) jump[s] = valid ? cp.jump[s][ib] : -1;
   T* tab = warp_all + warp * warp_vals;                   // [32][14]
   T* mbw = tab + 32 * kCmTabStride;                       // [maxdepth+1][32]
   T* big = mbw + (maxdepth + 1) * 32;                     // phase A: [32][22]; phase C: G stashes [slot][6][32] | tile
-  T* tile = big + 6 * m.n_slot_a * 32;                    // [IPW][n][n]
-  T* mytile = tile + g * nn;
   T* mytab = tab + lane * kCmTabStride;
   const int nsteps = cp.nsteps;
-  const int tile_vals = IPW * nn;
-  const bool pair_ok = (tile_vals & 1) == 0;              // slab is a whole number of aligned pairs
 
   const int64_t ngroups = (B + IPW - 1) / IPW;
   for (int64_t grp = (int64_t)blockIdx.x * nwarps + warp; grp < ngroups; grp += (int64_t)gridDim.x * nwarps) {
@@ -201,7 +330,7 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
     // ------------------------------------------------------------------ phase A: articulated inertias
     for (int d = maxdepth; d >= 0; --d) {
       if (depth == d) {
-        for (int c = i + 1; c < sub_end; c = imdl[2 * c].z) {                   // children of i
+        for (int c = i + 1; c < sub_end; c = imdl[c].y) {                   // children of i
           const V2* src = reinterpret_cast<const V2*>(big + (gbase + c) * kCmIaStride);
 #pragma unroll
           for (int k = 0; k < 11; ++k) { const V2 t = src[k]; IA[2 * k] += t.x; IA[2 * k + 1] += t.y; }
@@ -276,98 +405,306 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
       __syncwarp();
     }
 
-    // ------------------------------------------------------------------ phase B: walk to the root
-    {
-      T F[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-      int a = valid ? i : -1;
-      for (int t = 0; t <= maxdepth; ++t) {
-        if (a >= 0) {
-          const V2* ta = reinterpret_cast<const V2*>(tab + (gbase + a) * kCmTabStride);
-          const int4 ia = imdl[2 * a];
-          const int da = imdl[2 * a + 1].x;
-          const V2 t0 = ta[0], t1 = ta[1];
-          const T wa[3] = {t0.x, t0.y, t1.x};
-          const T invD = t1.y;
-          const T sF = ia.y == 0 ? dot3s(wa, F) : dot3s(wa, F + 3);
-          const T mij = (a == i ? invD : T(0)) - invD * sF;                    // :700-708
-          mbw[da * 32 + lane] = mij;
-          if (ia.x >= 0) {
-            const V2 t2 = ta[2], t3 = ta[3], t4 = ta[4], t5 = ta[5], t6 = ta[6];
-            F[0] = fma_t(t2.x, mij, F[0]); F[1] = fma_t(t2.y, mij, F[1]); F[2] = fma_t(t3.x, mij, F[2]);   // :721-726
-            F[3] = fma_t(t3.y, mij, F[3]); F[4] = fma_t(t4.x, mij, F[4]); F[5] = fma_t(t4.y, mij, F[5]);
-            const T ra[3] = {t5.x, t5.y, t6.x};
-            cross3_add(ra, F + 3, F);                                          // moment about the parent's origin
-          }
-          a = ia.x;
-        }
-      }
-    }
-    __syncwarp();
-    // zero the output tile (entries between different root components stay zero)
-    if (pair_ok) {
-      V2 z; z.x = T(0); z.y = T(0);
-      for (int k = lane; k < (tile_vals >> 1); k += 32) reinterpret_cast<V2*>(tile)[k] = z;
-    } else {
-      for (int k = lane; k < tile_vals; k += 32) tile[k] = T(0);
-    }
-    __syncwarp();
-
-    // ------------------------------------------------------------------ phase C: preorder sweep
-    {
-      T Gv[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-      const int oin = oi * n;
-      for (int t = 0; t < mp.maxcomp; ++t) {
-        const int a = comp_root + t;
-        if (valid && a <= i) {
-          const V2* ta = reinterpret_cast<const V2*>(tab + (gbase + a) * kCmTabStride);
-          const int4 ia = imdl[2 * a], ja = imdl[2 * a + 1];
-          const V2 t0 = ta[0], t1 = ta[1];
-          T mij = (i < ia.z) ? mbw[ja.x * 32 + lane] : T(0);
-          if (ia.x < 0) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) Gv[k] = T(0);
-          } else {
-            if (ia.x != a - 1) {
-              const T* gs = big + (ja.w * 6) * 32 + lane;
-#pragma unroll
-              for (int k = 0; k < 6; ++k) Gv[k] = gs[k * 32];
-            }
-            const V2 t2 = ta[2], t3 = ta[3], t4 = ta[4], t5 = ta[5], t6 = ta[6];
-            const T ra[3] = {t5.x, t5.y, t6.x};
-            cross3_add(Gv, ra, Gv + 3);                                        // velocity at p_a: v += w x r
-            const T lo = fma_t(t3.x, Gv[2], fma_t(t2.y, Gv[1], t2.x * Gv[0]));
-            const T hi = fma_t(t4.y, Gv[5], fma_t(t4.x, Gv[4], t3.y * Gv[3]));
-            mij = fma_t(-t1.y, lo + hi, mij);                                  // :771-773
-          }
-          if (ia.y == 0) {
-            Gv[0] = fma_t(t0.x, mij, Gv[0]); Gv[1] = fma_t(t0.y, mij, Gv[1]); Gv[2] = fma_t(t1.x, mij, Gv[2]);   // :774-781
-          } else {
-            Gv[3] = fma_t(t0.x, mij, Gv[3]); Gv[4] = fma_t(t0.y, mij, Gv[4]); Gv[5] = fma_t(t1.x, mij, Gv[5]);
-          }
-          if (ja.z >= 0) {
-            T* gs = big + (ja.z * 6) * 32 + lane;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) gs[k * 32] = Gv[k];
-          }
-          mytile[ia.w * n + oi] = mij;
-          mytile[oin + ia.w] = mij;                                            // :799-804
-        }
-      }
-    }
-    __syncwarp();
-    // ------------------------------------------------------------------ coalesced slab write
-    {
-      const int64_t first = grp * IPW;
-      const int count = (int)((B - first) < IPW ? (B - first) : IPW) * nn;
-      T* dst = Minv + first * nn;
-      if (pair_ok && count == tile_vals) {
-        for (int k = lane; k < (tile_vals >> 1); k += 32) reinterpret_cast<V2*>(dst)[k] = reinterpret_cast<const V2*>(tile)[k];
-      } else {
-        for (int k = lane; k < count; k += 32) dst[k] = tile[k];
-      }
-    }
+    minv_column_phases<T, G, PRISM>(n, maxdepth, mp.maxcomp, m.n_slot_a, valid, i, gbase, lane, oi, comp_root, imdl, tab, mbw, big,
+                             Minv + grp * IPW * (int64_t)nn, (int)((B - grp * IPW) < IPW ? (B - grp * IPW) : IPW));
     __syncwarp();
   }
+}
+
+// =============================================================================================
+// Hybrid mapping: phase A does not parallelise over the bodies of one knot point (it is a serial
+// recursion along every root path), so a warp takes 32 knot points at a time and runs
+//   stage 1  ONE KNOT POINT PER LANE: rotation sweep root -> leaf, articulated-inertia sweep
+//            leaf -> root (the parent's rotation is re-derived from the child's, only branch points
+//            and chain ends are stashed), writing each body's (w, 1/D, U, r) to a warp-private
+//            scratch table in global memory (written and re-read within microseconds: L2 traffic);
+//   stage 2  ONE COLUMN PER LANE (minv_column_phases), IPW knot points per pass, reading the table
+//            back with coalesced loads.
+// Every lane is busy in both stages; the model is read from the constant bank in stage 1
+// (warp-uniform body index) and from a shared-memory index table in stage 2.
+constexpr int kHyScrStride = 16;     // w(3) invD | U(6) | r(3) pad | f1 f2   (eight aligned pairs)
+
+template <typename T>
+__host__ __device__ inline int hybrid_minv_warp_vals(int n, int G, int maxdepth, int nslot_a, int nslot_b) {
+  const int ipw = 32 / G;
+  const int s2 = 32 * kCmTabStride + (maxdepth + 1) * 32 + 6 * nslot_a * 32 + ((ipw * n * n + 3) & ~3);
+  const int s1 = (22 * nslot_a + 9 * nslot_b) * 32;
+  return s1 > s2 ? s1 : s2;
+}
+template <typename T>
+__host__ __device__ inline size_t hybrid_minv_smem_bytes(int n, int G, int maxdepth, int nslot_a, int nslot_b, int warps) {
+  return (size_t)warps * hybrid_minv_warp_vals<T>(n, G, maxdepth, nslot_a, nslot_b) * sizeof(T) + (size_t)n * 4 * sizeof(int);
+}
+
+template <typename T, int G, bool PRISM>
+__global__ void __launch_bounds__(kCmMaxWarps * 32)
+minv_hybrid_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__ DfsPlan plan,
+                   const __grid_constant__ CoopMinvPlan mp, int maxdepth, int64_t B, const T* __restrict__ q,
+                   T* __restrict__ Minv, T* __restrict__ scratch) {
+  constexpr int IPW = 32 / G;
+  typedef typename Vec2<T>::type V2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = m.n;
+  const int nn = n * n;
+  const int nwarps = blockDim.x >> 5;
+  const int warp_vals = hybrid_minv_warp_vals<T>(n, G, maxdepth, m.n_slot_a, m.n_slot_b);
+  int4* imdl = reinterpret_cast<int4*>(smem_raw);                            // [n]
+  T* warp_all = reinterpret_cast<T*>(smem_raw + (size_t)n * sizeof(int4));
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int p = m.parent[i];
+    imdl[i] = make_int4(p, plan.sub_end[i], plan.orig[i], cm_pack(mp.depth[i], m.slot_a[i], p >= 0 ? m.slot_a[p] : -1, m.kind[i]));
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / G, i2 = lane - g * G;
+  const bool valid = i2 < n;
+  const int ib = valid ? i2 : 0;
+  const int gbase = g * G;
+  const int oi = imdl[ib].z;
+  const int comp_root = mp.comp_root[ib];
+  T* ws = warp_all + warp * warp_vals;
+  // stage-2 views
+  T* tab = ws;                                            // [32][14]
+  T* mbw = tab + 32 * kCmTabStride;                       // [maxdepth+1][32]
+  T* big = mbw + (maxdepth + 1) * 32;                     // G stashes [slot][6][32] | tile
+  // stage-1 views (same memory, different time)
+  T* sta = ws;                                            // [slot_a][22][32]
+  T* stb = sta + m.n_slot_a * 22 * 32;                    // [slot_b][9][32]
+#define HSTA(s, k) sta[((s) * 22 + (k)) * 32 + lane]
+#define HSTB(s, k) stb[((s) * 9 + (k)) * 32 + lane]
+  T* myscr = scratch + (size_t)(blockIdx.x * nwarps + warp) * 32 * n * kHyScrStride;   // [32][n][16]
+  T* scr = myscr + (size_t)lane * n * kHyScrStride;
+
+  const int64_t ntasks = (B + 31) / 32;
+  for (int64_t task = (int64_t)blockIdx.x * nwarps + warp; task < ntasks; task += (int64_t)gridDim.x * nwarps) {
+    // ================================================================ stage 1: lane = knot point
+    {
+      int64_t b = task * 32 + lane;
+      if (b >= B) b = B - 1;                              // duplicate work, never stored
+      const T* qb = q + b * n;
+      T E[9];
+      // ---- rotations, root -> leaf
+#pragma unroll 1
+      for (int i = 0; i < n; ++i) {
+        T f1, f2;
+        {
+          const T qi = qb[plan.orig[i]];
+          if (!PRISM || m.kind[i] == 0) sincos_t(qi, &f2, &f1);
+          else { f1 = qi; f2 = T(0); }
+        }
+        {
+          V2 t; t.x = f1; t.y = f2;
+          __stcg(reinterpret_cast<V2*>(scr + i * kHyScrStride + 14), t);
+        }
+        const int par = m.parent[i];
+        T Ep[9];
+        if (par < 0) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) Ep[k] = (k % 4 == 0) ? T(1) : T(0);
+        } else if (par != i - 1) {
+          const int s = m.slot_a[par];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) Ep[k] = HSTA(s, k);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) Ep[k] = E[k];
+        }
+        T Ej[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Ej[k] = fma_t(m.EC[i][k], f2, fma_t(m.EB[i][k], f1, m.EA[i][k]));
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc)
+            E[3 * rr + cc] = Ej[3 * rr] * Ep[cc] + Ej[3 * rr + 1] * Ep[3 + cc] + Ej[3 * rr + 2] * Ep[6 + cc];
+        const int sa = m.slot_a[i], sb = m.slot_b[i];
+        if (sa >= 0) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) HSTA(sa, k) = E[k];
+        }
+        if (sb >= 0) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) HSTB(sb, k) = E[k];
+        }
+      }
+      // ---- articulated inertias, leaf -> root
+      for (int s = 0; s < m.n_slot_a; ++s)
+#pragma unroll
+        for (int k = 0; k < 22; ++k) HSTA(s, k) = T(0);
+      T IA[21];
+#pragma unroll 1
+      for (int i = n - 1; i >= 0; --i) {
+        const bool chained = (i != n - 1) && (m.parent[i + 1] == i);
+        if (!chained && i != n - 1) {
+          const int s = m.slot_b[i];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) E[k] = HSTB(s, k);
+        }
+        const V2 ff = __ldcg(reinterpret_cast<const V2*>(scr + i * kHyScrStride + 14));
+        const int kind = PRISM ? m.kind[i] : 0;
+        const int par = m.parent[i];
+        // own rigid inertia about p_i, world-aligned axes
+        {
+          const T mi = m.mass[i];
+          T hr[3];
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) hr[cc] = E[cc] * m.h[i][0] + E[3 + cc] * m.h[i][1] + E[6 + cc] * m.h[i][2];
+          T IbE[9];
+          const T xx = m.Ib[i][0], xy = m.Ib[i][1], xz = m.Ib[i][2], yy = m.Ib[i][3], yz = m.Ib[i][4], zz = m.Ib[i][5];
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) {
+            IbE[cc] = xx * E[cc] + xy * E[3 + cc] + xz * E[6 + cc];
+            IbE[3 + cc] = xy * E[cc] + yy * E[3 + cc] + yz * E[6 + cc];
+            IbE[6 + cc] = xz * E[cc] + yz * E[3 + cc] + zz * E[6 + cc];
+          }
+          T own[6];
+          int idx = 0;
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+            for (int cc = rr; cc < 3; ++cc)
+              own[idx++] = E[rr] * IbE[cc] + E[3 + rr] * IbE[3 + cc] + E[6 + rr] * IbE[6 + cc];
+          if (chained) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) IA[k] += own[k];
+            IA[7] -= hr[2]; IA[8] += hr[1]; IA[9] += hr[2]; IA[11] -= hr[0]; IA[12] -= hr[1]; IA[13] += hr[0];
+            IA[15] += mi; IA[18] += mi; IA[20] += mi;
+          } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) IA[k] = own[k];
+            IA[6] = T(0); IA[7] = -hr[2]; IA[8] = hr[1];
+            IA[9] = hr[2]; IA[10] = T(0); IA[11] = -hr[0];
+            IA[12] = -hr[1]; IA[13] = hr[0]; IA[14] = T(0);
+            IA[15] = mi; IA[16] = T(0); IA[17] = T(0); IA[18] = mi; IA[19] = T(0); IA[20] = mi;
+          }
+        }
+        const int sa = m.slot_a[i];
+        if (sa >= 0) {
+#pragma unroll
+          for (int k = 0; k < 21; ++k) IA[k] += HSTA(sa, k);
+        }
+        T w[3], rw[3], Ej[9];
+        {
+          const T f1 = ff.x, f2 = ff.y;
+          T r[3], t[3];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) Ej[k] = fma_t(m.EC[i][k], f2, fma_t(m.EB[i][k], f1, m.EA[i][k]));
+#pragma unroll
+          for (int k = 0; k < 3; ++k) r[k] = fma_t(m.rC[i][k], f2, fma_t(m.rB[i][k], f1, m.rA[i][k]));
+#pragma unroll
+          for (int k = 0; k < 3; ++k) t[k] = Ej[3 * k] * r[0] + Ej[3 * k + 1] * r[1] + Ej[3 * k + 2] * r[2];
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) {
+            rw[cc] = E[cc] * t[0] + E[3 + cc] * t[1] + E[6 + cc] * t[2];       // r_i = p_i - p_parent, world axes
+            w[cc] = E[cc] * m.axis[i][0] + E[3 + cc] * m.axis[i][1] + E[6 + cc] * m.axis[i][2];
+          }
+        }
+        T U[6];
+        if (kind == 0) {
+          sym3_mul(IA, w, U);
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) U[3 + cc] = IA[6 + cc] * w[0] + IA[9 + cc] * w[1] + IA[12 + cc] * w[2];
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr) U[rr] = IA[6 + 3 * rr] * w[0] + IA[7 + 3 * rr] * w[1] + IA[8 + 3 * rr] * w[2];
+          sym3_mul(IA + 15, w, U + 3);
+        }
+        const T D = kind == 0 ? dot3s(w, U) : dot3s(w, U + 3);
+        const T invD = T(1) / D;                                               // RBDReference.py:698-700
+        {
+          V2* dst = reinterpret_cast<V2*>(scr + i * kHyScrStride);
+          V2 t;
+          t.x = w[0]; t.y = w[1]; __stcg(dst + 0, t);
+          t.x = w[2]; t.y = invD; __stcg(dst + 1, t);
+          t.x = U[0]; t.y = U[1]; __stcg(dst + 2, t);
+          t.x = U[2]; t.y = U[3]; __stcg(dst + 3, t);
+          t.x = U[4]; t.y = U[5]; __stcg(dst + 4, t);
+          t.x = rw[0]; t.y = rw[1]; __stcg(dst + 5, t);
+          t.x = rw[2]; t.y = T(0); __stcg(dst + 6, t);
+        }
+        if (par >= 0) {
+          T Us[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) Us[k] = U[k] * invD;
+          IA[0] -= U[0] * Us[0]; IA[1] -= U[0] * Us[1]; IA[2] -= U[0] * Us[2];
+          IA[3] -= U[1] * Us[1]; IA[4] -= U[1] * Us[2]; IA[5] -= U[2] * Us[2];
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) IA[6 + 3 * rr + cc] -= U[rr] * Us[3 + cc];
+          IA[15] -= U[3] * Us[3]; IA[16] -= U[3] * Us[4]; IA[17] -= U[3] * Us[5];
+          IA[18] -= U[4] * Us[4]; IA[19] -= U[4] * Us[5]; IA[20] -= U[5] * Us[5];
+          const T Cm[9] = {IA[15], IA[16], IA[17], IA[16], IA[18], IA[19], IA[17], IA[19], IA[20]};
+          T RC[9], W[9];
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) {
+            RC[cc] = rw[1] * Cm[6 + cc] - rw[2] * Cm[3 + cc];
+            RC[3 + cc] = rw[2] * Cm[cc] - rw[0] * Cm[6 + cc];
+            RC[6 + cc] = rw[0] * Cm[3 + cc] - rw[1] * Cm[cc];
+          }
+#pragma unroll
+          for (int k = 0; k < 9; ++k) { W[k] = fma_t(T(0.5), RC[k], IA[6 + k]); IA[6 + k] += RC[k]; }
+          T RW[9];
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb) {
+            RW[bb] = rw[1] * W[3 * bb + 2] - rw[2] * W[3 * bb + 1];
+            RW[3 + bb] = rw[2] * W[3 * bb] - rw[0] * W[3 * bb + 2];
+            RW[6 + bb] = rw[0] * W[3 * bb + 1] - rw[1] * W[3 * bb];
+          }
+          IA[0] += T(2) * RW[0];
+          IA[1] += RW[1] + RW[3];
+          IA[2] += RW[2] + RW[6];
+          IA[3] += T(2) * RW[4];
+          IA[4] += RW[5] + RW[7];
+          IA[5] += T(2) * RW[8];
+          if (par != i - 1) {
+            const int s = m.slot_a[par];
+#pragma unroll
+            for (int k = 0; k < 21; ++k) HSTA(s, k) += IA[k];
+          } else {
+            T Ep[9];                                       // E_parent = E_J^T E
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+              for (int cc = 0; cc < 3; ++cc)
+                Ep[3 * rr + cc] = Ej[rr] * E[cc] + Ej[3 + rr] * E[3 + cc] + Ej[6 + rr] * E[6 + cc];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) E[k] = Ep[k];
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ================================================================ stage 2: lane = column
+    {
+      V2 pre[7];                                          // table rows of the next pass, in flight
+      const V2* src0 = reinterpret_cast<const V2*>(myscr + ((size_t)g * n + ib) * kHyScrStride);
+      const size_t pass_stride = (size_t)IPW * n * kHyScrStride / 2;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) pre[k] = __ldcg(src0 + k);
+      for (int pass = 0; pass < G; ++pass) {
+        const int64_t first = task * 32 + pass * IPW;
+        if (first >= B) break;
+        {
+          V2* dst = reinterpret_cast<V2*>(tab + lane * kCmTabStride);
+#pragma unroll
+          for (int k = 0; k < 7; ++k) dst[k] = pre[k];
+        }
+        __syncwarp();
+        if (pass + 1 < G) {
+          const V2* src = src0 + (size_t)(pass + 1) * pass_stride;
+#pragma unroll
+          for (int k = 0; k < 7; ++k) pre[k] = __ldcg(src + k);
+        }
+        minv_column_phases<T, G, PRISM>(n, maxdepth, mp.maxcomp, m.n_slot_a, valid, i2, gbase, lane, oi, comp_root, imdl, tab,
+                                        mbw, big, Minv + first * (int64_t)nn, (int)((B - first) < IPW ? (B - first) : IPW));
+        __syncwarp();
+      }
+    }
+  }
+#undef HSTA
+#undef HSTB
 }
 
 }  // namespace rbd

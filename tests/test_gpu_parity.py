@@ -70,7 +70,7 @@ def test_generic_body_frame_kernels_vs_reference_golden(golden):
 
 
 @requires_cuda
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3, 4])
 def test_world_kernel_variants_vs_reference_golden(golden, variant):
     """Both world-frame mappings (2: knot point per thread, 3: body per lane) against the goldens."""
     from rbdreference_b200 import RBDReference
@@ -92,6 +92,10 @@ def test_world_kernel_variants_vs_reference_golden(golden, variant):
         dc = eng.rnea_grad(_t(qq), _t(qqd), _t(qqdd), c_out=cbuf)
         assert rel_err(dc.cpu().numpy(), bo.rnea_grad(qq, qqd, qqdd)) < TOL_F64
         assert rel_err(cbuf.cpu().numpy(), bo.rnea(qq, qqd, qqdd)[0]) < TOL_F64
+        Mref = bo.minv(qq)
+        assert rel_err(eng.minv(_t(qq)).cpu().numpy(), Mref) < TOL_F64
+        eng32 = _engine(rb, torch.float32)
+        assert rel_err(eng32.minv(_t(qq).float()).cpu().numpy(), Mref) < TOL_F32
     finally:
         RBDReference.set_kernel_variant(0)
 
