@@ -134,6 +134,23 @@ int rbd_minv_fpass_f64(const rbd_model_t* m, int64_t B, const double* q, double*
 int rbd_minv_fpass_f32(const rbd_model_t* m, int64_t B, const float* q, float* Minv, float* F, const float* U,
                        const float* Dinv, void* stream);
 
+/* ---- forward dynamics ---------------------------------------------------- */
+/* forward_dynamics (RBDReference.py:1369-1372): qdd = Minv (u - c), c = rnea(q, qd) with the S*qdd
+ * term skipped and GRAVITY = -9.81 (the reference's defaults).  u, qdd: (B, n).  Minv_out (B, n, n)
+ * may be NULL; when given it receives minv(q).  Three launches (rnea, minv, product); temporaries
+ * are stream-ordered allocations from a private memory pool. */
+int rbd_forward_dynamics_f64(const rbd_model_t* m, int64_t B, const double* q, const double* qd, const double* u,
+                             double* qdd, double* Minv_out, void* stream);
+int rbd_forward_dynamics_f32(const rbd_model_t* m, int64_t B, const float* q, const float* qd, const float* u,
+                             float* qdd, float* Minv_out, void* stream);
+/* forward_dynamics_grad (RBDReference.py:1374-1384): qdd_dq = -Minv dc_dq, qdd_dqd = -Minv dc_dqd with
+ * dc_du = rnea_grad(q, qd, qdd), qdd = forward_dynamics(q, qd, u).  qdd_dq, qdd_dqd: (B, n, n);
+ * qdd_out (B, n) may be NULL.  minv is evaluated once (the reference evaluates it twice, :1371/:1381). */
+int rbd_forward_dynamics_grad_f64(const rbd_model_t* m, int64_t B, const double* q, const double* qd,
+                                  const double* u, double* qdd_dq, double* qdd_dqd, double* qdd_out, void* stream);
+int rbd_forward_dynamics_grad_f32(const rbd_model_t* m, int64_t B, const float* q, const float* qd, const float* u,
+                                  float* qdd_dq, float* qdd_dqd, float* qdd_out, void* stream);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
 /* Runs a dependent-chain FMA micro-benchmark on `stream`'s device and returns the achieved
  * FLOP/s (2 per FMA) in *flops_per_s; is_f64 selects DFMA or FFMA.  Used only to put a measured

@@ -38,10 +38,12 @@ def run_case(name, make, B, seed):
     q = rng.uniform(-np.pi, np.pi, (B, n))
     qd = rng.uniform(-1.0, 1.0, (B, n))
     qdd = rng.uniform(-1.0, 1.0, (B, n))
-    out = dict(q=q, qd=qd, qdd=qdd, gravity_alt=np.array(-3.7))
+    u = rng.uniform(-10.0, 10.0, (B, n))
+    out = dict(q=q, qd=qd, qdd=qdd, u=u, gravity_alt=np.array(-3.7))
     keys = ["c", "v", "a", "f", "c_noqdd", "a_noqdd", "f_noqdd", "c_galt", "f_fpass", "dc_du", "dc_du_damped",
             "dc_du_noqdd", "dv_dq", "da_dq", "df_dq", "dv_dqd", "da_dqd", "df_dqd", "dc_dq", "dc_dqd",
-            "df_dq_acc", "df_dqd_acc", "Minv", "Minv_sparse", "Minv_b", "F_b", "U", "Dinv", "F_f", "H"]
+            "df_dq_acc", "df_dqd_acc", "Minv", "Minv_sparse", "Minv_b", "F_b", "U", "Dinv", "F_f", "H",
+            "fd_qdd", "fd_dq", "fd_dqd"]
     acc = {k: [] for k in keys}
     for k in range(B):
         v, a, f = ref.rnea_fpass(q[k], qd[k], qdd[k])
@@ -69,6 +71,9 @@ def run_case(name, make, B, seed):
         ref.minv_fpass(q[k], Mb, Fb, U, D)
         acc["F_f"].append(Fb.copy())
         acc["H"].append(ref.crba(q[k]))
+        acc["fd_qdd"].append(ref.forward_dynamics(q[k], qd[k], u[k]))
+        fdq, fdqd = ref.forward_dynamics_grad(q[k], qd[k], u[k])
+        acc["fd_dq"].append(fdq); acc["fd_dqd"].append(fdqd)
     for key in keys:
         out[key] = np.stack(acc[key])
     # model tables, to detect drift of rbdreference_b200/robots.py against the fixture

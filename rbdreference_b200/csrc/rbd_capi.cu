@@ -17,6 +17,7 @@
 #include "rbd_coop_kernels.cuh"
 #include "rbd_coop_minv_kernels.cuh"
 #include "rbd_pass_kernels.cuh"
+#include "rbd_fd_kernels.cuh"
 
 using namespace rbd;
 
@@ -334,6 +335,89 @@ int launch_minv_fpass(const rbd_model* m, int64_t B, const T* q, T* Minv, T* F, 
   return cuda_status("rbd_minv_fpass");
 }
 
+// ---- forward dynamics (RBDReference.py:1369-1384): compositions of the fused drivers plus the
+// per-knot-point products of rbd_fd_kernels.cuh; temporaries are stream-ordered pool allocations.
+template <typename T, bool SPLIT>
+int launch_fd_apply(int n, int mcols, int64_t B, const T* A, const T* R1, const T* R2, T alpha, T* out0, T* out1,
+                    void* stream) {
+  const size_t per_knot = (size_t)(n * n + 2 * n * mcols) * sizeof(T);
+  int KB = (int)((size_t)(96 * 1024) / per_knot);
+  if (KB < 1) KB = 1;
+  if (KB > 32) KB = 32;
+  const size_t smem = per_knot * KB;
+  auto kern = fd_apply_kernel<T, SPLIT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+  if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+  int64_t blocks = (B + KB - 1) / KB;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  kern<<<(unsigned)blocks, kFdThreads, smem, (cudaStream_t)stream>>>(n, mcols, KB, B, A, R1, R2, alpha, out0, out1);
+  return cuda_status("rbd_forward_dynamics(apply)");
+}
+
+struct PoolBuf {
+  void* p = nullptr;
+  cudaStream_t s;
+  explicit PoolBuf(cudaStream_t st) : s(st) {}
+  int alloc(size_t bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(RBD_E_NO_DEVICE, "no CUDA device");
+    cudaMemPool_t pool = scratch_pool(dev);
+    if (!pool) return fail(RBD_E_NO_DEVICE, "cannot create the scratch memory pool");
+    cudaError_t e = cudaMallocFromPoolAsync(&p, bytes, pool, s);
+    if (e != cudaSuccess) { p = nullptr; return fail((int)e, cudaGetErrorString(e)); }
+    return 0;
+  }
+  ~PoolBuf() { if (p) cudaFreeAsync(p, s); }
+};
+
+template <typename T>
+int launch_forward_dynamics(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* u, T* qdd, T* Minv_out,
+                            void* stream) {
+  RBD_CHECK_ARGS(m && q && qd && u && qdd && B >= 0, "rbd_forward_dynamics: null argument or negative B");
+  if (B == 0) return 0;
+  const int n = m->d.n;
+  PoolBuf c((cudaStream_t)stream), Mi((cudaStream_t)stream);
+  int rc = c.alloc((size_t)B * n * sizeof(T));
+  if (rc) return rc;
+  T* Minv = Minv_out;
+  if (!Minv) {
+    rc = Mi.alloc((size_t)B * n * n * sizeof(T));
+    if (rc) return rc;
+    Minv = (T*)Mi.p;
+  }
+  // c = rnea(q, qd) with the S*qdd term skipped (:1370), Minv = minv(q) (:1371), qdd = Minv (u - c) (:1372)
+  rc = launch_rnea<T>(m, B, q, qd, nullptr, T(-9.81), (T*)c.p, nullptr, nullptr, nullptr, stream);
+  if (rc) return rc;
+  rc = launch_minv<T>(m, B, q, 1, Minv, stream);
+  if (rc) return rc;
+  return launch_fd_apply<T, false>(n, 1, B, Minv, u, (const T*)c.p, T(1), qdd, nullptr, stream);
+}
+
+template <typename T>
+int launch_forward_dynamics_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* u, T* qdd_dq,
+                                 T* qdd_dqd, T* qdd_out, void* stream) {
+  RBD_CHECK_ARGS(m && q && qd && u && qdd_dq && qdd_dqd && B >= 0, "rbd_forward_dynamics_grad: null argument or negative B");
+  if (B == 0) return 0;
+  const int n = m->d.n;
+  PoolBuf Mi((cudaStream_t)stream), dd((cudaStream_t)stream), dc((cudaStream_t)stream);
+  int rc = Mi.alloc((size_t)B * n * n * sizeof(T));
+  if (rc) return rc;
+  rc = dc.alloc((size_t)B * n * 2 * n * sizeof(T));
+  if (rc) return rc;
+  T* qdd = qdd_out;
+  if (!qdd) {
+    rc = dd.alloc((size_t)B * n * sizeof(T));
+    if (rc) return rc;
+    qdd = (T*)dd.p;
+  }
+  rc = launch_forward_dynamics<T>(m, B, q, qd, u, qdd, (T*)Mi.p, stream);                       // :1377
+  if (rc) return rc;
+  rc = launch_rnea_grad<T>(m, B, q, qd, qdd, T(-9.81), 0, (T*)dc.p, nullptr, stream);           // :1378
+  if (rc) return rc;
+  // qdd_dq = -Minv dc_dq, qdd_dqd = -Minv dc_dqd (:1381-1383); the reference recomputes minv (:1381)
+  return launch_fd_apply<T, true>(n, 2 * n, B, (const T*)Mi.p, (const T*)dc.p, nullptr, T(-1), qdd_dq, qdd_dqd, stream);
+}
+
 template <typename T>
 void fill_model(const RbdModelDesc* d, DevModel<T>& out) {
   std::memset(&out, 0, sizeof(out));
@@ -603,6 +687,14 @@ int rbd_model_uses_world_kernels(const rbd_model_t* m) { return (m && m->fast_ok
   int rbd_minv_fpass_##SUF(const rbd_model_t* m, int64_t B, const T* q, T* Minv, T* F, const T* U, const T* Dinv,    \
                            void* stream) {                                                                           \
     return launch_minv_fpass<T>(m, B, q, Minv, F, U, Dinv, stream);                                                  \
+  }                                                                                                                  \
+  int rbd_forward_dynamics_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* qd, const T* u, T* qdd,       \
+                                 T* Minv_out, void* stream) {                                                        \
+    return launch_forward_dynamics<T>(m, B, q, qd, u, qdd, Minv_out, stream);                                        \
+  }                                                                                                                  \
+  int rbd_forward_dynamics_grad_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* qd, const T* u,          \
+                                      T* qdd_dq, T* qdd_dqd, T* qdd_out, void* stream) {                             \
+    return launch_forward_dynamics_grad<T>(m, B, q, qd, u, qdd_dq, qdd_dqd, qdd_out, stream);                        \
   }
 
 RBD_DEFINE(f64, double)

@@ -485,11 +485,13 @@ minv_hybrid_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant
       const T* qb = q + b * n;
       T E[9];
       // ---- rotations, root -> leaf
+      T qnext = qb[plan.orig[0]];
 #pragma unroll 1
       for (int i = 0; i < n; ++i) {
         T f1, f2;
         {
-          const T qi = qb[plan.orig[i]];
+          const T qi = qnext;
+          if (i + 1 < n) qnext = qb[plan.orig[i + 1]];    // in flight while this body is processed
           if (!PRISM || m.kind[i] == 0) sincos_t(qi, &f2, &f1);
           else { f1 = qi; f2 = T(0); }
         }
@@ -533,6 +535,7 @@ minv_hybrid_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant
 #pragma unroll
         for (int k = 0; k < 22; ++k) HSTA(s, k) = T(0);
       T IA[21];
+      V2 ffnext = __ldcg(reinterpret_cast<const V2*>(scr + (n - 1) * kHyScrStride + 14));
 #pragma unroll 1
       for (int i = n - 1; i >= 0; --i) {
         const bool chained = (i != n - 1) && (m.parent[i + 1] == i);
@@ -541,7 +544,8 @@ minv_hybrid_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant
 #pragma unroll
           for (int k = 0; k < 9; ++k) E[k] = HSTB(s, k);
         }
-        const V2 ff = __ldcg(reinterpret_cast<const V2*>(scr + i * kHyScrStride + 14));
+        const V2 ff = ffnext;
+        if (i > 0) ffnext = __ldcg(reinterpret_cast<const V2*>(scr + (i - 1) * kHyScrStride + 14));
         const int kind = PRISM ? m.kind[i] : 0;
         const int par = m.parent[i];
         // own rigid inertia about p_i, world-aligned axes

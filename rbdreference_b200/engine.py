@@ -297,23 +297,23 @@ class RBDReference:
     # compositions of the hot-path kernels
     # ------------------------------------------------------------------------------------
     def forward_dynamics(self, q, qd, u):
-        """RBDReference.py:1371-1374: Minv @ (u - c) with c = rnea(q, qd) (qdd omitted upstream)."""
-        c = self.rnea(q, qd, outputs="c")
-        Minv = self.minv(q)
-        if isinstance(Minv, torch.Tensor):
-            u_t = u if isinstance(u, torch.Tensor) else torch.as_tensor(u)
-            return torch.matmul(Minv, (u_t.to(Minv) - c).unsqueeze(-1)).squeeze(-1)
-        return np.matmul(Minv, (np.asarray(u) - c)[..., None])[..., 0]
+        """RBDReference.py:1369-1372: Minv @ (u - c) with c = rnea(q, qd) (qdd omitted upstream).
+        rnea + minv + one fused (u - c) / matrix-vector kernel, all inside the C library."""
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq, dqd, du = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(u, (n,), "u")
+        qdd = ctx.empty(n)
+        self._call("forward_dynamics", ctx, dq, dqd, du, qdd, None)
+        return ctx.ret(qdd)
 
     def forward_dynamics_grad(self, q, qd, u):
-        """RBDReference.py:1376-1384 -> (qdd_dq, qdd_dqd)."""
-        qdd = self.forward_dynamics(q, qd, u)
-        dc_du = self.rnea_grad(q, qd, qdd)
-        Minv = self.minv(q)
+        """RBDReference.py:1374-1384 -> (qdd_dq, qdd_dqd) = (-Minv dc_dq, -Minv dc_dqd)."""
+        ctx = self._Ctx(self, q, 1)
         n = self.n
-        if isinstance(Minv, torch.Tensor):
-            return -torch.matmul(Minv, dc_du[..., :n]), -torch.matmul(Minv, dc_du[..., n:])
-        return -np.matmul(Minv, dc_du[..., :n]), -np.matmul(Minv, dc_du[..., n:])
+        dq, dqd, du = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(u, (n,), "u")
+        o1, o2 = ctx.empty(n, n), ctx.empty(n, n)
+        self._call("forward_dynamics_grad", ctx, dq, dqd, du, o1, o2, None)
+        return ctx.ret(o1), ctx.ret(o2)
 
     # ------------------------------------------------------------------------------------
     def uses_world_kernels(self) -> bool:

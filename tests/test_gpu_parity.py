@@ -319,6 +319,47 @@ def test_full_size_properties_atlas_256k():
 
 
 @requires_cuda
+def test_forward_dynamics_vs_reference_golden(golden):
+    """rbd_forward_dynamics / rbd_forward_dynamics_grad (rnea + minv + rnea_grad plus the
+    hand-written per-knot-point product kernel) against outputs of the unmodified reference."""
+    name, rb, g = golden
+    q, qd, u = g["q"], g["qd"], g["u"]
+    # the result is a product of Minv (entries up to 1e3 for light links) with O(10) vectors: allow the
+    # conditioning of that product on top of the north-star bars
+    for dtype, tol in ((torch.float64, 10 * TOL_F64), (torch.float32, 10 * TOL_F32)):
+        eng = _engine(rb, dtype)
+        assert rel_err(eng.forward_dynamics(q, qd, u), g["fd_qdd"]) < tol
+        d1, d2 = eng.forward_dynamics_grad(q, qd, u)
+        assert rel_err(d1, g["fd_dq"]) < tol and rel_err(d2, g["fd_dqd"]) < tol
+    eng = _engine(rb)
+    one = eng.forward_dynamics(q[0], qd[0], u[0])               # single knot point, reference shapes
+    assert one.shape == (eng.n,) and rel_err(one, g["fd_qdd"][0]) < 10 * TOL_F64
+    e1, e2 = eng.forward_dynamics_grad(q[0], qd[0], u[0])
+    assert e1.shape == (eng.n, eng.n) and rel_err(e2, g["fd_dqd"][0]) < 10 * TOL_F64
+
+
+@requires_cuda
+@pytest.mark.parametrize("name,B", [("iiwa14", 1000), ("hyq", 333), ("atlas", 97)])
+def test_forward_dynamics_batches_vs_oracle(name, B):
+    """Ragged batches (not multiples of the kernels' group sizes) against the CPU oracle."""
+    rb = make_robot(name)
+    eng, bo = _engine(rb), BatchOracle(rb)
+    n = eng.n
+    q, qd, _ = random_states(n, B, seed=77)
+    u = np.random.default_rng(78).uniform(-10, 10, (B, n))
+    Minv = bo.minv(q)
+    c = bo.rnea(q, qd)[0]
+    qdd_ref = np.einsum("bij,bj->bi", Minv, u - c)
+    qdd = eng.forward_dynamics(_t(q), _t(qd), _t(u)).cpu().numpy()
+    assert rel_err(qdd, qdd_ref) < 10 * TOL_F64
+    dc = bo.rnea_grad(q, qd, qdd_ref)
+    d1, d2 = eng.forward_dynamics_grad(_t(q), _t(qd), _t(u))
+    assert rel_err(d1.cpu().numpy(), -np.einsum("bij,bjk->bik", Minv, dc[:, :, :n])) < 10 * TOL_F64
+    assert rel_err(d2.cpu().numpy(), -np.einsum("bij,bjk->bik", Minv, dc[:, :, n:])) < 10 * TOL_F64
+    assert eng.forward_dynamics(_t(q[:0]), _t(qd[:0]), _t(u[:0])).shape == (0, n)     # empty batch
+
+
+@requires_cuda
 def test_forward_dynamics_compositions():
     """forward_dynamics / forward_dynamics_grad as compositions."""
     from oracle.rbd_oracle import ScalarOracle

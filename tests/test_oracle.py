@@ -53,6 +53,9 @@ def test_scalar_oracle_vs_golden(golden):
         assert rel_err(so.minv(q[k]), g["Minv"][k]) < PIN
         assert rel_err(so.minv(q[k], output_dense=False), g["Minv_sparse"][k]) < PIN
         assert rel_err(so.crba(q[k]), g["H"][k]) < PIN
+        assert rel_err(so.forward_dynamics(q[k], qd[k], g["u"][k]), g["fd_qdd"][k]) < PIN
+        r1, r2 = so.forward_dynamics_grad(q[k], qd[k], g["u"][k])
+        assert rel_err(r1, g["fd_dq"][k]) < PIN and rel_err(r2, g["fd_dqd"][k]) < PIN
 
 
 def test_batch_oracle_vs_golden(golden):
