@@ -128,7 +128,7 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
     const int n = fm.n;
     const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
     const int ipw = 32 / G;
-    const int tile_stride = (ipw * n * 2 * n + 1) & ~1;
+    const int tile_stride = coop_grad_tile_stride(n, ipw);
     const size_t smem = (size_t)(n * kCoopMdlStride + kCoopWarps * 32 * kCoopVecStride + kCoopWarps * tile_stride) * sizeof(T) +
                         (size_t)n * kCoopIntStride * sizeof(int);
     if (smem <= kMaxDynSmem) {
@@ -610,12 +610,14 @@ int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out) {
     for (int i = 0; i < n; ++i) {
       const int p = m->fd_dfs.parent[i];
       cp.jump[0][i] = p;
+      if (p < 0) cp.comp_begin[cp.ncomp++] = i;
       depth[i] = p < 0 ? 0 : depth[p] + 1;
       if (depth[i] > cp.maxdepth) cp.maxdepth = depth[i];
     }
     for (int s = 1; s < 5; ++s)
       for (int i = 0; i < n; ++i) cp.jump[s][i] = cp.jump[s - 1][i] < 0 ? -1 : cp.jump[s - 1][cp.jump[s - 1][i]];
     while ((1 << cp.nsteps) < cp.maxdepth + 1) ++cp.nsteps;
+    cp.comp_begin[cp.ncomp] = n;
     CoopMinvPlan& mp = m->coop_minv;
     std::memset(&mp, 0, sizeof(mp));
     for (int i = 0; i < n; ++i) {

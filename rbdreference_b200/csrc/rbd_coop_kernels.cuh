@@ -30,11 +30,19 @@ constexpr int kCoopVecStride = 19;     // S(6) Psi_dot(6) Psi_ddot(6) + pad (odd
 struct CoopPlan {
   int nsteps;                          // pointer-jumping rounds
   int maxdepth;                        // longest ancestor chain
+  int ncomp;                           // root components; component c = bodies [comp_begin[c], comp_begin[c+1])
+  int comp_begin[RBD_MAX_DOF + 1];
   int jump[5][RBD_MAX_DOF];            // jump[s][i] = ancestor of i at distance 2^s (DFS ids) or -1
 };
 
 template <typename T>
 __device__ __forceinline__ T shfl_t(T x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+
+constexpr int kCoopScanStride = 29;    // 28 composite values per body, odd stride
+__host__ __device__ inline int coop_grad_tile_stride(int n, int ipw) {
+  const int t = ipw * n * 2 * n, s = 32 * kCoopScanStride;
+  return ((t > s ? t : s) + 1) & ~1;
+}
 
 template <typename T, int G>
 __global__ void __launch_bounds__(kCoopWarps * 32)
@@ -46,11 +54,10 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = m.n;
   const int n2 = 2 * n;
-  const int tile_vals = IPW * n * n2;                  // dc_du values per warp
   T* mdl = reinterpret_cast<T*>(smem_raw);                                   // [n][51]
   T* vec_all = mdl + n * kCoopMdlStride;                                     // [warps][32][19]
   T* tile_all = vec_all + kCoopWarps * 32 * kCoopVecStride;                  // [warps][tile_vals (+1)]
-  const int tile_stride = (tile_vals + 1) & ~1;
+  const int tile_stride = coop_grad_tile_stride(n, IPW);   // also holds the 32 x 29 composite-scan buffer
   int* imdl = reinterpret_cast<int*>(tile_all + kCoopWarps * tile_stride);   // [n][10]
 
   // ---- robot constants -> shared memory (once per CTA)
@@ -92,6 +99,7 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
   const int par = valid ? ip[0] : -1;
   const int kind = ip[1];
   const int sub_end = ip[2];
+  const bool cut = valid && sub_end < plan.comp_end[ib];   // bodies of the same component follow the subtree
   const int oi = ip[3];
   T* vec = vec_all + warp * 32 * kCoopVecStride;
   T* tile = tile_all + warp * tile_stride;
@@ -100,7 +108,21 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
   const int nsteps = cp.nsteps;
 
   const int64_t ngroups = (B + IPW - 1) / IPW;
-  for (int64_t grp = (int64_t)blockIdx.x * kCoopWarps + warp; grp < ngroups; grp += (int64_t)gridDim.x * kCoopWarps) {
+  const int64_t gstride = (int64_t)gridDim.x * kCoopWarps;
+  // the inputs of the next knot points are requested one iteration ahead (HBM latency is hidden
+  // behind a whole evaluation)
+  T q_nx = T(0), qd_nx = T(0), qdd_nx = T(0);
+  {
+    const int64_t grp0 = (int64_t)blockIdx.x * kCoopWarps + warp;
+    if (grp0 < ngroups) {
+      int64_t b = grp0 * IPW + g;
+      if (b >= B) b = B - 1;
+      q_nx = q[b * n + oi];
+      qd_nx = qd[b * n + oi];
+      qdd_nx = qdd ? qdd[b * n + oi] : T(0);
+    }
+  }
+  for (int64_t grp = (int64_t)blockIdx.x * kCoopWarps + warp; grp < ngroups; grp += gstride) {
     int64_t b = grp * IPW + g;
     if (b >= B) b = B - 1;                                    // duplicate work, never stored
 
@@ -108,9 +130,16 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
     T E[9], p[3], S[6], Pd[6], Pdd[6], v[6], a[6];
     T qdi, qddi;
     {
-      const T qi = q[b * n + oi];
-      qdi = qd[b * n + oi];
-      qddi = qdd ? qdd[b * n + oi] : T(0);
+      const T qi = q_nx;
+      qdi = qd_nx;
+      qddi = qdd_nx;
+      if (grp + gstride < ngroups) {
+        int64_t bn = (grp + gstride) * IPW + g;
+        if (bn >= B) bn = B - 1;
+        q_nx = q[bn * n + oi];
+        qd_nx = qd[bn * n + oi];
+        qdd_nx = qdd ? qdd[bn * n + oi] : T(0);
+      }
       T f1, f2;
       if (kind == 0) sincos_t(qi, &f2, &f1);
       else { f1 = qi; f2 = T(0); }
@@ -271,24 +300,39 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
         for (int k = 0; k < 28; ++k) acc[k] = T(0);
       }
     }
-    // suffix scan inside the group, then remove what lies beyond the subtree
-#pragma unroll
-    for (int d = 1; d < G; d <<= 1) {
-      const bool take = (i + d) < G;
-#pragma unroll
-      for (int k = 0; k < 28; ++k) {
-        const T t = __shfl_down_sync(0xffffffffu, acc[k], d, G);
-        if (take) acc[k] += t;
-      }
-    }
+    // subtree composites = suffix sums over the contiguous preorder range of the subtree, restarted
+    // at every root component.  Transposed through shared memory: every lane parks its 28 own
+    // terms, lane c < 28 then runs the sequential suffix sum of component c over the bodies of each
+    // knot point of the warp, and every body reads back PS(i) - PS(subtree_end(i)).
     {
-      const bool cut = valid && sub_end < n;
-      const int sl = gbase + (cut ? sub_end : 0);
+      T* cs = tile;                                           // [32][29], the tile is not live yet
+      T* mine = cs + lane * kCoopScanStride;
 #pragma unroll
-      for (int k = 0; k < 28; ++k) {
-        const T t = shfl_t(acc[k], sl);
-        if (cut) acc[k] -= t;
+      for (int k = 0; k < 28; ++k) mine[k] = acc[k];
+      __syncwarp();
+      if (lane < 28) {
+#pragma unroll
+        for (int gg = 0; gg < IPW; ++gg) {
+          T* col = cs + (gg * G) * kCoopScanStride + lane;
+          for (int cidx = 0; cidx < cp.ncomp; ++cidx) {
+            T run = T(0);
+            const int first = cp.comp_begin[cidx];
+            for (int bdy = cp.comp_begin[cidx + 1] - 1; bdy >= first; --bdy) {
+              run += col[bdy * kCoopScanStride];
+              col[bdy * kCoopScanStride] = run;
+            }
+          }
+        }
       }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 28; ++k) acc[k] = mine[k];
+      if (cut) {
+        const T* beyond = cs + (gbase + sub_end) * kCoopScanStride;
+#pragma unroll
+        for (int k = 0; k < 28; ++k) acc[k] -= beyond[k];
+      }
+      __syncwarp();                                           // the buffer becomes the output tile again
     }
 
     // ------------------------------------------------------------------ F vectors, diagonal, zero fill
