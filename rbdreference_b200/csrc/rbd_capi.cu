@@ -128,11 +128,15 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
     const int n = fm.n;
     const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
     const int ipw = 32 / G;
-    const int tile_stride = coop_grad_tile_stride(n, ipw);
-    const size_t smem = (size_t)(n * kCoopMdlStride + kCoopWarps * 32 * kCoopVecStride + kCoopWarps * tile_stride) * sizeof(T) +
+    // large robots: the output tile is produced in two halves (dc_dq, dc_dqd) to halve its shared memory
+    const bool split = false;   // measured on B200 (Atlas): halving the tile does not pay (FP64 1.19e8 vs 1.2e8+, FP32 1.6e8 vs 2.4e8)
+    const int tile_stride = coop_grad_tile_stride(n, ipw, split);
+    const size_t smem = (size_t)(((n * kCoopMdlStride + 1) & ~1) + kCoopWarps * 32 * kCoopVecStride + kCoopWarps * tile_stride) * sizeof(T) +
                         (size_t)n * kCoopIntStride * sizeof(int);
     if (smem <= kMaxDynSmem) {
-      auto kern = G == 8 ? rnea_grad_coop_kernel<T, 8> : (G == 16 ? rnea_grad_coop_kernel<T, 16> : rnea_grad_coop_kernel<T, 32>);
+      auto kern = G == 8 ? rnea_grad_coop_kernel<T, 8, false>
+                         : (G == 16 ? rnea_grad_coop_kernel<T, 16, false>
+                                    : (split ? rnea_grad_coop_kernel<T, 32, true> : rnea_grad_coop_kernel<T, 32, false>));
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
       if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
       const int64_t ngroups = (B + ipw - 1) / ipw;

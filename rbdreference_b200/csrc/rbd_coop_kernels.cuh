@@ -39,12 +39,12 @@ template <typename T>
 __device__ __forceinline__ T shfl_t(T x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 
 constexpr int kCoopScanStride = 29;    // 28 composite values per body, odd stride
-__host__ __device__ inline int coop_grad_tile_stride(int n, int ipw) {
-  const int t = ipw * n * 2 * n, s = 32 * kCoopScanStride;
+__host__ __device__ inline int coop_grad_tile_stride(int n, int ipw, bool split) {
+  const int t = ipw * n * (split ? n : 2 * n), s = 32 * kCoopScanStride;
   return ((t > s ? t : s) + 1) & ~1;
 }
 
-template <typename T, int G>
+template <typename T, int G, bool SPLIT>
 __global__ void __launch_bounds__(kCoopWarps * 32)
 rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__ DfsPlan plan,
                       const __grid_constant__ CoopPlan cp, int64_t B, const T* __restrict__ q,
@@ -55,9 +55,9 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
   const int n = m.n;
   const int n2 = 2 * n;
   T* mdl = reinterpret_cast<T*>(smem_raw);                                   // [n][51]
-  T* vec_all = mdl + n * kCoopMdlStride;                                     // [warps][32][19]
+  T* vec_all = mdl + ((n * kCoopMdlStride + 1) & ~1);                        // [warps][32][19]
   T* tile_all = vec_all + kCoopWarps * 32 * kCoopVecStride;                  // [warps][tile_vals (+1)]
-  const int tile_stride = coop_grad_tile_stride(n, IPW);   // also holds the 32 x 29 composite-scan buffer
+  const int tile_stride = coop_grad_tile_stride(n, IPW, SPLIT);   // also holds the 32 x 29 composite-scan buffer
   int* imdl = reinterpret_cast<int*>(tile_all + kCoopWarps * tile_stride);   // [n][10]
 
   // ---- robot constants -> shared memory (once per CTA)
@@ -104,7 +104,6 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
   T* vec = vec_all + warp * 32 * kCoopVecStride;
   T* tile = tile_all + warp * tile_stride;
   T* myvec = vec + lane * kCoopVecStride;
-  T* mytile = tile + g * n * n2;
   const int nsteps = cp.nsteps;
 
   const int64_t ngroups = (B + IPW - 1) / IPW;
@@ -375,17 +374,9 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
     }
     const bool store = valid && (grp * IPW + g) < B;
     if (c_out && store) c_out[b * n + oi] = dot6s(S, fC);
-    if (valid) {
-      T* row = mytile + oi * n2;
-      for (int k = 0; k < n2; ++k) row[k] = T(0);            // structural zeros of row i
-    }
-    __syncwarp();
-    if (valid) {
-      T ddd = dot6s(S, F2);
-      if (use_damping) ddd += mb[49];                         // RBDReference.py:1341
-      mytile[oi * n2 + oi] = dot6s(S, F1);
-      mytile[oi * n2 + n + oi] = ddd;
-    }
+    T F1q[6];                                                 // F1 with the prismatic quirk of :1292 folded in
+#pragma unroll
+    for (int k = 0; k < 6; ++k) F1q[k] = F1[k];
     if (kind == 1) {
       // reference quirk for prismatic joints: X^T(-crm(f)S) instead of X^T(S x* f) (:1292)
       T nrot[3], dl[3], da[3], t3[3];
@@ -396,35 +387,82 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
       cross3(S + 3, fC + 3, da);
       cross3(p, dl, t3);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { F1[k] += t3[k] - da[k]; F1[3 + k] += dl[k]; }
+      for (int k = 0; k < 3; ++k) { F1q[k] += t3[k] - da[k]; F1q[3 + k] += dl[k]; }
     }
-    // ------------------------------------------------------------------ ancestors of i
-    {
-      int j = par;
-      for (int t = 0; t < cp.maxdepth; ++t) {
-        if (j >= 0) {
-          const T* vj = vec + (gbase + j) * kCoopVecStride;
-          T Sj[6], Pdj[6], Pddj[6];
+    // The tile holds dc_du of the warp's knot points (SPLIT = false) or one half of it at a time
+    // (SPLIT = true: dc_dq, then dc_dqd - half the shared memory, for large robots).
+    constexpr int NPASS = SPLIT ? 2 : 1;
+    const int tw = SPLIT ? n : n2;                            // tile row width
+    const int tvals = IPW * n * tw;
+    T* mytile2 = tile + g * n * tw;
 #pragma unroll
-          for (int k = 0; k < 6; ++k) { Sj[k] = vj[k]; Pdj[k] = vj[6 + k]; Pddj[k] = vj[12 + k]; }
-          const int oj = imdl[j * kCoopIntStride + 3];
-          mytile[oj * n2 + oi] = dot6s(Sj, F1);
-          mytile[oj * n2 + n + oi] = dot6s(Sj, F2);
-          mytile[oi * n2 + oj] = fma_t(T(2), dot3s(F3, Pdj), dot6s(F4, Pddj));
-          mytile[oi * n2 + n + oj] = T(2) * (dot6s(F4, Pdj) + dot3s(F3, Sj));
-          j = imdl[j * kCoopIntStride];
+    for (int half = 0; half < NPASS; ++half) {
+      const bool do_q = !SPLIT || half == 0, do_qd = !SPLIT || half == 1;
+      const int qd_off = SPLIT ? 0 : n;                       // column offset of the dc_dqd block inside the tile
+      {
+        typedef typename Vec2<T>::type V2;
+        V2 z; z.x = T(0); z.y = T(0);
+        for (int k = lane; k < ((tvals + 1) >> 1); k += 32) reinterpret_cast<V2*>(tile)[k] = z;   // structural zeros
+      }
+      __syncwarp();
+      if (valid) {
+        if (do_q) mytile2[oi * tw + oi] = dot6s(S, F1);
+        if (do_qd) {
+          T ddd = dot6s(S, F2);
+          if (use_damping) ddd += mb[49];                     // RBDReference.py:1341
+          mytile2[oi * tw + qd_off + oi] = ddd;
         }
       }
+      // ---------------------------------------------------------------- ancestors of i
+      {
+        int j = par;
+        for (int t = 0; t < cp.maxdepth; ++t) {
+          if (j >= 0) {
+            const T* vj = vec + (gbase + j) * kCoopVecStride;
+            T Sj[6], Pdj[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { Sj[k] = vj[k]; Pdj[k] = vj[6 + k]; }
+            const int oj = imdl[j * kCoopIntStride + 3];
+            if (do_q) {
+              T Pddj[6];
+#pragma unroll
+              for (int k = 0; k < 6; ++k) Pddj[k] = vj[12 + k];
+              mytile2[oj * tw + oi] = dot6s(Sj, F1q);
+              mytile2[oi * tw + oj] = fma_t(T(2), dot3s(F3, Pdj), dot6s(F4, Pddj));
+            }
+            if (do_qd) {
+              mytile2[oj * tw + qd_off + oi] = dot6s(Sj, F2);
+              mytile2[oi * tw + qd_off + oj] = T(2) * (dot6s(F4, Pdj) + dot3s(F3, Sj));
+            }
+            j = imdl[j * kCoopIntStride];
+          }
+        }
+      }
+      __syncwarp();
+      // ---------------------------------------------------------------- coalesced write
+      {
+        const int64_t first = grp * IPW;
+        const int nk = (int)((B - first) < IPW ? (B - first) : IPW);
+        T* dst = dc_du + first * n * n2;
+        if (!SPLIT) {
+          typedef typename Vec2<T>::type V2;
+          const int count = nk * n * n2;
+          if (((IPW * n * n2) & 1) == 0 && nk == IPW && (reinterpret_cast<uintptr_t>(dc_du) & (sizeof(V2) - 1)) == 0) {
+            for (int k = lane; k < (count >> 1); k += 32) __stcs(reinterpret_cast<V2*>(dst) + k, reinterpret_cast<const V2*>(tile)[k]);
+          } else {
+            for (int k = lane; k < count; k += 32) __stcs(dst + k, tile[k]);
+          }
+        } else {
+          // rows of n values go to columns [half*n, half*n + n) of the (n, 2n) result
+          const int count = nk * n * n;
+          for (int k = lane; k < count; k += 32) {
+            const int r = k / n, c = k - r * n;               // r runs over (knot, row)
+            __stcs(dst + (int64_t)r * n2 + half * n + c, tile[k]);
+          }
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    // ------------------------------------------------------------------ coalesced slab write
-    {
-      const int64_t first = grp * IPW;
-      const int count = (int)((B - first) < IPW ? (B - first) : IPW) * n * n2;
-      T* dst = dc_du + first * n * n2;
-      for (int k = lane; k < count; k += 32) dst[k] = tile[k];
-    }
-    __syncwarp();
   }
 }
 
