@@ -72,6 +72,8 @@ int rbd_model_uses_world_kernels(const rbd_model_t* m);
  * generic body-frame kernels (the reference's own recursion), 2 = world-frame kernels with one
  * knot point per thread, 3 = warp-cooperative kernels (one body per lane), 4 = hybrid minv kernel
  * (knot point per lane for the articulated inertias, column per lane for the rows of Minv; other
+ * operations behave as 0), 5 = lane minv kernel (knot point per lane in every phase, per-body table
+ * and output tile in shared memory; robots too large for it run the generic kernel; other
  * operations behave as 0).  Used by the tests and the benchmark to cross-check / compare. */
 int rbd_set_kernel_variant(int variant);
 

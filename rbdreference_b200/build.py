@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "librbd_b200.so")
 SOURCES = ["rbd_capi.cu"]
 HEADERS = ["rbd_common.cuh", "rbd_pass_kernels.cuh", "rbd_fused_kernels.cuh", "rbd_grad_kernels.cuh",
-           "rbd_minv_kernels.cuh", "rbd_coop_kernels.cuh", "rbd_coop_minv_kernels.cuh", os.path.join("..", "..", "include", "rbd_b200.h")]
+           "rbd_minv_kernels.cuh", "rbd_coop_kernels.cuh", "rbd_coop_minv_kernels.cuh", "rbd_lane_minv_kernels.cuh", "rbd_fd_kernels.cuh", os.path.join("..", "..", "include", "rbd_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

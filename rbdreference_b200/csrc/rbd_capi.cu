@@ -16,6 +16,7 @@
 #include "rbd_minv_kernels.cuh"
 #include "rbd_coop_kernels.cuh"
 #include "rbd_coop_minv_kernels.cuh"
+#include "rbd_lane_minv_kernels.cuh"
 #include "rbd_pass_kernels.cuh"
 #include "rbd_fd_kernels.cuh"
 
@@ -121,7 +122,7 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
   RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_rnea_grad: null model/q/qd/dc_du or negative B");
   if (B == 0) return 0;
   int variant = g_variant.load(std::memory_order_relaxed);
-  if (variant == 4) variant = 0;                       // 4 only selects among the minv kernels
+  if (variant >= 4) variant = 0;                       // 4, 5 only select among the minv kernels
   if (m->fast_ok && (variant == 0 || variant == 3)) {
     // warp-cooperative kernel: one body per lane, 32/G knot points per warp
     const FastModel<T>& fm = pick_dfs<T>(m);
@@ -182,7 +183,35 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
     //   HyQ    n=12: hybrid 6.1e8 | 8.5e8    cooperative 8.8e8 | 1.2e9    thread 5.2e8
     //   iiwa14 n=7 : hybrid 8.5e8 | 1.38e9   cooperative 7.8e8 | 1.2e9    thread 1.13e9 | 1.88e9 (body frame)
     const int n = m->d.n;
-    variant = n > 16 ? 4 : (n > 8 ? 3 : (std::is_same<T, double>::value ? 2 : 1));
+    //   iiwa14 n=7 : lane 1.34e9 | 2.62e9 (knot point per lane, table + tile in shared memory)
+    variant = n > 16 ? 4 : (n > 8 ? 3 : 5);
+  }
+  if (m->fast_ok && dense && variant == 5) {
+    // knot point per lane in every phase, per-body table + output tile in shared memory
+    const FastModel<T>& fm = pick_dfs<T>(m);
+    const int n = fm.n;
+    constexpr int GC = 4;
+    auto kern = fm.has_prismatic ? minv_lane_kernel<T, GC, true> : minv_lane_kernel<T, GC, false>;
+    int warps = 0, best = 0, ctas = 0;
+    size_t smem = 0;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    for (int w = 1; w <= kLmMaxWarps; ++w) {
+      const size_t sz = lane_minv_smem_bytes<T, GC>(n, fm.n_slot_a, fm.n_slot_b, w);
+      if (sz > kMaxDynSmem) break;
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, sz) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (nb * w >= best) { best = nb * w; warps = w; smem = sz; ctas = nb; }
+    }
+    int dev = 0, sms = 0;
+    if (warps > 0 && cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) {
+      const int64_t ntasks = (B + 31) / 32;
+      int64_t blocks = (ntasks + warps - 1) / warps;
+      if (blocks > (int64_t)sms * ctas) blocks = (int64_t)sms * ctas;
+      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop_minv, B, q, Minv);
+      return cuda_status("rbd_minv(lane)");
+    }
   }
   if (m->fast_ok && dense && variant == 4) {
     // hybrid kernel: knot point per lane for the articulated inertias, column per lane for the
@@ -643,9 +672,9 @@ int rbd_model_destroy(rbd_model_t* m) {
 int rbd_model_num_dof(const rbd_model_t* m) { return m ? m->d.n : RBD_E_INVALID_ARGUMENT; }
 
 int rbd_set_kernel_variant(int variant) {
-  if (variant < 0 || variant > 4)
+  if (variant < 0 || variant > 5)
     return fail(RBD_E_INVALID_ARGUMENT,
-                "rbd_set_kernel_variant: 0 auto, 1 generic, 2 world (thread per knot point), 3 cooperative, 4 hybrid (minv)");
+                "rbd_set_kernel_variant: 0 auto, 1 generic, 2 world (thread per knot point), 3 cooperative, 4 hybrid (minv), 5 lane (minv)");
   g_variant.store(variant, std::memory_order_relaxed);
   return 0;
 }

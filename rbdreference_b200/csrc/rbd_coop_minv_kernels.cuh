@@ -83,7 +83,9 @@ __host__ __device__ inline int cm_pack(int depth, int slot, int pslot, int kind)
 // Phases B and C of the header comment plus the mirrored, coalesced store, for the IPW knot points
 // whose per-body table is in `tab`.  Lane (g, i) is column i of knot point g.
 // imdl[a] = {parent, sub_end, orig, cm_pack(...)}.  PRISM = false: every joint is revolute.
-template <typename T, int G, bool PRISM>
+// ZERO = false: the caller zeroed the tile and nothing else touched it since (every entry inside a
+// root component is rewritten on each call, entries between components are never written).
+template <typename T, int G, bool PRISM, bool ZERO = true>
 __device__ __forceinline__ void minv_column_phases(int n, int maxdepth, int maxcomp, int nslot, bool valid, int i, int gbase,
                                                    int lane, int oi, int comp_root, const int4* imdl, const T* tab, T* mbw,
                                                    T* big, T* __restrict__ dst, int nknots) {
@@ -96,11 +98,13 @@ __device__ __forceinline__ void minv_column_phases(int n, int maxdepth, int maxc
   const int tile_vals = IPW * nn;
   const bool pair_ok = (tile_vals & 1) == 0;              // slab is a whole number of aligned pairs
   // zero the output tile (entries between different root components stay zero)
-  if (pair_ok) {
-    V2 z; z.x = T(0); z.y = T(0);
-    for (int k = lane; k < (tile_vals >> 1); k += 32) reinterpret_cast<V2*>(tile)[k] = z;
-  } else {
-    for (int k = lane; k < tile_vals; k += 32) tile[k] = T(0);
+  if (ZERO) {
+    if (pair_ok) {
+      V2 z; z.x = T(0); z.y = T(0);
+      for (int k = lane; k < (tile_vals >> 1); k += 32) reinterpret_cast<V2*>(tile)[k] = z;
+    } else {
+      for (int k = lane; k < tile_vals; k += 32) tile[k] = T(0);
+    }
   }
   // ------------------------------------------------------------------ phase B: walk to the root
   {
@@ -484,14 +488,30 @@ minv_hybrid_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant
       if (b >= B) b = B - 1;                              // duplicate work, never stored
       const T* qb = q + b * n;
       T E[9];
-      // ---- rotations, root -> leaf
-      T qnext = qb[plan.orig[0]];
+      // ---- rotations, root -> leaf; q is fetched four bodies ahead (the loads of a lane are 8 bytes
+      // out of every n*8, so their latency has to be covered by independent work)
+      T qpre[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) qpre[u] = qb[plan.orig[u < n ? u : 0]];
+      if (lane < 2) {
+        // next task's slab of q -> L2
+        const int64_t nxt = task + (int64_t)gridDim.x * nwarps;
+        if (nxt < ntasks) {
+          const char* pq = reinterpret_cast<const char*>(q + nxt * 32 * n);
+          const int bytes = 32 * n * (int)sizeof(T);
+          for (int off = lane * 128; off < bytes; off += 2 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pq + off));
+        }
+      }
 #pragma unroll 1
-      for (int i = 0; i < n; ++i) {
+      for (int i0 = 0; i0 < n; i0 += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u;
+        if (i >= n) break;
         T f1, f2;
         {
-          const T qi = qnext;
-          if (i + 1 < n) qnext = qb[plan.orig[i + 1]];    // in flight while this body is processed
+          const T qi = qpre[u];
+          if (i + 4 < n) qpre[u] = qb[plan.orig[i + 4]];  // in flight while the next four bodies are processed
           if (!PRISM || m.kind[i] == 0) sincos_t(qi, &f2, &f1);
           else { f1 = qi; f2 = T(0); }
         }
@@ -530,12 +550,14 @@ minv_hybrid_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant
           for (int k = 0; k < 9; ++k) HSTB(sb, k) = E[k];
         }
       }
+      }
       // ---- articulated inertias, leaf -> root
       for (int s = 0; s < m.n_slot_a; ++s)
 #pragma unroll
         for (int k = 0; k < 22; ++k) HSTA(s, k) = T(0);
       T IA[21];
       V2 ffnext = __ldcg(reinterpret_cast<const V2*>(scr + (n - 1) * kHyScrStride + 14));
+      V2 ffnext2 = __ldcg(reinterpret_cast<const V2*>(scr + (n > 1 ? n - 2 : 0) * kHyScrStride + 14));
 #pragma unroll 1
       for (int i = n - 1; i >= 0; --i) {
         const bool chained = (i != n - 1) && (m.parent[i + 1] == i);
@@ -545,7 +567,8 @@ minv_hybrid_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant
           for (int k = 0; k < 9; ++k) E[k] = HSTB(s, k);
         }
         const V2 ff = ffnext;
-        if (i > 0) ffnext = __ldcg(reinterpret_cast<const V2*>(scr + (i - 1) * kHyScrStride + 14));
+        ffnext = ffnext2;                                 // (f1, f2) arrive two bodies ahead
+        if (i > 1) ffnext2 = __ldcg(reinterpret_cast<const V2*>(scr + (i - 2) * kHyScrStride + 14));
         const int kind = PRISM ? m.kind[i] : 0;
         const int par = m.parent[i];
         // own rigid inertia about p_i, world-aligned axes
@@ -687,6 +710,12 @@ minv_hybrid_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant
       const size_t pass_stride = (size_t)IPW * n * kHyScrStride / 2;
 #pragma unroll
       for (int k = 0; k < 7; ++k) pre[k] = __ldcg(src0 + k);
+      {
+        // stage 1 used this memory for its stashes: clear the output tile once per task
+        T* tile = big + 6 * m.n_slot_a * 32;
+        const int tile_vals = IPW * nn;
+        for (int k = lane; k < tile_vals; k += 32) tile[k] = T(0);
+      }
       for (int pass = 0; pass < G; ++pass) {
         const int64_t first = task * 32 + pass * IPW;
         if (first >= B) break;
@@ -701,8 +730,9 @@ minv_hybrid_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant
 #pragma unroll
           for (int k = 0; k < 7; ++k) pre[k] = __ldcg(src + k);
         }
-        minv_column_phases<T, G, PRISM>(n, maxdepth, mp.maxcomp, m.n_slot_a, valid, i2, gbase, lane, oi, comp_root, imdl, tab,
-                                        mbw, big, Minv + first * (int64_t)nn, (int)((B - first) < IPW ? (B - first) : IPW));
+        minv_column_phases<T, G, PRISM, false>(n, maxdepth, mp.maxcomp, m.n_slot_a, valid, i2, gbase, lane, oi, comp_root, imdl,
+                                               tab, mbw, big, Minv + first * (int64_t)nn,
+                                               (int)((B - first) < IPW ? (B - first) : IPW));
         __syncwarp();
       }
     }

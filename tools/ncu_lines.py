@@ -17,7 +17,11 @@ for r in rows:
     if r[0] == "Line No": hdr = {h: i for i, h in enumerate(r)}; hdr_list = r; continue
     if hdr is None: continue
     if r[0] != "":   # source line summary row
-        g = lambda h: int(r[hdr[h]] or 0) if r[hdr[h]] not in ("-", "") else 0
+        def g(h):
+            try:
+                return int((r[hdr[h]] or "0").split("(")[0])
+            except (ValueError, IndexError):
+                return 0
         lines.append(dict(file=cur_file, line=int(r[0]), src=r[1].strip(), smp=g("# Samples"), inst=g("Instructions Executed"),
                           wait=g("stall_wait"), short=g("stall_short_sb"), long=g("stall_long_sb"), mio=g("stall_mio"),
                           math=g("stall_math"), br=g("stall_branch_resolving"), noinst=g("stall_no_inst"), bar=g("stall_barrier"),
