@@ -1,46 +1,21 @@
 // rbd_capi.cu - C ABI of librbd_b200.so (declared in include/rbd_b200.h).
 // Plain pointers and sizes only; no torch types; never synchronises; no CPU fallback.
-#include <cmath>
-#include <cstdio>
-#include <cstring>
-#include <cstdlib>
-#include <type_traits>
-#include <atomic>
-#include <mutex>
-#include <new>
-
-#include "../../include/rbd_b200.h"
-#include "rbd_common.cuh"
+#include "rbd_internal.cuh"
 #include "rbd_fused_kernels.cuh"
-#include "rbd_grad_kernels.cuh"
-#include "rbd_minv_kernels.cuh"
-#include "rbd_coop_kernels.cuh"
-#include "rbd_coop_minv_kernels.cuh"
-#include "rbd_lane_minv_kernels.cuh"
 #include "rbd_pass_kernels.cuh"
 #include "rbd_fd_kernels.cuh"
 
 using namespace rbd;
 
-struct rbd_model {
-  DevModel<double> d;
-  DevModel<float> f;
-  FastModel<double> fd;     // world-frame kernels (rigid-body inertias only)
-  FastModel<float> ff;
-  bool fast_ok;             // FastModel valid (rigid inertias, 1-DoF revolute/prismatic joints)
-  FastModel<double> fd_dfs; // the same robot renumbered in depth-first preorder (minv kernel)
-  FastModel<float> ff_dfs;
-  DfsPlan plan;
-  CoopPlan coop;
-  CoopMinvPlan coop_minv;
-};
-
 namespace {
-
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_variant{0};          // 0 auto, 1 force the generic body-frame kernels
-constexpr size_t kMaxDynSmem = 227 * 1024;
+}  // namespace
+
+namespace rbd_host {
+
+std::atomic<int> g_variant{0};
+
 // shared-memory budget per warp beyond which the local-memory variants are used
 // (RBD_SMEM_LIMIT_KB overrides it for experiments)
 size_t smem_limit() {
@@ -50,7 +25,6 @@ size_t smem_limit() {
   }();
   return v;
 }
-#define kGradSmemLimit smem_limit()
 
 // Stream-ordered scratch allocations come from one private pool per device that keeps its
 // memory between calls (release threshold = max), so steady-state calls never reach the driver's
@@ -90,224 +64,11 @@ int cuda_status(const char* what) {
   return 0;
 }
 
-template <typename T> const DevModel<T>& pick(const rbd_model* m);
-template <> const DevModel<double>& pick<double>(const rbd_model* m) { return m->d; }
-template <> const DevModel<float>& pick<float>(const rbd_model* m) { return m->f; }
-template <typename T> const FastModel<T>& pick_dfs(const rbd_model* m);
-template <> const FastModel<double>& pick_dfs<double>(const rbd_model* m) { return m->fd_dfs; }
-template <> const FastModel<float>& pick_dfs<float>(const rbd_model* m) { return m->ff_dfs; }
-template <typename T> const FastModel<T>& pick_fast(const rbd_model* m);
-template <> const FastModel<double>& pick_fast<double>(const rbd_model* m) { return m->fd; }
-template <> const FastModel<float>& pick_fast<float>(const rbd_model* m) { return m->ff; }
+}  // namespace rbd_host
 
+using namespace rbd_host;
 
-inline unsigned blocks_for(int64_t B, int threads) { return (unsigned)((B + threads - 1) / threads); }
-
-#define RBD_CHECK_ARGS(cond, msg) \
-  do { if (!(cond)) return fail(RBD_E_INVALID_ARGUMENT, msg); } while (0)
-
-template <typename T>
-int launch_rnea(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, T* c, T* v, T* a,
-                T* f, void* stream) {
-  RBD_CHECK_ARGS(m && q && qd && c && B >= 0, "rbd_rnea: null model/q/qd/c or negative B");
-  if (B == 0) return 0;
-  rnea_fused_kernel<T><<<blocks_for(B, kFusedThreads), kFusedThreads, 0, (cudaStream_t)stream>>>(
-      pick<T>(m), B, q, qd, qdd, g, c, v, a, f);
-  return cuda_status("rbd_rnea");
-}
-
-template <typename T>
-int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, int damp,
-                     T* dc_du, T* c_out, void* stream) {
-  RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_rnea_grad: null model/q/qd/dc_du or negative B");
-  if (B == 0) return 0;
-  int variant = g_variant.load(std::memory_order_relaxed);
-  if (variant >= 4) variant = 0;                       // 4, 5 only select among the minv kernels
-  if (m->fast_ok && (variant == 0 || variant == 3)) {
-    // warp-cooperative kernel: one body per lane, 32/G knot points per warp
-    const FastModel<T>& fm = pick_dfs<T>(m);
-    const int n = fm.n;
-    const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
-    const int ipw = 32 / G;
-    // large robots: the output tile is produced in two halves (dc_dq, dc_dqd) to halve its shared memory
-    const bool split = false;   // measured on B200 (Atlas): halving the tile does not pay (FP64 1.19e8 vs 1.2e8+, FP32 1.6e8 vs 2.4e8)
-    const int tile_stride = coop_grad_tile_stride(n, ipw, split);
-    const size_t smem = (size_t)(((n * kCoopMdlStride + 1) & ~1) + kCoopWarps * 32 * kCoopVecStride + kCoopWarps * tile_stride) * sizeof(T) +
-                        (size_t)n * kCoopIntStride * sizeof(int);
-    if (smem <= kMaxDynSmem) {
-      auto kern = G == 8 ? rnea_grad_coop_kernel<T, 8, false>
-                         : (G == 16 ? rnea_grad_coop_kernel<T, 16, false>
-                                    : (split ? rnea_grad_coop_kernel<T, 32, true> : rnea_grad_coop_kernel<T, 32, false>));
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-      const int64_t ngroups = (B + ipw - 1) / ipw;
-      int64_t blocks = (ngroups + kCoopWarps - 1) / kCoopWarps;
-      const int64_t cap = 148 * 16;
-      if (blocks > cap) blocks = cap;
-      kern<<<(unsigned)blocks, kCoopWarps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, B, q, qd, qdd, g, damp,
-                                                                              dc_du, c_out);
-      return cuda_status("rbd_rnea_grad(coop)");
-    }
-  }
-  const FastModel<T>& fm = pick_fast<T>(m);
-  if (m->fast_ok && (variant == 0 || variant == 2)) {
-    // (a fully unrolled compile-time-n instantiation was measured 28 % slower on B200: the
-    //  straight-line code no longer fits the instruction cache with ~5 resident warps per SM)
-    const size_t stash = (size_t)(fm.n_slot_a * 28 + fm.n_slot_b * 24) * 32 * sizeof(T);
-    size_t smem = (size_t)fm.n * kVecPerBody * 32 * sizeof(T) + stash;
-    auto kern = rnea_grad_world_kernel<T, 0, 1>;
-    if (smem > kGradSmemLimit) {          // large trees: per-body vectors go to local memory
-      kern = rnea_grad_world_kernel<T, 1, 8>;   // (tighter register caps measured slower: spills)
-      smem = stash;
-    }
-    if (smem <= kMaxDynSmem) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-      kern<<<blocks_for(B, 32), 32, smem, (cudaStream_t)stream>>>(fm, B, q, qd, qdd, g, damp, dc_du, c_out);
-      return cuda_status("rbd_rnea_grad(world)");
-    }
-  }
-  rnea_grad_fused_kernel<T><<<blocks_for(B, kFusedThreads), kFusedThreads, 0, (cudaStream_t)stream>>>(
-      pick<T>(m), B, q, qd, qdd, g, damp, dc_du, c_out);
-  return cuda_status("rbd_rnea_grad");
-}
-
-template <typename T>
-int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream) {
-  RBD_CHECK_ARGS(m && q && Minv && B >= 0, "rbd_minv: null model/q/Minv or negative B");
-  if (B == 0) return 0;
-  int variant = g_variant.load(std::memory_order_relaxed);
-  if (variant == 0 && m->fast_ok && dense) {
-    // automatic choice, measured on B200 (evals/s FP64 | FP32 at the BASELINE batch sizes):
-    //   Atlas  n=30: hybrid 1.21e8 | 2.0e8   cooperative 1.19e8 | 1.8e8   thread 5.8e7 | 7.1e7
-    //   HyQ    n=12: hybrid 6.1e8 | 8.5e8    cooperative 8.8e8 | 1.2e9    thread 5.2e8
-    //   iiwa14 n=7 : hybrid 8.5e8 | 1.38e9   cooperative 7.8e8 | 1.2e9    thread 1.13e9 | 1.88e9 (body frame)
-    const int n = m->d.n;
-    //   iiwa14 n=7 : lane 1.34e9 | 2.62e9 (knot point per lane, table + tile in shared memory)
-    variant = n > 16 ? 4 : (n > 8 ? 3 : 5);
-  }
-  if (m->fast_ok && dense && variant == 5) {
-    // knot point per lane in every phase, per-body table + output tile in shared memory
-    const FastModel<T>& fm = pick_dfs<T>(m);
-    const int n = fm.n;
-    constexpr int GC = 4;
-    auto kern = fm.has_prismatic ? minv_lane_kernel<T, GC, true> : minv_lane_kernel<T, GC, false>;
-    int warps = 0, best = 0, ctas = 0;
-    size_t smem = 0;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-    for (int w = 1; w <= kLmMaxWarps; ++w) {
-      const size_t sz = lane_minv_smem_bytes<T, GC>(n, fm.n_slot_a, fm.n_slot_b, w);
-      if (sz > kMaxDynSmem) break;
-      int nb = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, sz) != cudaSuccess) { cudaGetLastError(); continue; }
-      if (nb * w >= best) { best = nb * w; warps = w; smem = sz; ctas = nb; }
-    }
-    int dev = 0, sms = 0;
-    if (warps > 0 && cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) {
-      const int64_t ntasks = (B + 31) / 32;
-      int64_t blocks = (ntasks + warps - 1) / warps;
-      if (blocks > (int64_t)sms * ctas) blocks = (int64_t)sms * ctas;
-      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop_minv, B, q, Minv);
-      return cuda_status("rbd_minv(lane)");
-    }
-  }
-  if (m->fast_ok && dense && variant == 4) {
-    // hybrid kernel: knot point per lane for the articulated inertias, column per lane for the
-    // rows of Minv, per-body table handed over through an L2-resident scratch buffer
-    const FastModel<T>& fm = pick_dfs<T>(m);
-    const int n = fm.n;
-    const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
-    auto kern = fm.has_prismatic
-                    ? (G == 8 ? minv_hybrid_kernel<T, 8, true> : (G == 16 ? minv_hybrid_kernel<T, 16, true> : minv_hybrid_kernel<T, 32, true>))
-                    : (G == 8 ? minv_hybrid_kernel<T, 8, false> : (G == 16 ? minv_hybrid_kernel<T, 16, false> : minv_hybrid_kernel<T, 32, false>));
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-    int warps = 0, best = 0, ctas = 0;
-    size_t smem = 0;
-    for (int w = 4; w <= kCmMaxWarps; ++w) {
-      const size_t sz = hybrid_minv_smem_bytes<T>(n, G, m->coop.maxdepth, fm.n_slot_a, fm.n_slot_b, w);
-      if (sz > kMaxDynSmem) break;
-      int nb = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, sz) != cudaSuccess) { cudaGetLastError(); continue; }
-      if (nb * w > best) { best = nb * w; warps = w; smem = sz; ctas = nb; }
-    }
-    int dev = 0, sms = 0;
-    if (warps > 0 && cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) {
-      const int64_t ntasks = (B + 31) / 32;
-      int64_t blocks = (ntasks + warps - 1) / warps;
-      if (blocks > (int64_t)sms * ctas) blocks = (int64_t)sms * ctas;
-      T* scratch = nullptr;
-      const size_t scratch_bytes = (size_t)blocks * warps * 32 * n * kHyScrStride * sizeof(T);
-      cudaMemPool_t pool = scratch_pool(dev);
-      if (!pool) return fail(RBD_E_NO_DEVICE, "rbd_minv: cannot create the scratch memory pool");
-      e = cudaMallocFromPoolAsync((void**)&scratch, scratch_bytes, pool, (cudaStream_t)stream);
-      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop_minv, m->coop.maxdepth, B, q, Minv,
-                                                                         scratch);
-      const int rc = cuda_status("rbd_minv(hybrid)");
-      cudaFreeAsync(scratch, (cudaStream_t)stream);
-      return rc;
-    }
-  }
-  if (m->fast_ok && dense && variant == 3) {
-    // warp-cooperative kernel (local world-aligned frames: accurate in FP32 as well)
-    const FastModel<T>& fm = pick_dfs<T>(m);
-    const int n = fm.n;
-    const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
-    auto kern = fm.has_prismatic
-                    ? (G == 8 ? minv_coop_kernel<T, 8, true> : (G == 16 ? minv_coop_kernel<T, 16, true> : minv_coop_kernel<T, 32, true>))
-                    : (G == 8 ? minv_coop_kernel<T, 8, false> : (G == 16 ? minv_coop_kernel<T, 16, false> : minv_coop_kernel<T, 32, false>));
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-    // warps per CTA: the choice that keeps the most warps resident per SM (the model copy is
-    // shared by the CTA, the rest of the shared memory is per warp)
-    int warps = 0, best = 0;
-    size_t smem = 0;
-    for (int w = 4; w <= kCmMaxWarps; ++w) {
-      const size_t sz = coop_minv_smem_bytes<T>(n, G, m->coop.maxdepth, fm.n_slot_a, w);
-      if (sz > kMaxDynSmem) break;
-      int nb = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, sz) != cudaSuccess) { cudaGetLastError(); continue; }
-      if (nb * w > best) { best = nb * w; warps = w; smem = sz; }
-    }
-    if (warps > 0) {
-      const int ipw = 32 / G;
-      const int64_t ngroups = (B + ipw - 1) / ipw;
-      int64_t blocks = (ngroups + warps - 1) / warps;
-      const int64_t cap = 148 * 16;
-      if (blocks > cap) blocks = cap;
-      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, m->coop_minv, B, q, Minv);
-      return cuda_status("rbd_minv(coop)");
-    }
-  }
-  // thread-per-knot-point world-frame kernel.  FP32: coordinates about the world origin lose
-  // digits on light distal links far from the base (m |p|^2 cancellation, measured 1.2e-4 on
-  // Atlas), so in single precision this family is never selected.
-  if (m->fast_ok && dense && std::is_same<T, double>::value && variant == 2) {
-    const FastModel<T>& fm = pick_dfs<T>(m);
-    const int n = fm.n;
-    const size_t stash = (size_t)(fm.n_slot_a * kMinvSlotA + fm.n_slot_b * kMinvSlotB) * 32 * sizeof(T);
-    size_t smem = (size_t)(n * (kMinvPerBody + 6) + n * (n + 1) / 2) * 32 * sizeof(T) + stash;
-    // measured on B200 (iiwa14, 1M points): shared-memory variant 8.8e8 evals/s (4 warps/SM),
-    // local-memory variant 1.12e9 evals/s (12 warps/SM) -> local memory is the default here
-    auto kern = minv_world_kernel<T, 1, 12>;
-    static const bool force_smem = std::getenv("RBD_MINV_SMEM") != nullptr;
-    if (force_smem && smem <= kMaxDynSmem) kern = minv_world_kernel<T, 0, 1>;
-    else smem = stash;
-    if (smem <= kMaxDynSmem) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-      kern<<<blocks_for(B, 32), 32, smem, (cudaStream_t)stream>>>(fm, m->plan, B, q, Minv);
-      return cuda_status("rbd_minv(world)");
-    }
-  }
-  minv_fused_kernel<T><<<blocks_for(B, kFusedThreads), kFusedThreads, 0, (cudaStream_t)stream>>>(
-      pick<T>(m), B, q, dense, Minv);
-  return cuda_status("rbd_minv");
-}
+namespace {
 
 template <typename T>
 int launch_rnea_fpass(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, T* v, T* a,

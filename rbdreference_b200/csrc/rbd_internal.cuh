@@ -1,0 +1,73 @@
+// rbd_internal.cuh - host-side declarations shared by the translation units of librbd_b200.so.
+// The library is built from several .cu files compiled in parallel (rbdreference_b200/build.py):
+//   rbd_capi.cu         C ABI, model compilation, per-pass and forward-dynamics launchers
+//   rbd_launch_rnea.cu  launch_rnea<T>       (rnea kernels)
+//   rbd_launch_grad.cu  launch_rnea_grad<T>  (rnea_grad kernels)
+//   rbd_launch_minv.cu  launch_minv<T>       (minv kernels)
+// The three launcher files are compiled once per precision (-DRBD_LAUNCH_T=double / float).
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <type_traits>
+#include <atomic>
+#include <mutex>
+#include <new>
+
+#include "../../include/rbd_b200.h"
+#include "rbd_common.cuh"
+#include "rbd_grad_kernels.cuh"
+#include "rbd_minv_kernels.cuh"
+#include "rbd_coop_kernels.cuh"
+#include "rbd_coop_minv_kernels.cuh"
+
+struct rbd_model {
+  rbd::DevModel<double> d;
+  rbd::DevModel<float> f;
+  rbd::FastModel<double> fd;     // world-frame kernels (rigid-body inertias only)
+  rbd::FastModel<float> ff;
+  bool fast_ok;                  // FastModel valid (rigid inertias, 1-DoF revolute/prismatic joints)
+  rbd::FastModel<double> fd_dfs; // the same robot renumbered in depth-first preorder
+  rbd::FastModel<float> ff_dfs;
+  rbd::DfsPlan plan;
+  rbd::CoopPlan coop;
+  rbd::CoopMinvPlan coop_minv;
+};
+
+namespace rbd_host {
+
+constexpr size_t kMaxDynSmem = 227 * 1024;
+extern std::atomic<int> g_variant;      // 0 auto, 1 force the generic body-frame kernels, 2.. see rbd_b200.h
+size_t smem_limit();                    // shared-memory budget per warp of the world-frame grad kernel
+cudaMemPool_t scratch_pool(int dev);    // private stream-ordered pool for scratch buffers
+int fail(int code, const char* msg);    // records the message for rbd_last_error_string()
+int cuda_status(const char* what);      // cudaGetLastError -> status code; counts the launch
+
+template <typename T> inline const rbd::DevModel<T>& pick(const rbd_model* m);
+template <> inline const rbd::DevModel<double>& pick<double>(const rbd_model* m) { return m->d; }
+template <> inline const rbd::DevModel<float>& pick<float>(const rbd_model* m) { return m->f; }
+template <typename T> inline const rbd::FastModel<T>& pick_dfs(const rbd_model* m);
+template <> inline const rbd::FastModel<double>& pick_dfs<double>(const rbd_model* m) { return m->fd_dfs; }
+template <> inline const rbd::FastModel<float>& pick_dfs<float>(const rbd_model* m) { return m->ff_dfs; }
+template <typename T> inline const rbd::FastModel<T>& pick_fast(const rbd_model* m);
+template <> inline const rbd::FastModel<double>& pick_fast<double>(const rbd_model* m) { return m->fd; }
+template <> inline const rbd::FastModel<float>& pick_fast<float>(const rbd_model* m) { return m->ff; }
+
+inline unsigned blocks_for(int64_t B, int threads) { return (unsigned)((B + threads - 1) / threads); }
+
+#define RBD_CHECK_ARGS(cond, msg) \
+  do { if (!(cond)) return fail(RBD_E_INVALID_ARGUMENT, msg); } while (0)
+#define kGradSmemLimit smem_limit()
+
+// fused drivers (defined in rbd_launch_*.cu, explicitly instantiated for double and float)
+template <typename T>
+int launch_rnea(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, T* c, T* v, T* a,
+                T* f, void* stream);
+template <typename T>
+int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, int damp,
+                     T* dc_du, T* c_out, void* stream);
+template <typename T>
+int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream);
+
+}  // namespace rbd_host

@@ -1,0 +1,61 @@
+// rbd_launch_rnea.cu - part of librbd_b200.so (see rbd_internal.cuh); compiled with -DRBD_LAUNCH_T=double|float.
+#include "rbd_internal.cuh"
+#include "rbd_fused_kernels.cuh"
+#include "rbd_lane_rnea_kernels.cuh"
+
+#ifndef RBD_LAUNCH_T
+#error "compile with -DRBD_LAUNCH_T=double or -DRBD_LAUNCH_T=float"
+#endif
+
+using namespace rbd;
+
+namespace rbd_host {
+
+template <typename T>
+int launch_rnea(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, T* c, T* v, T* a,
+                T* f, void* stream) {
+  RBD_CHECK_ARGS(m && q && qd && c && B >= 0, "rbd_rnea: null model/q/qd/c or negative B");
+  if (B == 0) return 0;
+  const int variant = g_variant.load(std::memory_order_relaxed);
+  if (m->fast_ok && variant != 1) {
+    // knot point per lane, depth-first chains in registers, coalesced staging (rbd_lane_rnea_kernels.cuh)
+    const FastModel<T>& fm = pick_dfs<T>(m);
+    const int n = fm.n;
+    const bool vaf = v || a || f;
+    const bool localf = !vaf && (size_t)lane_rnea_warp_vals(n, fm.n_slot_a, false, false) * sizeof(T) > 32 * 1024;
+    const size_t per_warp = (size_t)lane_rnea_warp_vals(n, fm.n_slot_a, localf, vaf) * sizeof(T);
+    if (per_warp <= 72 * 1024) {
+      void (*kern)(const FastModel<T>, const DfsPlan, int64_t, const T*, const T*, const T*, T, T*, T*, T*, T*);
+      if (vaf)
+        kern = n <= 8 ? rnea_lane_kernel<T, false, true, 8> : (n <= 16 ? rnea_lane_kernel<T, false, true, 16> : rnea_lane_kernel<T, false, true, 0>);
+      else if (localf)
+        kern = rnea_lane_kernel<T, true, false, 0>;
+      else
+        kern = n <= 8 ? rnea_lane_kernel<T, false, false, 8> : (n <= 16 ? rnea_lane_kernel<T, false, false, 16> : rnea_lane_kernel<T, false, false, 0>);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+      int warps = 0, best = 0;
+      for (int w = 1; w <= 4; ++w) {
+        const size_t sz = per_warp * w;
+        if (sz > kMaxDynSmem) break;
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, sz) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (nb * w >= best) { best = nb * w; warps = w; }
+      }
+      if (warps > 0) {
+        const int64_t ntasks = (B + 31) / 32;
+        kern<<<(unsigned)((ntasks + warps - 1) / warps), warps * 32, per_warp * warps, (cudaStream_t)stream>>>(
+            fm, m->plan, B, q, qd, qdd, g, c, v, a, f);
+        return cuda_status("rbd_rnea(lane)");
+      }
+    }
+  }
+  rnea_fused_kernel<T><<<blocks_for(B, kFusedThreads), kFusedThreads, 0, (cudaStream_t)stream>>>(
+      pick<T>(m), B, q, qd, qdd, g, c, v, a, f);
+  return cuda_status("rbd_rnea");
+}
+
+template int launch_rnea<RBD_LAUNCH_T>(const rbd_model*, int64_t, const RBD_LAUNCH_T*, const RBD_LAUNCH_T*, const RBD_LAUNCH_T*,
+                                       RBD_LAUNCH_T, RBD_LAUNCH_T*, RBD_LAUNCH_T*, RBD_LAUNCH_T*, RBD_LAUNCH_T*, void*);
+
+}  // namespace rbd_host

@@ -226,6 +226,32 @@ def test_batched_cuda_tensors_vs_oracle(name, B):
 
 
 @requires_cuda
+@pytest.mark.parametrize("name,B", [("iiwa14", 1000), ("hyq", 777), ("atlas", 333), ("tree13", 257), ("tree9", 65)])
+def test_rnea_kernel_paths_vs_oracle(name, B):
+    """rnea: lane kernel (shared-memory / local-memory f rows, c only / all outputs, FP64 / FP32)
+    and the generic body-frame kernel (variant 1) against the oracle."""
+    from rbdreference_b200 import RBDReference
+    rb = make_robot(name)
+    bo = BatchOracle(rb)
+    q, qd, qdd = random_states(rb.get_num_vel(), B, seed=7 + B)
+    rc, rv, ra, rf = bo.rnea(q, qd, qdd)
+    rc0 = bo.rnea(q, qd)[0]
+    for variant in (0, 1):
+        RBDReference.set_kernel_variant(variant)
+        try:
+            for dtype, tol in ((torch.float64, TOL_F64), (torch.float32, TOL_F32)):
+                eng = _engine(rb, dtype)
+                tq, tqd, tqdd = _t(q, dtype), _t(qd, dtype), _t(qdd, dtype)
+                assert rel_err(eng.rnea(tq, tqd, tqdd, outputs="c").cpu().numpy(), rc) < tol
+                assert rel_err(eng.rnea(tq, tqd, outputs="c").cpu().numpy(), rc0) < tol
+                c, v, a, f = eng.rnea(tq, tqd, tqdd)
+                for got, ref in ((c, rc), (v, rv), (a, ra), (f, rf)):
+                    assert rel_err(got.cpu().numpy(), ref) < tol
+        finally:
+            RBDReference.set_kernel_variant(0)
+
+
+@requires_cuda
 @pytest.mark.parametrize("B", [1, 2, 31, 32, 33, 127, 129, 1000])
 def test_ragged_batch_sizes(B):
     rb = make_robot("hyq")
