@@ -41,7 +41,11 @@ __host__ __device__ inline size_t lane_minv_smem_bytes(int n, int nslot_a, int n
   return (size_t)warps * lane_minv_warp_vals<GC>(n, nslot_a, nslot_b) * sizeof(T);
 }
 
-template <typename T, int GC, bool PRISM>
+// NMAX >= n > 0: the stage-1 loops over bodies are fully unrolled (guarded by the runtime n), so
+// model constants become immediates; NMAX = 0: rolled loops.  NMAX2: the same for the stage-2 loops
+// over column groups and bodies (measured on B200, iiwa14: unrolling stage 2 as well overflows the
+// instruction cache - 1.18e9 instead of 1.34e9 evals/s FP64).
+template <typename T, int GC, bool PRISM, int NMAX, int NMAX2>
 __global__ void __launch_bounds__(kLmMaxWarps * 32)
 minv_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__ DfsPlan plan,
                  const __grid_constant__ CoopMinvPlan mp, int64_t B, const T* __restrict__ q, T* __restrict__ Minv) {
@@ -98,8 +102,9 @@ minv_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
     {
       T E[9];
       // ---- rotations, root -> leaf
-#pragma unroll 1
-      for (int i = 0; i < n; ++i) {
+#pragma unroll(NMAX > 0 ? NMAX : 1)
+      for (int i = 0; i < (NMAX > 0 ? NMAX : n); ++i) {
+        if (NMAX > 0 && i >= n) break;
         T f1, f2;
         {
           const T qi = ffq[(i * 2) * 32 + lane];
@@ -145,9 +150,10 @@ minv_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
         for (int k = 0; k < 22; ++k) LSTA(s, k) = T(0);
       // IA = [[A, Bm], [Bm^T, C]] : A sym (0..5), Bm 3x3 row-major (6..14), C sym (15..20)
       T IA[21];
-#pragma unroll 1
-      for (int i = n - 1; i >= 0; --i) {
-        const bool chained = (i != n - 1) && (m.parent[i + 1] == i);
+#pragma unroll(NMAX > 0 ? NMAX : 1)
+      for (int i = (NMAX > 0 ? NMAX : n) - 1; i >= 0; --i) {
+        if (NMAX > 0 && i >= n) continue;
+        const bool chained = (i != n - 1) && (m.parent[i + 1 < RBD_MAX_DOF ? i + 1 : i] == i);
         if (!chained && i != n - 1) {
           const int s = m.slot_b[i];
 #pragma unroll
@@ -283,8 +289,9 @@ minv_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
     __syncwarp();
     // ================================================================ stage 2 (the tile aliases f1 f2)
     for (int k = 0; k < nn; ++k) mytile[k] = T(0);        // entries between root components stay zero
-#pragma unroll 1
-    for (int j0 = 0; j0 < n; j0 += GC) {
+#pragma unroll(NMAX2 > 0 ? (NMAX2 + GC - 1) / GC : 1)
+    for (int j0 = 0; j0 < (NMAX2 > 0 ? NMAX2 : n); j0 += GC) {
+      if (NMAX2 > 0 && j0 >= n) break;
       const int jtop = (j0 + GC < n ? j0 + GC : n) - 1;   // last column of the group
       int oj[GC];
 #pragma unroll
@@ -295,8 +302,9 @@ minv_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
       for (int c = 0; c < GC; ++c)
 #pragma unroll
         for (int k = 0; k < 6; ++k) V[c][k] = T(0);
-#pragma unroll 1
-      for (int a = jtop; a >= 0; --a) {
+#pragma unroll(NMAX2 > 0 ? NMAX2 : 1)
+      for (int a = (NMAX2 > 0 ? (j0 + GC < NMAX2 ? j0 + GC : NMAX2) - 1 : jtop); a >= 0; --a) {
+        if (NMAX2 > 0 && a > jtop) continue;
         const int send = plan.sub_end[a];
         if (send <= j0) continue;                         // no column of the group below body a
         T w[3], U[6], r[3];
@@ -337,8 +345,9 @@ minv_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
       }
       // ---------------------------------------------------------------- phase C: root -> leaf
       const int cr0 = mp.comp_root[j0];                   // first body any column of the group couples with
-#pragma unroll 1
-      for (int a = cr0; a <= jtop; ++a) {
+#pragma unroll(NMAX2 > 0 ? NMAX2 : 1)
+      for (int a = (NMAX2 > 0 ? 0 : cr0); a <= (NMAX2 > 0 ? (j0 + GC < NMAX2 ? j0 + GC : NMAX2) - 1 : jtop); ++a) {
+        if (NMAX2 > 0 && (a < cr0 || a > jtop)) continue;
         const int cend = plan.comp_end[a];
         if (cend <= j0) continue;                         // a's root component ends before the group
         const int send = plan.sub_end[a];

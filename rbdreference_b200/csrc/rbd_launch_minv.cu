@@ -30,7 +30,8 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
     const FastModel<T>& fm = pick_dfs<T>(m);
     const int n = fm.n;
     constexpr int GC = 4;
-    auto kern = fm.has_prismatic ? minv_lane_kernel<T, GC, true> : minv_lane_kernel<T, GC, false>;
+    auto kern = n <= 8 ? (fm.has_prismatic ? minv_lane_kernel<T, GC, true, 8, 0> : minv_lane_kernel<T, GC, false, 8, 0>)
+                       : (fm.has_prismatic ? minv_lane_kernel<T, GC, true, 0, 0> : minv_lane_kernel<T, GC, false, 0, 0>);
     int warps = 0, best = 0, ctas = 0;
     size_t smem = 0;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
