@@ -60,6 +60,8 @@ def _cpu_worker_run(args):
             acc += float(impl.rnea_grad(q[k], qd[k], qdd[k])[0, 0])
         elif op == "minv":
             acc += float(impl.minv(q[k])[0, 0])
+        elif op == "crba":
+            acc += float(impl.crba(q[k])[0, 0])
         else:
             acc += float(impl.rnea(q[k], qd[k], qdd[k])[0][0])
     return acc
@@ -94,7 +96,7 @@ class CpuReference:
 def per_eval_cpu_seconds(robot_name, op):
     """Rough single-core cost used only to size the bounded sample."""
     base = {"iiwa14": 6e-3, "hyq": 9e-3, "atlas": 65e-3}.get(robot_name, 20e-3)
-    return base * {"rnea_grad": 1.0, "minv": 0.15, "rnea": 0.09}[op]
+    return base * {"rnea_grad": 1.0, "minv": 0.15, "rnea": 0.09, "crba": 0.1}[op]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -190,7 +192,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--robot", default="iiwa14")
-    ap.add_argument("--op", default="rnea_grad", choices=["rnea_grad", "minv", "rnea"])
+    ap.add_argument("--op", default="rnea_grad", choices=["rnea_grad", "minv", "rnea", "crba"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="knot points per GPU")
     ap.add_argument("--variant", type=int, default=0, help="kernel family: 0 auto, 1 generic, 2 world/thread, 3 cooperative, 4 hybrid minv, 5 lane minv")
@@ -284,6 +286,9 @@ def run_ours(args):
     elif args.op == "minv":
         out = torch.empty(B, n, n, dtype=tdtype, device=dev)
         step = lambda: eng.minv(q, out=out)
+    elif args.op == "crba":
+        out = torch.empty(B, n, n, dtype=tdtype, device=dev)
+        step = lambda: eng.crba(q, out=out)
     else:
         out = None
         step = lambda: eng.rnea(q, qd, qdd, outputs="c")
@@ -387,7 +392,7 @@ def measure_e2e(args, eng, torch, dist, dev, rank, world, n, B, tdtype, itemsize
     hq, hqd, hqdd = (torch.from_numpy(x.astype(np_dtype)).pin_memory() for x in synth_host(n, B, 0xE2E + rank))
     if args.op == "rnea_grad":
         out_tail = (n, 2 * n)
-    elif args.op == "minv":
+    elif args.op in ("minv", "crba"):
         out_tail = (n, n)
     else:
         out_tail = (n,)
@@ -407,13 +412,15 @@ def measure_e2e(args, eng, torch, dist, dev, rank, world, n, B, tdtype, itemsize
             k = ci % nbuf
             with torch.cuda.stream(streams[k]):
                 dq[k][:m].copy_(hq[lo:hi], non_blocking=True)
-                if args.op != "minv":
+                if args.op not in ("minv", "crba"):
                     dqd[k][:m].copy_(hqd[lo:hi], non_blocking=True)
                     dqdd[k][:m].copy_(hqdd[lo:hi], non_blocking=True)
                 if args.op == "rnea_grad":
                     eng.rnea_grad(dq[k][:m], dqd[k][:m], dqdd[k][:m], out=dout[k][:m])
                 elif args.op == "minv":
                     eng.minv(dq[k][:m], out=dout[k][:m])
+                elif args.op == "crba":
+                    eng.crba(dq[k][:m], out=dout[k][:m])
                 else:
                     dout[k][:m].copy_(eng.rnea(dq[k][:m], dqd[k][:m], dqdd[k][:m], outputs="c"))
                 hout[lo:hi].copy_(dout[k][:m], non_blocking=True)
@@ -433,7 +440,7 @@ def measure_e2e(args, eng, torch, dist, dev, rank, world, n, B, tdtype, itemsize
     t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    n_in = 1 if args.op == "minv" else 3
+    n_in = 1 if args.op in ("minv", "crba") else 3
     h2d = n_in * n * itemsize * B
     d2h = int(np.prod(out_tail)) * itemsize * B
     return {"value": world * B * steps / float(t.item()), "unit": "evals/s", "h2d_bytes_per_step": int(h2d),

@@ -153,6 +153,12 @@ int rbd_forward_dynamics_grad_f64(const rbd_model_t* m, int64_t B, const double*
 int rbd_forward_dynamics_grad_f32(const rbd_model_t* m, int64_t B, const float* q, const float* qd, const float* u,
                                   float* qdd_dq, float* qdd_dqd, float* qdd_out, void* stream);
 
+/* ---- joint-space inertia matrix ---------------------------------------- */
+/* crba, fixed-base branch (RBDReference.py:1026-1124, the `else` at :1090): H (B, n, n), symmetric,
+ * H[i,j] = 0 for bodies on different branches.  One launch. */
+int rbd_crba_f64(const rbd_model_t* m, int64_t B, const double* q, double* H, void* stream);
+int rbd_crba_f32(const rbd_model_t* m, int64_t B, const float* q, float* H, void* stream);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
 /* Runs a dependent-chain FMA micro-benchmark on `stream`'s device and returns the achieved
  * FLOP/s (2 per FMA) in *flops_per_s; is_f64 selects DFMA or FFMA.  Used only to put a measured

@@ -191,7 +191,57 @@ __device__ __forceinline__ void minv_column_phases(int n, int maxdepth, int maxc
   }
 }
 
+// Composite-rigid-body algorithm (RBDReference.py:1090-1124, fixed-base branch) on the same
+// table: with the rank-one downdate of phase A switched off, IA is the composite inertia IC, the
+// table row of body i holds U_i = IC_i S_i and D_i = S_i.U_i = H[i,i] (in the invD slot), and lane
+// (g, i) carries fh = U_i up its root path (:1113-1122): H[i,a] = H[a,i] = S_a . fh for every
+// ancestor a, fh re-expressed about each parent's origin on the way.
 template <typename T, int G, bool PRISM>
+__device__ __forceinline__ void crba_column_phase(int n, int maxdepth, bool valid, int i, int gbase, int lane, int oi,
+                                                  const int4* imdl, const T* tab, T* tile, T* __restrict__ dst, int nknots) {
+  constexpr int IPW = 32 / G;
+  typedef typename Vec2<T>::type V2;
+  const int nn = n * n;
+  const int g = lane / G;
+  T* mytile = tile + g * nn;
+  const int tile_vals = IPW * nn;
+  for (int k = lane; k < tile_vals; k += 32) tile[k] = T(0);   // unrelated pairs of bodies (:1106)
+  __syncwarp();
+  if (valid) {
+    TabEntry<T> e;
+    tab_load(tab + (gbase + i) * kCmTabStride, e);
+    T F[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) F[k] = e.U[k];
+    mytile[oi * n + oi] = e.invD;                                               // H[i,i] (:1111)
+    int a = i;
+    for (int t = 0; t < maxdepth; ++t) {
+      const int par = imdl[a].x;
+      if (par < 0) break;
+      cross3_add(e.r, F + 3, F);                                               // X^T fh (:1117): about the parent's origin
+      a = par;
+      tab_load(tab + (gbase + a) * kCmTabStride, e);
+      const int4 ia = imdl[a];
+      const bool pris = PRISM && ((ia.w >> 24) != 0);
+      const T h = pris ? dot3s(e.w, F + 3) : dot3s(e.w, F);                    // :1121
+      mytile[oi * n + ia.z] = h;
+      mytile[ia.z * n + oi] = h;                                               // :1122
+    }
+  }
+  __syncwarp();
+  {
+    const int count = nknots * nn;
+    if ((tile_vals & 1) == 0 && count == tile_vals && (reinterpret_cast<uintptr_t>(dst) & (sizeof(V2) - 1)) == 0) {
+      for (int k = lane; k < (tile_vals >> 1); k += 32) __stcs(reinterpret_cast<V2*>(dst) + k, reinterpret_cast<const V2*>(tile)[k]);
+    } else {
+      for (int k = lane; k < count; k += 32) __stcs(dst + k, tile[k]);
+    }
+  }
+}
+
+// CRBA = false: minv (Minv out).  CRBA = true: the joint-space inertia matrix H (same launch
+// geometry and shared-memory layout; phases B and C are replaced by crba_column_phase).
+template <typename T, int G, bool PRISM, bool CRBA = false>
 __global__ void __launch_bounds__(kCmMaxWarps * 32)
 minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__ DfsPlan plan,
                  const __grid_constant__ CoopPlan cp, const __grid_constant__ CoopMinvPlan mp, int64_t B,
@@ -355,7 +405,7 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
           V2* dst = reinterpret_cast<V2*>(mytab);
           V2 t;
           t.x = w[0]; t.y = w[1]; dst[0] = t;
-          t.x = w[2]; t.y = invD; dst[1] = t;
+          t.x = w[2]; t.y = CRBA ? D : invD; dst[1] = t;
           t.x = U[0]; t.y = U[1]; dst[2] = t;
           t.x = U[2]; t.y = U[3]; dst[3] = t;
           t.x = U[4]; t.y = U[5]; dst[4] = t;
@@ -364,6 +414,7 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
         }
         if (par >= 0) {
           // IA -= U U^T / D                                                   (:728-731)
+          if (!CRBA) {
           T Us[6];
 #pragma unroll
           for (int k = 0; k < 6; ++k) Us[k] = U[k] * invD;
@@ -375,7 +426,8 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
             for (int cc = 0; cc < 3; ++cc) IA[6 + 3 * rr + cc] -= U[rr] * Us[3 + cc];
           IA[15] -= U[3] * Us[3]; IA[16] -= U[3] * Us[4]; IA[17] -= U[3] * Us[5];
           IA[18] -= U[4] * Us[4]; IA[19] -= U[4] * Us[5]; IA[20] -= U[5] * Us[5];
-          // translate to the parent's origin (:732-733 with X = [[1,0],[-r x,1]]):
+          }
+          // translate to the parent's origin (:732-733 / :1100-1103 with X = [[1,0],[-r x,1]]):
           //   Bm' = Bm + R C,  A' = A + R W^T + W R^T,  W = Bm + R C / 2,  R = r x
           const T Cm[9] = {IA[15], IA[16], IA[17], IA[16], IA[18], IA[19], IA[17], IA[19], IA[20]};
           T RC[9], W[9];
@@ -409,8 +461,12 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
       __syncwarp();
     }
 
-    minv_column_phases<T, G, PRISM>(n, maxdepth, mp.maxcomp, m.n_slot_a, valid, i, gbase, lane, oi, comp_root, imdl, tab, mbw, big,
-                             Minv + grp * IPW * (int64_t)nn, (int)((B - grp * IPW) < IPW ? (B - grp * IPW) : IPW));
+    if (CRBA)
+      crba_column_phase<T, G, PRISM>(n, maxdepth, valid, i, gbase, lane, oi, imdl, tab, big + 6 * m.n_slot_a * 32,
+                                     Minv + grp * IPW * (int64_t)nn, (int)((B - grp * IPW) < IPW ? (B - grp * IPW) : IPW));
+    else
+      minv_column_phases<T, G, PRISM>(n, maxdepth, mp.maxcomp, m.n_slot_a, valid, i, gbase, lane, oi, comp_root, imdl, tab, mbw, big,
+                                      Minv + grp * IPW * (int64_t)nn, (int)((B - grp * IPW) < IPW ? (B - grp * IPW) : IPW));
     __syncwarp();
   }
 }

@@ -459,6 +459,82 @@ minv_fused_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __r
 }
 
 // =============================================================================================
+// crba, fixed-base branch (RBDReference.py:1090-1124), generic inertias: composite inertias as
+// dense 6x6 in per-thread local memory, IC_p += X^T IC_i X leaf -> root (:1096-1103), then
+// fh = IC_i S_i carried up the root path, H[i,j] = H[j,i] = S_j . fh (:1108-1122).
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kFusedThreads)
+crba_fused_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __restrict__ q, T* __restrict__ H) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int n = m.n;
+  const T* qb = q + b * n;
+  T IC[RBD_MAX_DOF][36], lb[RBD_MAX_DOF][2];
+  for (int i = 0; i < n; ++i) {
+#pragma unroll
+    for (int k = 0; k < 36; ++k) IC[i][k] = m.I[i][k];
+    joint_basis(m, i, qb[i], lb[i][0], lb[i][1]);
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    const int p = m.parent[i];
+    if (p < 0) continue;
+    T X[18];
+    build_X(m, i, lb[i][0], lb[i][1], X);
+    // column k of IC_i X, then X^T of it, accumulated into column k of IC_p
+    for (int k = 0; k < 6; ++k) {
+      T xk[6], col[6], t[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) xk[r] = T(0);
+      // column k of X = [[E,0],[L,E]]
+      if (k < 3) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { xk[r] = X[3 * r + k]; xk[3 + r] = X[9 + 3 * r + k]; }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) xk[3 + r] = X[3 * r + (k - 3)];
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        T acc = T(0);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc = fma_t(IC[i][6 * r + c], xk[c], acc);
+        col[r] = acc;
+      }
+      XT_apply(X, col, t);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) IC[p][6 * r + k] += t[r];
+    }
+  }
+  T* Hb = H + b * (int64_t)n * n;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) Hb[i * n + j] = T(0);
+  for (int i = 0; i < n; ++i) {
+    T fh[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      T acc = T(0);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc = fma_t(IC[i][6 * r + c], m.S[i][c], acc);
+      fh[r] = acc;
+    }
+    Hb[i * n + i] = dot6(m.S[i], fh);
+    int j = i;
+    while (m.parent[j] >= 0) {
+      T X[18], t[6];
+      build_X(m, j, lb[j][0], lb[j][1], X);
+      XT_apply(X, fh, t);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) fh[r] = t[r];
+      j = m.parent[j];
+      const T h = dot6(m.S[j], fh);
+      Hb[i * n + j] = h;
+      Hb[j * n + i] = h;
+    }
+  }
+}
+
+// =============================================================================================
 // FMA peak micro-benchmark: 8 independent dependent-chains per thread.
 // =============================================================================================
 template <typename T>

@@ -69,5 +69,7 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
                      T* dc_du, T* c_out, void* stream);
 template <typename T>
 int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream);
+template <typename T>
+int launch_crba(const rbd_model* m, int64_t B, const T* q, T* H, void* stream);
 
 }  // namespace rbd_host

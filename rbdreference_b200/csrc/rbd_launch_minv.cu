@@ -149,6 +149,46 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
   return cuda_status("rbd_minv");
 }
 
+// crba (RBDReference.py:1026-1124, fixed base): warp-cooperative kernel (the minv kernel with the
+// articulated downdate switched off) for rigid-body inertias, generic dense kernel otherwise.
+template <typename T>
+int launch_crba(const rbd_model* m, int64_t B, const T* q, T* H, void* stream) {
+  RBD_CHECK_ARGS(m && q && H && B >= 0, "rbd_crba: null model/q/H or negative B");
+  if (B == 0) return 0;
+  const int variant = g_variant.load(std::memory_order_relaxed);
+  if (m->fast_ok && variant != 1) {
+    const FastModel<T>& fm = pick_dfs<T>(m);
+    const int n = fm.n;
+    const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+    auto kern = fm.has_prismatic
+                    ? (G == 8 ? minv_coop_kernel<T, 8, true, true> : (G == 16 ? minv_coop_kernel<T, 16, true, true> : minv_coop_kernel<T, 32, true, true>))
+                    : (G == 8 ? minv_coop_kernel<T, 8, false, true> : (G == 16 ? minv_coop_kernel<T, 16, false, true> : minv_coop_kernel<T, 32, false, true>));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    int warps = 0, best = 0;
+    size_t smem = 0;
+    for (int w = 4; w <= kCmMaxWarps; ++w) {
+      const size_t sz = coop_minv_smem_bytes<T>(n, G, m->coop.maxdepth, fm.n_slot_a, w);
+      if (sz > kMaxDynSmem) break;
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, sz) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (nb * w > best) { best = nb * w; warps = w; smem = sz; }
+    }
+    if (warps > 0) {
+      const int ipw = 32 / G;
+      const int64_t ngroups = (B + ipw - 1) / ipw;
+      int64_t blocks = (ngroups + warps - 1) / warps;
+      const int64_t cap = 148 * 16;
+      if (blocks > cap) blocks = cap;
+      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, m->coop_minv, B, q, H);
+      return cuda_status("rbd_crba(coop)");
+    }
+  }
+  crba_fused_kernel<T><<<blocks_for(B, kFusedThreads), kFusedThreads, 0, (cudaStream_t)stream>>>(pick<T>(m), B, q, H);
+  return cuda_status("rbd_crba");
+}
+
+template int launch_crba<RBD_LAUNCH_T>(const rbd_model*, int64_t, const RBD_LAUNCH_T*, RBD_LAUNCH_T*, void*);
 template int launch_minv<RBD_LAUNCH_T>(const rbd_model*, int64_t, const RBD_LAUNCH_T*, int, RBD_LAUNCH_T*, void*);
 
 }  // namespace rbd_host

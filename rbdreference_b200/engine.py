@@ -315,6 +315,15 @@ class RBDReference:
         self._call("forward_dynamics_grad", ctx, dq, dqd, du, o1, o2, None)
         return ctx.ret(o1), ctx.ret(o2)
 
+    def crba(self, q, out=None):
+        """RBDReference.py:1026-1124 (fixed-base branch) -> joint-space inertia matrix H (n, n)."""
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq = ctx.dev(q, (n,), "q")
+        H = out if (out is not None and ctx.kind == "torch" and ctx.batched) else ctx.empty(n, n)
+        self._call("crba", ctx, dq, H)
+        return ctx.ret(H)
+
     # ------------------------------------------------------------------------------------
     def uses_world_kernels(self) -> bool:
         """True if the fused drivers run the world-frame kernels for this robot."""

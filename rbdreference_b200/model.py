@@ -65,6 +65,10 @@ class RobotModel:
             return int(rnea + 2 * np.sum(132 * P + 212 * A + 4) + 2 * 72 * np.sum(Bi[nr]) + 72 * np.sum(nr))
         if op == "minv":
             return int(np.sum(55 + 2 * ST) + np.sum(906 + 84 * ST[nr]) + np.sum(66 + 81 * C[nr]))
+        if op == "crba":
+            # X build 54 per body; X^T IC X + add = 2 * 396 + 36 per non-root body (:1100-1103);
+            # IC S and S.fh = 66 + 11 per body, X^T fh and S.fh = 66 + 11 per (body, ancestor) pair (:1108-1122)
+            return int(54 * n + 828 * np.sum(nr) + np.sum(77 + 77 * P))
         raise KeyError(op)
 
     def io_bytes(self, op: str, itemsize: int = 8, full_rnea: bool = False) -> int:
@@ -74,7 +78,7 @@ class RobotModel:
             return (3 * n + n + (18 * n if full_rnea else 0)) * itemsize
         if op == "rnea_grad":
             return (3 * n + 2 * n * n) * itemsize
-        if op == "minv":
+        if op in ("minv", "crba"):
             return (n + n * n) * itemsize
         raise KeyError(op)
 

@@ -252,6 +252,36 @@ def test_rnea_kernel_paths_vs_oracle(name, B):
 
 
 @requires_cuda
+def test_crba_vs_reference_golden_and_oracle(golden):
+    """crba (RBDReference.py:1090-1124): goldens from the live reference, batched oracle, both kernel
+    families, both precisions, and H @ Minv = I."""
+    from rbdreference_b200 import RBDReference
+    name, rb, g = golden
+    bo = BatchOracle(rb)
+    n = rb.get_num_vel()
+    B = 301
+    q, _, _ = random_states(n, B, seed=11)
+    Href = bo.crba(q)
+    for variant in (0, 1):
+        RBDReference.set_kernel_variant(variant)
+        try:
+            eng = _engine(rb)
+            assert rel_err(eng.crba(g["q"]), g["H"]) < TOL_F64
+            H1 = eng.crba(g["q"][0])
+            assert H1.shape == (n, n) and rel_err(H1, g["H"][0]) < TOL_F64
+            H = eng.crba(_t(q))
+            assert H.shape == (B, n, n) and rel_err(H.cpu().numpy(), Href) < TOL_F64
+            assert torch.equal(H, H.transpose(1, 2))
+            e32 = _engine(rb, torch.float32)
+            assert rel_err(e32.crba(_t(q, torch.float32)).cpu().numpy(), Href) < TOL_F32
+            if variant == 0:
+                eye = torch.bmm(H, eng.minv(_t(q)))
+                assert float((eye - torch.eye(n, dtype=torch.float64, device="cuda")).abs().max()) < 1e-8
+        finally:
+            RBDReference.set_kernel_variant(0)
+
+
+@requires_cuda
 @pytest.mark.parametrize("B", [1, 2, 31, 32, 33, 127, 129, 1000])
 def test_ragged_batch_sizes(B):
     rb = make_robot("hyq")
