@@ -4,7 +4,7 @@
 
 The library is a plain C-ABI shared object (include/rbd_b200.h); it is git-ignored but travels
 with the working tree to the GPU box.  The translation units are compiled in parallel
-(`nvcc -c`, one process each) and linked with `nvcc -shared`; the three fused-driver launchers
+(`nvcc -c`, one process each) and linked with `nvcc -shared`; the launcher files
 are compiled once per precision (-DRBD_LAUNCH_T=double / float).
 """
 from __future__ import annotations
@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(PKG_DIR, "librbd_b200.so")
 
 # (object name, source, extra defines)
 UNITS = [("rbd_capi.o", "rbd_capi.cu", [])]
-for _src in ("rbd_launch_rnea.cu", "rbd_launch_grad.cu", "rbd_launch_minv.cu"):
+for _src in ("rbd_launch_rnea.cu", "rbd_launch_grad.cu", "rbd_launch_minv.cu", "rbd_launch_pass.cu"):
     for _t in ("double", "float"):
         UNITS.append(("%s_%s.o" % (_src[:-3], _t), _src, ["-DRBD_LAUNCH_T=%s" % _t]))
 

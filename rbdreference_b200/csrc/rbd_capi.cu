@@ -71,46 +71,6 @@ using namespace rbd_host;
 namespace {
 
 template <typename T>
-int launch_rnea_fpass(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, T* v, T* a,
-                      T* f, void* stream) {
-  RBD_CHECK_ARGS(m && q && qd && v && a && f && B >= 0, "rbd_rnea_fpass: null argument or negative B");
-  if (B == 0) return 0;
-  rnea_fpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
-      pick<T>(m), B, q, qd, qdd, g, v, a, f);
-  return cuda_status("rbd_rnea_fpass");
-}
-
-template <typename T>
-int launch_rnea_bpass(const rbd_model* m, int64_t B, const T* q, T* f, T* c, void* stream) {
-  RBD_CHECK_ARGS(m && q && f && c && B >= 0, "rbd_rnea_bpass: null argument or negative B");
-  if (B == 0) return 0;
-  rnea_bpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
-      pick<T>(m), B, q, f, c);
-  return cuda_status("rbd_rnea_bpass");
-}
-
-template <typename T, bool DQ>
-int launch_grad_fpass(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* v, const T* a, T g,
-                      T* dv, T* da, T* df, void* stream) {
-  RBD_CHECK_ARGS(m && q && qd && v && (a || !DQ) && dv && da && df && B >= 0,
-                 "rbd_rnea_grad_fpass: null argument or negative B");
-  if (B == 0) return 0;
-  rnea_grad_fpass_kernel<T, DQ><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
-      pick<T>(m), B, q, qd, v, a, g, dv, da, df);
-  return cuda_status("rbd_rnea_grad_fpass");
-}
-
-template <typename T, bool DQ>
-int launch_grad_bpass(const rbd_model* m, int64_t B, const T* q, const T* f, T* df, int damp, T* dc,
-                      void* stream) {
-  RBD_CHECK_ARGS(m && q && (f || !DQ) && df && dc && B >= 0, "rbd_rnea_grad_bpass: null argument or negative B");
-  if (B == 0) return 0;
-  rnea_grad_bpass_kernel<T, DQ><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
-      pick<T>(m), B, q, f, df, damp, dc);
-  return cuda_status("rbd_rnea_grad_bpass");
-}
-
-template <typename T>
 int launch_minv_bpass(const rbd_model* m, int64_t B, const T* q, T* Minv, T* F, T* U, T* Dinv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && F && U && Dinv && B >= 0, "rbd_minv_bpass: null argument or negative B");
   if (B == 0) return 0;

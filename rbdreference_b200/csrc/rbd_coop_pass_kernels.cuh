@@ -1,0 +1,236 @@
+// rbd_coop_pass_kernels.cuh - the four gradient passes (RBDReference.py:1127-1343) with one
+// DERIVATIVE COLUMN PER LANE: lane (g, c) of a warp owns column c of knot point g (G = 8 / 16 / 32
+// lanes per knot point, 32 / G knot points per warp pass).
+//
+// The reference's recursions never mix columns: dv/da/df[:, c, i] only depend on [:, c, parent(i)]
+// (forward passes) and df[:, c, parent] only receives X^T df[:, c, i] (backward passes).  So every
+// lane runs the body loop on its own column, and the (6, n, NB) tensors of the warp's knot points
+// live in a shared-memory tile that has the layout of the warp's contiguous slab in HBM (rows
+// padded to an odd pitch): they are read / written with coalesced full-line accesses instead of
+// the 8-byte accesses 6 n^2 * 8 bytes apart of a knot-point-per-thread mapping.
+// Same arithmetic as the generic kernels in rbd_pass_kernels.cuh (body frame, dense 6x6 inertia,
+// any S), so any model the reference accepts is served.
+#pragma once
+#include "rbd_common.cuh"
+
+namespace rbd {
+
+constexpr int kCpMaxWarps = 8;
+
+__host__ __device__ inline int cp_pitch(int n) { return n | 1; }
+// values of T per warp
+__host__ __device__ inline int cp_fpass_warp_vals(int n, int G) {
+  const int ipw = 32 / G;
+  return ipw * (3 * 6 * n * cp_pitch(n) + 12 * n + 3 * n);      // dv da df tiles | v a rows | f1 f2 qd
+}
+__host__ __device__ inline int cp_bpass_warp_vals(int n, int G) {
+  const int ipw = 32 / G;
+  return ipw * (6 * n * cp_pitch(n) + n * n + 6 * n + 2 * n);   // df tile | dc tile | f rows | f1 f2
+}
+
+// copy `count` values of a [rows][n] slab between global memory and a tile of pitch cp_pitch(n)
+template <typename T, bool TO_SMEM>
+__device__ __forceinline__ void cp_copy(T* tile, T* __restrict__ gmem, int n, int count, int total, int lane) {
+  const int np = cp_pitch(n);
+  int row = lane / n, col = lane - row * n;
+  const int drow = 32 / n, dcol = 32 - drow * n;
+  for (int e = lane; e < total; e += 32) {
+    if (TO_SMEM) tile[row * np + col] = e < count ? gmem[e] : T(0);
+    else if (e < count) __stcs(gmem + e, tile[row * np + col]);
+    row += drow; col += dcol;
+    if (col >= n) { col -= n; row += 1; }
+  }
+}
+
+// ---- rnea_grad_fpass_dq / _dqd (:1127-1187, :1189-1255) --------------------------------------
+template <typename T, int G, bool DQ>
+__global__ void __launch_bounds__(kCpMaxWarps * 32)
+grad_fpass_coop_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __restrict__ q,
+                       const T* __restrict__ qd, const T* __restrict__ v, const T* __restrict__ a, T gravity,
+                       T* __restrict__ dv, T* __restrict__ da, T* __restrict__ df) {
+  constexpr int IPW = 32 / G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = m.n, np = cp_pitch(n);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane / G, c = lane - g * G;
+  const bool valid = c < n;
+  const int tvals = 6 * n * np;                           // one knot point's padded tile
+  T* ws = reinterpret_cast<T*>(smem_raw) + (size_t)warp * cp_fpass_warp_vals(n, G);
+  T* tv = ws;                                             // [IPW][6 n][np]
+  T* ta = tv + IPW * tvals;
+  T* tf = ta + IPW * tvals;
+  T* sv = tf + IPW * tvals;                               // [IPW][6][n]
+  T* sa = sv + IPW * 6 * n;
+  T* sj = sa + IPW * 6 * n;                               // [IPW][n][3]: f1 f2 qd
+  const int64_t slab = (int64_t)6 * n * n;
+  const int64_t ngroups = (B + IPW - 1) / IPW;
+  for (int64_t grp = (int64_t)blockIdx.x * nwarps + warp; grp < ngroups; grp += (int64_t)gridDim.x * nwarps) {
+    const int64_t first = grp * IPW;
+    const int nk = (int)((B - first) < IPW ? (B - first) : IPW);
+    if (valid) {
+      int64_t b = first + g;
+      if (b >= B) b = B - 1;
+      T f1, f2;
+      joint_basis(m, c, q[b * n + c], f1, f2);
+      T* d = sj + (g * n + c) * 3;
+      d[0] = f1; d[1] = f2; d[2] = qd[b * n + c];
+    }
+    for (int e = lane; e < IPW * 6 * n; e += 32) {
+      const bool ok = e < nk * 6 * n;
+      sv[e] = ok ? v[first * 6 * n + e] : T(0);
+      if (DQ) sa[e] = ok ? a[first * 6 * n + e] : T(0);
+    }
+    __syncwarp();
+    if (valid) {
+      T* mv = tv + g * tvals + c * np;                    // element (r, c, i) at (r n + c) np + i
+      T* ma = ta + g * tvals + c * np;
+      T* mf = tf + g * tvals + c * np;
+      const int rstride = n * np;
+      const T* vb = sv + g * 6 * n;
+      const T* ab = sa + g * 6 * n;
+      for (int i = 0; i < n; ++i) {
+        const T* ji = sj + (g * n + i) * 3;
+        T X[18];
+        build_X(m, i, ji[0], ji[1], X);
+        const T qdi = ji[2];
+        const int p = m.parent[i];
+        T S[6], vi[6], Iv[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { S[r] = m.S[i][r]; vi[r] = vb[r * n + i]; }
+        mat6_apply(m.I[i], vi, Iv);                                            // :1180 / :1248
+        T dvc[6], dac[6];
+        if (p >= 0) {
+          T pv[6], pa[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) { pv[r] = mv[r * rstride + p]; pa[r] = ma[r * rstride + p]; }
+          X_apply(X, pv, dvc);                                                 // :1158 / :1230
+          X_apply(X, pa, dac);                                                 // :1163 / :1234
+        } else {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) { dvc[r] = T(0); dac[r] = T(0); }
+        }
+        T seed_a[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+        if (c == i) {
+          // seed terms of the column of the body's own joint
+          if (DQ) {
+            T par[6], t[6], seed_v[6];
+            if (p >= 0) {
+#pragma unroll
+              for (int r = 0; r < 6; ++r) par[r] = vb[r * n + p];
+              X_apply(X, par, t);
+              crm_mul(t, S, seed_v);                                           // :1159
+#pragma unroll
+              for (int r = 0; r < 6; ++r) { dvc[r] += seed_v[r]; par[r] = ab[r * n + p]; }
+            } else {
+#pragma unroll
+              for (int r = 0; r < 6; ++r) par[r] = T(0);
+              par[5] = -gravity;                                               // :1137
+            }
+            X_apply(X, par, t);
+            crm_mul(t, S, seed_a);                                             // :1173 / :1175
+          } else {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) dvc[r] += S[r];                        // :1231
+            crm_mul(vi, S, seed_a);                                            // :1243
+          }
+        }
+        T t[6];
+        crm_mul(dvc, S, t);                                                    // :1170 / :1240
+#pragma unroll
+        for (int r = 0; r < 6; ++r) dac[r] = fma_t(qdi, t[r], dac[r]) + seed_a[r];
+        T Ida[6], Idv[6], t1[6], t2[6];
+        mat6_apply(m.I[i], dac, Ida);                                          // :1179 / :1247
+        mat6_apply(m.I[i], dvc, Idv);
+        crf_mul(dvc, Iv, t1);                                                  // :1184 / :1251
+        crf_mul(vi, Idv, t2);                                                  // :1185 / :1252
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          mv[r * rstride + i] = dvc[r];
+          ma[r * rstride + i] = dac[r];
+          mf[r * rstride + i] = Ida[r] + t1[r] + t2[r];
+        }
+      }
+    }
+    __syncwarp();
+    cp_copy<T, false>(tv, dv + first * slab, n, nk * 6 * n * n, IPW * 6 * n * n, lane);
+    cp_copy<T, false>(ta, da + first * slab, n, nk * 6 * n * n, IPW * 6 * n * n, lane);
+    cp_copy<T, false>(tf, df + first * slab, n, nk * 6 * n * n, IPW * 6 * n * n, lane);
+    __syncwarp();
+  }
+}
+
+// ---- rnea_grad_bpass_dq / _dqd (:1257-1297, :1299-1343) --------------------------------------
+// df arrives from the caller (arbitrary contents), is accumulated IN PLACE and written back.
+template <typename T, int G, bool DQ>
+__global__ void __launch_bounds__(kCpMaxWarps * 32)
+grad_bpass_coop_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __restrict__ q,
+                       const T* __restrict__ f, T* __restrict__ df, int use_damping, T* __restrict__ dc) {
+  constexpr int IPW = 32 / G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = m.n, np = cp_pitch(n), nn = n * n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane / G, c = lane - g * G;
+  const bool valid = c < n;
+  const int tvals = 6 * n * np;
+  T* ws = reinterpret_cast<T*>(smem_raw) + (size_t)warp * cp_bpass_warp_vals(n, G);
+  T* td = ws;                                             // [IPW][6 n][np]
+  T* tc = td + IPW * tvals;                               // [IPW][n][n]
+  T* sf = tc + IPW * nn;                                  // [IPW][6][n]
+  T* sj = sf + IPW * 6 * n;                               // [IPW][n][2]
+  const int64_t slab = (int64_t)6 * n * n;
+  const int64_t ngroups = (B + IPW - 1) / IPW;
+  for (int64_t grp = (int64_t)blockIdx.x * nwarps + warp; grp < ngroups; grp += (int64_t)gridDim.x * nwarps) {
+    const int64_t first = grp * IPW;
+    const int nk = (int)((B - first) < IPW ? (B - first) : IPW);
+    if (valid) {
+      int64_t b = first + g;
+      if (b >= B) b = B - 1;
+      T f1, f2;
+      joint_basis(m, c, q[b * n + c], f1, f2);
+      sj[(g * n + c) * 2] = f1; sj[(g * n + c) * 2 + 1] = f2;
+    }
+    if (DQ) {
+      for (int e = lane; e < IPW * 6 * n; e += 32) sf[e] = e < nk * 6 * n ? f[first * 6 * n + e] : T(0);
+    }
+    cp_copy<T, true>(td, df + first * slab, n, nk * 6 * n * n, IPW * 6 * n * n, lane);
+    __syncwarp();
+    if (valid) {
+      T* md = td + g * tvals + c * np;
+      T* mc = tc + g * nn;
+      const int rstride = n * np;
+      for (int i = n - 1; i >= 0; --i) {
+        const int p = m.parent[i];
+        T col[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) col[r] = md[r * rstride + i];
+        T val = dot6(m.S[i], col);                                             // :1284 / :1325
+        if (!DQ && use_damping && c == i) val += m.damping[i];                 // :1341
+        mc[i * n + c] = val;
+        if (p >= 0) {
+          T X[18], t[6];
+          build_X(m, i, sj[(g * n + i) * 2], sj[(g * n + i) * 2 + 1], X);
+          XT_apply(X, col, t);                                                 // :1291 / :1331
+          if (DQ && c == i) {
+            T fi[6], S[6], fxs[6], t2[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { fi[r] = sf[g * 6 * n + r * n + i]; S[r] = m.S[i][r]; }
+            crm_mul(fi, S, fxs);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) fxs[r] = -fxs[r];                      // fxS :166-168
+            XT_apply(X, fxs, t2);                                              // :1292
+#pragma unroll
+            for (int r = 0; r < 6; ++r) t[r] += t2[r];                         // :1293-1294
+          }
+#pragma unroll
+          for (int r = 0; r < 6; ++r) md[r * rstride + p] += t[r];
+        }
+      }
+    }
+    __syncwarp();
+    cp_copy<T, false>(td, df + first * slab, n, nk * 6 * n * n, IPW * 6 * n * n, lane);
+    for (int e = lane; e < nk * nn; e += 32) __stcs(dc + first * nn + e, tc[e]);
+    __syncwarp();
+  }
+}
+
+}  // namespace rbd

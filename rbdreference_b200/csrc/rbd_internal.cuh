@@ -3,8 +3,9 @@
 //   rbd_capi.cu         C ABI, model compilation, per-pass and forward-dynamics launchers
 //   rbd_launch_rnea.cu  launch_rnea<T>       (rnea kernels)
 //   rbd_launch_grad.cu  launch_rnea_grad<T>  (rnea_grad kernels)
-//   rbd_launch_minv.cu  launch_minv<T>       (minv kernels)
-// The three launcher files are compiled once per precision (-DRBD_LAUNCH_T=double / float).
+//   rbd_launch_minv.cu  launch_minv<T>, launch_crba<T>
+//   rbd_launch_pass.cu  launch_grad_fpass / launch_grad_bpass (the four gradient passes)
+// The launcher files are compiled once per precision (-DRBD_LAUNCH_T=double / float).
 #pragma once
 #include <cmath>
 #include <cstdio>
@@ -69,6 +70,17 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
                      T* dc_du, T* c_out, void* stream);
 template <typename T>
 int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream);
+template <typename T>
+int launch_rnea_fpass(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, T* v, T* a,
+                      T* f, void* stream);
+template <typename T>
+int launch_rnea_bpass(const rbd_model* m, int64_t B, const T* q, T* f, T* c, void* stream);
+template <typename T, bool DQ>
+int launch_grad_fpass(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* v, const T* a, T g,
+                      T* dv, T* da, T* df, void* stream);
+template <typename T, bool DQ>
+int launch_grad_bpass(const rbd_model* m, int64_t B, const T* q, const T* f, T* df, int damp, T* dc,
+                      void* stream);
 template <typename T>
 int launch_crba(const rbd_model* m, int64_t B, const T* q, T* H, void* stream);
 

@@ -29,7 +29,10 @@ __host__ __device__ inline int lane_rnea_warp_vals(int n, int nslot_a, bool loca
 // every model constant into an immediate constant-bank operand of the FP instruction that uses it
 // (measured on B200: iiwa14 +8 % FP64 / +31 % FP32).  NMAX = 0: rolled loops with indexed constant
 // loads, for large robots (unrolling 32 bodies costs more in instruction fetch than it saves).
-template <typename T, bool LOCALF, bool VAF, int NMAX>
+// MODE 0: rnea.  MODE 1: rnea_fpass only (:559-598; VAF = true; f_out = the bodies' own forces, c is
+// not touched).  MODE 2: rnea_bpass only (:600-621; f_out holds f on entry - staged with coalesced
+// loads - and the accumulated forces on exit, c is written; qd / qdd / v_out / a_out are unused).
+template <typename T, bool LOCALF, bool VAF, int NMAX, int MODE = 0>
 __global__ void __launch_bounds__(kLrMaxWarps * 32)
 rnea_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__ DfsPlan plan, int64_t B,
                  const T* __restrict__ q, const T* __restrict__ qd, const T* __restrict__ qdd, T gravity,
@@ -65,10 +68,26 @@ rnea_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
       const bool ok = e < count;
       const int row = plan.pos[jn] * 3;
       io[(row + 0) * kLrStride + kn] = ok ? __ldg(q + base + e) : T(0);
-      io[(row + 1) * kLrStride + kn] = ok ? __ldg(qd + base + e) : T(0);
-      io[(row + 2) * kLrStride + kn] = (ok && qdd) ? __ldg(qdd + base + e) : T(0);
+      if (MODE != 2) {
+        io[(row + 1) * kLrStride + kn] = ok ? __ldg(qd + base + e) : T(0);
+        io[(row + 2) * kLrStride + kn] = (ok && qdd) ? __ldg(qdd + base + e) : T(0);
+      }
       kn += dk; jn += dj;
       if (jn >= n) { jn -= n; kn += 1; }
+    }
+  }
+  if (MODE == 2 && !LOCALF) {
+    // stage f (B, 6, NB): element e of the slab = knot e / 6n, row r = (e % 6n) / n, body i = e % n
+    const int n6 = 6 * n;
+    const int count = nk * n6;
+    const int64_t base = first * n6;
+    int kn = lane / n6, rem = lane - kn * n6;
+    int rr = rem / n, jn = rem - rr * n;
+    for (int e = lane; e < 32 * n6; e += 32) {
+      fb[(plan.pos[jn] * 6 + rr) * kLrStride + kn] = e < count ? f_out[base + e] : T(0);
+      jn += 32;
+      while (jn >= n) { jn -= n; rr += 1; }
+      while (rr >= 6) { rr -= 6; kn += 1; }
     }
   }
   __syncwarp();
@@ -77,6 +96,7 @@ rnea_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
   T vc[6], ac[6];                                         // (v, a) of the body just processed
 #pragma unroll(NMAX > 0 ? NMAX : 1)
   for (int i = 0; i < (NMAX > 0 ? NMAX : n); ++i) {
+    if (MODE == 2) break;
     if (NMAX > 0 && i >= n) break;
     const int par = m.parent[i];
     const int kind = m.kind[i];
@@ -160,6 +180,7 @@ rnea_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
   T carry[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};      // X^T f of body i + 1 when its parent is i
 #pragma unroll(NMAX > 0 ? NMAX : 1)
   for (int i = (NMAX > 0 ? NMAX : n) - 1; i >= 0; --i) {
+    if (MODE == 1) break;
     if (NMAX > 0 && i >= n) continue;
     const bool chained = (i != n - 1) && (m.parent[i + 1 < RBD_MAX_DOF ? i + 1 : i] == i);
     T f[6];
@@ -168,9 +189,14 @@ rnea_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
     const int kind = m.kind[i];
     const T ax[3] = {m.axis[i][0], m.axis[i][1], m.axis[i][2]};
     const T ci = kind == 0 ? dot3s(ax, f) : dot3s(ax, f + 3);                  // :613
-    const T f1 = IO(i, 0), f2 = IO(i, 1);
+    T f1 = IO(i, 0), f2 = IO(i, 1);
+    if (MODE == 2) {                                      // the slot still holds q
+      const T qi = f1;
+      if (kind == 0) sincos_t(qi, &f2, &f1);
+      else { f1 = qi; f2 = T(0); }
+    }
     IO(i, 2) = ci;
-    if (VAF) {
+    if (VAF || MODE == 2) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) FB(i, k) = f[k];                             // the accumulated force (:619, :628)
     }
@@ -201,7 +227,7 @@ rnea_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
   __syncwarp();
 
   // ---------------------------------------------------------------- coalesced stores
-  {
+  if (MODE != 1) {
     const int count = nk * n;
     T* dst = c + first * n;
     int kn = lane / n, jn = lane - kn * n;
@@ -212,9 +238,9 @@ rnea_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
       if (jn >= n) { jn -= n; kn += 1; }
     }
   }
-  if (VAF) {
+  if (VAF || MODE == 2) {
     if (LOCALF) {
-      // not instantiated: VAF needs the shared-memory f rows
+      // not instantiated: these modes need the shared-memory f rows
     } else {
       // (B, 6, NB): element e of the slab = knot e / 6n, row r = (e % 6n) / n, body i = e % n
       const int n6 = 6 * n;
@@ -224,8 +250,8 @@ rnea_lane_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
       int rr = rem / n, jn = rem - rr * n;
       for (int e = lane; e < count; e += 32) {
         const int row = (plan.pos[jn] * 6 + rr) * kLrStride + kn;
-        if (v_out) __stcs(v_out + base + e, vb[row]);
-        if (a_out) __stcs(a_out + base + e, ab[row]);
+        if (VAF && v_out) __stcs(v_out + base + e, vb[row]);
+        if (VAF && a_out) __stcs(a_out + base + e, ab[row]);
         if (f_out) __stcs(f_out + base + e, fb[row]);
         // advance e by 32
         jn += 32;

@@ -1,6 +1,7 @@
 // rbd_launch_rnea.cu - part of librbd_b200.so (see rbd_internal.cuh); compiled with -DRBD_LAUNCH_T=double|float.
 #include "rbd_internal.cuh"
 #include "rbd_fused_kernels.cuh"
+#include "rbd_pass_kernels.cuh"
 #include "rbd_lane_rnea_kernels.cuh"
 
 #ifndef RBD_LAUNCH_T
@@ -55,6 +56,76 @@ int launch_rnea(const rbd_model* m, int64_t B, const T* q, const T* qd, const T*
   return cuda_status("rbd_rnea");
 }
 
+// Launch geometry of rnea_lane_kernel: warps per CTA that keep the most warps resident.
+template <typename K>
+static bool lane_rnea_geometry(K kern, size_t per_warp, int* warps_out) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  int warps = 0, best = 0;
+  for (int w = 1; w <= 4; ++w) {
+    const size_t sz = per_warp * w;
+    if (sz > kMaxDynSmem) break;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, sz) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (nb * w >= best) { best = nb * w; warps = w; }
+  }
+  *warps_out = warps;
+  return warps > 0;
+}
+
+// rnea_fpass (RBDReference.py:559-598): the forward half of the lane kernel when the robot has
+// rigid-body inertias and its staging rows fit in shared memory, else the generic pass kernel.
+template <typename T>
+int launch_rnea_fpass(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, T* v, T* a,
+                      T* f, void* stream) {
+  RBD_CHECK_ARGS(m && q && qd && v && a && f && B >= 0, "rbd_rnea_fpass: null argument or negative B");
+  if (B == 0) return 0;
+  if (m->fast_ok && g_variant.load(std::memory_order_relaxed) != 1) {
+    const FastModel<T>& fm = pick_dfs<T>(m);
+    const int n = fm.n;
+    const size_t per_warp = (size_t)lane_rnea_warp_vals(n, fm.n_slot_a, false, true) * sizeof(T);
+    auto kern = n <= 8 ? rnea_lane_kernel<T, false, true, 8, 1> : (n <= 16 ? rnea_lane_kernel<T, false, true, 16, 1> : rnea_lane_kernel<T, false, true, 0, 1>);
+    int warps = 0;
+    if (per_warp <= 72 * 1024 && lane_rnea_geometry(kern, per_warp, &warps)) {
+      const int64_t ntasks = (B + 31) / 32;
+      kern<<<(unsigned)((ntasks + warps - 1) / warps), warps * 32, per_warp * warps, (cudaStream_t)stream>>>(
+          fm, m->plan, B, q, qd, qdd, g, nullptr, v, a, f);
+      return cuda_status("rbd_rnea_fpass(lane)");
+    }
+  }
+  rnea_fpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
+      pick<T>(m), B, q, qd, qdd, g, v, a, f);
+  return cuda_status("rbd_rnea_fpass");
+}
+
+// rnea_bpass (RBDReference.py:600-621): f is accumulated in place.
+template <typename T>
+int launch_rnea_bpass(const rbd_model* m, int64_t B, const T* q, T* f, T* c, void* stream) {
+  RBD_CHECK_ARGS(m && q && f && c && B >= 0, "rbd_rnea_bpass: null argument or negative B");
+  if (B == 0) return 0;
+  if (m->fast_ok && g_variant.load(std::memory_order_relaxed) != 1) {
+    const FastModel<T>& fm = pick_dfs<T>(m);
+    const int n = fm.n;
+    const size_t per_warp = (size_t)lane_rnea_warp_vals(n, fm.n_slot_a, false, false) * sizeof(T);
+    auto kern = n <= 8 ? rnea_lane_kernel<T, false, false, 8, 2> : (n <= 16 ? rnea_lane_kernel<T, false, false, 16, 2> : rnea_lane_kernel<T, false, false, 0, 2>);
+    int warps = 0;
+    if (per_warp <= 48 * 1024 && lane_rnea_geometry(kern, per_warp, &warps)) {
+      const int64_t ntasks = (B + 31) / 32;
+      kern<<<(unsigned)((ntasks + warps - 1) / warps), warps * 32, per_warp * warps, (cudaStream_t)stream>>>(
+          fm, m->plan, B, q, nullptr, nullptr, T(0), c, nullptr, nullptr, f);
+      return cuda_status("rbd_rnea_bpass(lane)");
+    }
+  }
+  rnea_bpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
+      pick<T>(m), B, q, f, c);
+  return cuda_status("rbd_rnea_bpass");
+}
+
+template int launch_rnea_fpass<RBD_LAUNCH_T>(const rbd_model*, int64_t, const RBD_LAUNCH_T*, const RBD_LAUNCH_T*,
+                                             const RBD_LAUNCH_T*, RBD_LAUNCH_T, RBD_LAUNCH_T*, RBD_LAUNCH_T*, RBD_LAUNCH_T*, void*);
+template int launch_rnea_bpass<RBD_LAUNCH_T>(const rbd_model*, int64_t, const RBD_LAUNCH_T*, RBD_LAUNCH_T*, RBD_LAUNCH_T*, void*);
 template int launch_rnea<RBD_LAUNCH_T>(const rbd_model*, int64_t, const RBD_LAUNCH_T*, const RBD_LAUNCH_T*, const RBD_LAUNCH_T*,
                                        RBD_LAUNCH_T, RBD_LAUNCH_T*, RBD_LAUNCH_T*, RBD_LAUNCH_T*, RBD_LAUNCH_T*, void*);
 

@@ -130,7 +130,18 @@ def test_non_rigid_inertia_falls_back_to_generic_kernels():
 
 
 @requires_cuda
-def test_pass_helpers_vs_reference_golden(golden):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_pass_helpers_vs_reference_golden(golden, variant):
+    """variant 0: lane / column-per-lane pass kernels; variant 1: the generic knot-point-per-thread ones."""
+    from rbdreference_b200 import RBDReference
+    RBDReference.set_kernel_variant(variant)
+    try:
+        _check_pass_helpers(golden)
+    finally:
+        RBDReference.set_kernel_variant(0)
+
+
+def _check_pass_helpers(golden):
     name, rb, g = golden
     eng = _engine(rb)
     q, qd, qdd = g["q"], g["qd"], g["qdd"]
@@ -247,8 +258,35 @@ def test_rnea_kernel_paths_vs_oracle(name, B):
                 c, v, a, f = eng.rnea(tq, tqd, tqdd)
                 for got, ref in ((c, rc), (v, rv), (a, ra), (f, rf)):
                     assert rel_err(got.cpu().numpy(), ref) < tol
+                # the two passes on their own (lane kernel modes 1 / 2, or the generic pass kernels)
+                v1, a1, f1 = eng.rnea_fpass(tq, tqd, tqdd)
+                assert rel_err(v1.cpu().numpy(), rv) < tol and rel_err(a1.cpu().numpy(), ra) < tol
+                c2, f2 = eng.rnea_bpass(tq, f1)
+                assert f2.data_ptr() == f1.data_ptr()                       # in place (:619)
+                assert rel_err(c2.cpu().numpy(), rc) < tol and rel_err(f2.cpu().numpy(), rf) < tol
         finally:
             RBDReference.set_kernel_variant(0)
+
+
+@requires_cuda
+@pytest.mark.parametrize("name,B", [("iiwa14", 131), ("hyq", 67), ("atlas", 9), ("tree13", 33)])
+def test_gradient_passes_batched_vs_oracle(name, B):
+    """The four gradient passes on ragged batches (partial warp groups), FP64 and FP32."""
+    rb = make_robot(name)
+    bo = BatchOracle(rb)
+    n = rb.get_num_vel()
+    q, qd, qdd = random_states(n, B, seed=3 * B)
+    c, v, a, f = bo.rnea(q, qd, qdd)
+    ref = bo.rnea_grad(q, qd, qdd)
+    for dtype, tol in ((torch.float64, TOL_F64), (torch.float32, TOL_F32)):
+        eng = _engine(rb, dtype)
+        tq, tqd = _t(q, dtype), _t(qd, dtype)
+        dv, da, df = eng.rnea_grad_fpass_dq(tq, tqd, _t(v, dtype), _t(a, dtype))
+        dv2, da2, df2 = eng.rnea_grad_fpass_dqd(tq, tqd, _t(v, dtype))
+        dc_dq = eng.rnea_grad_bpass_dq(tq, _t(f, dtype), df)
+        dc_dqd = eng.rnea_grad_bpass_dqd(tq, df2)
+        got = torch.cat((dc_dq, dc_dqd), dim=2).cpu().numpy()
+        assert rel_err(got, ref) < tol
 
 
 @requires_cuda
