@@ -159,6 +159,16 @@ int rbd_forward_dynamics_grad_f32(const rbd_model_t* m, int64_t B, const float* 
 int rbd_crba_f64(const rbd_model_t* m, int64_t B, const double* q, double* H, void* stream);
 int rbd_crba_f32(const rbd_model_t* m, int64_t B, const float* q, float* H, void* stream);
 
+/* ---- articulated-body algorithm ---------------------------------------- */
+/* aba, fixed-base branch (RBDReference.py:817, :940-1024): qdd (B, n) from q, qd, tau (B, n).  Follows
+ * the reference to the letter, INCLUDING :984, where every body's bias force pA is set to element 0
+ * of crf(v) I v broadcast over its six entries; results therefore equal the reference's aba(), not
+ * forward_dynamics().  f_ext is ignored by this branch upstream and has no argument here. */
+int rbd_aba_f64(const rbd_model_t* m, int64_t B, const double* q, const double* qd, const double* tau,
+                double gravity, double* qdd, void* stream);
+int rbd_aba_f32(const rbd_model_t* m, int64_t B, const float* q, const float* qd, const float* tau,
+                float gravity, float* qdd, void* stream);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
 /* Runs a dependent-chain FMA micro-benchmark on `stream`'s device and returns the achieved
  * FLOP/s (2 per FMA) in *flops_per_s; is_f64 selects DFMA or FFMA.  Used only to put a measured

@@ -43,7 +43,7 @@ def run_case(name, make, B, seed):
     keys = ["c", "v", "a", "f", "c_noqdd", "a_noqdd", "f_noqdd", "c_galt", "f_fpass", "dc_du", "dc_du_damped",
             "dc_du_noqdd", "dv_dq", "da_dq", "df_dq", "dv_dqd", "da_dqd", "df_dqd", "dc_dq", "dc_dqd",
             "df_dq_acc", "df_dqd_acc", "Minv", "Minv_sparse", "Minv_b", "F_b", "U", "Dinv", "F_f", "H",
-            "fd_qdd", "fd_dq", "fd_dqd"]
+            "fd_qdd", "fd_dq", "fd_dqd", "aba_qdd", "aba_qdd_galt"]
     acc = {k: [] for k in keys}
     for k in range(B):
         v, a, f = ref.rnea_fpass(q[k], qd[k], qdd[k])
@@ -74,6 +74,8 @@ def run_case(name, make, B, seed):
         acc["fd_qdd"].append(ref.forward_dynamics(q[k], qd[k], u[k]))
         fdq, fdqd = ref.forward_dynamics_grad(q[k], qd[k], u[k])
         acc["fd_dq"].append(fdq); acc["fd_dqd"].append(fdqd)
+        acc["aba_qdd"].append(ref.aba(q[k], qd[k], u[k]))
+        acc["aba_qdd_galt"].append(ref.aba(q[k], qd[k], u[k], GRAVITY=-3.7))
     for key in keys:
         out[key] = np.stack(acc[key])
     # model tables, to detect drift of rbdreference_b200/robots.py against the fixture

@@ -299,6 +299,52 @@ class ScalarOracle:
         Minv = self.minv(q)
         return -Minv @ dc_du[:, : self.n], -Minv @ dc_du[:, self.n:]
 
+    # -- ABA (fixed base) - SURVEY.md 8f rank 4 --------------------------------------------
+    def aba(self, q, qd, tau, f_ext=None, GRAVITY=-9.81):
+        """Articulated-body algorithm, RBDReference.py:817 (fixed-base branch :940-1024).
+
+        Follows the reference to the letter, including :984 where the bias force of every
+        body is set to ELEMENT 0 of crf(v) I v broadcast over all six entries (`...[0]` on a
+        1-D product).  f_ext is ignored by the fixed-base branch."""
+        n = self.n
+        v = np.zeros((6, n)); c = np.zeros((6, n)); a = np.zeros((6, n))
+        d = np.zeros(n); U = np.zeros((6, n)); u = np.zeros(n)
+        IA = [None] * n
+        pA = np.zeros((6, n))
+        qdd = np.zeros(n)
+        Xs = [self._X(i, q) for i in range(n)]
+        for i in range(n):
+            p = self.parent[i]
+            S = self.S[i]
+            if p == -1:
+                v[:, i] = S * qd[i]                                     # :957
+            else:
+                v[:, i] = Xs[i] @ v[:, p] + S * qd[i]                   # :960-961
+                c[:, i] = qd[i] * (crm(v[:, i]) @ S)                    # :962 (_mxS :56-59)
+            IA[i] = self.I[i].copy()                                    # :966
+            pA[:, i] = (crf(v[:, i]) @ self.I[i] @ v[:, i])[0]          # :978-984 (element 0, broadcast)
+        for i in range(n - 1, -1, -1):
+            S = self.S[i]
+            p = self.parent[i]
+            U[:, i] = IA[i] @ S                                         # :990
+            d[i] = S @ U[:, i]                                          # :991
+            u[i] = tau[i] - S @ pA[:, i]                                # :992
+            if p != -1:
+                Ia = IA[i] - np.outer(U[:, i], U[:, i]) / d[i]          # :996-997
+                pa = pA[:, i] + Ia @ c[:, i] + U[:, i] * u[i] / d[i]    # :999
+                IA[p] = IA[p] + Xs[i].T @ Ia @ Xs[i]                    # :1001-1004
+                pA[:, p] = pA[:, p] + Xs[i].T @ pa                      # :1006-1007
+        g = self._gravity(GRAVITY)
+        for i in range(n):
+            p = self.parent[i]
+            if p == -1:
+                a[:, i] = Xs[i] @ g + c[:, i]                           # :1015
+            else:
+                a[:, i] = Xs[i] @ a[:, p] + c[:, i]                     # :1017
+            qdd[i] = (u[i] - U[:, i] @ a[:, i]) / d[i]                  # :1020-1021
+            a[:, i] = a[:, i] + qdd[i] * self.S[i]                      # :1022
+        return qdd
+
 
 # ----------------------------------------------------------------------------------------
 # batched oracle: the same recursions vectorised over a leading batch axis
@@ -557,3 +603,44 @@ class BatchOracle:
                 H[:, i, j] = fh @ self.S[j]
                 H[:, j, i] = H[:, i, j]
         return H
+
+    # -- ABA (fixed base), same quirk at :984 as ScalarOracle.aba -------------------------
+    def aba(self, q, qd, tau, GRAVITY=-9.81):
+        q, qd, tau = self._prep(q, qd, tau)
+        B, n = q.shape[0], self.n
+        Xs = self._Xs(q)
+        crm_b = lambda x: np.stack([crm(x[k]) for k in range(x.shape[0])]).astype(self.dtype)
+        v = [None] * n; c = [np.zeros((B, 6), dtype=self.dtype) for _ in range(n)]
+        IA = [np.broadcast_to(self.I[i], (B, 6, 6)).copy() for i in range(n)]
+        pA = [None] * n
+        for i in range(n):
+            p, S = self.parent[i], self.S[i]
+            if p == -1:
+                v[i] = qd[:, i:i + 1] * S
+            else:
+                v[i] = np.einsum("bij,bj->bi", Xs[i], v[p]) + qd[:, i:i + 1] * S
+                c[i] = qd[:, i:i + 1] * (crm_b(v[i]) @ S)
+            Iv = v[i] @ self.I[i].T
+            full = np.einsum("bji,bj->bi", -crm_b(v[i]), Iv)               # crf(v) I v = -crm(v)^T I v
+            pA[i] = np.repeat(full[:, :1], 6, axis=1)                      # :984
+        U = [None] * n; d = [None] * n; u = [None] * n
+        for i in range(n - 1, -1, -1):
+            p, S = self.parent[i], self.S[i]
+            U[i] = IA[i] @ S
+            d[i] = U[i] @ S
+            u[i] = tau[:, i] - pA[i] @ S
+            if p != -1:
+                Ia = IA[i] - U[i][:, :, None] * U[i][:, None, :] / d[i][:, None, None]
+                pa = pA[i] + np.einsum("bij,bj->bi", Ia, c[i]) + U[i] * (u[i] / d[i])[:, None]
+                IA[p] = IA[p] + np.einsum("bji,bjk,bkl->bil", Xs[i], Ia, Xs[i])
+                pA[p] = pA[p] + np.einsum("bji,bj->bi", Xs[i], pa)
+        g = np.zeros(6, dtype=self.dtype); g[5] = -GRAVITY
+        a = [None] * n
+        qdd = np.zeros((B, n), dtype=self.dtype)
+        for i in range(n):
+            p = self.parent[i]
+            ap = np.broadcast_to(g, (B, 6)) if p == -1 else a[p]
+            ai = np.einsum("bij,bj->bi", Xs[i], ap) + c[i]
+            qdd[:, i] = (u[i] - np.einsum("bi,bi->b", U[i], ai)) / d[i]
+            a[i] = ai + qdd[:, i:i + 1] * self.S[i]
+        return qdd

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(PKG_DIR, "librbd_b200.so")
 
 PASS_SYMBOLS = ["rnea_fpass", "rnea_bpass", "rnea_grad_fpass_dq", "rnea_grad_fpass_dqd",
                 "rnea_grad_bpass_dq", "rnea_grad_bpass_dqd", "minv_bpass", "minv_fpass"]
-FUSED_SYMBOLS = ["rnea", "rnea_grad", "minv", "forward_dynamics", "forward_dynamics_grad", "crba"]
+FUSED_SYMBOLS = ["rnea", "rnea_grad", "minv", "forward_dynamics", "forward_dynamics_grad", "crba", "aba"]
 PLAIN_SYMBOLS = ["rbd_abi_version", "rbd_last_error_string", "rbd_model_create", "rbd_model_destroy",
                  "rbd_model_num_dof", "rbd_model_uses_world_kernels", "rbd_set_kernel_variant",
                  "rbd_measure_fma_peak", "rbd_launch_count"]
@@ -76,6 +76,7 @@ def load_library():
             "forward_dynamics": [P, c_int64, P, P, P, P, P, P],
             "forward_dynamics_grad": [P, c_int64, P, P, P, P, P, P, P],
             "crba": [P, c_int64, P, P, P],
+            "aba": [P, c_int64, P, P, P, real, P, P],
         }
         for base, argtypes in sig.items():
             fn = getattr(lib, "rbd_%s_%s" % (base, suf))

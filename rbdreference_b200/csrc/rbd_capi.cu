@@ -416,6 +416,10 @@ int rbd_model_uses_world_kernels(const rbd_model_t* m) { return (m && m->fast_ok
   int rbd_crba_##SUF(const rbd_model_t* m, int64_t B, const T* q, T* H, void* stream) {                              \
     return launch_crba<T>(m, B, q, H, stream);                                                                       \
   }                                                                                                                  \
+  int rbd_aba_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* qd, const T* tau, T gravity, T* qdd,       \
+                    void* stream) {                                                                                  \
+    return launch_aba<T>(m, B, q, qd, tau, gravity, qdd, stream);                                                    \
+  }                                                                                                                  \
   int rbd_rnea_fpass_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* qd, const T* qdd, T gravity, T* v,  \
                            T* a, T* f, void* stream) {                                                               \
     return launch_rnea_fpass<T>(m, B, q, qd, qdd, gravity, v, a, f, stream);                                         \

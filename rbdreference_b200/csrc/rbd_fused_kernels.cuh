@@ -535,6 +535,142 @@ crba_fused_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __r
 }
 
 // =============================================================================================
+// aba, fixed-base branch (RBDReference.py:817, :940-1024), one knot point per thread, the
+// reference's recursion to the letter: v / c forward (:951-984), articulated inertia IA (dense 6x6,
+// per-thread local memory) and bias force pA leaf -> root (:986-1007), accelerations root -> leaf
+// (:1009-1022).  Reference quirk kept: :984 assigns ELEMENT 0 of crf(v) I v to all six entries of
+// pA (`np.matmul(temp, v)[0]` on a 1-D product); f_ext is ignored by this branch.
+// =============================================================================================
+template <typename T>
+__device__ __forceinline__ void congruence_add(const T* __restrict__ A, const T (&X)[18], T* __restrict__ P) {
+  // P += X^T A X for dense row-major 6x6 A, P and X = [[E,0],[L,E]]
+  for (int k = 0; k < 6; ++k) {
+    T xk[6], col[6], t[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) xk[r] = T(0);
+    if (k < 3) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { xk[r] = X[3 * r + k]; xk[3 + r] = X[9 + 3 * r + k]; }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) xk[3 + r] = X[3 * r + (k - 3)];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      T acc = T(0);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc = fma_t(A[6 * r + c], xk[c], acc);
+      col[r] = acc;
+    }
+    XT_apply(X, col, t);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) P[6 * r + k] += t[r];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFusedThreads)
+aba_fused_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __restrict__ q,
+                 const T* __restrict__ qd, const T* __restrict__ tau, T gravity, T* __restrict__ qdd) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int n = m.n;
+  const T* qb = q + b * n;
+  const T* qdb = qd + b * n;
+  const T* taub = tau + b * n;
+  T IA[RBD_MAX_DOF][36], lv[RBD_MAX_DOF][6], lc[RBD_MAX_DOF][6], lp[RBD_MAX_DOF][6], lU[RBD_MAX_DOF][6];
+  T lb[RBD_MAX_DOF][2], ld[RBD_MAX_DOF], lu[RBD_MAX_DOF];
+  for (int i = 0; i < n; ++i) {
+    joint_basis(m, i, qb[i], lb[i][0], lb[i][1]);
+    const int p = m.parent[i];
+    const T qdi = qdb[i];
+    T vi[6], ci[6];
+    if (p < 0) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) { vi[r] = m.S[i][r] * qdi; ci[r] = T(0); }                  // :957
+    } else {
+      T X[18], vp[6], t[6];
+      build_X(m, i, lb[i][0], lb[i][1], X);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) vp[r] = lv[p][r];
+      X_apply(X, vp, vi);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) vi[r] = fma_t(m.S[i][r], qdi, vi[r]);                        // :960-961
+      crm_mul(vi, m.S[i], t);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) ci[r] = qdi * t[r];                                          // :962
+    }
+    T Iv[6], x[6];
+    mat6_apply(m.I[i], vi, Iv);
+    crf_mul(vi, Iv, x);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { lv[i][r] = vi[r]; lc[i][r] = ci[r]; lp[i][r] = x[0]; }       // :984 (element 0)
+#pragma unroll
+    for (int k = 0; k < 36; ++k) IA[i][k] = m.I[i][k];                                         // :966
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    const int p = m.parent[i];
+    T U[6], pa[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      T acc = T(0);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc = fma_t(IA[i][6 * r + c], m.S[i][c], acc);
+      U[r] = acc;                                                                              // :990
+      pa[r] = lp[i][r];
+    }
+    const T d = dot6(m.S[i], U);                                                               // :991
+    const T u = taub[i] - dot6(m.S[i], pa);                                                    // :992
+#pragma unroll
+    for (int r = 0; r < 6; ++r) lU[i][r] = U[r];
+    ld[i] = d; lu[i] = u;
+    if (p >= 0) {
+      T Ia[36];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) Ia[6 * r + c] = IA[i][6 * r + c] - U[r] * U[c] / d;        // :996-997
+      const T ud = u / d;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        T acc = pa[r];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc = fma_t(Ia[6 * r + c], lc[i][c], acc);
+        pa[r] = fma_t(U[r], ud, acc);                                                          // :999
+      }
+      T X[18], t[6];
+      build_X(m, i, lb[i][0], lb[i][1], X);
+      congruence_add(Ia, X, IA[p]);                                                            // :1001-1004
+      XT_apply(X, pa, t);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) lp[p][r] += t[r];                                            // :1006-1007
+    }
+  }
+  T* out = qdd + b * n;
+  for (int i = 0; i < n; ++i) {
+    const int p = m.parent[i];
+    T X[18], ap[6], ai[6];
+    build_X(m, i, lb[i][0], lb[i][1], X);
+    if (p < 0) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) ap[r] = T(0);
+      ap[5] = -gravity;                                                                        // :941-942
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) ap[r] = lv[p][r];                                            // lv re-used for a
+    }
+    X_apply(X, ap, ai);
+    T U[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { ai[r] += lc[i][r]; U[r] = lU[i][r]; }                        // :1015 / :1017
+    const T qddi = (lu[i] - dot6(U, ai)) / ld[i];                                              // :1020-1021
+    out[i] = qddi;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) lv[i][r] = fma_t(m.S[i][r], qddi, ai[r]);                      // :1022
+  }
+}
+
+// =============================================================================================
 // FMA peak micro-benchmark: 8 independent dependent-chains per thread.
 // =============================================================================================
 template <typename T>

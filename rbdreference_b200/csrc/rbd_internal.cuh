@@ -83,5 +83,7 @@ int launch_grad_bpass(const rbd_model* m, int64_t B, const T* q, const T* f, T* 
                       void* stream);
 template <typename T>
 int launch_crba(const rbd_model* m, int64_t B, const T* q, T* H, void* stream);
+template <typename T>
+int launch_aba(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* tau, T g, T* qdd, void* stream);
 
 }  // namespace rbd_host

@@ -188,6 +188,17 @@ int launch_crba(const rbd_model* m, int64_t B, const T* q, T* H, void* stream) {
   return cuda_status("rbd_crba");
 }
 
+// aba (RBDReference.py:817, fixed-base branch): one launch, knot point per thread.
+template <typename T>
+int launch_aba(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* tau, T g, T* qdd, void* stream) {
+  RBD_CHECK_ARGS(m && q && qd && tau && qdd && B >= 0, "rbd_aba: null argument or negative B");
+  if (B == 0) return 0;
+  aba_fused_kernel<T><<<blocks_for(B, kFusedThreads), kFusedThreads, 0, (cudaStream_t)stream>>>(pick<T>(m), B, q, qd, tau, g, qdd);
+  return cuda_status("rbd_aba");
+}
+template int launch_aba<RBD_LAUNCH_T>(const rbd_model*, int64_t, const RBD_LAUNCH_T*, const RBD_LAUNCH_T*, const RBD_LAUNCH_T*,
+                                      RBD_LAUNCH_T, RBD_LAUNCH_T*, void*);
+
 template int launch_crba<RBD_LAUNCH_T>(const rbd_model*, int64_t, const RBD_LAUNCH_T*, RBD_LAUNCH_T*, void*);
 template int launch_minv<RBD_LAUNCH_T>(const rbd_model*, int64_t, const RBD_LAUNCH_T*, int, RBD_LAUNCH_T*, void*);
 

@@ -315,6 +315,16 @@ class RBDReference:
         self._call("forward_dynamics_grad", ctx, dq, dqd, du, o1, o2, None)
         return ctx.ret(o1), ctx.ret(o2)
 
+    def aba(self, q, qd, tau, f_ext=None, GRAVITY=-9.81):
+        """RBDReference.py:817 (fixed-base branch :940-1024) -> qdd (n,).  Reproduces the reference's
+        aba() including its :984 bias-force quirk; f_ext is ignored, as upstream."""
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq, dqd, dtau = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(tau, (n,), "tau")
+        qdd = ctx.empty(n)
+        self._call("aba", ctx, dq, dqd, dtau, float(GRAVITY), qdd)
+        return ctx.ret(qdd)
+
     def crba(self, q, out=None):
         """RBDReference.py:1026-1124 (fixed-base branch) -> joint-space inertia matrix H (n, n)."""
         ctx = self._Ctx(self, q, 1)

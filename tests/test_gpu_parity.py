@@ -290,6 +290,29 @@ def test_gradient_passes_batched_vs_oracle(name, B):
 
 
 @requires_cuda
+def test_aba_vs_reference_golden_and_oracle(golden):
+    """aba (RBDReference.py:817): goldens from the live reference (default and alternate gravity),
+    batched oracle, FP32."""
+    name, rb, g = golden
+    bo = BatchOracle(rb)
+    n = rb.get_num_vel()
+    eng = _engine(rb)
+    assert rel_err(eng.aba(g["q"], g["qd"], g["u"]), g["aba_qdd"]) < TOL_F64
+    assert rel_err(eng.aba(g["q"], g["qd"], g["u"], GRAVITY=-3.7), g["aba_qdd_galt"]) < TOL_F64
+    one = eng.aba(g["q"][0], g["qd"][0], g["u"][0])
+    assert one.shape == (n,) and rel_err(one, g["aba_qdd"][0]) < TOL_F64
+    B = 513
+    q, qd, _ = random_states(n, B, seed=21)
+    tau = np.random.default_rng(5).uniform(-10, 10, (B, n))
+    ref = bo.aba(q, qd, tau)
+    got = eng.aba(_t(q), _t(qd), _t(tau))
+    assert got.shape == (B, n) and rel_err(got.cpu().numpy(), ref) < TOL_F64
+    e32 = _engine(rb, torch.float32)
+    got32 = e32.aba(_t(q, torch.float32), _t(qd, torch.float32), _t(tau, torch.float32))
+    assert rel_err(got32.cpu().numpy(), ref) < 20 * TOL_F32      # qdd = (u - U.a)/d amplifies FP32 rounding on light distal links
+
+
+@requires_cuda
 def test_crba_vs_reference_golden_and_oracle(golden):
     """crba (RBDReference.py:1090-1124): goldens from the live reference, batched oracle, both kernel
     families, both precisions, and H @ Minv = I."""

@@ -56,6 +56,8 @@ def test_scalar_oracle_vs_golden(golden):
         assert rel_err(so.forward_dynamics(q[k], qd[k], g["u"][k]), g["fd_qdd"][k]) < PIN
         r1, r2 = so.forward_dynamics_grad(q[k], qd[k], g["u"][k])
         assert rel_err(r1, g["fd_dq"][k]) < PIN and rel_err(r2, g["fd_dqd"][k]) < PIN
+        assert rel_err(so.aba(q[k], qd[k], g["u"][k]), g["aba_qdd"][k]) < PIN
+        assert rel_err(so.aba(q[k], qd[k], g["u"][k], GRAVITY=-3.7), g["aba_qdd_galt"][k]) < PIN
 
 
 def test_batch_oracle_vs_golden(golden):
@@ -77,6 +79,8 @@ def test_batch_oracle_vs_golden(golden):
         assert rel_err(mp[key], g[gk]) < PIN, key
     assert rel_err(bo.minv(q, output_dense=False), g["Minv_sparse"]) < PIN
     assert rel_err(bo.crba(q), g["H"]) < PIN
+    assert rel_err(bo.aba(q, qd, g["u"]), g["aba_qdd"]) < PIN
+    assert rel_err(bo.aba(q, qd, g["u"], GRAVITY=-3.7), g["aba_qdd_galt"]) < PIN
 
 
 @pytest.mark.parametrize("name", ["iiwa14", "hyq", "atlas"])
