@@ -195,7 +195,7 @@ def parse_args():
     ap.add_argument("--op", default="rnea_grad", choices=["rnea_grad", "minv", "rnea", "crba"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="knot points per GPU")
-    ap.add_argument("--variant", type=int, default=0, help="kernel family: 0 auto, 1 generic, 2 world/thread, 3 cooperative, 4 hybrid minv, 5 lane minv")
+    ap.add_argument("--variant", type=int, default=0, help="kernel family: 0 auto, 1 generic, 2 world/thread, 3 cooperative, 4 hybrid minv, 5 lane minv, 6 lane2 minv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()

@@ -74,7 +74,8 @@ int rbd_model_uses_world_kernels(const rbd_model_t* m);
  * (knot point per lane for the articulated inertias, column per lane for the rows of Minv; other
  * operations behave as 0), 5 = lane minv kernel (knot point per lane in every phase, per-body table
  * and output tile in shared memory; robots too large for it run the generic kernel; other
- * operations behave as 0).  Used by the tests and the benchmark to cross-check / compare. */
+ * operations behave as 0), 6 = lane2 minv kernel (knot point per lane, per-body table in an L2-resident
+ * scratch buffer; for large robots; other operations behave as 0).  Used by the tests and the benchmark to cross-check / compare. */
 int rbd_set_kernel_variant(int variant);
 
 /* ---- fused drivers ------------------------------------------------------------------------ */

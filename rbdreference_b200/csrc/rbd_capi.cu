@@ -380,6 +380,26 @@ int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out) {
       mp.comp_root[i] = p < 0 ? i : mp.comp_root[p];
       if (i - mp.comp_root[i] + 1 > mp.maxcomp) mp.maxcomp = i - mp.comp_root[i] + 1;
     }
+    // visit lists of the lane2 minv kernel: bodies a phase of a column group has to touch
+    Lane2Plan& lp = m->lane2;
+    std::memset(&lp, 0, sizeof(lp));
+    lp.ngroups = (n + kL2GC - 1) / kL2GC;
+    lp.ok = m->fast_ok && cp.maxdepth < kL2MaxDepth && m->fd_dfs.n_slot_a <= kL2MaxSlots;
+    for (int g = 0; g < lp.ngroups && lp.ok; ++g) {
+      const int j0 = g * kL2GC, jtop = (j0 + kL2GC < n ? j0 + kL2GC : n) - 1;
+      bool firstB = true, firstC = true;
+      for (int a = jtop; a >= 0; --a)
+        if (m->plan.sub_end[a] > j0 && lp.nsteps < kL2MaxSteps) {
+          lp.seq[lp.nsteps++] = (unsigned short)(a | (firstB ? 64 : 0) | (g << 7));
+          firstB = false;
+        }
+      for (int a = mp.comp_root[j0]; a <= jtop; ++a)
+        if (m->plan.comp_end[a] > j0 && lp.nsteps < kL2MaxSteps) {
+          lp.seq[lp.nsteps++] = (unsigned short)(a | 32 | (firstC ? 64 : 0) | (g << 7));
+          firstC = false;
+        }
+      if (lp.nsteps >= kL2MaxSteps) lp.ok = 0;
+    }
   }
   *out = m;
   return 0;
@@ -393,9 +413,9 @@ int rbd_model_destroy(rbd_model_t* m) {
 int rbd_model_num_dof(const rbd_model_t* m) { return m ? m->d.n : RBD_E_INVALID_ARGUMENT; }
 
 int rbd_set_kernel_variant(int variant) {
-  if (variant < 0 || variant > 5)
+  if (variant < 0 || variant > 6)
     return fail(RBD_E_INVALID_ARGUMENT,
-                "rbd_set_kernel_variant: 0 auto, 1 generic, 2 world (thread per knot point), 3 cooperative, 4 hybrid (minv), 5 lane (minv)");
+                "rbd_set_kernel_variant: 0 auto, 1 generic, 2 world (thread per knot point), 3 cooperative, 4 hybrid (minv), 5 lane (minv), 6 lane2 (minv)");
   g_variant.store(variant, std::memory_order_relaxed);
   return 0;
 }

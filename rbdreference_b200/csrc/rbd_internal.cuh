@@ -22,6 +22,7 @@
 #include "rbd_minv_kernels.cuh"
 #include "rbd_coop_kernels.cuh"
 #include "rbd_coop_minv_kernels.cuh"
+#include "rbd_lane2_minv_kernels.cuh"
 
 struct rbd_model {
   rbd::DevModel<double> d;
@@ -34,6 +35,7 @@ struct rbd_model {
   rbd::DfsPlan plan;
   rbd::CoopPlan coop;
   rbd::CoopMinvPlan coop_minv;
+  rbd::Lane2Plan lane2;
 };
 
 namespace rbd_host {

@@ -22,7 +22,10 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
     //   HyQ    n=12: hybrid 6.1e8 | 8.5e8    cooperative 8.8e8 | 1.2e9    thread 5.2e8
     //   iiwa14 n=7 : hybrid 8.5e8 | 1.38e9   cooperative 7.8e8 | 1.2e9    thread 1.13e9 | 1.88e9 (body frame)
     const int n = m->d.n;
-    //   iiwa14 n=7 : lane 1.34e9 | 2.62e9 (knot point per lane, table + tile in shared memory)
+    //   iiwa14 n=7 : lane 1.49e9 | 2.60e9 (knot point per lane, table + tile in shared memory)
+    //   Atlas       : lane2 (variant 6: knot point per lane, table in an L2 scratch, cp.async ring) 0.97e8 | 1.3e8 -
+    //                 its 8-byte result stores 7.2 KB apart are partial-sector writes (DRAM read-modify-write),
+    //                 which costs more than the idle lanes of the column-per-lane phases it avoids
     variant = n > 16 ? 4 : (n > 8 ? 3 : 5);
   }
   if (m->fast_ok && dense && variant == 5) {
@@ -51,6 +54,40 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
       if (blocks > (int64_t)sms * ctas) blocks = (int64_t)sms * ctas;
       kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop_minv, B, q, Minv);
       return cuda_status("rbd_minv(lane)");
+    }
+  }
+  if (m->fast_ok && dense && variant == 6 && m->lane2.ok) {
+    // knot point per lane in every phase, per-body table in an L2-resident [body][field][lane] scratch
+    const FastModel<T>& fm = pick_dfs<T>(m);
+    const int n = fm.n;
+    auto kern = fm.has_prismatic ? minv_lane2_kernel<T, true> : minv_lane2_kernel<T, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) {
+      // resident warps per SM: bounded by shared memory and by the L2 budget of the scratch blocks
+      static const long l2_budget_mb = [] { const char* v = std::getenv("RBD_LANE2_L2_MB"); return v ? std::atol(v) : 96L; }();
+      static const int max_warps = [] { const char* v = std::getenv("RBD_LANE2_WARPS"); return v ? std::atoi(v) : kL2MaxWarps; }();
+      const size_t per_warp_smem = (size_t)lane2_warp_vals<T>(m->coop.maxdepth, fm.n_slot_a, fm.n_slot_b) * sizeof(T);
+      const size_t per_warp_scr = lane2_scratch_vals_per_warp<T>(n) * sizeof(T);
+      int warps = max_warps < kL2MaxWarps ? max_warps : kL2MaxWarps;
+      while (warps > 1 && ((size_t)warps * per_warp_smem > kMaxDynSmem ||
+                           (size_t)warps * sms * per_warp_scr > (size_t)l2_budget_mb * 1024 * 1024)) --warps;
+      if (warps >= 1 && (size_t)warps * per_warp_smem <= kMaxDynSmem) {
+        const int64_t ntasks = (B + 31) / 32;
+        int64_t blocks = (ntasks + warps - 1) / warps;
+        if (blocks > sms) blocks = sms;                   // one CTA per SM: the L2 budget counts on it
+        T* scratch = nullptr;
+        cudaMemPool_t pool = scratch_pool(dev);
+        if (!pool) return fail(RBD_E_NO_DEVICE, "rbd_minv: cannot create the scratch memory pool");
+        e = cudaMallocFromPoolAsync((void**)&scratch, (size_t)blocks * warps * per_warp_scr, pool, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+        kern<<<(unsigned)blocks, warps * 32, warps * per_warp_smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop_minv, m->lane2,
+                                                                                           m->coop.maxdepth, B, q, Minv, scratch);
+        const int rc = cuda_status("rbd_minv(lane2)");
+        cudaFreeAsync(scratch, (cudaStream_t)stream);
+        return rc;
+      }
     }
   }
   if (m->fast_ok && dense && variant == 4) {

@@ -70,7 +70,7 @@ def test_generic_body_frame_kernels_vs_reference_golden(golden):
 
 
 @requires_cuda
-@pytest.mark.parametrize("variant", [2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [2, 3, 4, 5, 6])
 def test_world_kernel_variants_vs_reference_golden(golden, variant):
     """Both world-frame mappings (2: knot point per thread, 3: body per lane) against the goldens."""
     from rbdreference_b200 import RBDReference
