@@ -95,15 +95,47 @@ template <typename T, bool SPLIT>
 int launch_fd_apply(int n, int mcols, int64_t B, const T* A, const T* R1, const T* R2, T alpha, T* out0, T* out1,
                     void* stream) {
   const size_t per_knot = (size_t)(n * n + 2 * n * mcols) * sizeof(T);
-  int KB = (int)((size_t)(96 * 1024) / per_knot);
+  // small per-CTA batches: several CTAs per SM keep loads, products and stores of different batches overlapped
+  int KB = (int)((size_t)(28 * 1024) / per_knot);
   if (KB < 1) KB = 1;
   if (KB > 32) KB = 32;
   const size_t smem = per_knot * KB;
+  if (mcols > 1 && std::is_same<T, double>::value && !R2 && g_variant.load(std::memory_order_relaxed) != 1) {
+    // FP64 tensor-core product (forward_dynamics_grad)
+    const FdMmaShape sh = fd_mma_shape(n, mcols);
+    const size_t per_knot_m = (size_t)sh.vals * sizeof(double);
+    int KM = (int)((size_t)(28 * 1024) / per_knot_m);
+    if (KM < 1) KM = 1;
+    if (KM > 32) KM = 32;
+    auto mk = fd_apply_mma_kernel<SPLIT>;
+    cudaError_t e = cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    int64_t blocks = (B + KM - 1) / KM;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    mk<<<(unsigned)blocks, kFdMmaThreads, per_knot_m * KM, (cudaStream_t)stream>>>(
+        n, mcols, KM, B, (const double*)A, (const double*)R1, (double)alpha, (double*)out0, (double*)out1);
+    return cuda_status("rbd_forward_dynamics(apply, mma)");
+  }
+  if (mcols > 1) {
+    // register-tiled product (forward_dynamics_grad)
+    const size_t per_knot_t = fd_tiled_vals_per_knot(n, mcols) * sizeof(T);
+    int KT = (int)((size_t)(28 * 1024) / per_knot_t);
+    if (KT < 1) KT = 1;
+    if (KT > 32) KT = 32;
+    const size_t smem_t = per_knot_t * KT + 64;
+    auto tk = fd_apply_tiled_kernel<T, SPLIT>;
+    cudaError_t e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    int64_t blocks = (B + KT - 1) / KT;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tk<<<(unsigned)blocks, kFdTiledThreads, smem_t, (cudaStream_t)stream>>>(n, mcols, KT, B, A, R1, R2, alpha, out0, out1);
+    return cuda_status("rbd_forward_dynamics(apply, tiled)");
+  }
   auto kern = fd_apply_kernel<T, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
   if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
   int64_t blocks = (B + KB - 1) / KB;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
   kern<<<(unsigned)blocks, kFdThreads, smem, (cudaStream_t)stream>>>(n, mcols, KB, B, A, R1, R2, alpha, out0, out1);
   return cuda_status("rbd_forward_dynamics(apply)");
 }

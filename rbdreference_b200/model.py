@@ -65,6 +65,13 @@ class RobotModel:
             return int(rnea + 2 * np.sum(132 * P + 212 * A + 4) + 2 * 72 * np.sum(Bi[nr]) + 72 * np.sum(nr))
         if op == "minv":
             return int(np.sum(55 + 2 * ST) + np.sum(906 + 84 * ST[nr]) + np.sum(66 + 81 * C[nr]))
+        if op == "fd":
+            # forward_dynamics (:1369-1372): rnea + minv + (u - c) and one n x n mat-vec
+            return int(self.flops("rnea") + self.flops("minv") + n + 2 * n * n)
+        if op == "fd_grad":
+            # forward_dynamics_grad (:1374-1384): fd + rnea_grad + the n x n by n x 2n product
+            # (the reference's second minv evaluation at :1381 is not counted)
+            return int(self.flops("fd") + self.flops("rnea_grad") + 2 * n * n * 2 * n)
         if op == "crba":
             # X build 54 per body; X^T IC X + add = 2 * 396 + 36 per non-root body (:1100-1103);
             # IC S and S.fh = 66 + 11 per body, X^T fh and S.fh = 66 + 11 per (body, ancestor) pair (:1108-1122)
@@ -80,6 +87,10 @@ class RobotModel:
             return (3 * n + 2 * n * n) * itemsize
         if op in ("minv", "crba"):
             return (n + n * n) * itemsize
+        if op == "fd":
+            return (3 * n + n) * itemsize
+        if op == "fd_grad":
+            return (3 * n + 2 * n * n) * itemsize
         raise KeyError(op)
 
 

@@ -477,9 +477,19 @@ def test_forward_dynamics_batches_vs_oracle(name, B):
     qdd = eng.forward_dynamics(_t(q), _t(qd), _t(u)).cpu().numpy()
     assert rel_err(qdd, qdd_ref) < 10 * TOL_F64
     dc = bo.rnea_grad(q, qd, qdd_ref)
-    d1, d2 = eng.forward_dynamics_grad(_t(q), _t(qd), _t(u))
-    assert rel_err(d1.cpu().numpy(), -np.einsum("bij,bjk->bik", Minv, dc[:, :, :n])) < 10 * TOL_F64
-    assert rel_err(d2.cpu().numpy(), -np.einsum("bij,bjk->bik", Minv, dc[:, :, n:])) < 10 * TOL_F64
+    from rbdreference_b200 import RBDReference
+    for variant in (0, 1):      # 0: FP64 tensor-core product (mma.sync m8n8k4); 1: register-tiled product + generic drivers
+        RBDReference.set_kernel_variant(variant)
+        try:
+            d1, d2 = eng.forward_dynamics_grad(_t(q), _t(qd), _t(u))
+            assert rel_err(d1.cpu().numpy(), -np.einsum("bij,bjk->bik", Minv, dc[:, :, :n])) < 10 * TOL_F64
+            assert rel_err(d2.cpu().numpy(), -np.einsum("bij,bjk->bik", Minv, dc[:, :, n:])) < 10 * TOL_F64
+        finally:
+            RBDReference.set_kernel_variant(0)
+    e32 = _engine(rb, torch.float32)                       # FP32: register-tiled product
+    f1, f2 = e32.forward_dynamics_grad(_t(q, torch.float32), _t(qd, torch.float32), _t(u, torch.float32))
+    assert rel_err(f1.cpu().numpy(), -np.einsum("bij,bjk->bik", Minv, dc[:, :, :n])) < 50 * TOL_F32
+    assert rel_err(f2.cpu().numpy(), -np.einsum("bij,bjk->bik", Minv, dc[:, :, n:])) < 50 * TOL_F32
     assert eng.forward_dynamics(_t(q[:0]), _t(qd[:0]), _t(u[:0])).shape == (0, n)     # empty batch
 
 
