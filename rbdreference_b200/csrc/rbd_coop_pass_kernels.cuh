@@ -28,18 +28,33 @@ __host__ __device__ inline int cp_bpass_warp_vals(int n, int G) {
   return ipw * (6 * n * cp_pitch(n) + n * n + 6 * n + 2 * n);   // df tile | dc tile | f rows | f1 f2
 }
 
-// copy `count` values of a [rows][n] slab between global memory and a tile of pitch cp_pitch(n)
+__device__ __forceinline__ void cp_async_val(double* dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_val(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+// copy `count` values of a [rows][n] slab between global memory and a tile of pitch cp_pitch(n).
+// Global -> shared uses cp.async: all of a lane's copies are in flight at once (a load + store per
+// iteration keeps one load per lane in flight and is latency-bound); the caller's __syncwarp follows
+// the wait.
 template <typename T, bool TO_SMEM>
 __device__ __forceinline__ void cp_copy(T* tile, T* __restrict__ gmem, int n, int count, int total, int lane) {
   const int np = cp_pitch(n);
   int row = lane / n, col = lane - row * n;
   const int drow = 32 / n, dcol = 32 - drow * n;
   for (int e = lane; e < total; e += 32) {
-    if (TO_SMEM) tile[row * np + col] = e < count ? gmem[e] : T(0);
-    else if (e < count) __stcs(gmem + e, tile[row * np + col]);
+    if (TO_SMEM) {
+      if (e < count) cp_async_val(tile + row * np + col, gmem + e);
+      else tile[row * np + col] = T(0);
+    } else if (e < count) {
+      __stcs(gmem + e, tile[row * np + col]);
+    }
     row += drow; col += dcol;
     if (col >= n) { col -= n; row += 1; }
   }
+  if (TO_SMEM) asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // ---- rnea_grad_fpass_dq / _dqd (:1127-1187, :1189-1255) --------------------------------------
