@@ -1,7 +1,7 @@
 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -1 gpurun_out/bench_default.json | cut -c1-300
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; tail -1 gpurun_out/bench_ref.json | cut -c1-200
 : > gpurun_out/matrix.jsonl
-for r in iiwa14 hyq atlas; do for op in rnea_grad minv rnea crba; do for dt in f64 f32; do
+for r in iiwa14 hyq atlas; do for op in rnea_grad minv rnea crba fd fd_grad; do for dt in f64 f32; do
   b=1048576; if [ $r = atlas ]; then b=262144; fi
   python bench.py --robot $r --op $op --dtype $dt --batch $b --steps 20 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 >> gpurun_out/matrix.jsonl
 done; done; done
@@ -15,4 +15,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:rnea_grad_coop -c 1 -o gpurun_out/prof_grad_coop_iiwa3 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu12.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:minv_lane -c 1 -o gpurun_out/prof_minv_lane_iiwa2 python bench.py --op minv --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu13.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:minv_hybrid -c 1 -o gpurun_out/prof_minv_hybrid_atlas4 python bench.py --op minv --robot atlas --batch 262144 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu14.log 2>&1
-ls -la gpurun_out/*.ncu-rep | tail -4
+ncu --set full --clock-control none --import-source on -k regex:fd_apply_mma -c 1 -o gpurun_out/prof_fd_mma_atlas2 python bench.py --op fd_grad --robot atlas --batch 262144 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu19.log 2>&1
+python tools/bench_passes.py --reps 5 --batch 1048576 > gpurun_out/passes.jsonl 2>/dev/null
+python tools/bench_passes.py --reps 5 --robot hyq --batch 262144 >> gpurun_out/passes.jsonl 2>/dev/null
+python tools/bench_passes.py --reps 5 --robot atlas --batch 65536 >> gpurun_out/passes.jsonl 2>/dev/null
+ls -la gpurun_out/*.ncu-rep | tail -5
