@@ -289,6 +289,132 @@ def test_gradient_passes_batched_vs_oracle(name, B):
         assert rel_err(got, ref) < tol
 
 
+# ---------------------------------------------------------------------------------------------
+# concurrency: one immutable handle, many host threads and streams
+# ---------------------------------------------------------------------------------------------
+@requires_cuda
+@pytest.mark.parametrize("name", ["iiwa14", "atlas"])
+def test_concurrent_threads_and_streams_are_deterministic(name):
+    """Four host threads share one engine, each on its own stream (scratch buffers and temporaries
+    are stream-ordered pool allocations): results must equal the single-threaded ones bit for bit."""
+    import threading
+    rb = make_robot(name)
+    eng = _engine(rb)
+    n = eng.n
+    B = 2048 if name == "iiwa14" else 512
+    data = []
+    for t in range(4):
+        q, qd, qdd = random_states(n, B, seed=100 + t)
+        tq, tqd, tqdd = _t(q), _t(qd), _t(qdd)
+        ref = (eng.rnea_grad(tq, tqd, tqdd).clone(), eng.minv(tq).clone(),
+               torch.cat(eng.forward_dynamics_grad(tq, tqd, tqdd), dim=2).clone())
+        data.append((tq, tqd, tqdd, ref))
+    torch.cuda.synchronize()
+    errors = []
+
+    def work(t):
+        try:
+            tq, tqd, tqdd, ref = data[t]
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for _ in range(10):
+                    got = (eng.rnea_grad(tq, tqd, tqdd), eng.minv(tq), torch.cat(eng.forward_dynamics_grad(tq, tqd, tqdd), dim=2))
+                    stream.synchronize()
+                    for g, r in zip(got, ref):
+                        if not torch.equal(g, r):
+                            errors.append("thread %d: result differs from the single-threaded run" % t)
+                            return
+        except Exception as exc:  # pragma: no cover
+            errors.append("thread %d: %r" % (t, exc))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+
+
+# ---------------------------------------------------------------------------------------------
+# sizes at the edges of the kernels' design space
+# ---------------------------------------------------------------------------------------------
+def _edge_robot(kind):
+    from rbdreference_b200 import robots
+    if kind == "one":
+        return robots.random_tree(1, seed=3)
+    if kind == "two":
+        return robots.random_tree(2, seed=4, branching=0.0)
+    if kind == "chain32":           # RBD_MAX_DOF bodies in one chain: depth 31, five pointer-jumping rounds
+        return robots.random_tree(32, seed=5, branching=0.0, prismatic=0.1)
+    if kind == "bush32":            # RBD_MAX_DOF bodies, many roots and branch points
+        return robots.random_tree(32, seed=6, branching=0.6, prismatic=0.2)
+    if kind == "stars":             # every body hangs off the base: n root components of one body
+        return _stars(9)
+    raise KeyError(kind)
+
+
+def _stars(n):
+    from rbdreference_b200 import robots
+    rb = robots.random_tree(n, seed=8, branching=0.0)
+    for j in rb.joints:
+        j.parent = -1
+    return robots.Robot("stars%d" % n, rb.joints)
+
+
+@requires_cuda
+@pytest.mark.parametrize("kind", ["one", "two", "chain32", "bush32", "stars"])
+def test_edge_topologies_all_drivers_vs_oracle(kind):
+    """n = 1, 2 and RBD_MAX_DOF, the deepest and the flattest trees: every fused driver, every kernel
+    variant that serves the size, both precisions, ragged batch."""
+    from rbdreference_b200 import RBDReference
+    rb = _edge_robot(kind)
+    bo = BatchOracle(rb)
+    n = rb.get_num_vel()
+    B = 77
+    q, qd, qdd = random_states(n, B, seed=31)
+    u = np.random.default_rng(9).uniform(-5, 5, (B, n))
+    rc, rv, ra, rf = bo.rnea(q, qd, qdd)
+    rdc, rM, rH, raba = bo.rnea_grad(q, qd, qdd), bo.minv(q), bo.crba(q), bo.aba(q, qd, u)
+    c0 = bo.rnea(q, qd)[0]
+    rqdd = np.einsum("bij,bj->bi", rM, u - c0)
+    # deep chains of random links are ill-conditioned: bars scale with what FP64 / FP32 can deliver there
+    scale = 1.0 if n <= 16 else 1e3
+    for variant in (0, 1, 2, 3, 4, 5, 6):
+        RBDReference.set_kernel_variant(variant)
+        try:
+            eng = _engine(rb)
+            tq, tqd, tqdd, tu = _t(q), _t(qd), _t(qdd), _t(u)
+            c, v, a, f = eng.rnea(tq, tqd, tqdd)
+            for got, ref in ((c, rc), (v, rv), (a, ra), (f, rf)):
+                assert rel_err(got.cpu().numpy(), ref) < TOL_F64 * scale, (variant, "rnea")
+            assert rel_err(eng.rnea_grad(tq, tqd, tqdd).cpu().numpy(), rdc) < TOL_F64 * scale, (variant, "rnea_grad")
+            assert rel_err(eng.minv(tq).cpu().numpy(), rM) < TOL_F64 * scale, (variant, "minv")
+            assert rel_err(eng.crba(tq).cpu().numpy(), rH) < TOL_F64 * scale, (variant, "crba")
+            if variant in (0, 1):
+                assert rel_err(eng.aba(tq, tqd, tu).cpu().numpy(), raba) < TOL_F64 * scale * 10, (variant, "aba")
+                assert rel_err(eng.forward_dynamics(tq, tqd, tu).cpu().numpy(), rqdd) < TOL_F64 * scale * 10, (variant, "fd")
+                d1, d2 = eng.forward_dynamics_grad(tq, tqd, tu)
+                dc = bo.rnea_grad(q, qd, rqdd)
+                # one bar for [qdd_dq | qdd_dqd]: dc_dqd is exactly zero for some of these robots (a single
+                # body on a fixed axis has no velocity-dependent torque), so its own scale would be rounding noise
+                got = torch.cat((d1, d2), dim=2).cpu().numpy()
+                assert rel_err(got, -np.einsum("bij,bjk->bik", rM, dc)) < TOL_F64 * scale * 10, (variant, "fd_grad")
+                e32 = _engine(rb, torch.float32)
+                f32 = torch.float32
+                if n <= 16:
+                    assert rel_err(e32.rnea_grad(_t(q, f32), _t(qd, f32), _t(qdd, f32)).cpu().numpy(), rdc) < TOL_F32 * 10
+                    assert rel_err(e32.minv(_t(q, f32)).cpu().numpy(), rM) < TOL_F32 * 10
+                    assert rel_err(e32.rnea(_t(q, f32), _t(qd, f32), _t(qdd, f32), outputs="c").cpu().numpy(), rc) < TOL_F32 * 10
+        finally:
+            RBDReference.set_kernel_variant(0)
+    # the pass helpers (column-per-lane tiles at G = 8 / 32) on the same robots
+    eng = _engine(rb)
+    dv, da, df = eng.rnea_grad_fpass_dq(tq, tqd, _t(rv), _t(ra))
+    dv2, da2, df2 = eng.rnea_grad_fpass_dqd(tq, tqd, _t(rv))
+    got = torch.cat((eng.rnea_grad_bpass_dq(tq, _t(rf), df), eng.rnea_grad_bpass_dqd(tq, df2)), dim=2)
+    assert rel_err(got.cpu().numpy(), rdc) < TOL_F64 * scale
+
+
 @requires_cuda
 def test_aba_vs_reference_golden_and_oracle(golden):
     """aba (RBDReference.py:817): goldens from the live reference (default and alternate gravity),
