@@ -433,6 +433,13 @@ int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out) {
       if (lp.nsteps >= kL2MaxSteps) lp.ok = 0;
     }
   }
+  {
+    // create the current device's scratch pool now, so that no call made later under CUDA-graph
+    // capture has to create it (pool creation is not allowed while a global-mode capture is open)
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) scratch_pool(dev);
+    cudaGetLastError();
+  }
   *out = m;
   return 0;
 }

@@ -27,6 +27,11 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
     //                 its 8-byte result stores 7.2 KB apart are partial-sector writes (DRAM read-modify-write),
     //                 which costs more than the idle lanes of the column-per-lane phases it avoids
     variant = n > 16 ? 4 : (n > 8 ? 3 : 5);
+    // Small batches (MPC-sized): the knot-point-per-lane kernels process 32 knot points per warp one
+    // after the other, so below one wave of tasks their time is the latency of a single task
+    // (iiwa14 48 us, Atlas 243 us, flat from 1k to 16k knot points); the cooperative kernel spreads
+    // the same batch over 8x - 32x more warps (measured crossover near 32k knot points for both).
+    if (B < 32768) variant = 3;
   }
   if (m->fast_ok && dense && variant == 5) {
     // knot point per lane in every phase, per-body table + output tile in shared memory

@@ -335,6 +335,39 @@ def test_concurrent_threads_and_streams_are_deterministic(name):
     assert not errors, errors
 
 
+@requires_cuda
+@pytest.mark.parametrize("name", ["iiwa14", "atlas"])
+def test_calls_are_cuda_graph_capturable(name):
+    """Small-batch MPC loops are launch-bound: the fused drivers only enqueue stream-ordered work
+    (kernels, pool allocations), so a whole step can be captured in a CUDA graph and replayed."""
+    rb = make_robot(name)
+    eng = _engine(rb)
+    n, B = eng.n, 256
+    sq, sqd, sqdd = (torch.zeros(B, n, dtype=torch.float64, device="cuda") for _ in range(3))
+    out_dc = torch.empty(B, n, 2 * n, dtype=torch.float64, device="cuda")
+    out_M = torch.empty(B, n, n, dtype=torch.float64, device="cuda")
+    q, qd, qdd = random_states(n, B, seed=5)
+    sq.copy_(_t(q)); sqd.copy_(_t(qd)); sqdd.copy_(_t(qdd))
+    # warm up outside the capture (the library creates its scratch memory pool on first use)
+    eng.rnea_grad(sq, sqd, sqdd, out=out_dc); eng.minv(sq, out=out_M); eng.forward_dynamics_grad(sq, sqd, sqdd)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        eng.rnea_grad(sq, sqd, sqdd, out=out_dc)
+        eng.minv(sq, out=out_M)
+        fd1, fd2 = eng.forward_dynamics_grad(sq, sqd, sqdd)
+    for seed in (6, 7):
+        q, qd, qdd = random_states(n, B, seed=seed)
+        sq.copy_(_t(q)); sqd.copy_(_t(qd)); sqdd.copy_(_t(qdd))
+        graph.replay()
+        torch.cuda.synchronize()
+        got = (out_dc.clone(), out_M.clone(), fd1.clone(), fd2.clone())
+        e1, e2 = eng.forward_dynamics_grad(sq, sqd, sqdd)
+        ref = (eng.rnea_grad(sq, sqd, sqdd), eng.minv(sq), e1, e2)
+        for g, r in zip(got, ref):
+            assert torch.equal(g, r)
+
+
 # ---------------------------------------------------------------------------------------------
 # sizes at the edges of the kernels' design space
 # ---------------------------------------------------------------------------------------------
