@@ -44,7 +44,10 @@ __host__ __device__ inline int coop_grad_tile_stride(int n, int ipw, bool split)
   return ((t > s ? t : s) + 1) & ~1;
 }
 
-template <typename T, int G, bool SPLIT>
+// CONLY = true: rnea only (c into c_out; dc_du is not touched): the forward scans, the composite
+// force f^C by a 6-value segmented scan and c_i = S_i . f^C_i.  Used for small (MPC-sized) batches,
+// where the knot-point-per-lane rnea kernel is bound by the latency of one 32-knot-point task.
+template <typename T, int G, bool SPLIT, bool CONLY = false>
 __global__ void __launch_bounds__(kCoopWarps * 32)
 rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__ DfsPlan plan,
                       const __grid_constant__ CoopPlan cp, int64_t B, const T* __restrict__ q,
@@ -228,7 +231,7 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
       for (int k = 0; k < 6; ++k) Pdd[k] += t6[k];
     }
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { myvec[k] = S[k]; myvec[6 + k] = Pd[k]; myvec[12 + k] = Pdd[k]; }
+    for (int k = 0; k < 6; ++k) { if (!CONLY) { myvec[k] = S[k]; myvec[6 + k] = Pd[k]; myvec[12 + k] = Pdd[k]; } }
 
     // ------------------------------------------------------------------ own terms -> subtree composites
     // 0 m | 1..3 h | 4..9 Ibar | 10..15 Sym | 16..18 n | 19..21 l | 22..27 f
@@ -304,12 +307,13 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
     // terms, lane c < 28 then runs the sequential suffix sum of component c over the bodies of each
     // knot point of the warp, and every body reads back PS(i) - PS(subtree_end(i)).
     {
+      constexpr int K0 = CONLY ? 22 : 0;                      // rnea only needs the force composite (22..27)
       T* cs = tile;                                           // [32][29], the tile is not live yet
       T* mine = cs + lane * kCoopScanStride;
 #pragma unroll
-      for (int k = 0; k < 28; ++k) mine[k] = acc[k];
+      for (int k = K0; k < 28; ++k) mine[k] = acc[k];
       __syncwarp();
-      if (lane < 28) {
+      if (lane >= K0 && lane < 28) {
 #pragma unroll
         for (int gg = 0; gg < IPW; ++gg) {
           T* col = cs + (gg * G) * kCoopScanStride + lane;
@@ -325,13 +329,17 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
       }
       __syncwarp();
 #pragma unroll
-      for (int k = 0; k < 28; ++k) acc[k] = mine[k];
+      for (int k = K0; k < 28; ++k) acc[k] = mine[k];
       if (cut) {
         const T* beyond = cs + (gbase + sub_end) * kCoopScanStride;
 #pragma unroll
-        for (int k = 0; k < 28; ++k) acc[k] -= beyond[k];
+        for (int k = K0; k < 28; ++k) acc[k] -= beyond[k];
       }
       __syncwarp();                                           // the buffer becomes the output tile again
+    }
+    if (CONLY) {
+      if (valid && (grp * IPW + g) < B) c_out[b * n + oi] = dot6s(S, acc + 22);     // :613
+      continue;
     }
 
     // ------------------------------------------------------------------ F vectors, diagonal, zero fill

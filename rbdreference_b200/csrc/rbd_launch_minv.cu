@@ -30,8 +30,8 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
     // Small batches (MPC-sized): the knot-point-per-lane kernels process 32 knot points per warp one
     // after the other, so below one wave of tasks their time is the latency of a single task
     // (iiwa14 48 us, Atlas 243 us, flat from 1k to 16k knot points); the cooperative kernel spreads
-    // the same batch over 8x - 32x more warps (measured crossover near 32k knot points for both).
-    if (B < 32768) variant = 3;
+    // the same batch over 8x - 32x more warps (measured crossovers: iiwa14 ~8k, Atlas ~24k knot points).
+    if (B < (n <= 8 ? 8192 : 24576)) variant = 3;
   }
   if (m->fast_ok && dense && variant == 5) {
     // knot point per lane in every phase, per-body table + output tile in shared memory

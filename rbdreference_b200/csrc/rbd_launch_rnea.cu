@@ -1,6 +1,7 @@
 // rbd_launch_rnea.cu - part of librbd_b200.so (see rbd_internal.cuh); compiled with -DRBD_LAUNCH_T=double|float.
 #include "rbd_internal.cuh"
 #include "rbd_fused_kernels.cuh"
+#include "rbd_coop_kernels.cuh"
 #include "rbd_pass_kernels.cuh"
 #include "rbd_lane_rnea_kernels.cuh"
 
@@ -18,6 +19,33 @@ int launch_rnea(const rbd_model* m, int64_t B, const T* q, const T* qd, const T*
   RBD_CHECK_ARGS(m && q && qd && c && B >= 0, "rbd_rnea: null model/q/qd/c or negative B");
   if (B == 0) return 0;
   const int variant = g_variant.load(std::memory_order_relaxed);
+  const int nd = m->d.n;
+  // measured crossovers against the lane kernel: iiwa14 ~16k, Atlas ~4k knot points
+  const int64_t small = nd <= 8 ? 16384 : (nd <= 16 ? 8192 : 4096);
+  if (m->fast_ok && !(v || a || f) && ((variant == 0 && B < small) || variant == 3)) {
+    // Small batches, c only: the warp-cooperative rnea_grad kernel in its rnea-only mode (one body per
+    // lane).  The lane kernel below works through 32 knot points per warp, so below one wave of tasks
+    // its time is the latency of one task (Atlas: 79 us, flat from 1k to 16k knot points; the
+    // cooperative kernel needs 50 us for 1k and 88 us for 4k Atlas knot points).
+    const FastModel<T>& fm = pick_dfs<T>(m);
+    const int n = fm.n;
+    const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+    const int ipw = 32 / G;
+    const int tile_stride = coop_grad_tile_stride(n, ipw, false);
+    const size_t smem = (size_t)(((n * kCoopMdlStride + 1) & ~1) + kCoopWarps * 32 * kCoopVecStride + kCoopWarps * tile_stride) * sizeof(T) +
+                        (size_t)n * kCoopIntStride * sizeof(int);
+    if (smem <= kMaxDynSmem) {
+      auto kern = G == 8 ? rnea_grad_coop_kernel<T, 8, false, true>
+                         : (G == 16 ? rnea_grad_coop_kernel<T, 16, false, true> : rnea_grad_coop_kernel<T, 32, false, true>);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+      const int64_t ngroups = (B + ipw - 1) / ipw;
+      int64_t blocks = (ngroups + kCoopWarps - 1) / kCoopWarps;
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      kern<<<(unsigned)blocks, kCoopWarps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, B, q, qd, qdd, g, 0, nullptr, c);
+      return cuda_status("rbd_rnea(coop)");
+    }
+  }
   if (m->fast_ok && variant != 1) {
     // knot point per lane, depth-first chains in registers, coalesced staging (rbd_lane_rnea_kernels.cuh)
     const FastModel<T>& fm = pick_dfs<T>(m);

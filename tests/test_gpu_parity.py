@@ -247,7 +247,7 @@ def test_rnea_kernel_paths_vs_oracle(name, B):
     q, qd, qdd = random_states(rb.get_num_vel(), B, seed=7 + B)
     rc, rv, ra, rf = bo.rnea(q, qd, qdd)
     rc0 = bo.rnea(q, qd)[0]
-    for variant in (0, 1):
+    for variant in (0, 1, 2):      # 0: cooperative c-only kernel (small batch) / lane kernel; 1: generic; 2: lane kernel
         RBDReference.set_kernel_variant(variant)
         try:
             for dtype, tol in ((torch.float64, TOL_F64), (torch.float32, TOL_F32)):
