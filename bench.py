@@ -66,6 +66,8 @@ def _cpu_worker_run(args):
             acc += float(impl.forward_dynamics(q[k], qd[k], qdd[k])[0])
         elif op == "fd_grad":
             acc += float(impl.forward_dynamics_grad(q[k], qd[k], qdd[k])[0][0, 0])
+        elif op == "ee_grad":
+            acc += float(np.asarray(impl.end_effector_pose_gradient(q[k])[0])[0, 0])
         else:
             acc += float(impl.rnea(q[k], qd[k], qdd[k])[0][0])
     return acc
@@ -100,7 +102,8 @@ class CpuReference:
 def per_eval_cpu_seconds(robot_name, op):
     """Rough single-core cost used only to size the bounded sample."""
     base = {"iiwa14": 6e-3, "hyq": 9e-3, "atlas": 65e-3}.get(robot_name, 20e-3)
-    return base * {"rnea_grad": 1.0, "minv": 0.15, "rnea": 0.09, "crba": 0.1, "fd": 0.25, "fd_grad": 1.6}[op]
+    return base * {"rnea_grad": 1.0, "minv": 0.15, "rnea": 0.09, "crba": 0.1, "fd": 0.25, "fd_grad": 1.6,
+                   "ee_grad": 0.25}[op]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -196,7 +199,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--robot", default="iiwa14")
-    ap.add_argument("--op", default="rnea_grad", choices=["rnea_grad", "minv", "rnea", "crba", "fd", "fd_grad"])
+    ap.add_argument("--op", default="rnea_grad", choices=["rnea_grad", "minv", "rnea", "crba", "fd", "fd_grad", "ee_grad"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="knot points per GPU")
     ap.add_argument("--variant", type=int, default=0, help="kernel family: 0 auto, 1 generic, 2 world/thread, 3 cooperative, 4 hybrid minv, 5 lane minv, 6 lane2 minv")
@@ -299,6 +302,9 @@ def run_ours(args):
     elif args.op == "fd_grad":
         out = None
         step = lambda: eng.forward_dynamics_grad(q, qd, qdd)
+    elif args.op == "ee_grad":
+        out = None
+        step = lambda: eng.end_effector_pose_gradient(q)          # every leaf joint, default offset
     else:
         out = None
         step = lambda: eng.rnea(q, qd, qdd, outputs="c")
@@ -344,7 +350,7 @@ def run_ours(args):
 
     # ---- e2e: public API with HOST buffers, H2D + kernel + D2H inside the timed region ----
     e2e = None
-    if not args.no_e2e and args.op not in ("fd", "fd_grad"):
+    if not args.no_e2e and args.op not in ("fd", "fd_grad", "ee_grad"):
         e2e = measure_e2e(args, eng, torch, dist, dev, rank, world, n, B, tdtype, itemsize)
 
     # ---- roofline of the dominant (only) kernel: algorithmic flops / bytes per launch ----

@@ -170,6 +170,48 @@ int rbd_aba_f64(const rbd_model_t* m, int64_t B, const double* q, const double* 
 int rbd_aba_f32(const rbd_model_t* m, int64_t B, const float* q, const float* qd, const float* tau,
                 float gravity, float* qdd, void* stream);
 
+/* ---- end-effector kinematics --------------------------------------------- */
+/* end_effector_pose (RBDReference.py:220-283) and end_effector_pose_gradient (:295-386).
+ * The reference takes ee_joint_names / ee_offsets per call and walks the robot's 4x4 homogeneous
+ * joint transforms (get_Xmat_hom_Func_by_id, get_dXmat_hom_Func_by_id) from each end effector to
+ * the base.  Here that selection is compiled once into a handle (rbdreference_b200/model.py probes
+ * the same getters): T_i(q) = TA + TB f1 + TC f2 and dT_i/dq = DA + DB f1 + DC f2 with
+ * (f1, f2) = (cos q, sin q) for kind 0 and (q, 0) for kind 1; only rows 0..2 are passed (row 3 is
+ * (0,0,0,1) for T and zero for dT).  ee_joint[e] is the moving joint the chain of end effector e
+ * starts from, ee_final[e] the rows 0..2 of the fixed-joint transform closing it (identity when a
+ * moving joint was named, get_transformation_matrix_hom() of the fixed joint otherwise, :277-280);
+ * offset is ee_offsets[0] = (x, y, z, w), the only offset the reference uses (:248, :335). */
+#define RBD_MAX_EE 32
+typedef struct RbdEeDesc {
+  int32_t n;                 /* joints                                                        */
+  const int32_t* parent;     /* [n]                                                           */
+  const int32_t* kind;       /* [n]                                                           */
+  const double* TA;          /* [n*12] row-major 3x4                                          */
+  const double* TB;
+  const double* TC;
+  const double* DA;          /* [n*12]                                                        */
+  const double* DB;
+  const double* DC;
+  int32_t n_ee;              /* 1..RBD_MAX_EE, in the reference's output order                */
+  const int32_t* ee_joint;   /* [n_ee]                                                        */
+  const double* ee_final;    /* [n_ee*12]                                                     */
+  double offset[4];
+} RbdEeDesc;
+typedef struct rbd_ee_model rbd_ee_model_t;
+int rbd_ee_model_create(const RbdEeDesc* desc, rbd_ee_model_t** out);
+int rbd_ee_model_destroy(rbd_ee_model_t* m);
+int rbd_ee_model_num_ee(const rbd_ee_model_t* m);
+/* pose (B, n_ee, 6) = [x y z roll pitch yaw] per end effector (the reference returns a list of
+ * (6,1) matrices).  One launch. */
+int rbd_end_effector_pose_f64(const rbd_ee_model_t* m, int64_t B, const double* q, double* pose, void* stream);
+int rbd_end_effector_pose_f32(const rbd_ee_model_t* m, int64_t B, const float* q, float* pose, void* stream);
+/* dpose (B, n_ee, 6, n): column j = d pose / d q_j, zero for joints off the chain (:359-361).
+ * pose (B, n_ee, 6) may be NULL; when given it receives end_effector_pose of the same launch. */
+int rbd_end_effector_pose_gradient_f64(const rbd_ee_model_t* m, int64_t B, const double* q, double* dpose,
+                                       double* pose, void* stream);
+int rbd_end_effector_pose_gradient_f32(const rbd_ee_model_t* m, int64_t B, const float* q, float* dpose,
+                                       float* pose, void* stream);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
 /* Runs a dependent-chain FMA micro-benchmark on `stream`'s device and returns the achieved
  * FLOP/s (2 per FMA) in *flops_per_s; is_f64 selects DFMA or FFMA.  Used only to put a measured

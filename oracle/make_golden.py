@@ -88,6 +88,44 @@ def run_case(name, make, B, seed):
     print("wrote %s (%d states, %.1f KB)" % (path, B, os.path.getsize(path) / 1024))
 
 
+# end-effector kinematics (RBDReference.py:190-386): which end effectors each golden case requests
+EE_SPECS = {
+    "iiwa14": [None, ["iiwa_joint_ee", "iiwa_joint_4", "iiwa_tool_tip"]],
+    "hyq": [None, ["rh_foot_joint", "lf_hfe_joint"]],
+    "atlas": [None, ["l_hand_mount", "back_bkx", "head_camera", "r_leg_akx"]],
+    "tree9": [None],
+    "tree13": [None, ["j5", "j12"]],
+}
+EE_OFFSETS = [(0.0, 0.0, 0.0, 1.0), (0.1, -0.2, 0.3, 1.0)]
+
+
+def run_ee_case(name, make, B, seed):
+    """tests/golden/ee_<name>.npz: end_effector_pose / _gradient of the unmodified reference."""
+    import json
+    import warnings
+    warnings.simplefilter("ignore")          # the reference builds np.matrix objects
+    rb = make()
+    ref = RBDReference(rb)
+    n = rb.get_num_vel()
+    q = np.random.default_rng(seed).uniform(-np.pi, np.pi, (B, n))
+    out = dict(q=q, specs=np.array(json.dumps(EE_SPECS[name])), offsets=np.array(EE_OFFSETS))
+    for si, names in enumerate(EE_SPECS[name]):
+        for oi, off in enumerate(EE_OFFSETS):
+            offs = [np.matrix([list(off)])]
+            pose = np.stack([np.stack([np.asarray(p)[:, 0] for p in ref.end_effector_pose(q[k], names, offs)])
+                             for k in range(B)])
+            grad = np.stack([np.stack([np.asarray(g) for g in ref.end_effector_pose_gradient(q[k], names, offs)])
+                             for k in range(B)])
+            out["pose_s%d_o%d" % (si, oi)] = pose
+            out["grad_s%d_o%d" % (si, oi)] = grad
+    path = os.path.join(ROOT, "tests", "golden", "ee_" + name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s (%d states, %.1f KB)" % (path, B, os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
+    only_ee = "--ee" in sys.argv          # regenerate only the end-effector fixtures
     for idx, (name, make, B) in enumerate(CASES):
-        run_case(name, make, B, seed=1000 + idx)
+        if not only_ee:
+            run_case(name, make, B, seed=1000 + idx)
+        run_ee_case(name, make, B, seed=2000 + idx)

@@ -345,6 +345,93 @@ class ScalarOracle:
             a[:, i] = a[:, i] + qdd[i] * self.S[i]                      # :1022
         return qdd
 
+    # -- end-effector kinematics ---------------------------------------
+    def select_end_effector_joints(self, ee_joint_names):
+        """RBDReference.py:190-211: leaf joints by default, else moving joints first, then fixed joints."""
+        if ee_joint_names is None:
+            return list(self.robot.get_leaf_nodes()), []
+        ee_jids, fixed_jids = [], []
+        for name in ee_joint_names:
+            joint = self.robot.get_joint_by_name(name)
+            if joint is not None:
+                ee_jids.append(joint.get_id())
+            else:
+                fjoint = self.robot.get_fixed_joint_by_name(name)
+                if fjoint is None:
+                    raise ValueError("Could not find joint or fixed joint named: " + name)   # :208
+                fixed_jids.append(fjoint.get_id())
+        return ee_jids, fixed_jids
+
+    def _ee_targets(self, ee_joint_names):
+        """(leaf joint id, final 4x4) per requested end effector, in the reference's output order."""
+        ee_jids, fixed_jids = self.select_end_effector_joints(ee_joint_names)
+        out = [(jid, np.eye(4)) for jid in ee_jids]
+        for fjid in fixed_jids:
+            fj = self.robot.get_fixed_joint_by_id(fjid)                                        # :277
+            parent = self.robot.get_joint_by_name(fj.parent_name)                              # :278
+            out.append((parent.get_id(), np.asarray(fj.get_transformation_matrix_hom(), dtype=float)))
+        return out
+
+    @staticmethod
+    def _ee_offset(ee_offsets):
+        return np.asarray(ee_offsets[0], dtype=float).reshape(4)    # only offsets[0] is used (:248, :335)
+
+    def _ee_chain(self, jid, q, final, dind=None):
+        """backwardChain / dbackward_chain, RBDReference.py:235-243, :312-324."""
+        X = np.array(final, dtype=float)
+        dX = np.array(final, dtype=float)
+        cur = jid
+        while cur != -1:
+            T = np.asarray(self.robot.get_Xmat_hom_Func_by_id(cur)(q[cur]), dtype=float)
+            dT = np.asarray(self.robot.get_dXmat_hom_Func_by_id(cur)(q[cur]), dtype=float) if cur == dind else T
+            dX = dT @ dX
+            X = T @ X
+            cur = self.parent[cur]
+        return X, dX
+
+    @staticmethod
+    def _ee_pose_from(X, off):
+        """xyz of the offset point and roll-pitch-yaw of the rotation, RBDReference.py:247-260."""
+        xyz = (X @ off)[:3]
+        roll = np.arctan2(X[2, 1], X[2, 2])
+        pitch = np.arctan2(-X[2, 0], np.sqrt(X[2, 2] * X[2, 2] + X[2, 1] * X[2, 1]))
+        yaw = np.arctan2(X[1, 0], X[0, 0])
+        return np.concatenate((xyz, [roll, pitch, yaw]))
+
+    @staticmethod
+    def _ee_dpose_from(X, dX, off):
+        """One column of the pose gradient, RBDReference.py:327-351."""
+        def darctan2(y, x, yp, xp):
+            return (-xp * y + x * yp) / (x * x + y * y)
+        dxyz = (dX @ off)[:3]
+        droll = darctan2(X[2, 1], X[2, 2], dX[2, 1], dX[2, 2])
+        sq = np.sqrt(X[2, 2] * X[2, 2] + X[2, 1] * X[2, 1])
+        dsq = (X[2, 2] * dX[2, 2] + X[2, 1] * dX[2, 1]) / sq
+        dpitch = darctan2(-X[2, 0], sq, -dX[2, 0], dsq)
+        dyaw = darctan2(X[1, 0], X[0, 0], dX[1, 0], dX[0, 0])
+        return np.concatenate((dxyz, [droll, dpitch, dyaw]))
+
+    def end_effector_pose(self, q, ee_joint_names=None, ee_offsets=((0, 0, 0, 1),)):
+        """RBDReference.py:220-283 -> list over end effectors of (6, 1) [x y z roll pitch yaw]."""
+        off = self._ee_offset(ee_offsets)
+        return [self._ee_pose_from(self._ee_chain(jid, q, fin)[0], off).reshape(6, 1)
+                for jid, fin in self._ee_targets(ee_joint_names)]
+
+    def end_effector_pose_gradient(self, q, ee_joint_names=None, ee_offsets=((0, 0, 0, 1),)):
+        """RBDReference.py:295-386 -> list over end effectors of (6, n); zero columns off the chain."""
+        off = self._ee_offset(ee_offsets)
+        n = self.robot.get_num_joints()
+        out = []
+        for jid, fin in self._ee_targets(ee_joint_names):
+            chain = set(self.robot.get_ancestors_by_id(jid)) | {jid}
+            G = np.zeros((6, n))
+            for dind in range(n):
+                if dind in chain:
+                    X, dX = self._ee_chain(jid, q, fin, dind)
+                    G[:, dind] = self._ee_dpose_from(X, dX, off)
+            out.append(G)
+        return out
+
 
 # ----------------------------------------------------------------------------------------
 # batched oracle: the same recursions vectorised over a leading batch axis
@@ -644,3 +731,77 @@ class BatchOracle:
             qdd[:, i] = (u[i] - np.einsum("bi,bi->b", U[i], ai)) / d[i]
             a[i] = ai + qdd[:, i:i + 1] * self.S[i]
         return qdd
+
+    # -- end-effector kinematics, vectorised (same chain products as ScalarOracle) ---------------
+    def _fit_hom(self):
+        """T(q) and dT(q) of every joint as A + B cos q + C sin q / A + B q, by probing."""
+        if hasattr(self, "_hom"):
+            return self._hom
+        rng = np.random.default_rng(999)
+        out = []
+        for i in range(self.NB):
+            coefs = []
+            for getter in (self.robot.get_Xmat_hom_Func_by_id, self.robot.get_dXmat_hom_Func_by_id):
+                fn = getter(i)
+                T0 = np.asarray(fn(0.0), dtype=float)
+                if self.kind[i]:
+                    Th, Tp = np.asarray(fn(np.pi / 2), dtype=float), np.asarray(fn(np.pi), dtype=float)
+                    A, Bm = 0.5 * (T0 + Tp), 0.5 * (T0 - Tp)
+                    C = Th - A
+                else:
+                    A, Bm, C = T0, np.asarray(fn(1.0), dtype=float) - T0, np.zeros((4, 4))
+                for t in rng.uniform(-3.0, 3.0, size=4):
+                    f1, f2 = (np.cos(t), np.sin(t)) if self.kind[i] else (t, 0.0)
+                    if np.max(np.abs(A + Bm * f1 + C * f2 - np.asarray(fn(t), dtype=float))) > 1e-12 * max(1.0, np.max(np.abs(T0))):
+                        raise ValueError("joint %d: homogeneous transform is not of 1-DoF form" % i)
+                coefs.append((A.astype(self.dtype), Bm.astype(self.dtype), C.astype(self.dtype)))
+            out.append(coefs)
+        self._hom = out
+        return out
+
+    def _hom_eval(self, i, qi, which):
+        A, Bm, C = self._fit_hom()[i][which]
+        if self.kind[i]:
+            return A + np.cos(qi)[:, None, None] * Bm + np.sin(qi)[:, None, None] * C
+        return A + qi[:, None, None] * Bm
+
+    def end_effector_pose(self, q, ee_joint_names=None, ee_offsets=((0, 0, 0, 1),), gradient=False):
+        """-> pose (B, n_ee, 6) [and gradient (B, n_ee, 6, n)]."""
+        (q,) = self._prep(q)
+        B, n = q.shape[0], self.n
+        so = ScalarOracle(self.robot)
+        targets = so._ee_targets(ee_joint_names)
+        off = so._ee_offset(ee_offsets).astype(self.dtype)
+        pose = np.zeros((B, len(targets), 6), dtype=self.dtype)
+        grad = np.zeros((B, len(targets), 6, n), dtype=self.dtype)
+
+        def darctan2(y, x, yp, xp):
+            return (-xp * y + x * yp) / (x * x + y * y)
+
+        for e, (jid, fin) in enumerate(targets):
+            chain = [jid] + list(self.robot.get_ancestors_by_id(jid))
+            chain = sorted(chain, reverse=True)            # leaf first (ids are topologically ordered)
+            T = {k: self._hom_eval(k, q[:, k], 0) for k in chain}
+            X = np.broadcast_to(np.asarray(fin, dtype=self.dtype), (B, 4, 4))
+            for k in chain:
+                X = T[k] @ X
+            pose[:, e, :3] = (X @ off)[:, :3]
+            pose[:, e, 3] = np.arctan2(X[:, 2, 1], X[:, 2, 2])
+            sq = np.sqrt(X[:, 2, 2] * X[:, 2, 2] + X[:, 2, 1] * X[:, 2, 1])
+            pose[:, e, 4] = np.arctan2(-X[:, 2, 0], sq)
+            pose[:, e, 5] = np.arctan2(X[:, 1, 0], X[:, 0, 0])
+            if not gradient:
+                continue
+            for dind in chain:
+                dX = np.broadcast_to(np.asarray(fin, dtype=self.dtype), (B, 4, 4))
+                for k in chain:
+                    dX = (self._hom_eval(k, q[:, k], 1) if k == dind else T[k]) @ dX
+                grad[:, e, :3, dind] = (dX @ off)[:, :3]
+                grad[:, e, 3, dind] = darctan2(X[:, 2, 1], X[:, 2, 2], dX[:, 2, 1], dX[:, 2, 2])
+                dsq = (X[:, 2, 2] * dX[:, 2, 2] + X[:, 2, 1] * dX[:, 2, 1]) / sq
+                grad[:, e, 4, dind] = darctan2(-X[:, 2, 0], sq, -dX[:, 2, 0], dsq)
+                grad[:, e, 5, dind] = darctan2(X[:, 1, 0], X[:, 0, 0], dX[:, 1, 0], dX[:, 0, 0])
+        return (pose, grad) if gradient else pose
+
+    def end_effector_pose_gradient(self, q, ee_joint_names=None, ee_offsets=((0, 0, 0, 1),)):
+        return self.end_effector_pose(q, ee_joint_names, ee_offsets, gradient=True)[1]

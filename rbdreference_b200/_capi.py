@@ -15,13 +15,15 @@ PASS_SYMBOLS = ["rnea_fpass", "rnea_bpass", "rnea_grad_fpass_dq", "rnea_grad_fpa
 FUSED_SYMBOLS = ["rnea", "rnea_grad", "minv", "forward_dynamics", "forward_dynamics_grad", "crba", "aba"]
 PLAIN_SYMBOLS = ["rbd_abi_version", "rbd_last_error_string", "rbd_model_create", "rbd_model_destroy",
                  "rbd_model_num_dof", "rbd_model_uses_world_kernels", "rbd_set_kernel_variant",
-                 "rbd_measure_fma_peak", "rbd_launch_count"]
+                 "rbd_measure_fma_peak", "rbd_launch_count",
+                 "rbd_ee_model_create", "rbd_ee_model_destroy", "rbd_ee_model_num_ee"]
+EE_SYMBOLS = ["end_effector_pose", "end_effector_pose_gradient"]
 
 
 def exported_symbols():
     """Every symbol include/rbd_b200.h declares."""
     out = list(PLAIN_SYMBOLS)
-    for base in FUSED_SYMBOLS + PASS_SYMBOLS:
+    for base in FUSED_SYMBOLS + PASS_SYMBOLS + EE_SYMBOLS:
         out += ["rbd_%s_f64" % base, "rbd_%s_f32" % base]
     return out
 
@@ -31,6 +33,14 @@ class RbdModelDesc(ctypes.Structure):
                 ("parent", POINTER(c_int32)), ("kind", POINTER(c_int32)),
                 ("S", POINTER(c_double)), ("XA", POINTER(c_double)), ("XB", POINTER(c_double)),
                 ("XC", POINTER(c_double)), ("I", POINTER(c_double)), ("damping", POINTER(c_double))]
+
+
+class RbdEeDesc(ctypes.Structure):
+    _fields_ = [("n", c_int32), ("parent", POINTER(c_int32)), ("kind", POINTER(c_int32)),
+                ("TA", POINTER(c_double)), ("TB", POINTER(c_double)), ("TC", POINTER(c_double)),
+                ("DA", POINTER(c_double)), ("DB", POINTER(c_double)), ("DC", POINTER(c_double)),
+                ("n_ee", c_int32), ("ee_joint", POINTER(c_int32)), ("ee_final", POINTER(c_double)),
+                ("offset", c_double * 4)]
 
 
 class RbdError(RuntimeError):
@@ -59,6 +69,9 @@ def load_library():
     lib.rbd_set_kernel_variant.argtypes = [c_int]
     lib.rbd_measure_fma_peak.argtypes = [c_int, POINTER(c_double), POINTER(c_double), c_void_p]
     lib.rbd_launch_count.restype = c_int64
+    lib.rbd_ee_model_create.argtypes = [POINTER(RbdEeDesc), POINTER(c_void_p)]
+    lib.rbd_ee_model_destroy.argtypes = [c_void_p]
+    lib.rbd_ee_model_num_ee.argtypes = [c_void_p]
     P = c_void_p
     for suf, real in (("f64", c_double), ("f32", c_float)):
         sig = {
@@ -77,6 +90,8 @@ def load_library():
             "forward_dynamics_grad": [P, c_int64, P, P, P, P, P, P, P],
             "crba": [P, c_int64, P, P, P],
             "aba": [P, c_int64, P, P, P, real, P, P],
+            "end_effector_pose": [P, c_int64, P, P, P],
+            "end_effector_pose_gradient": [P, c_int64, P, P, P, P],
         }
         for base, argtypes in sig.items():
             fn = getattr(lib, "rbd_%s_%s" % (base, suf))
@@ -129,6 +144,34 @@ class ModelHandle:
         try:
             if getattr(self, "ptr", None):
                 self._lib.rbd_model_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class EeModelHandle:
+    """Owns an rbd_ee_model_t* created from a compiled EeModel (model.compile_ee_model)."""
+
+    def __init__(self, ee):
+        lib = load_library()
+        k = self._keep = {name: np.ascontiguousarray(getattr(ee, name), dtype=np.float64)
+                          for name in ("TA", "TB", "TC", "DA", "DB", "DC", "ee_final")}
+        k["parent"] = np.ascontiguousarray(ee.parent, dtype=np.int32)
+        k["kind"] = np.ascontiguousarray(ee.kind, dtype=np.int32)
+        k["ee_joint"] = np.ascontiguousarray(ee.ee_joint, dtype=np.int32)
+        desc = RbdEeDesc(ee.n, _iptr(k["parent"]), _iptr(k["kind"]), _dptr(k["TA"]), _dptr(k["TB"]), _dptr(k["TC"]),
+                         _dptr(k["DA"]), _dptr(k["DB"]), _dptr(k["DC"]), ee.n_ee, _iptr(k["ee_joint"]),
+                         _dptr(k["ee_final"]), (c_double * 4)(*[float(x) for x in ee.offset]))
+        handle = c_void_p()
+        check(lib.rbd_ee_model_create(ctypes.byref(desc), ctypes.byref(handle)), "rbd_ee_model_create")
+        self.ptr = handle
+        self.n_ee = ee.n_ee
+        self._lib = lib
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None):
+                self._lib.rbd_ee_model_destroy(self.ptr)
                 self.ptr = None
         except Exception:
             pass

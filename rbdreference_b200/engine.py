@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from .model import RobotModel, compile_model
+from .model import RobotModel, compile_ee_model, compile_model, select_end_effector_joints
 
 __all__ = ["RBDReference"]
 
@@ -51,6 +51,7 @@ class RBDReference:
         self._lib = _capi.load_library()            # raises if the CUDA library is missing
         self._handle = _capi.ModelHandle(self.model)
         self._device = torch.device(device) if device is not None else None
+        self._ee_handles = {}                       # (names, offset) -> compiled end-effector handle
 
     # ------------------------------------------------------------------------------------
     # plumbing
@@ -127,7 +128,7 @@ class RBDReference:
             np.copyto(target, t.cpu().numpy().astype(target.dtype, copy=False))
             return target
 
-    def _call(self, name: str, ctx: "_Ctx", *args):
+    def _call(self, name: str, ctx: "_Ctx", *args, handle=None):
         if ctx.B == 0:
             return                                   # empty batch: nothing to launch
         fn = getattr(self._lib, "rbd_%s_%s" % (name, self._suffix))
@@ -139,7 +140,7 @@ class RBDReference:
                 conv.append(a)
         with torch.cuda.device(ctx.device):
             stream = torch.cuda.current_stream(ctx.device).cuda_stream
-            rc = fn(self._handle.ptr, ctx.B, *conv, stream)
+            rc = fn((handle or self._handle).ptr, ctx.B, *conv, stream)
         _capi.check(rc, "rbd_%s_%s" % (name, self._suffix))
 
     # ------------------------------------------------------------------------------------
@@ -333,6 +334,60 @@ class RBDReference:
         H = out if (out is not None and ctx.kind == "torch" and ctx.batched) else ctx.empty(n, n)
         self._call("crba", ctx, dq, H)
         return ctx.ret(H)
+
+    # ------------------------------------------------------------------------------------
+    # end-effector kinematics
+    # ------------------------------------------------------------------------------------
+    def select_end_effector_joints(self, ee_joint_names):
+        """RBDReference.py:190-211 -> (ee_jids, fixed_jids); ValueError for an unknown name."""
+        if isinstance(self.robot, RobotModel):
+            raise ValueError("end-effector kinematics need the robot object, not a compiled RobotModel")
+        return select_end_effector_joints(self.robot, ee_joint_names)
+
+    def _ee_handle(self, ee_joint_names, ee_offsets):
+        if isinstance(self.robot, RobotModel):
+            raise ValueError("end-effector kinematics need the robot object, not a compiled RobotModel")
+        off = (0.0, 0.0, 0.0, 1.0) if ee_offsets is None else tuple(
+            float(x) for x in np.asarray(ee_offsets[0], dtype=np.float64).reshape(-1))
+        key = (None if ee_joint_names is None else tuple(ee_joint_names), off)
+        h = self._ee_handles.get(key)
+        if h is None:
+            h = _capi.EeModelHandle(compile_ee_model(self.robot, ee_joint_names, [off]))
+            self._ee_handles[key] = h
+        return h
+
+    def end_effector_pose(self, q, ee_joint_names=None, ee_offsets=None):
+        """RBDReference.py:220-283.  One knot point -> list over end effectors of (6, 1) arrays
+        [x y z roll pitch yaw] (the reference returns np.matrix objects of that shape); batched
+        q (B, n) -> (B, n_ee, 6).  `ee_offsets=None` is the reference's default [[0, 0, 0, 1]]; as
+        upstream only ee_offsets[0] is used."""
+        h = self._ee_handle(ee_joint_names, ee_offsets)
+        ctx = self._Ctx(self, q, 1)
+        dq = ctx.dev(q, (self.n,), "q")
+        pose = ctx.empty(h.n_ee, 6)
+        self._call("end_effector_pose", ctx, dq, pose, handle=h)
+        out = ctx.ret(pose)
+        if not ctx.batched:
+            return [out[e].reshape(6, 1) for e in range(h.n_ee)]
+        return out
+
+    def end_effector_pose_gradient(self, q, ee_joint_names=None, ee_offsets=None, return_pose=False):
+        """RBDReference.py:295-386.  One knot point -> list over end effectors of (6, n) arrays;
+        batched -> (B, n_ee, 6, n).  `return_pose=True` (extension) also returns the pose computed by
+        the same launch."""
+        h = self._ee_handle(ee_joint_names, ee_offsets)
+        ctx = self._Ctx(self, q, 1)
+        n = self.n
+        dq = ctx.dev(q, (n,), "q")
+        grad = ctx.empty(h.n_ee, 6, n)
+        pose = ctx.empty(h.n_ee, 6) if return_pose else None
+        self._call("end_effector_pose_gradient", ctx, dq, grad, pose, handle=h)
+        g = ctx.ret(grad)
+        p = ctx.ret(pose)
+        if not ctx.batched:
+            g = [g[e] for e in range(h.n_ee)]
+            p = None if p is None else [p[e].reshape(6, 1) for e in range(h.n_ee)]
+        return (g, p) if return_pose else g
 
     # ------------------------------------------------------------------------------------
     def uses_world_kernels(self) -> bool:

@@ -25,7 +25,9 @@ import numpy as np
 
 MAX_DOF = 32  # kernel-parameter model limit (include/rbd_b200.h: RBD_MAX_DOF)
 
-__all__ = ["RobotModel", "compile_model", "MAX_DOF"]
+MAX_EE = 32   # include/rbd_b200.h: RBD_MAX_EE
+
+__all__ = ["RobotModel", "EeModel", "compile_model", "compile_ee_model", "select_end_effector_joints", "MAX_DOF", "MAX_EE"]
 
 
 @dataclasses.dataclass
@@ -76,6 +78,13 @@ class RobotModel:
             # X build 54 per body; X^T IC X + add = 2 * 396 + 36 per non-root body (:1100-1103);
             # IC S and S.fh = 66 + 11 per body, X^T fh and S.fh = 66 + 11 per (body, ancestor) pair (:1108-1122)
             return int(54 * n + 828 * np.sum(nr) + np.sum(77 + 77 * P))
+        if op == "ee_grad":
+            # end_effector_pose_gradient over every leaf (:295-386): per chain joint a 4x4 build (24) and,
+            # per derivative column, a full chain of 3x4 affine products (63 each, :312-324) plus the
+            # column extraction (:327-351, ~40)
+            leaves = [i for i in range(n) if not np.any(self.parent == i)]
+            L = A[leaves]
+            return int(np.sum(24 * L + L * (63 * L + 40)))
         raise KeyError(op)
 
     def io_bytes(self, op: str, itemsize: int = 8, full_rnea: bool = False) -> int:
@@ -91,6 +100,9 @@ class RobotModel:
             return (3 * n + n) * itemsize
         if op == "fd_grad":
             return (3 * n + 2 * n * n) * itemsize
+        if op == "ee_grad":
+            n_ee = sum(1 for i in range(n) if not np.any(self.parent == i))
+            return (n + n_ee * 6 * n) * itemsize
         raise KeyError(op)
 
 
@@ -190,3 +202,118 @@ def compile_model(robot, name: str | None = None, check_points: int = 6) -> Robo
     return RobotModel(name=name or getattr(robot, "name", "robot"), n=n, parent=parent, kind=kind, S=S,
                       XA=XA, XB=XB, XC=XC, I=I, damping=damping, anc_mask=anc_mask, subtree=subtree,
                       depth=depth, levels=levels)
+
+
+# ----------------------------------------------------------------------------------------------
+# end-effector kinematics (RBDReference.py:190-386)
+# ----------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class EeModel:
+    """Flat tables behind rbd_ee_model_create (include/rbd_b200.h: RbdEeDesc)."""
+    n: int
+    parent: np.ndarray      # (n,) int32
+    kind: np.ndarray        # (n,) int32
+    TA: np.ndarray          # (n,12) rows 0..2 of get_Xmat_hom_Func_by_id(i)(q) = TA + TB f1 + TC f2
+    TB: np.ndarray
+    TC: np.ndarray
+    DA: np.ndarray          # (n,12) the same for get_dXmat_hom_Func_by_id
+    DB: np.ndarray
+    DC: np.ndarray
+    ee_joint: np.ndarray    # (n_ee,) int32: moving joint each chain starts from
+    ee_final: np.ndarray    # (n_ee,12) fixed-joint transform closing the chain (identity rows otherwise)
+    offset: np.ndarray      # (4,) ee_offsets[0]
+
+    @property
+    def n_ee(self) -> int:
+        return int(self.ee_joint.shape[0])
+
+
+def select_end_effector_joints(robot, ee_joint_names):
+    """RBDReference.py:190-211: all leaf joints by default; otherwise the named moving joints followed
+    by the named fixed joints.  Raises the reference's ValueError for an unknown name (:208)."""
+    if ee_joint_names is None:
+        return [int(j) for j in robot.get_leaf_nodes()], []
+    ee_jids, fixed_jids = [], []
+    for name in ee_joint_names:
+        joint = robot.get_joint_by_name(name)
+        if joint is not None:
+            ee_jids.append(int(joint.get_id()))
+        else:
+            fjoint = robot.get_fixed_joint_by_name(name)
+            if fjoint is None:
+                raise ValueError("Could not find joint or fixed joint named: " + name)
+            fixed_jids.append(int(fjoint.get_id()))
+    return ee_jids, fixed_jids
+
+
+def _fit_hom(fn, affine: bool, rng, what: str, last_row) -> tuple:
+    """Recover A, B, C of a 4x4 joint function (A + B cos q + C sin q, or A + B q) by probing."""
+    M0 = np.asarray(fn(0.0), dtype=np.float64).reshape(4, 4)
+    if affine:
+        A, Bm, C = M0, np.asarray(fn(1.0), dtype=np.float64).reshape(4, 4) - M0, np.zeros((4, 4))
+    else:
+        Mh = np.asarray(fn(np.pi / 2), dtype=np.float64).reshape(4, 4)
+        Mp = np.asarray(fn(np.pi), dtype=np.float64).reshape(4, 4)
+        A, Bm = 0.5 * (M0 + Mp), 0.5 * (M0 - Mp)
+        C = Mh - A
+    tol = 1e-11 * max(1.0, float(np.max(np.abs(M0))))
+    for t in rng.uniform(-3.0, 3.0, size=6):
+        f1, f2 = (t, 0.0) if affine else (np.cos(t), np.sin(t))
+        Mt = np.asarray(fn(t), dtype=np.float64).reshape(4, 4)
+        if np.max(np.abs(A + f1 * Bm + f2 * C - Mt)) > tol:
+            raise ValueError("%s is not A + B*cos(q) + C*sin(q) / A + B*q" % what)
+        if np.max(np.abs(Mt[3] - np.asarray(last_row, dtype=np.float64))) > tol:
+            raise ValueError("%s: fourth row must be %s" % (what, list(last_row)))
+    out = []
+    for M in (A, Bm, C):
+        M = M[:3].reshape(12).copy()
+        M[np.abs(M) < 1e-15] = 0.0
+        out.append(M)
+    return tuple(out)
+
+
+def compile_ee_model(robot, ee_joint_names=None, ee_offsets=None) -> EeModel:
+    """Compile an end-effector selection (the per-call arguments of end_effector_pose /
+    end_effector_pose_gradient, RBDReference.py:220, :295) into flat tables."""
+    if getattr(robot, "floating_base", False):
+        raise NotImplementedError("end-effector kinematics: floating base is a TODO upstream (RBDReference.py:217, :287)")
+    n = int(robot.get_num_joints())
+    if not (1 <= n <= MAX_DOF):
+        raise ValueError("robot has %d joints; supported range is 1..%d" % (n, MAX_DOF))
+    parent = np.array([int(robot.get_parent_id(i)) for i in range(n)], dtype=np.int32)
+    for i in range(n):
+        if not (-1 <= parent[i] < i):
+            raise ValueError("joint ids must be topologically ordered (parent id < child id)")
+    rng = np.random.default_rng(20261018)
+    kind = np.zeros(n, dtype=np.int32)
+    tabs = {k: np.zeros((n, 12)) for k in ("TA", "TB", "TC", "DA", "DB", "DC")}
+    for i in range(n):
+        S = np.asarray(robot.get_S_by_id(i), dtype=np.float64).reshape(-1)
+        kind[i] = 0 if np.any(S[:3] != 0) else 1
+        tabs["TA"][i], tabs["TB"][i], tabs["TC"][i] = _fit_hom(
+            robot.get_Xmat_hom_Func_by_id(i), kind[i] == 1, rng, "joint %d: Xmat_hom(q)" % i, (0, 0, 0, 1))
+        tabs["DA"][i], tabs["DB"][i], tabs["DC"][i] = _fit_hom(
+            robot.get_dXmat_hom_Func_by_id(i), kind[i] == 1, rng, "joint %d: dXmat_hom(q)" % i, (0, 0, 0, 0))
+    ee_jids, fixed_jids = select_end_effector_joints(robot, ee_joint_names)
+    ee_joint, ee_final = [], []
+    for jid in ee_jids:
+        ee_joint.append(jid)
+        ee_final.append(np.eye(4)[:3].reshape(12))
+    for fjid in fixed_jids:                       # RBDReference.py:276-281
+        fj = robot.get_fixed_joint_by_id(fjid)
+        pj = robot.get_joint_by_name(fj.parent_name)
+        F = np.asarray(fj.get_transformation_matrix_hom(), dtype=np.float64).reshape(4, 4)
+        if np.max(np.abs(F[3] - np.array([0.0, 0.0, 0.0, 1.0]))) > 1e-12:
+            raise ValueError("fixed joint %r: fourth row of its transform must be [0, 0, 0, 1]" % fj.name)
+        ee_joint.append(int(pj.get_id()))
+        ee_final.append(F[:3].reshape(12))
+    if not (1 <= len(ee_joint) <= MAX_EE):
+        raise ValueError("%d end effectors requested; supported range is 1..%d" % (len(ee_joint), MAX_EE))
+    if ee_offsets is None:
+        offset = np.array([0.0, 0.0, 0.0, 1.0])
+    else:
+        offset = np.asarray(ee_offsets[0], dtype=np.float64).reshape(-1)      # only offsets[0] is used upstream
+        if offset.shape != (4,):
+            raise ValueError("ee_offsets[0] must have 4 entries (x, y, z, 1)")
+    return EeModel(n=n, parent=parent, kind=kind, ee_joint=np.array(ee_joint, dtype=np.int32),
+                   ee_final=np.stack(ee_final), offset=offset, **tabs)

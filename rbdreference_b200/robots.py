@@ -27,7 +27,7 @@ from typing import Callable, Dict, List, Sequence
 
 import numpy as np
 
-__all__ = ["Robot", "JointSpec", "iiwa14", "hyq", "atlas", "random_tree", "by_name"]
+__all__ = ["Robot", "JointSpec", "FixedJoint", "JointHandle", "iiwa14", "hyq", "atlas", "random_tree", "by_name"]
 
 
 # ----------------------------------------------------------------------------------------
@@ -99,6 +99,39 @@ class JointSpec:
         self.damping = float(damping)
 
 
+class JointHandle:
+    """What `robot.get_joint_by_name` hands back (RBDReference.py:204-206 only calls get_id)."""
+
+    def __init__(self, jid: int, name: str):
+        self._id = int(jid)
+        self.name = name
+
+    def get_id(self) -> int:
+        return self._id
+
+
+class FixedJoint:
+    """A fixed joint hanging off the child link of a moving joint (e.g. a tool flange):
+    `parent_name` names that moving joint, the transform maps flange-frame points to its frame
+    (RBDReference.py:277-280, :374-386)."""
+
+    def __init__(self, name, parent_name, xyz=(0.0, 0.0, 0.0), rpy=(0.0, 0.0, 0.0)):
+        self.name = name
+        self.parent_name = parent_name
+        self.xyz = np.asarray(xyz, dtype=float)
+        self.rpy = np.asarray(rpy, dtype=float)
+        self._id = -1
+
+    def get_id(self) -> int:
+        return self._id
+
+    def get_transformation_matrix_hom(self) -> np.ndarray:
+        T = np.eye(4)
+        T[:3, :3] = rpy_transform(self.rpy).T
+        T[:3, 3] = self.xyz
+        return T
+
+
 class Robot:
     """Duck-typed stand-in for a URDFParser robot (fixed base, 1-DoF joints).
 
@@ -108,7 +141,7 @@ class Robot:
 
     floating_base = False
 
-    def __init__(self, name: str, joints: List[JointSpec]):
+    def __init__(self, name: str, joints: List[JointSpec], fixed_joints=None):
         self.name = name
         self.joints = joints
         n = len(joints)
@@ -137,6 +170,14 @@ class Robot:
                 self._children[p].append(i)
         self._subtree = [self._collect_subtree(i) for i in range(n)]
         self._Xfuncs = [self._make_xfunc(i) for i in range(n)]
+        self._hom_funcs = [[self._make_hom_func(i, order) for i in range(n)] for order in range(3)]
+        self._joint_handles = [JointHandle(i, j.name) for i, j in enumerate(joints)]
+        self._fixed_joints = []
+        for fid, fj in enumerate(fixed_joints or []):
+            if fj.parent_name not in [j.name for j in joints]:
+                raise ValueError("fixed joint %r: unknown parent joint %r" % (fj.name, fj.parent_name))
+            fj._id = fid
+            self._fixed_joints.append(fj)
 
     # -- construction helpers -------------------------------------------------------------
     def _collect_subtree(self, i: int) -> List[int]:
@@ -156,6 +197,40 @@ class Robot:
             def xfunc(q, _axis=axis, _Xtree=Xtree):
                 return xlt(_axis * float(q)) @ _Xtree
         return xfunc
+
+    def _make_hom_func(self, i: int, order: int) -> Callable[[float], np.ndarray]:
+        """4x4 homogeneous transform of joint i (child-frame point -> parent-frame point) or its
+        first / second derivative in q: the point-transform counterpart of `Xmat(q)`."""
+        j = self.joints[i]
+        Rt = rpy_transform(j.rpy).T            # Etree^T
+        K = skew(j.axis)
+        K2 = K @ K
+        r = j.xyz
+        if j.kind == "revolute":
+            def hom(q, _Rt=Rt, _K=K, _K2=K2, _r=r, _o=order):
+                s, c = math.sin(float(q)), math.cos(float(q))
+                T = np.zeros((4, 4))
+                if _o == 0:
+                    T[:3, :3] = _Rt @ (np.eye(3) + s * _K + (1.0 - c) * _K2)
+                    T[:3, 3] = _r
+                    T[3, 3] = 1.0
+                elif _o == 1:
+                    T[:3, :3] = _Rt @ (c * _K + s * _K2)
+                else:
+                    T[:3, :3] = _Rt @ (-s * _K + c * _K2)
+                return T
+        else:
+            d = Rt @ j.axis
+            def hom(q, _Rt=Rt, _d=d, _r=r, _o=order):
+                T = np.zeros((4, 4))
+                if _o == 0:
+                    T[:3, :3] = _Rt
+                    T[:3, 3] = _r + _d * float(q)
+                    T[3, 3] = 1.0
+                elif _o == 1:
+                    T[:3, 3] = _d
+                return T
+        return hom
 
     # -- URDFParser getter surface (SURVEY.md 8b) -----------------------------------------
     def get_num_bodies(self) -> int:
@@ -214,6 +289,34 @@ class Robot:
     def get_joint_names(self) -> List[str]:
         return [j.name for j in self.joints]
 
+    # -- getters used by the end-effector kinematics (RBDReference.py:190-386) -------------
+    def get_Xmat_hom_Func_by_id(self, i: int) -> Callable[[float], np.ndarray]:
+        return self._hom_funcs[0][i]
+
+    def get_dXmat_hom_Func_by_id(self, i: int) -> Callable[[float], np.ndarray]:
+        return self._hom_funcs[1][i]
+
+    def get_d2Xmat_hom_Func_by_id(self, i: int) -> Callable[[float], np.ndarray]:
+        return self._hom_funcs[2][i]
+
+    def get_leaf_nodes(self) -> List[int]:
+        return [i for i in range(self._n) if not self._children[i]]
+
+    def get_joint_by_name(self, name: str):
+        for h in self._joint_handles:
+            if h.name == name:
+                return h
+        return None
+
+    def get_fixed_joint_by_name(self, name: str):
+        for fj in self._fixed_joints:
+            if fj.name == name:
+                return fj
+        return None
+
+    def get_fixed_joint_by_id(self, fid: int):
+        return self._fixed_joints[fid]
+
 
 # ----------------------------------------------------------------------------------------
 # benchmark robots
@@ -237,7 +340,9 @@ def iiwa14() -> Robot:
     for i, (xyz, rpy, m, com, idiag) in enumerate(rows):
         joints.append(JointSpec("iiwa_joint_%d" % (i + 1), i - 1, "revolute", (0, 0, 1), xyz, rpy,
                                 m, com, idiag, damping=0.5))
-    return Robot("iiwa14", joints)
+    fixed = [FixedJoint("iiwa_joint_ee", "iiwa_joint_7", xyz=(0, 0, 0.045)),
+             FixedJoint("iiwa_tool_tip", "iiwa_joint_7", xyz=(0.02, -0.01, 0.16), rpy=(0.1, -0.2, 0.3))]
+    return Robot("iiwa14", joints, fixed)
 
 
 def hyq() -> Robot:
@@ -261,7 +366,8 @@ def hyq() -> Robot:
                                 (0.35, 0.0, 0.0), (0, 0, 0),
                                 0.881, (0.1254, 0.0005 * fy, -0.0001), (0.000468, 0.012237, 0.012029),
                                 inertia_offdiag=(0.0, 0.000035, 0.0), damping=0.1))
-    return Robot("hyq", joints)
+    fixed = [FixedJoint(leg + "_foot_joint", leg + "_kfe_joint", xyz=(0.33, 0.0, 0.0)) for leg, _, _ in legs]
+    return Robot("hyq", joints, fixed)
 
 
 def atlas() -> Robot:
@@ -310,7 +416,10 @@ def atlas() -> Robot:
                   (0.00001, 0.000012, 0.000011))
         add(side + "_leg_akx", aky, (1, 0, 0), (0, 0, 0), 2.05, (0.027, 0.0, -0.067),
             (0.002, 0.007, 0.008), ioff=(0.0, 0.002, 0.0))
-    return Robot("atlas", J)
+    fixed = [FixedJoint("l_hand_mount", "l_arm_wry2", xyz=(0, 0.1, 0), rpy=(0, 0, _PI / 2)),
+             FixedJoint("r_hand_mount", "r_arm_wry2", xyz=(0, -0.1, 0), rpy=(0, 0, -_PI / 2)),
+             FixedJoint("head_camera", "neck_ry", xyz=(0.1, 0, 0.08))]
+    return Robot("atlas", J, fixed)
 
 
 def random_tree(n: int, seed: int = 0, branching: float = 0.35, prismatic: float = 0.2,

@@ -48,6 +48,19 @@ def golden(request):
     return name, make_robot(name), data
 
 
+def load_ee_golden(name):
+    """tests/golden/ee_<name>.npz (oracle/make_golden.py --ee): the unmodified reference's
+    end_effector_pose / end_effector_pose_gradient.  -> (q, [(names, offset, pose, grad), ...])"""
+    import json
+    d = np.load(os.path.join(GOLDEN_DIR, "ee_" + name + ".npz"))
+    specs = json.loads(str(d["specs"]))
+    cases = []
+    for si, names in enumerate(specs):
+        for oi, off in enumerate(d["offsets"]):
+            cases.append((names, [list(off)], d["pose_s%d_o%d" % (si, oi)], d["grad_s%d_o%d" % (si, oi)]))
+    return d["q"], cases
+
+
 def random_states(n, B, seed):
     rng = np.random.default_rng(seed)
     return (rng.uniform(-np.pi, np.pi, (B, n)), rng.uniform(-1, 1, (B, n)), rng.uniform(-1, 1, (B, n)))

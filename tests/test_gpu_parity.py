@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import TOL_F32, TOL_F64, make_robot, random_states, rel_err
+from conftest import GOLDEN_CASES, TOL_F32, TOL_F64, load_ee_golden, make_robot, random_states, rel_err
 from oracle.rbd_oracle import BatchOracle
 
 pytestmark = pytest.mark.gpu
@@ -665,3 +665,82 @@ def test_forward_dynamics_compositions():
         assert rel_err(qdd[k], so.forward_dynamics(q[k], qd[k], u[k])) < 1e-9
         r1, r2 = so.forward_dynamics_grad(q[k], qd[k], u[k])
         assert rel_err(dq[k], r1) < 1e-9 and rel_err(dqd[k], r2) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# end-effector kinematics: RBDReference.py:220-386
+# ---------------------------------------------------------------------------------------------
+@requires_cuda
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_end_effector_pose_and_gradient_vs_reference_golden(name):
+    """Default leaves, named moving + fixed joints, zero / non-zero offset; single knot point
+    (reference shapes: lists of (6,1) / (6,n)) and batched; FP64 and FP32."""
+    rb = make_robot(name)
+    eng, e32 = _engine(rb), _engine(rb, torch.float32)
+    q, cases = load_ee_golden(name)
+    n = eng.n
+    for names, off, pose, grad in cases:
+        P = eng.end_effector_pose(q[0], names, off)
+        G = eng.end_effector_pose_gradient(q[0], names, off)
+        assert isinstance(P, list) and len(P) == pose.shape[1] and P[0].shape == (6, 1) and G[0].shape == (6, n)
+        assert rel_err(np.stack(P)[:, :, 0], pose[0]) < TOL_F64 and rel_err(np.stack(G), grad[0]) < TOL_F64
+        Pb = eng.end_effector_pose(q, names, off)
+        Gb, Pb2 = eng.end_effector_pose_gradient(q, names, off, return_pose=True)
+        assert Pb.shape == pose.shape and Gb.shape == grad.shape
+        assert rel_err(Pb, pose) < TOL_F64 and rel_err(Pb2, pose) < TOL_F64 and rel_err(Gb, grad) < TOL_F64
+        assert rel_err(e32.end_effector_pose(q, names, off), pose) < TOL_F32
+        assert rel_err(e32.end_effector_pose_gradient(q, names, off), grad) < 20 * TOL_F32   # 1/(x^2+y^2) in the rpy columns
+    with pytest.raises(ValueError, match="Could not find joint or fixed joint named"):
+        eng.end_effector_pose(q[0], ["no_such_joint"])
+
+
+@requires_cuda
+@pytest.mark.parametrize("name,B", [("iiwa14", 4099), ("hyq", 1001), ("atlas", 1025), ("tree13", 333)])
+def test_end_effector_batched_vs_oracle(name, B):
+    """Ragged batches on the device against the vectorised oracle; zero columns off the chain."""
+    rb = make_robot(name)
+    eng, bo = _engine(rb), BatchOracle(rb)
+    n = eng.n
+    q = np.random.default_rng(B).uniform(-np.pi, np.pi, (B, n))
+    Pref, Gref = bo.end_effector_pose(q, gradient=True)
+    tq = _t(q)
+    P = eng.end_effector_pose(tq)
+    G, P2 = eng.end_effector_pose_gradient(tq, return_pose=True)
+    assert P.is_cuda and G.shape == (B, len(rb.get_leaf_nodes()), 6, n)
+    assert rel_err(P.cpu().numpy(), Pref) < TOL_F64 and torch.equal(P, P2)
+    # per knot point scaling: a pose close to the pitch singularity has huge rpy derivatives
+    Gn, scale = G.cpu().numpy(), np.maximum(1.0, np.abs(Gref).max(axis=(1, 2, 3), keepdims=True))
+    assert np.max(np.abs(Gn - Gref) / scale) < TOL_F64
+    for e, leaf in enumerate(rb.get_leaf_nodes()):
+        off_chain = [j for j in range(n) if j != leaf and j not in rb.get_ancestors_by_id(leaf)]
+        assert np.all(Gn[:, e][:, :, off_chain] == 0.0)
+    assert eng.end_effector_pose(tq[:0]).shape == (0, len(rb.get_leaf_nodes()), 6)
+
+
+@requires_cuda
+def test_end_effector_full_size_properties():
+    """2^20 iiwa14 knot points: the flange position keeps its distance to the last joint's origin,
+    rpy stay in range, the gradient matches central differences of the pose on a sample, and
+    sharded == unsharded bit for bit."""
+    rb = make_robot("iiwa14")
+    eng = _engine(rb)
+    B, n = 1 << 20, eng.n
+    g = torch.Generator(device="cuda").manual_seed(0xEE)
+    q = (torch.rand(B, n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * np.pi
+    names = ["iiwa_joint_7", "iiwa_joint_ee"]
+    P = eng.end_effector_pose(q, names)
+    assert torch.isfinite(P).all()
+    d = (P[:, 0, :3] - P[:, 1, :3]).norm(dim=1)
+    assert float((d - 0.045).abs().max()) < 1e-12            # fixed flange offset (robots.iiwa14)
+    assert float(P[..., 3].abs().max()) <= np.pi and float(P[..., 4].abs().max()) <= np.pi / 2 + 1e-12
+    G = eng.end_effector_pose_gradient(q, names)
+    assert float(G[:, :, :3, :].abs().max()) < 2.0            # |dp/dq_j| <= reach of the arm
+    h = 1e-6
+    idx = torch.arange(0, B, 4099, device="cuda")
+    for j in range(n):
+        dq = torch.zeros(n, dtype=torch.float64, device="cuda"); dq[j] = h
+        num = (eng.end_effector_pose(q[idx] + dq, names) - eng.end_effector_pose(q[idx] - dq, names))[..., :3] / (2 * h)
+        assert float((num - G[idx][:, :, :3, j]).abs().max()) < 1e-7
+    half = B // 2 + 17
+    G2 = torch.cat((eng.end_effector_pose_gradient(q[:half], names), eng.end_effector_pose_gradient(q[half:], names)))
+    assert torch.equal(G, G2)

@@ -18,7 +18,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = _capi.load_library()
     header = open(os.path.join(ROOT, "include", "rbd_b200.h")).read()
     declared = set(re.findall(r"\b(rbd_[a-z0-9_]+)\s*\(", header))
-    declared.discard("rbd_model")
+    declared -= {"rbd_model", "rbd_ee_model"}
     assert declared == set(_capi.exported_symbols()), declared ^ set(_capi.exported_symbols())
     for sym in sorted(declared):
         assert hasattr(lib, sym), "missing export " + sym
@@ -56,6 +56,46 @@ def test_model_compiler_reproduces_transforms(name):
         assert sorted(rb.get_subtree_by_id(i)) == m.subtree[i]
         anc = set(rb.get_ancestors_by_id(i)) | {i}
         assert anc == {c for c in range(n) if (int(m.anc_mask[i]) >> c) & 1}
+
+
+@pytest.mark.parametrize("name", ["iiwa14", "hyq", "atlas", "tree9", "tree13"])
+def test_ee_model_compiler_reproduces_hom_transforms(name):
+    """compile_ee_model recovers T(q) and dT(q) of every joint from the robot's own callables and
+    resolves the end-effector selection in the reference's order (RBDReference.py:190-211)."""
+    from rbdreference_b200.model import compile_ee_model
+    rb = make_robot(name)
+    ee = compile_ee_model(rb)
+    assert list(ee.ee_joint) == rb.get_leaf_nodes()
+    rng = np.random.default_rng(3)
+    for i in range(ee.n):
+        for t in rng.uniform(-3, 3, 3):
+            f1, f2 = (np.cos(t), np.sin(t)) if ee.kind[i] == 0 else (t, 0.0)
+            T = (ee.TA[i] + f1 * ee.TB[i] + f2 * ee.TC[i]).reshape(3, 4)
+            D = (ee.DA[i] + f1 * ee.DB[i] + f2 * ee.DC[i]).reshape(3, 4)
+            assert np.max(np.abs(T - rb.get_Xmat_hom_Func_by_id(i)(t)[:3])) < 1e-13
+            assert np.max(np.abs(D - rb.get_dXmat_hom_Func_by_id(i)(t)[:3])) < 1e-13
+    h = _capi.EeModelHandle(ee)
+    assert _capi.load_library().rbd_ee_model_num_ee(h.ptr) == len(rb.get_leaf_nodes())
+
+
+def test_ee_selection_order_and_errors():
+    from rbdreference_b200.model import compile_ee_model, select_end_effector_joints
+    rb = robots.iiwa14()
+    # moving joints first, then fixed joints, whatever the order of the names (:201-210)
+    assert select_end_effector_joints(rb, ["iiwa_joint_ee", "iiwa_joint_4", "iiwa_tool_tip"]) == ([3], [0, 1])
+    ee = compile_ee_model(rb, ["iiwa_joint_ee", "iiwa_joint_4", "iiwa_tool_tip"], [[0.1, 0.2, 0.3, 1.0]])
+    assert list(ee.ee_joint) == [3, 6, 6] and list(ee.offset) == [0.1, 0.2, 0.3, 1.0]
+    assert np.array_equal(ee.ee_final[0], np.eye(4)[:3].reshape(12))
+    assert np.allclose(ee.ee_final[1].reshape(3, 4)[:, 3], [0, 0, 0.045])
+    with pytest.raises(ValueError, match="Could not find joint or fixed joint named: nope"):
+        compile_ee_model(rb, ["nope"])
+    lib = _capi.load_library()
+    handle = ctypes.c_void_p()
+    assert lib.rbd_ee_model_create(None, ctypes.byref(handle)) == -1
+    bad = compile_ee_model(rb)
+    bad.ee_joint = np.array([9], dtype=np.int32)
+    with pytest.raises(_capi.RbdError):
+        _capi.EeModelHandle(bad)
 
 
 def test_model_compiler_flop_model_matches_survey_table():

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import rel_err, random_states, make_robot
+from conftest import GOLDEN_CASES, load_ee_golden, rel_err, random_states, make_robot
 from oracle.rbd_oracle import BatchOracle, ScalarOracle
 from oracle import build_ref
 
@@ -81,6 +81,42 @@ def test_batch_oracle_vs_golden(golden):
     assert rel_err(bo.crba(q), g["H"]) < PIN
     assert rel_err(bo.aba(q, qd, g["u"]), g["aba_qdd"]) < PIN
     assert rel_err(bo.aba(q, qd, g["u"], GRAVITY=-3.7), g["aba_qdd_galt"]) < PIN
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_end_effector_oracle_vs_golden(name):
+    """end_effector_pose / _gradient (RBDReference.py:220-386) of both oracle layers against the
+    reference's outputs: default leaves, named moving + fixed joints, zero and non-zero offset."""
+    rb = make_robot(name)
+    so, bo = ScalarOracle(rb), BatchOracle(rb)
+    q, cases = load_ee_golden(name)
+    n = rb.get_num_vel()
+    for names, off, pose, grad in cases:
+        for k in range(q.shape[0]):
+            P = so.end_effector_pose(q[k], names, off)
+            G = so.end_effector_pose_gradient(q[k], names, off)
+            assert len(P) == pose.shape[1] and P[0].shape == (6, 1) and G[0].shape == (6, n)
+            assert rel_err(np.stack(P)[:, :, 0], pose[k]) < PIN
+            assert rel_err(np.stack(G), grad[k]) < PIN
+        Pb, Gb = bo.end_effector_pose(q, names, off, gradient=True)
+        assert rel_err(Pb, pose) < PIN and rel_err(Gb, grad) < PIN
+    with pytest.raises(ValueError, match="Could not find joint or fixed joint named"):
+        so.end_effector_pose(q[0], ["no_such_joint"])
+
+
+@pytest.mark.parametrize("name", ["iiwa14", "atlas", "tree13"])
+def test_end_effector_gradient_is_the_derivative_of_the_pose(name):
+    rb = make_robot(name)
+    bo = BatchOracle(rb)
+    n = rb.get_num_vel()
+    q = np.random.default_rng(5).uniform(-1.2, 1.2, (6, n))
+    G = bo.end_effector_pose_gradient(q)
+    h = 1e-6
+    for j in range(n):
+        dq = np.zeros(n); dq[j] = h
+        num = (bo.end_effector_pose(q + dq) - bo.end_effector_pose(q - dq)) / (2 * h)
+        num[..., 3:] = (num[..., 3:] + np.pi / (2 * h)) % (np.pi / h) - np.pi / (2 * h)     # angle wrap
+        assert np.max(np.abs(num - G[..., j])) < 1e-6 * max(1.0, np.max(np.abs(G)))
 
 
 @pytest.mark.parametrize("name", ["iiwa14", "hyq", "atlas"])
