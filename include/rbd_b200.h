@@ -212,6 +212,39 @@ int rbd_end_effector_pose_gradient_f64(const rbd_ee_model_t* m, int64_t B, const
 int rbd_end_effector_pose_gradient_f32(const rbd_ee_model_t* m, int64_t B, const float* q, float* dpose,
                                        float* pose, void* stream);
 
+/* ---- floating base ----------------------------------------------------- */
+/* The `self.robot.floating_base` branches of rnea (RBDReference.py:585, :591), minv (:652-691,
+ * :761-779) and rnea_grad (:1141-1168, :1212-1238, :1267-1282, :1309-1341).  bodies.n = NB counts
+ * the base as body 0 (parent -1, S = eye(6) upstream; only I and damping of entry 0 are read);
+ * body i >= 1 is a 1-DoF joint with parent[i] in 0..i-1.  The base transform is
+ * X0 = xrot(E) xlt(p) with p = q[pos_off..+3] and E = R(quat)^T (transpose = 0) or R(quat)
+ * (transpose = 1), quat = q[quat_off..+4] a unit quaternion stored (x,y,z,w) (w_first = 0) or
+ * (w,x,y,z) (w_first = 1); (pos_off, quat_off) is (0, 3) or (4, 0).  rbdreference_b200/model.py
+ * finds the layout by probing the robot's own get_Xmat_Func_by_id(0).
+ * Shapes: q (B, NB+6) with joint i at q[i+6]; qd, qdd, c (B, NB+5) with the base twist
+ * [angular; linear] in base coordinates at [0:6] and joint i at [i+5]; v, a, f (B, 6, NB);
+ * dc_du (B, NB+5, 2(NB+5)); Minv (B, NB+5, NB+5).  Reference behaviour kept: output_dense mirrors only
+ * the leading NB x NB block (:799-804); velocity damping lands on [i, i] (body index) and on the
+ * block [0:5, 0:5] for the base (:1336-1341). */
+typedef struct RbdFbModelDesc {
+  RbdModelDesc bodies;
+  int32_t pos_off, quat_off, w_first, transpose;
+} RbdFbModelDesc;
+typedef struct rbd_fb_model rbd_fb_model_t;
+int rbd_fb_model_create(const RbdFbModelDesc* desc, rbd_fb_model_t** out);
+int rbd_fb_model_destroy(rbd_fb_model_t* m);
+int rbd_fb_model_num_vel(const rbd_fb_model_t* m);
+int rbd_fb_rnea_f64(const rbd_fb_model_t* m, int64_t B, const double* q, const double* qd, const double* qdd,
+                    double gravity, double* c, double* v, double* a, double* f, void* stream);
+int rbd_fb_rnea_f32(const rbd_fb_model_t* m, int64_t B, const float* q, const float* qd, const float* qdd,
+                    float gravity, float* c, float* v, float* a, float* f, void* stream);
+int rbd_fb_rnea_grad_f64(const rbd_fb_model_t* m, int64_t B, const double* q, const double* qd, const double* qdd,
+                         double gravity, int use_velocity_damping, double* dc_du, double* c_out, void* stream);
+int rbd_fb_rnea_grad_f32(const rbd_fb_model_t* m, int64_t B, const float* q, const float* qd, const float* qdd,
+                         float gravity, int use_velocity_damping, float* dc_du, float* c_out, void* stream);
+int rbd_fb_minv_f64(const rbd_fb_model_t* m, int64_t B, const double* q, int output_dense, double* Minv, void* stream);
+int rbd_fb_minv_f32(const rbd_fb_model_t* m, int64_t B, const float* q, int output_dense, float* Minv, void* stream);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
 /* Runs a dependent-chain FMA micro-benchmark on `stream`'s device and returns the achieved
  * FLOP/s (2 per FMA) in *flops_per_s; is_f64 selects DFMA or FFMA.  Used only to put a measured

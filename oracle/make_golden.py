@@ -123,9 +123,52 @@ def run_ee_case(name, make, B, seed):
     print("wrote %s (%d states, %.1f KB)" % (path, B, os.path.getsize(path) / 1024))
 
 
+# floating-base branches: the wrapped robots of rbdreference_b200.robots
+FB_CASES = [("hyq_fb", 5), ("atlas_fb", 3), ("iiwa14_fb", 5), ("tree9_fb", 4)]
+
+
+def make_fb_robot(name):
+    if name == "tree9_fb":
+        return robots.FloatingBaseRobot(robots.random_tree(9, seed=1), name="tree9_fb")
+    return robots.by_name(name)
+
+
+def run_fb_case(name, B, seed):
+    """tests/golden/fb_<name>.npz: rnea / rnea_grad / minv of the unmodified reference, floating base."""
+    import warnings
+    warnings.simplefilter("ignore")
+    rb = make_fb_robot(name)
+    ref = RBDReference(rb)
+    q, qd, qdd = rb.random_state(np.random.default_rng(seed), B)
+    keys = ["c", "v", "a", "f", "c_noqdd", "c_galt", "dc_du", "dc_du_damped", "dc_du_noqdd", "Minv", "Minv_sparse"]
+    acc = {k: [] for k in keys}
+    for k in range(B):
+        c, v, a, f = ref.rnea(q[k], qd[k], qdd[k])
+        for key, val in (("c", c), ("v", v), ("a", a), ("f", f)):
+            acc[key].append(np.array(val))
+        acc["c_noqdd"].append(ref.rnea(q[k], qd[k])[0])
+        acc["c_galt"].append(ref.rnea(q[k], qd[k], qdd[k], GRAVITY=-3.7)[0])
+        acc["dc_du"].append(ref.rnea_grad(q[k], qd[k], qdd[k]))
+        acc["dc_du_damped"].append(ref.rnea_grad(q[k], qd[k], qdd[k], USE_VELOCITY_DAMPING=True))
+        acc["dc_du_noqdd"].append(ref.rnea_grad(q[k], qd[k]))
+        acc["Minv"].append(ref.minv(q[k]))
+        acc["Minv_sparse"].append(ref.minv(q[k], output_dense=False))
+    out = dict(q=q, qd=qd, qdd=qdd, X0_first=rb.get_Xmat_Func_by_id(0)(q[0, 0:7]))
+    for key in keys:
+        out[key] = np.stack(acc[key])
+    path = os.path.join(ROOT, "tests", "golden", "fb_" + name[:-3] + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s (%d states, %.1f KB)" % (path, B, os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     only_ee = "--ee" in sys.argv          # regenerate only the end-effector fixtures
+    only_fb = "--fb" in sys.argv          # regenerate only the floating-base fixtures
     for idx, (name, make, B) in enumerate(CASES):
-        if not only_ee:
+        if not (only_ee or only_fb):
             run_case(name, make, B, seed=1000 + idx)
-        run_ee_case(name, make, B, seed=2000 + idx)
+        if not only_fb:
+            run_ee_case(name, make, B, seed=2000 + idx)
+    if not only_ee:
+        for idx, (name, B) in enumerate(FB_CASES):
+            run_fb_case(name, B, seed=3000 + idx)

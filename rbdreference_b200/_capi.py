@@ -16,14 +16,16 @@ FUSED_SYMBOLS = ["rnea", "rnea_grad", "minv", "forward_dynamics", "forward_dynam
 PLAIN_SYMBOLS = ["rbd_abi_version", "rbd_last_error_string", "rbd_model_create", "rbd_model_destroy",
                  "rbd_model_num_dof", "rbd_model_uses_world_kernels", "rbd_set_kernel_variant",
                  "rbd_measure_fma_peak", "rbd_launch_count",
-                 "rbd_ee_model_create", "rbd_ee_model_destroy", "rbd_ee_model_num_ee"]
+                 "rbd_ee_model_create", "rbd_ee_model_destroy", "rbd_ee_model_num_ee",
+                 "rbd_fb_model_create", "rbd_fb_model_destroy", "rbd_fb_model_num_vel"]
+FB_SYMBOLS = ["fb_rnea", "fb_rnea_grad", "fb_minv"]
 EE_SYMBOLS = ["end_effector_pose", "end_effector_pose_gradient"]
 
 
 def exported_symbols():
     """Every symbol include/rbd_b200.h declares."""
     out = list(PLAIN_SYMBOLS)
-    for base in FUSED_SYMBOLS + PASS_SYMBOLS + EE_SYMBOLS:
+    for base in FUSED_SYMBOLS + PASS_SYMBOLS + EE_SYMBOLS + FB_SYMBOLS:
         out += ["rbd_%s_f64" % base, "rbd_%s_f32" % base]
     return out
 
@@ -41,6 +43,11 @@ class RbdEeDesc(ctypes.Structure):
                 ("DA", POINTER(c_double)), ("DB", POINTER(c_double)), ("DC", POINTER(c_double)),
                 ("n_ee", c_int32), ("ee_joint", POINTER(c_int32)), ("ee_final", POINTER(c_double)),
                 ("offset", c_double * 4)]
+
+
+class RbdFbModelDesc(ctypes.Structure):
+    _fields_ = [("bodies", RbdModelDesc), ("pos_off", c_int32), ("quat_off", c_int32), ("w_first", c_int32),
+                ("transpose", c_int32)]
 
 
 class RbdError(RuntimeError):
@@ -72,6 +79,9 @@ def load_library():
     lib.rbd_ee_model_create.argtypes = [POINTER(RbdEeDesc), POINTER(c_void_p)]
     lib.rbd_ee_model_destroy.argtypes = [c_void_p]
     lib.rbd_ee_model_num_ee.argtypes = [c_void_p]
+    lib.rbd_fb_model_create.argtypes = [POINTER(RbdFbModelDesc), POINTER(c_void_p)]
+    lib.rbd_fb_model_destroy.argtypes = [c_void_p]
+    lib.rbd_fb_model_num_vel.argtypes = [c_void_p]
     P = c_void_p
     for suf, real in (("f64", c_double), ("f32", c_float)):
         sig = {
@@ -90,6 +100,9 @@ def load_library():
             "forward_dynamics_grad": [P, c_int64, P, P, P, P, P, P, P],
             "crba": [P, c_int64, P, P, P],
             "aba": [P, c_int64, P, P, P, real, P, P],
+            "fb_rnea": [P, c_int64, P, P, P, real, P, P, P, P, P],
+            "fb_rnea_grad": [P, c_int64, P, P, P, real, c_int, P, P, P],
+            "fb_minv": [P, c_int64, P, c_int, P, P],
             "end_effector_pose": [P, c_int64, P, P, P],
             "end_effector_pose_gradient": [P, c_int64, P, P, P, P],
         }
@@ -172,6 +185,32 @@ class EeModelHandle:
         try:
             if getattr(self, "ptr", None):
                 self._lib.rbd_ee_model_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class FbModelHandle:
+    """Owns an rbd_fb_model_t* created from a compiled FbModel (model.compile_fb_model)."""
+
+    def __init__(self, fb):
+        lib = load_library()
+        k = self._keep = {name: np.ascontiguousarray(getattr(fb, name), dtype=np.float64)
+                          for name in ("S", "XA", "XB", "XC", "I", "damping")}
+        k["parent"] = np.ascontiguousarray(fb.parent, dtype=np.int32)
+        k["kind"] = np.ascontiguousarray(fb.kind, dtype=np.int32)
+        bodies = RbdModelDesc(fb.NB, _iptr(k["parent"]), _iptr(k["kind"]), _dptr(k["S"]), _dptr(k["XA"]),
+                              _dptr(k["XB"]), _dptr(k["XC"]), _dptr(k["I"]), _dptr(k["damping"]))
+        desc = RbdFbModelDesc(bodies, fb.pos_off, fb.quat_off, fb.w_first, fb.transpose)
+        handle = c_void_p()
+        check(lib.rbd_fb_model_create(ctypes.byref(desc), ctypes.byref(handle)), "rbd_fb_model_create")
+        self.ptr = handle
+        self._lib = lib
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None):
+                self._lib.rbd_fb_model_destroy(self.ptr)
                 self.ptr = None
         except Exception:
             pass

@@ -21,7 +21,8 @@ OBJ_DIR = os.path.join(CSRC, "_build")
 LIB_PATH = os.path.join(PKG_DIR, "librbd_b200.so")
 
 # (object name, source, extra defines)
-UNITS = [("rbd_capi.o", "rbd_capi.cu", []), ("rbd_launch_ee.o", "rbd_launch_ee.cu", [])]
+UNITS = [("rbd_capi.o", "rbd_capi.cu", []), ("rbd_launch_ee.o", "rbd_launch_ee.cu", []),
+         ("rbd_launch_fb.o", "rbd_launch_fb.cu", [])]
 for _src in ("rbd_launch_rnea.cu", "rbd_launch_grad.cu", "rbd_launch_minv.cu", "rbd_launch_pass.cu"):
     for _t in ("double", "float"):
         UNITS.append(("%s_%s.o" % (_src[:-3], _t), _src, ["-DRBD_LAUNCH_T=%s" % _t]))

@@ -1,0 +1,128 @@
+// rbd_launch_fb.cu - part of librbd_b200.so: floating-base rnea / rnea_grad / minv (include/rbd_b200.h).
+// Reference: the `floating_base` branches of RBDReference.py:559-806 and :1127-1368.
+#include "rbd_internal.cuh"
+#include "rbd_fb_kernels.cuh"
+
+using namespace rbd;
+using namespace rbd_host;
+
+struct rbd_fb_model {
+  FbModel<double> d;
+  FbModel<float> f;
+};
+
+namespace {
+
+template <typename T> const FbModel<T>& pick_fb(const rbd_fb_model* m);
+template <> const FbModel<double>& pick_fb<double>(const rbd_fb_model* m) { return m->d; }
+template <> const FbModel<float>& pick_fb<float>(const rbd_fb_model* m) { return m->f; }
+
+template <typename T>
+void fill_fb(const RbdFbModelDesc* fd, FbModel<T>& out) {
+  std::memset(&out, 0, sizeof(out));
+  const RbdModelDesc* d = &fd->bodies;
+  const int n = d->n;
+  out.pos_off = fd->pos_off; out.quat_off = fd->quat_off; out.w_first = fd->w_first; out.transpose = fd->transpose;
+  DevModel<T>& o = out.d;
+  o.n = n;
+  for (int i = 0; i < n; ++i) {
+    o.parent[i] = d->parent[i];
+    o.kind[i] = d->kind[i];
+    o.damping[i] = (T)(d->damping ? d->damping[i] : 0.0);
+    for (int k = 0; k < 36; ++k) o.I[i][k] = (T)d->I[i * 36 + k];
+    if (i > 0) {
+      for (int k = 0; k < 6; ++k) o.S[i][k] = (T)d->S[i * 6 + k];
+      for (int k = 0; k < 18; ++k) {
+        o.XA[i][k] = (T)d->XA[i * 18 + k]; o.XB[i][k] = (T)d->XB[i * 18 + k]; o.XC[i][k] = (T)d->XC[i * 18 + k];
+      }
+    }
+    unsigned anc = 1u << i;
+    if (d->parent[i] >= 0) anc |= o.anc_mask[d->parent[i]];
+    o.anc_mask[i] = anc;
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    o.sub_mask[i] |= 1u << i;
+    if (d->parent[i] >= 0) o.sub_mask[d->parent[i]] |= o.sub_mask[i];
+  }
+}
+
+template <typename T>
+int launch_fb_rnea(const rbd_fb_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, T* c, T* v, T* a, T* f,
+                   void* stream) {
+  RBD_CHECK_ARGS(m && q && qd && c && B >= 0, "rbd_fb_rnea: null model/q/qd/c or negative B");
+  if (B == 0) return 0;
+  fb_rnea_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, qd, qdd, g, c, v, a, f);
+  return cuda_status("rbd_fb_rnea");
+}
+
+template <typename T>
+int launch_fb_rnea_grad(const rbd_fb_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, int damp, T* dc_du,
+                        T* c_out, void* stream) {
+  RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_fb_rnea_grad: null model/q/qd/dc_du or negative B");
+  if (B == 0) return 0;
+  fb_rnea_grad_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, qd, qdd, g, damp,
+                                                                                             dc_du, c_out);
+  return cuda_status("rbd_fb_rnea_grad");
+}
+
+template <typename T>
+int launch_fb_minv(const rbd_fb_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream) {
+  RBD_CHECK_ARGS(m && q && Minv && B >= 0, "rbd_fb_minv: null model/q/Minv or negative B");
+  if (B == 0) return 0;
+  fb_minv_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, dense, Minv);
+  return cuda_status("rbd_fb_minv");
+}
+
+}  // namespace
+
+extern "C" {
+
+int rbd_fb_model_create(const RbdFbModelDesc* fd, rbd_fb_model_t** out) {
+  if (!fd || !out) return fail(RBD_E_INVALID_ARGUMENT, "rbd_fb_model_create: null argument");
+  *out = nullptr;
+  const RbdModelDesc* d = &fd->bodies;
+  if (d->n < 1 || d->n > RBD_MAX_DOF) return fail(RBD_E_UNSUPPORTED, "rbd_fb_model_create: number of bodies outside 1..RBD_MAX_DOF");
+  if (!d->parent || !d->kind || !d->S || !d->XA || !d->XB || !d->XC || !d->I)
+    return fail(RBD_E_INVALID_ARGUMENT, "rbd_fb_model_create: null table pointer");
+  if (d->parent[0] != -1) return fail(RBD_E_INVALID_ARGUMENT, "rbd_fb_model_create: body 0 must be the floating base (parent -1)");
+  for (int i = 1; i < d->n; ++i) {
+    if (d->parent[i] < 0 || d->parent[i] >= i)
+      return fail(RBD_E_INVALID_ARGUMENT, "rbd_fb_model_create: parent[i] must satisfy 0 <= parent[i] < i for i >= 1");
+    if (d->kind[i] != 0 && d->kind[i] != 1)
+      return fail(RBD_E_INVALID_ARGUMENT, "rbd_fb_model_create: kind[i] must be 0 (revolute) or 1 (prismatic)");
+  }
+  const bool layout_ok = (fd->pos_off == 0 && fd->quat_off == 3) || (fd->pos_off == 4 && fd->quat_off == 0);
+  if (!layout_ok || (fd->w_first | 1) != 1 || (fd->transpose | 1) != 1)
+    return fail(RBD_E_INVALID_ARGUMENT, "rbd_fb_model_create: base layout must be position+quaternion or quaternion+position");
+  rbd_fb_model* m = new (std::nothrow) rbd_fb_model;
+  if (!m) return fail(RBD_E_INVALID_ARGUMENT, "rbd_fb_model_create: out of host memory");
+  fill_fb<double>(fd, m->d);
+  fill_fb<float>(fd, m->f);
+  *out = m;
+  return 0;
+}
+
+int rbd_fb_model_destroy(rbd_fb_model_t* m) {
+  delete m;
+  return 0;
+}
+
+int rbd_fb_model_num_vel(const rbd_fb_model_t* m) { return m ? m->d.d.n + 5 : RBD_E_INVALID_ARGUMENT; }
+
+#define RBD_FB_DEFINE(SUF, T)                                                                                        \
+  int rbd_fb_rnea_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* qdd, T gravity, T* c,  \
+                        T* v, T* a, T* f, void* stream) {                                                            \
+    return launch_fb_rnea<T>(m, B, q, qd, qdd, gravity, c, v, a, f, stream);                                         \
+  }                                                                                                                  \
+  int rbd_fb_rnea_grad_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* qdd, T gravity,   \
+                             int use_velocity_damping, T* dc_du, T* c_out, void* stream) {                           \
+    return launch_fb_rnea_grad<T>(m, B, q, qd, qdd, gravity, use_velocity_damping, dc_du, c_out, stream);            \
+  }                                                                                                                  \
+  int rbd_fb_minv_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, int output_dense, T* Minv, void* stream) {   \
+    return launch_fb_minv<T>(m, B, q, output_dense, Minv, stream);                                                   \
+  }
+
+RBD_FB_DEFINE(f64, double)
+RBD_FB_DEFINE(f32, float)
+
+}  // extern "C"

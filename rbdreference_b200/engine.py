@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from .model import RobotModel, compile_ee_model, compile_model, select_end_effector_joints
+from .model import FbModel, RobotModel, compile_ee_model, compile_fb_model, compile_model, select_end_effector_joints
 
 __all__ = ["RBDReference"]
 
@@ -45,11 +45,17 @@ class RBDReference:
         self.dtype = dtype
         self._suffix = _SUFFIX[dtype]
         self._np_dtype = np.float64 if dtype == torch.float64 else np.float32
-        self.model: RobotModel = robotObj if isinstance(robotObj, RobotModel) else compile_model(robotObj)
-        self.n = self.model.n
-        self.NB = self.model.n
         self._lib = _capi.load_library()            # raises if the CUDA library is missing
-        self._handle = _capi.ModelHandle(self.model)
+        self.floating_base = bool(getattr(robotObj, "floating_base", False)) or isinstance(robotObj, FbModel)
+        if self.floating_base:
+            # rnea / rnea_grad / minv of the reference's floating-base branches
+            self.model = robotObj if isinstance(robotObj, FbModel) else compile_fb_model(robotObj)
+            self.NB, self.n, self.nq = self.model.NB, self.model.nv, self.model.nq
+            self._handle = _capi.FbModelHandle(self.model)
+        else:
+            self.model = robotObj if isinstance(robotObj, RobotModel) else compile_model(robotObj)
+            self.n = self.nq = self.NB = self.model.n
+            self._handle = _capi.ModelHandle(self.model)
         self._device = torch.device(device) if device is not None else None
         self._ee_handles = {}                       # (names, offset) -> compiled end-effector handle
 
@@ -128,6 +134,12 @@ class RBDReference:
             np.copyto(target, t.cpu().numpy().astype(target.dtype, copy=False))
             return target
 
+    def _fixed_only(self, what: str):
+        if self.floating_base:
+            raise NotImplementedError(
+                "%s: no floating-base path (rnea, rnea_grad and minv are the floating-base entry points, "
+                "SURVEY.md 8f rank 3)" % what)
+
     def _call(self, name: str, ctx: "_Ctx", *args, handle=None):
         if ctx.B == 0:
             return                                   # empty batch: nothing to launch
@@ -148,6 +160,7 @@ class RBDReference:
     # ------------------------------------------------------------------------------------
     def rnea_fpass(self, q, qd, qdd=None, GRAVITY=-9.81):
         """RBDReference.py:559-598 -> (v, a, f), each (6, NB)."""
+        self._fixed_only("rnea_fpass")
         ctx = self._Ctx(self, q, 1)
         n = self.n
         dq, dqd, dqdd = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(qdd, (n,), "qdd")
@@ -157,6 +170,7 @@ class RBDReference:
 
     def rnea_bpass(self, q, f):
         """RBDReference.py:600-621 -> (c, f); `f` is accumulated in place and returned."""
+        self._fixed_only("rnea_bpass")
         ctx = self._Ctx(self, q, 1)
         n = self.n
         dq, df = ctx.dev(q, (n,), "q"), ctx.dev(f, (6, n), "f")
@@ -170,14 +184,15 @@ class RBDReference:
         `outputs="c"` (extension) skips writing v, a, f and returns only c.
         """
         ctx = self._Ctx(self, q, 1)
-        n = self.n
-        dq, dqd, dqdd = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(qdd, (n,), "qdd")
+        n, NB = self.n, self.NB
+        op = "fb_rnea" if self.floating_base else "rnea"
+        dq, dqd, dqdd = ctx.dev(q, (self.nq,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(qdd, (n,), "qdd")
         c = ctx.empty(n)
         if outputs == "c":
-            self._call("rnea", ctx, dq, dqd, dqdd, float(GRAVITY), c, None, None, None)
+            self._call(op, ctx, dq, dqd, dqdd, float(GRAVITY), c, None, None, None)
             return ctx.ret(c)
-        v, a, f = ctx.empty(6, n), ctx.empty(6, n), ctx.empty(6, n)
-        self._call("rnea", ctx, dq, dqd, dqdd, float(GRAVITY), c, v, a, f)
+        v, a, f = ctx.empty(6, NB), ctx.empty(6, NB), ctx.empty(6, NB)
+        self._call(op, ctx, dq, dqd, dqdd, float(GRAVITY), c, v, a, f)
         return ctx.ret(c), ctx.ret(v), ctx.ret(a), ctx.ret(f)
 
     # ------------------------------------------------------------------------------------
@@ -185,6 +200,7 @@ class RBDReference:
     # ------------------------------------------------------------------------------------
     def minv_bpass(self, q):
         """RBDReference.py:630-735 -> (Minv, F, U, Dinv) with Dinv = D (:698)."""
+        self._fixed_only("minv_bpass")
         ctx = self._Ctx(self, q, 1)
         n = self.n
         dq = ctx.dev(q, (n,), "q")
@@ -194,6 +210,7 @@ class RBDReference:
 
     def minv_fpass(self, q, Minv, F, U, Dinv):
         """RBDReference.py:737-783 -> Minv (the caller's array, updated in place; F is rewritten)."""
+        self._fixed_only("minv_fpass")
         ctx = self._Ctx(self, q, 1)
         n = self.n
         dq = ctx.dev(q, (n,), "q")
@@ -207,9 +224,9 @@ class RBDReference:
         """RBDReference.py:785-806 -> Minv (n, n)."""
         ctx = self._Ctx(self, q, 1)
         n = self.n
-        dq = ctx.dev(q, (n,), "q")
+        dq = ctx.dev(q, (self.nq,), "q")
         Minv = out if (out is not None and ctx.kind == "torch" and ctx.batched) else ctx.empty(n, n)
-        self._call("minv", ctx, dq, 1 if output_dense else 0, Minv)
+        self._call("fb_minv" if self.floating_base else "minv", ctx, dq, 1 if output_dense else 0, Minv)
         return ctx.ret(Minv)
 
     # ------------------------------------------------------------------------------------
@@ -217,6 +234,7 @@ class RBDReference:
     # ------------------------------------------------------------------------------------
     def rnea_grad_fpass_dq(self, q, qd, v, a, GRAVITY=-9.81):
         """RBDReference.py:1127-1187 -> (dv_dq, da_dq, df_dq), each (6, n, NB)."""
+        self._fixed_only("rnea_grad_fpass_dq")
         ctx = self._Ctx(self, q, 1)
         n = self.n
         dq, dqd = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd")
@@ -227,6 +245,7 @@ class RBDReference:
 
     def rnea_grad_fpass_dqd(self, q, qd, v):
         """RBDReference.py:1189-1255 -> (dv_dqd, da_dqd, df_dqd)."""
+        self._fixed_only("rnea_grad_fpass_dqd")
         ctx = self._Ctx(self, q, 1)
         n = self.n
         dq, dqd, dv_ = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(v, (6, n), "v")
@@ -236,6 +255,7 @@ class RBDReference:
 
     def rnea_grad_bpass_dq(self, q, f, df_dq):
         """RBDReference.py:1257-1297 -> dc_dq (n, n); `df_dq` is accumulated in place."""
+        self._fixed_only("rnea_grad_bpass_dq")
         ctx = self._Ctx(self, q, 1)
         n = self.n
         dq, df_, ddf = ctx.dev(q, (n,), "q"), ctx.dev(f, (6, n), "f"), ctx.dev(df_dq, (6, n, n), "df_dq")
@@ -246,6 +266,7 @@ class RBDReference:
 
     def rnea_grad_bpass_dqd(self, q, df_dqd, USE_VELOCITY_DAMPING=False):
         """RBDReference.py:1299-1343 -> dc_dqd (n, n); `df_dqd` is accumulated in place."""
+        self._fixed_only("rnea_grad_bpass_dqd")
         ctx = self._Ctx(self, q, 1)
         n = self.n
         dq, ddf = ctx.dev(q, (n,), "q"), ctx.dev(df_dqd, (6, n, n), "df_dqd")
@@ -261,12 +282,13 @@ class RBDReference:
         """
         ctx = self._Ctx(self, q, 1)
         n = self.n
-        dq, dqd, dqdd = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(qdd, (n,), "qdd")
+        dq, dqd, dqdd = ctx.dev(q, (self.nq,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(qdd, (n,), "qdd")
         use_out = out is not None and ctx.kind == "torch" and ctx.batched
         dc_du = out if use_out else ctx.empty(n, 2 * n)
         if use_out and (tuple(out.shape) != (ctx.B, n, 2 * n) or out.dtype != self.dtype or not out.is_contiguous()):
             raise ValueError("out must be a contiguous (B, n, 2n) tensor of the engine dtype")
-        self._call("rnea_grad", ctx, dq, dqd, dqdd, float(GRAVITY), 1 if USE_VELOCITY_DAMPING else 0, dc_du, c_out)
+        self._call("fb_rnea_grad" if self.floating_base else "rnea_grad", ctx, dq, dqd, dqdd, float(GRAVITY),
+                   1 if USE_VELOCITY_DAMPING else 0, dc_du, c_out)
         return ctx.ret(dc_du)
 
     def rnea_grad_passes(self, q, qd, qdd=None, GRAVITY=-9.81, USE_VELOCITY_DAMPING=False):
@@ -300,6 +322,7 @@ class RBDReference:
     def forward_dynamics(self, q, qd, u):
         """RBDReference.py:1369-1372: Minv @ (u - c) with c = rnea(q, qd) (qdd omitted upstream).
         rnea + minv + one fused (u - c) / matrix-vector kernel, all inside the C library."""
+        self._fixed_only("forward_dynamics")
         ctx = self._Ctx(self, q, 1)
         n = self.n
         dq, dqd, du = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(u, (n,), "u")
@@ -309,6 +332,7 @@ class RBDReference:
 
     def forward_dynamics_grad(self, q, qd, u):
         """RBDReference.py:1374-1384 -> (qdd_dq, qdd_dqd) = (-Minv dc_dq, -Minv dc_dqd)."""
+        self._fixed_only("forward_dynamics_grad")
         ctx = self._Ctx(self, q, 1)
         n = self.n
         dq, dqd, du = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(u, (n,), "u")
@@ -319,6 +343,7 @@ class RBDReference:
     def aba(self, q, qd, tau, f_ext=None, GRAVITY=-9.81):
         """RBDReference.py:817 (fixed-base branch :940-1024) -> qdd (n,).  Reproduces the reference's
         aba() including its :984 bias-force quirk; f_ext is ignored, as upstream."""
+        self._fixed_only("aba")
         ctx = self._Ctx(self, q, 1)
         n = self.n
         dq, dqd, dtau = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(tau, (n,), "tau")
@@ -328,6 +353,7 @@ class RBDReference:
 
     def crba(self, q, out=None):
         """RBDReference.py:1026-1124 (fixed-base branch) -> joint-space inertia matrix H (n, n)."""
+        self._fixed_only("crba")
         ctx = self._Ctx(self, q, 1)
         n = self.n
         dq = ctx.dev(q, (n,), "q")
@@ -361,6 +387,7 @@ class RBDReference:
         [x y z roll pitch yaw] (the reference returns np.matrix objects of that shape); batched
         q (B, n) -> (B, n_ee, 6).  `ee_offsets=None` is the reference's default [[0, 0, 0, 1]]; as
         upstream only ee_offsets[0] is used."""
+        self._fixed_only("end_effector_pose")
         h = self._ee_handle(ee_joint_names, ee_offsets)
         ctx = self._Ctx(self, q, 1)
         dq = ctx.dev(q, (self.n,), "q")
@@ -375,6 +402,7 @@ class RBDReference:
         """RBDReference.py:295-386.  One knot point -> list over end effectors of (6, n) arrays;
         batched -> (B, n_ee, 6, n).  `return_pose=True` (extension) also returns the pose computed by
         the same launch."""
+        self._fixed_only("end_effector_pose_gradient")
         h = self._ee_handle(ee_joint_names, ee_offsets)
         ctx = self._Ctx(self, q, 1)
         n = self.n
@@ -392,6 +420,8 @@ class RBDReference:
     # ------------------------------------------------------------------------------------
     def uses_world_kernels(self) -> bool:
         """True if the fused drivers run the world-frame kernels for this robot."""
+        if self.floating_base:
+            return False
         return bool(self._lib.rbd_model_uses_world_kernels(self._handle.ptr))
 
     @staticmethod

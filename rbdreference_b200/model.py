@@ -27,7 +27,7 @@ MAX_DOF = 32  # kernel-parameter model limit (include/rbd_b200.h: RBD_MAX_DOF)
 
 MAX_EE = 32   # include/rbd_b200.h: RBD_MAX_EE
 
-__all__ = ["RobotModel", "EeModel", "compile_model", "compile_ee_model", "select_end_effector_joints", "MAX_DOF", "MAX_EE"]
+__all__ = ["RobotModel", "EeModel", "compile_model", "compile_ee_model", "compile_fb_model", "FbModel", "select_end_effector_joints", "MAX_DOF", "MAX_EE"]
 
 
 @dataclasses.dataclass
@@ -317,3 +317,118 @@ def compile_ee_model(robot, ee_joint_names=None, ee_offsets=None) -> EeModel:
             raise ValueError("ee_offsets[0] must have 4 entries (x, y, z, 1)")
     return EeModel(n=n, parent=parent, kind=kind, ee_joint=np.array(ee_joint, dtype=np.int32),
                    ee_final=np.stack(ee_final), offset=offset, **tabs)
+
+
+# ----------------------------------------------------------------------------------------------
+# floating base (RBDReference.py: the `self.robot.floating_base` branches)
+# ----------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class FbModel:
+    """Flat tables behind rbd_fb_model_create (include/rbd_b200.h: RbdFbModelDesc).  Entry 0 of the
+    per-body tables is the base (only its inertia and damping are used)."""
+    name: str
+    NB: int
+    parent: np.ndarray
+    kind: np.ndarray
+    S: np.ndarray
+    XA: np.ndarray
+    XB: np.ndarray
+    XC: np.ndarray
+    I: np.ndarray
+    damping: np.ndarray
+    pos_off: int
+    quat_off: int
+    w_first: int
+    transpose: int
+
+    @property
+    def nv(self) -> int:
+        return self.NB + 5
+
+    @property
+    def nq(self) -> int:
+        return self.NB + 6
+
+
+def _fb_candidate(q7, pos_off, quat_off, w_first, transpose):
+    p = q7[pos_off:pos_off + 3]
+    qq = q7[quat_off:quat_off + 4]
+    w, x, y, z = (qq[0], qq[1], qq[2], qq[3]) if w_first else (qq[3], qq[0], qq[1], qq[2])
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    E = R if transpose else R.T
+    px = np.array([[0.0, -p[2], p[1]], [p[2], 0.0, -p[0]], [-p[1], p[0], 0.0]])
+    X = np.zeros((6, 6))
+    X[:3, :3] = E
+    X[3:, 3:] = E
+    X[3:, :3] = -E @ px
+    return X
+
+
+def compile_fb_model(robot, name: str | None = None) -> FbModel:
+    """Compile a floating-base robot: 1-DoF joints as in `compile_model`, base layout by probing
+    `get_Xmat_Func_by_id(0)` against X0 = xrot(E(quat)) xlt(position) in its eight layouts."""
+    NB = int(robot.get_num_bodies())
+    if not (2 <= NB <= MAX_DOF):
+        raise ValueError("floating-base robot has %d bodies; supported range is 2..%d" % (NB, MAX_DOF))
+    if int(robot.get_num_vel()) != NB + 5:
+        raise ValueError("floating base: expected num_vel == num_bodies + 5 (RBDReference.py:653)")
+    parent = np.array([int(robot.get_parent_id(i)) for i in range(NB)], dtype=np.int32)
+    if parent[0] != -1 or np.any(parent[1:] < 0) or np.any(parent[1:] >= np.arange(1, NB)):
+        raise ValueError("floating base: body 0 must be the only root and ids topologically ordered")
+    S0 = np.asarray(robot.get_S_by_id(0), dtype=np.float64)
+    if S0.shape != (6, 6) or not np.array_equal(S0, np.eye(6)):
+        raise ValueError("floating base: S of body 0 must be eye(6)")
+    if list(robot.get_joint_index_q(0)) != list(range(7)) or list(robot.get_joint_index_v(0)) != list(range(6)):
+        raise ValueError("floating base: the base must own q[0:7] and qd[0:6]")
+    for i in range(1, NB):
+        if int(robot.get_joint_index_q(i)) != i + 6 or int(robot.get_joint_index_v(i)) != i + 5:
+            raise ValueError("floating base: joint i must read q[i+6] and qd[i+5] (RBDReference.py:1143-1144)")
+
+    class _Joints:                                   # bodies 1.. through the fixed-base compiler
+        floating_base = False
+
+        def get_num_bodies(self): return NB - 1
+        def get_num_vel(self): return NB - 1
+        def get_parent_id(self, i): return int(robot.get_parent_id(i + 1)) - 1
+        def get_S_by_id(self, i): return robot.get_S_by_id(i + 1)
+        def get_Xmat_Func_by_id(self, i): return robot.get_Xmat_Func_by_id(i + 1)
+        def get_Imat_by_id(self, i): return robot.get_Imat_by_id(i + 1)
+        def get_damping_by_id(self, i): return robot.get_damping_by_id(i + 1)
+
+    jm = compile_model(_Joints(), name="joints")
+
+    def pad(a, first):
+        return np.concatenate((np.asarray(first, dtype=a.dtype).reshape((1,) + a.shape[1:]), a))
+
+    rng = np.random.default_rng(20261018)
+    f0 = robot.get_Xmat_Func_by_id(0)
+    samples = []
+    for _ in range(6):
+        q7 = rng.uniform(-1.0, 1.0, 7)
+        samples.append(q7)
+    layout = None
+    for pos_off, quat_off in ((0, 3), (4, 0)):
+        for w_first in (0, 1):
+            for transpose in (0, 1):
+                ok = True
+                for q7 in samples:
+                    q7 = q7.copy()
+                    q7[quat_off:quat_off + 4] /= np.linalg.norm(q7[quat_off:quat_off + 4])
+                    X = np.asarray(f0(q7), dtype=np.float64).reshape(6, 6)
+                    if np.max(np.abs(X - _fb_candidate(q7, pos_off, quat_off, w_first, transpose))) > 1e-11 * max(1.0, np.max(np.abs(X))):
+                        ok = False
+                        break
+                if ok and layout is None:
+                    layout = (pos_off, quat_off, w_first, transpose)
+    if layout is None:
+        raise ValueError("floating base: get_Xmat_Func_by_id(0) is not xrot(E(quaternion)) @ xlt(position) in any "
+                         "supported layout (position/quaternion order, w first/last, E = R or R^T)")
+    dget = getattr(robot, "get_damping_by_id", None)
+    return FbModel(name=name or getattr(robot, "name", "robot"), NB=NB, parent=parent,
+                   kind=pad(jm.kind, [0]), S=pad(jm.S, np.zeros(6)), XA=pad(jm.XA, np.zeros(18)),
+                   XB=pad(jm.XB, np.zeros(18)), XC=pad(jm.XC, np.zeros(18)),
+                   I=pad(jm.I, np.asarray(robot.get_Imat_by_id(0), dtype=np.float64).reshape(36)),
+                   damping=pad(jm.damping, [float(dget(0)) if dget is not None else 0.0]),
+                   pos_off=layout[0], quat_off=layout[1], w_first=layout[2], transpose=layout[3])

@@ -27,7 +27,7 @@ from typing import Callable, Dict, List, Sequence
 
 import numpy as np
 
-__all__ = ["Robot", "JointSpec", "FixedJoint", "JointHandle", "iiwa14", "hyq", "atlas", "random_tree", "by_name"]
+__all__ = ["Robot", "FloatingBaseRobot", "JointSpec", "FixedJoint", "JointHandle", "quat_rotation", "iiwa14", "hyq", "atlas", "random_tree", "by_name"]
 
 
 # ----------------------------------------------------------------------------------------
@@ -452,7 +452,112 @@ def random_tree(n: int, seed: int = 0, branching: float = 0.35, prismatic: float
     return Robot("random_tree_n%d_s%d" % (n, seed), joints)
 
 
-def by_name(name: str) -> Robot:
+def quat_rotation(quat_xyzw: Sequence[float]) -> np.ndarray:
+    """Rotation matrix R (body -> world) of a unit quaternion given as (x, y, z, w)."""
+    x, y, z, w = (float(t) for t in quat_xyzw)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+class FloatingBaseRobot:
+    """A fixed-base `Robot` put on a free-floating base body, with the getter conventions the
+    reference's floating-base branches rely on (RBDReference.py:585, :591, :652-691, :761-779,
+    :1141-1147, :1212-1218, :1267-1282, :1309-1315):
+
+    * body 0 is the base, joined to the world by one 6-DoF joint with S = eye(6); body i >= 1 is
+      body i-1 of the wrapped robot, bodies that were roots now hang off the base;
+    * q has NB + 6 entries: q[0:7] = base position (3) and unit quaternion (x, y, z, w), q[i + 6]
+      the angle of joint i; qd / qdd / c have NB + 5 entries: [0:6] = base twist in base
+      coordinates [angular; linear], [i + 5] = joint i;
+    * `get_joint_index_q/v/f(0)` return index lists, `get_Xmat_Func_by_id(0)` takes q[0:7] and
+      returns X = xrot(R(quat)^T) @ xlt(position).
+
+    URDFParser is not available here, so these conventions are this stand-in's; the
+    engine re-discovers the layout by probing `get_Xmat_Func_by_id(0)` (model.compile_fb_model).
+    """
+
+    floating_base = True
+
+    def __init__(self, base: Robot, base_mass=20.0, base_com=(0.01, -0.02, 0.03),
+                 base_inertia=(0.9, 1.1, 1.3), base_inertia_offdiag=(0.02, -0.03, 0.01), name=None):
+        self.base = base
+        self.name = name or (base.name + "_fb")
+        self._nb = base.get_num_bodies() + 1
+        ixx, iyy, izz = base_inertia
+        ixy, ixz, iyz = base_inertia_offdiag
+        self._I0 = mcI(base_mass, base_com, np.array([[ixx, ixy, ixz], [ixy, iyy, iyz], [ixz, iyz, izz]]))
+
+    @staticmethod
+    def base_transform(q7) -> np.ndarray:
+        q7 = np.asarray(q7, dtype=float).reshape(7)
+        return xrot(quat_rotation(q7[3:7]).T) @ xlt(q7[0:3])
+
+    def get_num_bodies(self) -> int:
+        return self._nb
+
+    def get_num_joints(self) -> int:
+        return self._nb
+
+    def get_num_vel(self) -> int:
+        return self._nb + 5
+
+    def get_num_pos(self) -> int:
+        return self._nb + 6
+
+    def get_parent_id(self, i: int) -> int:
+        return -1 if i == 0 else self.base.get_parent_id(i - 1) + 1
+
+    def get_S_by_id(self, i: int) -> np.ndarray:
+        return np.eye(6) if i == 0 else self.base.get_S_by_id(i - 1)
+
+    def get_joint_index_q(self, i: int):
+        return list(range(7)) if i == 0 else i + 6
+
+    def get_joint_index_v(self, i: int):
+        return list(range(6)) if i == 0 else i + 5
+
+    def get_joint_index_f(self, i: int):
+        return list(range(6)) if i == 0 else i + 5
+
+    def get_Xmat_Func_by_id(self, i: int):
+        return self.base_transform if i == 0 else self.base.get_Xmat_Func_by_id(i - 1)
+
+    def get_Imat_by_id(self, i: int) -> np.ndarray:
+        return self._I0.copy() if i == 0 else self.base.get_Imat_by_id(i - 1)
+
+    def get_Imats_dict_by_id(self) -> Dict[int, np.ndarray]:
+        return {i: self.get_Imat_by_id(i) for i in range(self._nb)}
+
+    def get_subtree_by_id(self, i: int) -> List[int]:
+        if i == 0:
+            return list(range(self._nb))
+        return [j + 1 for j in self.base.get_subtree_by_id(i - 1)]
+
+    def get_ancestors_by_id(self, i: int) -> List[int]:
+        out, p = [], self.get_parent_id(i)
+        while p != -1:
+            out.append(p)
+            p = self.get_parent_id(p)
+        return out
+
+    def get_damping_by_id(self, i: int) -> float:
+        return 0.3 if i == 0 else self.base.get_damping_by_id(i - 1)
+
+    def random_state(self, rng, B=None):
+        """Seeded (q, qd, qdd) with a unit base quaternion; leading axis B when given."""
+        shape = () if B is None else (B,)
+        nq, nv = self.get_num_pos(), self.get_num_vel()
+        q = rng.uniform(-np.pi, np.pi, shape + (nq,))
+        q[..., 0:3] = rng.uniform(-1.0, 1.0, shape + (3,))
+        quat = rng.normal(size=shape + (4,))
+        q[..., 3:7] = quat / np.linalg.norm(quat, axis=-1, keepdims=True)
+        return q, rng.uniform(-1, 1, shape + (nv,)), rng.uniform(-1, 1, shape + (nv,))
+
+
+def by_name(name: str):
+    if name.endswith("_fb"):
+        return FloatingBaseRobot(by_name(name[:-3]))
     table = {"iiwa14": iiwa14, "iiwa": iiwa14, "hyq": hyq, "atlas": atlas}
     if name not in table:
         raise KeyError("unknown robot %r (have %s)" % (name, sorted(table)))

@@ -48,6 +48,21 @@ def golden(request):
     return name, make_robot(name), data
 
 
+FB_CASES = ["hyq", "atlas", "iiwa14", "tree9"]
+
+
+def make_fb_robot(name):
+    """Floating-base robots of tests/golden/fb_<name>.npz (oracle/make_golden.py --fb)."""
+    from rbdreference_b200 import robots
+    if name == "tree9":
+        return robots.FloatingBaseRobot(robots.random_tree(9, seed=1), name="tree9_fb")
+    return robots.by_name(name + "_fb")
+
+
+def load_fb_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, "fb_" + name + ".npz")))
+
+
 def load_ee_golden(name):
     """tests/golden/ee_<name>.npz (oracle/make_golden.py --ee): the unmodified reference's
     end_effector_pose / end_effector_pose_gradient.  -> (q, [(names, offset, pose, grad), ...])"""

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, TOL_F32, TOL_F64, load_ee_golden, make_robot, random_states, rel_err
+from conftest import FB_CASES, GOLDEN_CASES, TOL_F32, TOL_F64, load_ee_golden, load_fb_golden, make_fb_robot, make_robot, random_states, rel_err
 from oracle.rbd_oracle import BatchOracle
 
 pytestmark = pytest.mark.gpu
@@ -744,3 +744,73 @@ def test_end_effector_full_size_properties():
     half = B // 2 + 17
     G2 = torch.cat((eng.end_effector_pose_gradient(q[:half], names), eng.end_effector_pose_gradient(q[half:], names)))
     assert torch.equal(G, G2)
+
+
+# ---------------------------------------------------------------------------------------------
+# floating base: the reference's `floating_base` branches of rnea / rnea_grad / minv
+# ---------------------------------------------------------------------------------------------
+@requires_cuda
+@pytest.mark.parametrize("name", FB_CASES)
+def test_floating_base_vs_reference_golden(name):
+    rb = make_fb_robot(name)
+    g = load_fb_golden(name)
+    eng, e32 = _engine(rb), _engine(rb, torch.float32)
+    assert eng.floating_base and eng.n == rb.get_num_vel() and eng.nq == rb.get_num_pos()
+    q, qd, qdd = g["q"], g["qd"], g["qdd"]
+    c, v, a, f = eng.rnea(q, qd, qdd)
+    for got, key in ((c, "c"), (v, "v"), (a, "a"), (f, "f")):
+        assert rel_err(got, g[key]) < TOL_F64, key
+    assert rel_err(eng.rnea(q, qd)[0], g["c_noqdd"]) < TOL_F64
+    assert rel_err(eng.rnea(q, qd, qdd, GRAVITY=-3.7)[0], g["c_galt"]) < TOL_F64
+    assert rel_err(eng.rnea(q, qd, qdd, outputs="c"), g["c"]) < TOL_F64
+    assert rel_err(eng.rnea_grad(q, qd, qdd), g["dc_du"]) < TOL_F64
+    assert rel_err(eng.rnea_grad(q, qd, qdd, USE_VELOCITY_DAMPING=True), g["dc_du_damped"]) < TOL_F64
+    assert rel_err(eng.rnea_grad(q, qd), g["dc_du_noqdd"]) < TOL_F64
+    assert rel_err(eng.minv(q), g["Minv"]) < TOL_F64
+    assert rel_err(eng.minv(q, output_dense=False), g["Minv_sparse"]) < TOL_F64
+    # one knot point, reference shapes
+    c1, v1, _, _ = eng.rnea(q[0], qd[0], qdd[0])
+    assert c1.shape == (eng.n,) and v1.shape == (6, eng.NB) and rel_err(c1, g["c"][0]) < TOL_F64
+    assert rel_err(eng.rnea_grad(q[0], qd[0], qdd[0]), g["dc_du"][0]) < TOL_F64
+    assert rel_err(eng.minv(q[0]), g["Minv"][0]) < TOL_F64
+    # FP32
+    assert rel_err(e32.rnea(q, qd, qdd)[0], g["c"]) < TOL_F32
+    assert rel_err(e32.rnea_grad(q, qd, qdd), g["dc_du"]) < TOL_F32
+    assert rel_err(e32.minv(q), g["Minv"]) < 5 * TOL_F32
+    with pytest.raises(NotImplementedError):
+        eng.crba(q)
+
+
+@requires_cuda
+@pytest.mark.parametrize("name,B", [("hyq", 257), ("atlas", 65)])
+def test_floating_base_batched_vs_oracle_and_identities(name, B):
+    """Ragged device batches against the scalar oracle; Minv inverts the mass matrix assembled
+    from the engine's own rnea columns; dc_dqd matches central differences of rnea."""
+    from oracle.rbd_oracle_fb import FloatingScalarOracle
+    rb = make_fb_robot(name)
+    eng, so = _engine(rb), FloatingScalarOracle(rb)
+    nv = eng.n
+    q, qd, qdd = rb.random_state(np.random.default_rng(B), B)
+    tq, tqd, tqdd = _t(q), _t(qd), _t(qdd)
+    cbuf = torch.empty(B, nv, dtype=torch.float64, device="cuda")
+    dc = eng.rnea_grad(tq, tqd, tqdd, c_out=cbuf).cpu().numpy()
+    M = eng.minv(tq).cpu().numpy()
+    c = eng.rnea(tq, tqd, tqdd, outputs="c").cpu().numpy()
+    assert np.array_equal(c, cbuf.cpu().numpy())
+    for k in range(0, B, 8):
+        assert rel_err(c[k], so.rnea(q[k], qd[k], qdd[k])[0]) < TOL_F64
+        assert rel_err(dc[k], so.rnea_grad(q[k], qd[k], qdd[k])) < TOL_F64
+        assert rel_err(M[k], so.minv(q[k])) < TOL_F64
+    zero = torch.zeros_like(tqd)
+    c0 = eng.rnea(tq, zero, zero, GRAVITY=0.0, outputs="c")
+    H = torch.stack([eng.rnea(tq, zero, torch.eye(nv, dtype=torch.float64, device="cuda")[j].expand(B, nv).contiguous(),
+                              GRAVITY=0.0, outputs="c") - c0 for j in range(nv)], dim=2)
+    eye = torch.eye(nv, dtype=torch.float64, device="cuda")
+    assert float((torch.as_tensor(M, device="cuda") @ H - eye).abs().max()) < 1e-9
+    h = 1e-6
+    scale = np.abs(dc).max(axis=(1, 2), keepdims=True)
+    for j in (0, 4, 5, 6, nv - 1):
+        dv = torch.zeros(nv, dtype=torch.float64, device="cuda"); dv[j] = h
+        num = ((eng.rnea(tq, tqd + dv, tqdd, outputs="c") - eng.rnea(tq, tqd - dv, tqdd, outputs="c")) / (2 * h)).cpu().numpy()
+        assert np.max(np.abs(num - dc[:, :, nv + j]) / scale[:, :, 0]) < 1e-7
+    assert eng.minv(tq[:0]).shape == (0, nv, nv)

@@ -18,7 +18,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = _capi.load_library()
     header = open(os.path.join(ROOT, "include", "rbd_b200.h")).read()
     declared = set(re.findall(r"\b(rbd_[a-z0-9_]+)\s*\(", header))
-    declared -= {"rbd_model", "rbd_ee_model"}
+    declared -= {"rbd_model", "rbd_ee_model", "rbd_fb_model"}
     assert declared == set(_capi.exported_symbols()), declared ^ set(_capi.exported_symbols())
     for sym in sorted(declared):
         assert hasattr(lib, sym), "missing export " + sym
@@ -96,6 +96,40 @@ def test_ee_selection_order_and_errors():
     bad.ee_joint = np.array([9], dtype=np.int32)
     with pytest.raises(_capi.RbdError):
         _capi.EeModelHandle(bad)
+
+
+def test_fb_model_compiler_finds_the_base_layout():
+    """compile_fb_model re-discovers position / quaternion layout and rotation sense of the base
+    transform by probing the robot's own callable, and rejects what it cannot represent."""
+    from rbdreference_b200.model import compile_fb_model
+    rb = robots.by_name("hyq_fb")
+    fb = compile_fb_model(rb)
+    assert (fb.NB, fb.nv, fb.nq) == (13, 18, 19)
+    assert (fb.pos_off, fb.quat_off, fb.w_first, fb.transpose) == (0, 3, 0, 0)
+    assert list(fb.parent[:5]) == [-1, 0, 1, 2, 0] and np.array_equal(fb.I[0].reshape(6, 6), rb.get_Imat_by_id(0))
+    assert np.array_equal(fb.XA[1:], compile_model(robots.hyq()).XA)
+    h = _capi.FbModelHandle(fb)
+    assert _capi.load_library().rbd_fb_model_num_vel(h.ptr) == 18
+
+    class QuatFirstW(robots.FloatingBaseRobot):       # q[0:7] = (w, x, y, z, px, py, pz), E = R
+        def get_Xmat_Func_by_id(self, i):
+            if i != 0:
+                return super().get_Xmat_Func_by_id(i)
+            return lambda q7: robots.xrot(robots.quat_rotation([q7[1], q7[2], q7[3], q7[0]])) @ robots.xlt(q7[4:7])
+    fb2 = compile_fb_model(QuatFirstW(robots.hyq()))
+    assert (fb2.pos_off, fb2.quat_off, fb2.w_first, fb2.transpose) == (4, 0, 1, 1)
+
+    class Odd(robots.FloatingBaseRobot):
+        def get_Xmat_Func_by_id(self, i):
+            if i != 0:
+                return super().get_Xmat_Func_by_id(i)
+            return lambda q7: 2.0 * robots.FloatingBaseRobot.base_transform(q7)
+    with pytest.raises(ValueError, match="supported layout"):
+        compile_fb_model(Odd(robots.hyq()))
+    bad = compile_fb_model(rb)
+    bad.parent = bad.parent.copy(); bad.parent[3] = -1
+    with pytest.raises(_capi.RbdError):
+        _capi.FbModelHandle(bad)
 
 
 def test_model_compiler_flop_model_matches_survey_table():

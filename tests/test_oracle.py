@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, load_ee_golden, rel_err, random_states, make_robot
+from conftest import FB_CASES, GOLDEN_CASES, load_ee_golden, load_fb_golden, make_fb_robot, rel_err, random_states, make_robot
 from oracle.rbd_oracle import BatchOracle, ScalarOracle
 from oracle import build_ref
 
@@ -117,6 +117,53 @@ def test_end_effector_gradient_is_the_derivative_of_the_pose(name):
         num = (bo.end_effector_pose(q + dq) - bo.end_effector_pose(q - dq)) / (2 * h)
         num[..., 3:] = (num[..., 3:] + np.pi / (2 * h)) % (np.pi / h) - np.pi / (2 * h)     # angle wrap
         assert np.max(np.abs(num - G[..., j])) < 1e-6 * max(1.0, np.max(np.abs(G)))
+
+
+@pytest.mark.parametrize("name", FB_CASES)
+def test_floating_base_oracle_vs_golden(name):
+    """The floating-base branches against the unmodified reference's outputs."""
+    from oracle.rbd_oracle_fb import FloatingScalarOracle
+    rb = make_fb_robot(name)
+    g = load_fb_golden(name)
+    so = FloatingScalarOracle(rb)
+    assert np.allclose(rb.get_Xmat_Func_by_id(0)(g["q"][0, 0:7]), g["X0_first"], rtol=0, atol=1e-15)
+    for k in range(g["q"].shape[0]):
+        q, qd, qdd = g["q"][k], g["qd"][k], g["qdd"][k]
+        c, v, a, f = so.rnea(q, qd, qdd)
+        for got, key in ((c, "c"), (v, "v"), (a, "a"), (f, "f")):
+            assert rel_err(got, g[key][k]) < PIN, key
+        assert rel_err(so.rnea(q, qd)[0], g["c_noqdd"][k]) < PIN
+        assert rel_err(so.rnea(q, qd, qdd, GRAVITY=-3.7)[0], g["c_galt"][k]) < PIN
+        assert rel_err(so.rnea_grad(q, qd, qdd), g["dc_du"][k]) < PIN
+        assert rel_err(so.rnea_grad(q, qd, qdd, USE_VELOCITY_DAMPING=True), g["dc_du_damped"][k]) < PIN
+        assert rel_err(so.rnea_grad(q, qd), g["dc_du_noqdd"][k]) < PIN
+        assert rel_err(so.minv(q), g["Minv"][k]) < PIN
+        assert rel_err(so.minv(q, output_dense=False), g["Minv_sparse"][k]) < PIN
+
+
+def test_floating_base_identities():
+    """Minv inverts the mass matrix assembled from rnea columns; dc_dqd and the joint columns of
+    dc_dq match central differences of rnea (the base columns of dc_dq are derivatives along base
+    twists, not along q[0:7])."""
+    from oracle.rbd_oracle_fb import FloatingScalarOracle
+    rb = make_fb_robot("hyq")
+    so = FloatingScalarOracle(rb)
+    nv = so.n
+    q, qd, qdd = rb.random_state(np.random.default_rng(3))
+    c0 = so.rnea(q, 0 * qd, 0 * qdd, GRAVITY=0.0)[0]
+    M = np.stack([so.rnea(q, 0 * qd, np.eye(nv)[j], GRAVITY=0.0)[0] - c0 for j in range(nv)], axis=1)
+    assert np.max(np.abs(M - M.T)) < 1e-12
+    assert np.max(np.abs(so.minv(q) @ M - np.eye(nv))) < 1e-11
+    dc = so.rnea_grad(q, qd, qdd)
+    h, scale = 1e-6, np.max(np.abs(dc))
+    for j in range(nv):
+        dv = np.zeros(nv); dv[j] = h
+        num = (so.rnea(q, qd + dv, qdd)[0] - so.rnea(q, qd - dv, qdd)[0]) / (2 * h)
+        assert np.max(np.abs(num - dc[:, nv + j])) / scale < 1e-8
+        if j >= 6:
+            dq = np.zeros(nv + 1); dq[j + 1] = h
+            num = (so.rnea(q + dq, qd, qdd)[0] - so.rnea(q - dq, qd, qdd)[0]) / (2 * h)
+            assert np.max(np.abs(num - dc[:, j])) / scale < 1e-8
 
 
 @pytest.mark.parametrize("name", ["iiwa14", "hyq", "atlas"])
