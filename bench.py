@@ -101,7 +101,8 @@ class CpuReference:
 
 def per_eval_cpu_seconds(robot_name, op):
     """Rough single-core cost used only to size the bounded sample."""
-    base = {"iiwa14": 6e-3, "hyq": 9e-3, "atlas": 65e-3}.get(robot_name, 20e-3)
+    base = {"iiwa14": 6e-3, "hyq": 9e-3, "atlas": 65e-3, "iiwa14_fb": 20e-3, "hyq_fb": 30e-3,
+            "atlas_fb": 120e-3}.get(robot_name, 20e-3)
     return base * {"rnea_grad": 1.0, "minv": 0.15, "rnea": 0.09, "crba": 0.1, "fd": 0.25, "fd_grad": 1.6,
                    "ee_grad": 0.25}[op]
 
@@ -212,8 +213,11 @@ def workload_name(args):
     return "%s %s %s, %d knot points per GPU" % (args.robot, args.op, "FP64" if args.dtype == "f64" else "FP32", args.batch)
 
 
-def synth_host(n, B, seed):
+def synth_host(n, B, seed, robot_name=None):
     rng = np.random.default_rng(seed)
+    if robot_name and robot_name.endswith("_fb"):           # floating base: q has n + 1 entries, unit quaternion
+        from rbdreference_b200 import robots
+        return robots.by_name(robot_name).random_state(rng, B)
     return (rng.uniform(-np.pi, np.pi, (B, n)), rng.uniform(-1, 1, (B, n)), rng.uniform(-1, 1, (B, n)))
 
 
@@ -230,7 +234,7 @@ def run_reference(args):
     # bounded sample per step: ~0.4 s of wall time on this host
     per = per_eval_cpu_seconds(args.robot, args.op)
     sample = int(max(cpu.cores, min(4096, round(0.4 * cpu.cores / per))))
-    q, qd, qdd = synth_host(n, sample, 0xB200)
+    q, qd, qdd = synth_host(n, sample, 0xB200, args.robot)
     for _ in range(max(args.warmup, 1)):
         cpu.run(q, qd, qdd)
     t = 0.0
@@ -284,7 +288,13 @@ def run_ours(args):
 
     # synthetic inputs, resident in HBM: same fp64 draws for both precisions
     gen = torch.Generator(device=dev).manual_seed(0xB200 + rank)
-    q = ((torch.rand(B, n, generator=gen, device=dev, dtype=torch.float64) * 2 - 1) * np.pi).to(tdtype)
+    q = (torch.rand(B, eng.nq, generator=gen, device=dev, dtype=torch.float64) * 2 - 1) * np.pi
+    if eng.floating_base:                          # q[0:7] = base position + unit quaternion
+        if args.op not in ("rnea", "rnea_grad", "minv"):
+            raise SystemExit("bench.py: floating-base robots support --op rnea | rnea_grad | minv")
+        q[:, 0:3] /= np.pi
+        q[:, 3:7] /= q[:, 3:7].norm(dim=1, keepdim=True)
+    q = q.to(tdtype)
     qd = (torch.rand(B, n, generator=gen, device=dev, dtype=torch.float64) * 2 - 1).to(tdtype)
     qdd = (torch.rand(B, n, generator=gen, device=dev, dtype=torch.float64) * 2 - 1).to(tdtype)
     if args.op == "rnea_grad":
@@ -350,7 +360,7 @@ def run_ours(args):
 
     # ---- e2e: public API with HOST buffers, H2D + kernel + D2H inside the timed region ----
     e2e = None
-    if not args.no_e2e and args.op not in ("fd", "fd_grad", "ee_grad"):
+    if not args.no_e2e and args.op not in ("fd", "fd_grad", "ee_grad") and not eng.floating_base:
         e2e = measure_e2e(args, eng, torch, dist, dev, rank, world, n, B, tdtype, itemsize)
 
     # ---- roofline of the dominant (only) kernel: algorithmic flops / bytes per launch ----
@@ -468,7 +478,7 @@ def measure_cpu_baseline(args, n):
     cpu = CpuReference(args.robot, args.op)
     per = per_eval_cpu_seconds(args.robot, args.op)
     sample = int(max(cpu.cores, min(16384, round(12.0 * cpu.cores / per))))   # ~12 s of wall time
-    q, qd, qdd = synth_host(n, sample, 0xB200)
+    q, qd, qdd = synth_host(n, sample, 0xB200, args.robot)
     cpu.run(q[: cpu.cores], qd[: cpu.cores], qdd[: cpu.cores])                # warm the workers
     t = cpu.run(q, qd, qdd)
     cpu.close()

@@ -349,6 +349,42 @@ class FbModel:
     def nq(self) -> int:
         return self.NB + 6
 
+    def flops(self, op: str) -> int:
+        """Algorithmic flops per evaluation: the SURVEY.md 8d formulae with the base counted as one
+        body that owns six derivative / matrix columns (S = eye(6)) instead of one."""
+        NB = self.NB
+        depth = np.zeros(NB, dtype=np.int64)
+        size = np.ones(NB, dtype=np.int64)
+        for i in range(1, NB):
+            depth[i] = depth[self.parent[i]] + 1
+        for i in range(NB - 1, 0, -1):
+            size[self.parent[i]] += size[i]
+        own = np.where(np.arange(NB) == 0, 6, 1)
+        P = np.where(np.arange(NB) == 0, 0, 5 + depth)           # columns owned by ancestors
+        A = P + own
+        STc = size + np.where(np.arange(NB) == 0, 5, 0)          # columns owned by the subtree
+        Bi = A + STc - own
+        nr = np.arange(NB) > 0
+        rnea = int(NB * (54 + 132 + 10 + 168) + 72 * np.sum(nr))
+        if op == "rnea":
+            return rnea
+        if op == "rnea_grad":
+            return int(rnea + 2 * np.sum(132 * P + 212 * A + 4) + 2 * 72 * np.sum(Bi[nr]) + 72 * np.sum(nr))
+        if op == "minv":
+            nv = NB + 5
+            return int(np.sum(55 + 2 * STc) + np.sum(906 + 84 * STc[nr]) + np.sum(66 + 81 * nv) * np.sum(nr) + 6 * 6 * 6 * 2)
+        raise KeyError(op)
+
+    def io_bytes(self, op: str, itemsize: int = 8, full_rnea: bool = False) -> int:
+        nv, nq = self.nv, self.nq
+        if op == "rnea":
+            return (nq + 2 * nv + nv + (18 * self.NB if full_rnea else 0)) * itemsize
+        if op == "rnea_grad":
+            return (nq + 2 * nv + 2 * nv * nv) * itemsize
+        if op == "minv":
+            return (nq + nv * nv) * itemsize
+        raise KeyError(op)
+
 
 def _fb_candidate(q7, pos_off, quat_off, w_first, transpose):
     p = q7[pos_off:pos_off + 3]
