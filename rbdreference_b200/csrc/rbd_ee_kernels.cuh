@@ -61,16 +61,30 @@ __device__ __forceinline__ T darctan2(T y, T x, T yp, T xp) { return (-xp * y + 
 
 // pose_out   (B, n_ee, 6)      [x y z roll pitch yaw], may be null when GRAD
 // grad_out   (B, n_ee, 6, n)   only when GRAD
-template <typename T, bool GRAD>
+// COEF_SMEM: joint coefficients staged in shared memory (small robots); otherwise they are read from
+// the constant bank (large robots, where 72 n values per CTA would cost more occupancy than they save).
+template <typename T, bool GRAD, bool COEF_SMEM>
 __global__ void __launch_bounds__(kEeMaxWarps * 32)
 ee_pose_kernel(const __grid_constant__ EeModel<T> m, int64_t B, const T* __restrict__ q, T* __restrict__ pose_out,
                T* __restrict__ grad_out, int grad_pitch) {
   extern __shared__ __align__(16) unsigned char ee_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int n = m.n, n_ee = m.n_ee;
+  // joint coefficients: [n][72] = TA | TB | TC | DA | DB | DC.  The joint index comes from the chain
+  // table at run time; indexed constant-bank loads stalled the FMA chain (ncu: short scoreboard), a
+  // broadcast shared-memory load does not.
+  T* coef = reinterpret_cast<T*>(ee_smem_raw);
+  if (COEF_SMEM) {
+    for (int k = threadIdx.x; k < n * 72; k += blockDim.x) {
+      const int j = k / 72, w = k - j * 72, which = w / 12, idx = w - which * 12;
+      const T* src = which == 0 ? m.TA[j] : which == 1 ? m.TB[j] : which == 2 ? m.TC[j] : which == 3 ? m.DA[j] : which == 4 ? m.DB[j] : m.DC[j];
+      coef[k] = src[idx];
+    }
+    __syncthreads();
+  }
   const int pose_vals = 32 * n_ee * 6;
   const int per_warp = pose_vals + (GRAD ? 32 * grad_pitch : 0);
-  T* pose_tile = reinterpret_cast<T*>(ee_smem_raw) + (size_t)warp * per_warp;
+  T* pose_tile = coef + (COEF_SMEM ? ((n * 72 + 1) & ~1) : 0) + (size_t)warp * per_warp;
   T* grad_tile = pose_tile + pose_vals;
   const int64_t ntask = (B + 31) / 32;
   for (int64_t task = (int64_t)blockIdx.x * nwarps + warp; task < ntask; task += (int64_t)gridDim.x * nwarps) {
@@ -94,7 +108,8 @@ ee_pose_kernel(const __grid_constant__ EeModel<T> m, int64_t B, const T* __restr
         f1s[t] = f1; f2s[t] = f2;
         T Tk[12], Nw[12];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) { suf[t][k] = M[k]; Tk[k] = fma_t(m.TC[j][k], f2, fma_t(m.TB[j][k], f1, m.TA[j][k])); }
+        for (int k = 0; k < 12; ++k) { suf[t][k] = M[k]; Tk[k] = COEF_SMEM ? fma_t(coef[j * 72 + 24 + k], f2, fma_t(coef[j * 72 + 12 + k], f1, coef[j * 72 + k]))
+                                                                  : fma_t(m.TC[j][k], f2, fma_t(m.TB[j][k], f1, m.TA[j][k])); }
         mul34(Tk, M, T(1), Nw);
 #pragma unroll
         for (int k = 0; k < 12; ++k) M[k] = Nw[k];
@@ -121,8 +136,10 @@ ee_pose_kernel(const __grid_constant__ EeModel<T> m, int64_t B, const T* __restr
 #pragma unroll
           for (int k = 0; k < 12; ++k) {
             S[k] = suf[t][k];
-            dT[k] = fma_t(m.DC[j][k], f2, fma_t(m.DB[j][k], f1, m.DA[j][k]));
-            Tk[k] = fma_t(m.TC[j][k], f2, fma_t(m.TB[j][k], f1, m.TA[j][k]));
+            dT[k] = COEF_SMEM ? fma_t(coef[j * 72 + 60 + k], f2, fma_t(coef[j * 72 + 48 + k], f1, coef[j * 72 + 36 + k]))
+                              : fma_t(m.DC[j][k], f2, fma_t(m.DB[j][k], f1, m.DA[j][k]));
+            Tk[k] = COEF_SMEM ? fma_t(coef[j * 72 + 24 + k], f2, fma_t(coef[j * 72 + 12 + k], f1, coef[j * 72 + k]))
+                              : fma_t(m.TC[j][k], f2, fma_t(m.TB[j][k], f1, m.TA[j][k]));
           }
           mul34(dT, S, T(1), W);       // hidden row of dT is zero, of S it is (0,0,0,1)
           mul34(P, W, T(0), dX);
@@ -141,10 +158,23 @@ ee_pose_kernel(const __grid_constant__ EeModel<T> m, int64_t B, const T* __restr
         __syncwarp();
         // a knot point's (6, n) block of this end effector is contiguous in HBM
         const int row = 6 * n;
-        for (int r = 0; r < nlive; ++r) {
-          T* dst = grad_out + ((b0 + r) * n_ee + e) * (int64_t)row;
-          const T* src = grad_tile + r * grad_pitch;
-          for (int k = lane; k < row; k += 32) __stcs(dst + k, src[k]);
+        if (n_ee == 1) {
+          // the whole warp's slab is contiguous: full 256-byte stores whatever the row length
+          T* dst = grad_out + b0 * (int64_t)row;
+          const int total = nlive * row;
+          int r = 0, c = lane;
+          while (c >= row) { c -= row; ++r; }
+          for (int k = lane; k < total; k += 32) {
+            __stcs(dst + k, grad_tile[r * grad_pitch + c]);
+            c += 32;
+            while (c >= row) { c -= row; ++r; }
+          }
+        } else {
+          for (int r = 0; r < nlive; ++r) {
+            T* dst = grad_out + ((b0 + r) * n_ee + e) * (int64_t)row;
+            const T* src = grad_tile + r * grad_pitch;
+            for (int k = lane; k < row; k += 32) __stcs(dst + k, src[k]);
+          }
         }
         __syncwarp();
       }
