@@ -179,8 +179,12 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
     for (int r = 0; r < 6; ++r) cb[r] = lf[0][r];
     for (int i = 1; i < NB; ++i) cb[i + 5] = dot6(m.d.S[i], lf[i]);
   }
-  T* out = dc_du + b * (int64_t)2 * nv * nv;
+  T* gout = dc_du + b * (int64_t)2 * nv * nv;
   const int ld = 2 * nv;
+  // Results are produced one column at a time but stored row-major: four columns are collected in
+  // obuf[row][dq | dqd][column & 3] and flushed as 32-byte pieces of each row, so that the 8-byte
+  // stores of one thread fill whole sectors (ncu, before: 22 GB of DRAM traffic for 1.4 GB of results).
+  T obuf[kFbMaxNv][8];
   T sdv[RBD_MAX_DOF][12], sda[RBD_MAX_DOF][12], sdf[RBD_MAX_DOF][12];   // per body: d/dq (6) | d/dqd (6) of column c
   T Xg[6];                                                                  // X0 a_base (:1175)
   {
@@ -189,6 +193,7 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
   }
   for (int c = 0; c < nv; ++c) {
     const int bc = c < 6 ? 0 : c - 5;
+    const int cg = c & 3;
     const unsigned sub = m.d.sub_mask[bc];
     for (int i = bc; i < NB; ++i) {
       if (!((sub >> i) & 1u)) continue;
@@ -271,8 +276,8 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
 #pragma unroll
       for (int r = 0; r < 6; ++r) { Fq[r] = sdf[i][r]; Fd[r] = sdf[i][6 + r]; }
       if (i == 0) break;                        // base column: rows 0..5 are written below
-      out[(i + 5) * ld + c] = dot6(m.d.S[i], Fq);                              // :1284
-      out[(i + 5) * ld + nv + c] = dot6(m.d.S[i], Fd);                         // :1325
+      obuf[i + 5][cg] = dot6(m.d.S[i], Fq);                                    // :1284
+      obuf[i + 5][4 + cg] = dot6(m.d.S[i], Fd);                                // :1325
       T X[18], tq[6], td[6];
       build_X(m.d, i, lb[i][0], lb[i][1], X);
       if (i == bc) {                                                           // :1292-1294
@@ -298,8 +303,8 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
     if (bc != 0) {
       for (int j = m.d.parent[bc]; j > 0; j = m.d.parent[j]) {
         touched |= 1u << j;
-        out[(j + 5) * ld + c] = dot6(m.d.S[j], Fq);
-        out[(j + 5) * ld + nv + c] = dot6(m.d.S[j], Fd);
+        obuf[j + 5][cg] = dot6(m.d.S[j], Fq);
+        obuf[j + 5][4 + cg] = dot6(m.d.S[j], Fd);
         T X[18], tq[6], td[6];
         build_X(m.d, j, lb[j][0], lb[j][1], X);
         XT_apply(X, Fq, tq);
@@ -310,15 +315,24 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
     }
 #pragma unroll
     for (int r = 0; r < 6; ++r) {                                              // :1282, :1325 with S = eye(6)
-      out[r * ld + c] = Fq[r];
-      out[r * ld + nv + c] = Fd[r];
+      obuf[r][cg] = Fq[r];
+      obuf[r][4 + cg] = Fd[r];
     }
     for (int i = 1; i < NB; ++i) {
       if ((touched >> i) & 1u) continue;
-      out[(i + 5) * ld + c] = T(0);
-      out[(i + 5) * ld + nv + c] = T(0);
+      obuf[i + 5][cg] = T(0);
+      obuf[i + 5][4 + cg] = T(0);
+    }
+    if (cg == 3 || c == nv - 1) {
+      const int c0 = c - cg;
+      for (int row = 0; row < nv; ++row) {
+        T* orow = gout + row * ld + c0;
+        for (int k = 0; k <= cg; ++k) orow[k] = obuf[row][k];
+        for (int k = 0; k <= cg; ++k) orow[nv + k] = obuf[row][4 + k];
+      }
     }
   }
+  T* out = gout;
   if (use_damping) {                                                           // :1336-1341, to the letter
     for (int r = 0; r < 5; ++r)
       for (int cc = 0; cc < 5; ++cc) out[r * ld + nv + cc] += m.d.damping[0];
@@ -416,7 +430,9 @@ fb_minv_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restr
   }
   T colM[kFbMaxNv];
   T colF[RBD_MAX_DOF][6];
+  T obuf[kFbMaxNv][4];      // four finished columns, flushed as 32-byte pieces of each row
   for (int j = 0; j < nv; ++j) {
+    const int jg = j & 3;
     for (int i = 0; i < nv; ++i) colM[i] = T(0);
     if (j < 6) {
 #pragma unroll
@@ -445,7 +461,7 @@ fb_minv_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restr
     }
     // forward pass restricted to column j (:760-781)
 #pragma unroll
-    for (int r = 0; r < 6; ++r) { colF[0][r] = colM[r]; Mb[r * nv + j] = colM[r]; }   // :779
+    for (int r = 0; r < 6; ++r) { colF[0][r] = colM[r]; obuf[r][jg] = colM[r]; }     // :779
     for (int i = 1; i < NB; ++i) {
       const int p = m.d.parent[i];
       T X[18], Fp[6], Fi[6];
@@ -456,12 +472,24 @@ fb_minv_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restr
       X_apply(X, Fp, Fi);
 #pragma unroll
       for (int r = 0; r < 6; ++r) colF[i][r] = fma_t(m.d.S[i][r], mij, Fi[r]); // :774-776
-      Mb[(i + 5) * nv + j] = mij;
+      obuf[i + 5][jg] = mij;
     }
-  }
-  if (output_dense) {                                                          // :799-804: range(NB), not nv
-    for (int col = 0; col < NB; ++col)
-      for (int row = col + 1; row < NB; ++row) Mb[row * nv + col] = Mb[col * nv + row];
+    // :799-804 mirrors the leading NB x NB block (range(NB), not nv): Minv[row, col] = Minv[col, row]
+    // for col < row < NB.  Column j is final above its diagonal, so it also IS the left part of row j,
+    // which is contiguous in memory; entries of the block below the diagonal are not stored from the
+    // column pass at all.
+    if (output_dense && j < NB)
+      for (int i = 0; i < j; ++i) Mb[j * nv + i] = obuf[i][jg];
+    if (jg == 3 || j == nv - 1) {
+      const int j0 = j - jg;
+      for (int row = 0; row < nv; ++row) {
+        T* orow = Mb + row * nv + j0;
+        for (int k = 0; k <= jg; ++k) {
+          const bool mirrored = output_dense && row < NB && row > j0 + k;      // j0 + k < row < NB: filled by row `row`'s pass
+          if (!mirrored) orow[k] = obuf[row][k];
+        }
+      }
+    }
   }
 }
 

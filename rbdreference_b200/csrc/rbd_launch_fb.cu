@@ -46,6 +46,14 @@ void fill_fb(const RbdFbModelDesc* fd, FbModel<T>& out) {
   }
 }
 
+// Occupancy throttle: the per-thread local arrays of the gradient / inverse kernels (5-15 KB) only stay
+// in the 126 MB L2 when few enough threads are resident; a dummy dynamic shared-memory request caps
+// the CTAs per SM (RBD_FB_SMEM_KB overrides it for experiments).
+size_t fb_throttle_smem(int default_kb) {
+  static int env = [] { const char* e = std::getenv("RBD_FB_SMEM_KB"); return e ? std::atoi(e) : -1; }();
+  return (size_t)(env >= 0 ? env : default_kb) * 1024;
+}
+
 template <typename T>
 int launch_fb_rnea(const rbd_fb_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, T* c, T* v, T* a, T* f,
                    void* stream) {
@@ -60,8 +68,13 @@ int launch_fb_rnea_grad(const rbd_fb_model* m, int64_t B, const T* q, const T* q
                         T* c_out, void* stream) {
   RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_fb_rnea_grad: null model/q/qd/dc_du or negative B");
   if (B == 0) return 0;
-  fb_rnea_grad_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, qd, qdd, g, damp,
-                                                                                             dc_du, c_out);
+  const size_t smem = fb_throttle_smem(0);
+  auto kern = fb_rnea_grad_kernel<T>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+  }
+  kern<<<blocks_for(B, kFbThreads), kFbThreads, smem, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, qd, qdd, g, damp, dc_du, c_out);
   return cuda_status("rbd_fb_rnea_grad");
 }
 
@@ -69,7 +82,13 @@ template <typename T>
 int launch_fb_minv(const rbd_fb_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && B >= 0, "rbd_fb_minv: null model/q/Minv or negative B");
   if (B == 0) return 0;
-  fb_minv_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, dense, Minv);
+  const size_t smem = fb_throttle_smem(0);
+  auto kern = fb_minv_kernel<T>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+  }
+  kern<<<blocks_for(B, kFbThreads), kFbThreads, smem, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, dense, Minv);
   return cuda_status("rbd_fb_minv");
 }
 
