@@ -244,6 +244,16 @@ int rbd_fb_rnea_grad_f32(const rbd_fb_model_t* m, int64_t B, const float* q, con
                          float gravity, int use_velocity_damping, float* dc_du, float* c_out, void* stream);
 int rbd_fb_minv_f64(const rbd_fb_model_t* m, int64_t B, const double* q, int output_dense, double* Minv, void* stream);
 int rbd_fb_minv_f32(const rbd_fb_model_t* m, int64_t B, const float* q, int output_dense, float* Minv, void* stream);
+/* forward_dynamics / forward_dynamics_grad (RBDReference.py:1369-1384) of a floating-base robot: the
+ * same compositions as rbd_forward_dynamics*, u / qdd (B, NB+5), qdd_dq / qdd_dqd (B, NB+5, NB+5). */
+int rbd_fb_forward_dynamics_f64(const rbd_fb_model_t* m, int64_t B, const double* q, const double* qd, const double* u,
+                                double* qdd, double* Minv_out, void* stream);
+int rbd_fb_forward_dynamics_f32(const rbd_fb_model_t* m, int64_t B, const float* q, const float* qd, const float* u,
+                                float* qdd, float* Minv_out, void* stream);
+int rbd_fb_forward_dynamics_grad_f64(const rbd_fb_model_t* m, int64_t B, const double* q, const double* qd,
+                                     const double* u, double* qdd_dq, double* qdd_dqd, double* qdd_out, void* stream);
+int rbd_fb_forward_dynamics_grad_f32(const rbd_fb_model_t* m, int64_t B, const float* q, const float* qd, const float* u,
+                                     float* qdd_dq, float* qdd_dqd, float* qdd_out, void* stream);
 
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
 /* Runs a dependent-chain FMA micro-benchmark on `stream`'s device and returns the achieved

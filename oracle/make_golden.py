@@ -140,9 +140,14 @@ def run_fb_case(name, B, seed):
     rb = make_fb_robot(name)
     ref = RBDReference(rb)
     q, qd, qdd = rb.random_state(np.random.default_rng(seed), B)
-    keys = ["c", "v", "a", "f", "c_noqdd", "c_galt", "dc_du", "dc_du_damped", "dc_du_noqdd", "Minv", "Minv_sparse"]
+    keys = ["c", "v", "a", "f", "c_noqdd", "c_galt", "dc_du", "dc_du_damped", "dc_du_noqdd", "Minv", "Minv_sparse",
+            "fd_qdd", "fd_dq", "fd_dqd"]
     acc = {k: [] for k in keys}
+    u = np.random.default_rng(seed + 500).uniform(-10.0, 10.0, qd.shape)
     for k in range(B):
+        acc["fd_qdd"].append(ref.forward_dynamics(q[k], qd[k], u[k]))
+        fdq, fdqd = ref.forward_dynamics_grad(q[k], qd[k], u[k])
+        acc["fd_dq"].append(fdq); acc["fd_dqd"].append(fdqd)
         c, v, a, f = ref.rnea(q[k], qd[k], qdd[k])
         for key, val in (("c", c), ("v", v), ("a", a), ("f", f)):
             acc[key].append(np.array(val))
@@ -153,7 +158,7 @@ def run_fb_case(name, B, seed):
         acc["dc_du_noqdd"].append(ref.rnea_grad(q[k], qd[k]))
         acc["Minv"].append(ref.minv(q[k]))
         acc["Minv_sparse"].append(ref.minv(q[k], output_dense=False))
-    out = dict(q=q, qd=qd, qdd=qdd, X0_first=rb.get_Xmat_Func_by_id(0)(q[0, 0:7]))
+    out = dict(q=q, qd=qd, qdd=qdd, u=u, X0_first=rb.get_Xmat_Func_by_id(0)(q[0, 0:7]))
     for key in keys:
         out[key] = np.stack(acc[key])
     path = os.path.join(ROOT, "tests", "golden", "fb_" + name[:-3] + ".npz")

@@ -235,3 +235,14 @@ class FloatingScalarOracle:
         dc_dq = self.rnea_grad_bpass_dq(q, f, df_dq)
         dc_dqd = self.rnea_grad_bpass_dqd(q, df_dqd, USE_VELOCITY_DAMPING)
         return np.hstack((dc_dq, dc_dqd))
+
+    # -- compositions (robot-agnostic upstream, RBDReference.py:1369-1384) ---------------------
+    def forward_dynamics(self, q, qd, u):
+        c = self.rnea(q, qd)[0]                                                  # :1370 (qdd omitted)
+        return self.minv(q) @ (u - c)                                            # :1371-1372
+
+    def forward_dynamics_grad(self, q, qd, u):
+        qdd = self.forward_dynamics(q, qd, u)                                    # :1377
+        dc_du = self.rnea_grad(q, qd, qdd)                                       # :1378
+        Minv = self.minv(q)                                                      # :1381
+        return -Minv @ dc_du[:, : self.n], -Minv @ dc_du[:, self.n:]             # :1379 splits at len(qd)

@@ -18,7 +18,7 @@ PLAIN_SYMBOLS = ["rbd_abi_version", "rbd_last_error_string", "rbd_model_create",
                  "rbd_measure_fma_peak", "rbd_launch_count",
                  "rbd_ee_model_create", "rbd_ee_model_destroy", "rbd_ee_model_num_ee",
                  "rbd_fb_model_create", "rbd_fb_model_destroy", "rbd_fb_model_num_vel"]
-FB_SYMBOLS = ["fb_rnea", "fb_rnea_grad", "fb_minv"]
+FB_SYMBOLS = ["fb_rnea", "fb_rnea_grad", "fb_minv", "fb_forward_dynamics", "fb_forward_dynamics_grad"]
 EE_SYMBOLS = ["end_effector_pose", "end_effector_pose_gradient"]
 
 
@@ -103,6 +103,8 @@ def load_library():
             "fb_rnea": [P, c_int64, P, P, P, real, P, P, P, P, P],
             "fb_rnea_grad": [P, c_int64, P, P, P, real, c_int, P, P, P],
             "fb_minv": [P, c_int64, P, c_int, P, P],
+            "fb_forward_dynamics": [P, c_int64, P, P, P, P, P, P],
+            "fb_forward_dynamics_grad": [P, c_int64, P, P, P, P, P, P, P],
             "end_effector_pose": [P, c_int64, P, P, P],
             "end_effector_pose_gradient": [P, c_int64, P, P, P, P],
         }

@@ -64,31 +64,6 @@ int cuda_status(const char* what) {
   return 0;
 }
 
-}  // namespace rbd_host
-
-using namespace rbd_host;
-
-namespace {
-
-template <typename T>
-int launch_minv_bpass(const rbd_model* m, int64_t B, const T* q, T* Minv, T* F, T* U, T* Dinv, void* stream) {
-  RBD_CHECK_ARGS(m && q && Minv && F && U && Dinv && B >= 0, "rbd_minv_bpass: null argument or negative B");
-  if (B == 0) return 0;
-  minv_bpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
-      pick<T>(m), B, q, Minv, F, U, Dinv);
-  return cuda_status("rbd_minv_bpass");
-}
-
-template <typename T>
-int launch_minv_fpass(const rbd_model* m, int64_t B, const T* q, T* Minv, T* F, const T* U, const T* Dinv,
-                      void* stream) {
-  RBD_CHECK_ARGS(m && q && Minv && F && U && Dinv && B >= 0, "rbd_minv_fpass: null argument or negative B");
-  if (B == 0) return 0;
-  minv_fpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
-      pick<T>(m), B, q, Minv, F, U, Dinv);
-  return cuda_status("rbd_minv_fpass");
-}
-
 // ---- forward dynamics (RBDReference.py:1369-1384): compositions of the fused drivers plus the
 // per-knot-point products of rbd_fd_kernels.cuh; temporaries are stream-ordered pool allocations.
 template <typename T, bool SPLIT>
@@ -140,21 +115,35 @@ int launch_fd_apply(int n, int mcols, int64_t B, const T* A, const T* R1, const 
   return cuda_status("rbd_forward_dynamics(apply)");
 }
 
-struct PoolBuf {
-  void* p = nullptr;
-  cudaStream_t s;
-  explicit PoolBuf(cudaStream_t st) : s(st) {}
-  int alloc(size_t bytes) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return fail(RBD_E_NO_DEVICE, "no CUDA device");
-    cudaMemPool_t pool = scratch_pool(dev);
-    if (!pool) return fail(RBD_E_NO_DEVICE, "cannot create the scratch memory pool");
-    cudaError_t e = cudaMallocFromPoolAsync(&p, bytes, pool, s);
-    if (e != cudaSuccess) { p = nullptr; return fail((int)e, cudaGetErrorString(e)); }
-    return 0;
-  }
-  ~PoolBuf() { if (p) cudaFreeAsync(p, s); }
-};
+template int launch_fd_apply<double, false>(int, int, int64_t, const double*, const double*, const double*, double, double*, double*, void*);
+template int launch_fd_apply<double, true>(int, int, int64_t, const double*, const double*, const double*, double, double*, double*, void*);
+template int launch_fd_apply<float, false>(int, int, int64_t, const float*, const float*, const float*, float, float*, float*, void*);
+template int launch_fd_apply<float, true>(int, int, int64_t, const float*, const float*, const float*, float, float*, float*, void*);
+
+}  // namespace rbd_host
+
+using namespace rbd_host;
+
+namespace {
+
+template <typename T>
+int launch_minv_bpass(const rbd_model* m, int64_t B, const T* q, T* Minv, T* F, T* U, T* Dinv, void* stream) {
+  RBD_CHECK_ARGS(m && q && Minv && F && U && Dinv && B >= 0, "rbd_minv_bpass: null argument or negative B");
+  if (B == 0) return 0;
+  minv_bpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
+      pick<T>(m), B, q, Minv, F, U, Dinv);
+  return cuda_status("rbd_minv_bpass");
+}
+
+template <typename T>
+int launch_minv_fpass(const rbd_model* m, int64_t B, const T* q, T* Minv, T* F, const T* U, const T* Dinv,
+                      void* stream) {
+  RBD_CHECK_ARGS(m && q && Minv && F && U && Dinv && B >= 0, "rbd_minv_fpass: null argument or negative B");
+  if (B == 0) return 0;
+  minv_fpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
+      pick<T>(m), B, q, Minv, F, U, Dinv);
+  return cuda_status("rbd_minv_fpass");
+}
 
 template <typename T>
 int launch_forward_dynamics(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* u, T* qdd, T* Minv_out,

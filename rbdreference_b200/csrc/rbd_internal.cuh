@@ -63,6 +63,29 @@ inline unsigned blocks_for(int64_t B, int threads) { return (unsigned)((B + thre
   do { if (!(cond)) return fail(RBD_E_INVALID_ARGUMENT, msg); } while (0)
 #define kGradSmemLimit smem_limit()
 
+// stream-ordered temporary from the private scratch pool, freed (stream-ordered) on scope exit
+struct PoolBuf {
+  void* p = nullptr;
+  cudaStream_t s;
+  explicit PoolBuf(cudaStream_t st) : s(st) {}
+  int alloc(size_t bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(RBD_E_NO_DEVICE, "no CUDA device");
+    cudaMemPool_t pool = scratch_pool(dev);
+    if (!pool) return fail(RBD_E_NO_DEVICE, "cannot create the scratch memory pool");
+    cudaError_t e = cudaMallocFromPoolAsync(&p, bytes, pool, s);
+    if (e != cudaSuccess) { p = nullptr; return fail((int)e, cudaGetErrorString(e)); }
+    return 0;
+  }
+  ~PoolBuf() { if (p) cudaFreeAsync(p, s); }
+};
+
+// Y = alpha A (R1 - R2) per knot point, the product of forward_dynamics(_grad) (rbd_fd_kernels.cuh); defined and
+// explicitly instantiated in rbd_capi.cu
+template <typename T, bool SPLIT>
+int launch_fd_apply(int n, int mcols, int64_t B, const T* A, const T* R1, const T* R2, T alpha, T* out0, T* out1,
+                    void* stream);
+
 // fused drivers (defined in rbd_launch_*.cu, explicitly instantiated for double and float)
 template <typename T>
 int launch_rnea(const rbd_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, T* c, T* v, T* a,

@@ -46,14 +46,6 @@ void fill_fb(const RbdFbModelDesc* fd, FbModel<T>& out) {
   }
 }
 
-// Occupancy throttle: the per-thread local arrays of the gradient / inverse kernels (5-15 KB) only stay
-// in the 126 MB L2 when few enough threads are resident; a dummy dynamic shared-memory request caps
-// the CTAs per SM (RBD_FB_SMEM_KB overrides it for experiments).
-size_t fb_throttle_smem(int default_kb) {
-  static int env = [] { const char* e = std::getenv("RBD_FB_SMEM_KB"); return e ? std::atoi(e) : -1; }();
-  return (size_t)(env >= 0 ? env : default_kb) * 1024;
-}
-
 template <typename T>
 int launch_fb_rnea(const rbd_fb_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, T* c, T* v, T* a, T* f,
                    void* stream) {
@@ -68,13 +60,8 @@ int launch_fb_rnea_grad(const rbd_fb_model* m, int64_t B, const T* q, const T* q
                         T* c_out, void* stream) {
   RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_fb_rnea_grad: null model/q/qd/dc_du or negative B");
   if (B == 0) return 0;
-  const size_t smem = fb_throttle_smem(0);
-  auto kern = fb_rnea_grad_kernel<T>;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-  }
-  kern<<<blocks_for(B, kFbThreads), kFbThreads, smem, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, qd, qdd, g, damp, dc_du, c_out);
+  fb_rnea_grad_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, qd, qdd, g, damp,
+                                                                                             dc_du, c_out);
   return cuda_status("rbd_fb_rnea_grad");
 }
 
@@ -82,14 +69,56 @@ template <typename T>
 int launch_fb_minv(const rbd_fb_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && B >= 0, "rbd_fb_minv: null model/q/Minv or negative B");
   if (B == 0) return 0;
-  const size_t smem = fb_throttle_smem(0);
-  auto kern = fb_minv_kernel<T>;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-  }
-  kern<<<blocks_for(B, kFbThreads), kFbThreads, smem, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, dense, Minv);
+  fb_minv_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, dense, Minv);
   return cuda_status("rbd_fb_minv");
+}
+
+// forward_dynamics / forward_dynamics_grad (RBDReference.py:1369-1384) are robot-agnostic compositions; with a
+// floating base they run the three kernels above plus the per-knot-point product of rbd_fd_kernels.cuh.
+template <typename T>
+int launch_fb_forward_dynamics(const rbd_fb_model* m, int64_t B, const T* q, const T* qd, const T* u, T* qdd, T* Minv_out,
+                               void* stream) {
+  RBD_CHECK_ARGS(m && q && qd && u && qdd && B >= 0, "rbd_fb_forward_dynamics: null argument or negative B");
+  if (B == 0) return 0;
+  const int nv = m->d.d.n + 5;
+  PoolBuf c((cudaStream_t)stream), Mi((cudaStream_t)stream);
+  int rc = c.alloc((size_t)B * nv * sizeof(T));
+  if (rc) return rc;
+  T* Minv = Minv_out;
+  if (!Minv) {
+    rc = Mi.alloc((size_t)B * nv * nv * sizeof(T));
+    if (rc) return rc;
+    Minv = (T*)Mi.p;
+  }
+  rc = launch_fb_rnea<T>(m, B, q, qd, nullptr, T(-9.81), (T*)c.p, nullptr, nullptr, nullptr, stream);     // :1370
+  if (rc) return rc;
+  rc = launch_fb_minv<T>(m, B, q, 1, Minv, stream);                                                       // :1371
+  if (rc) return rc;
+  return launch_fd_apply<T, false>(nv, 1, B, Minv, u, (const T*)c.p, T(1), qdd, nullptr, stream);         // :1372
+}
+
+template <typename T>
+int launch_fb_forward_dynamics_grad(const rbd_fb_model* m, int64_t B, const T* q, const T* qd, const T* u, T* qdd_dq,
+                                    T* qdd_dqd, T* qdd_out, void* stream) {
+  RBD_CHECK_ARGS(m && q && qd && u && qdd_dq && qdd_dqd && B >= 0, "rbd_fb_forward_dynamics_grad: null argument or negative B");
+  if (B == 0) return 0;
+  const int nv = m->d.d.n + 5;
+  PoolBuf Mi((cudaStream_t)stream), dd((cudaStream_t)stream), dc((cudaStream_t)stream);
+  int rc = Mi.alloc((size_t)B * nv * nv * sizeof(T));
+  if (rc) return rc;
+  rc = dc.alloc((size_t)B * nv * 2 * nv * sizeof(T));
+  if (rc) return rc;
+  T* qdd = qdd_out;
+  if (!qdd) {
+    rc = dd.alloc((size_t)B * nv * sizeof(T));
+    if (rc) return rc;
+    qdd = (T*)dd.p;
+  }
+  rc = launch_fb_forward_dynamics<T>(m, B, q, qd, u, qdd, (T*)Mi.p, stream);                               // :1377
+  if (rc) return rc;
+  rc = launch_fb_rnea_grad<T>(m, B, q, qd, qdd, T(-9.81), 0, (T*)dc.p, nullptr, stream);                   // :1378
+  if (rc) return rc;
+  return launch_fd_apply<T, true>(nv, 2 * nv, B, (const T*)Mi.p, (const T*)dc.p, nullptr, T(-1), qdd_dq, qdd_dqd, stream);
 }
 
 }  // namespace
@@ -139,6 +168,14 @@ int rbd_fb_model_num_vel(const rbd_fb_model_t* m) { return m ? m->d.d.n + 5 : RB
   }                                                                                                                  \
   int rbd_fb_minv_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, int output_dense, T* Minv, void* stream) {   \
     return launch_fb_minv<T>(m, B, q, output_dense, Minv, stream);                                                   \
+  }                                                                                                                  \
+  int rbd_fb_forward_dynamics_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* u, T* qdd, \
+                                    T* Minv_out, void* stream) {                                                     \
+    return launch_fb_forward_dynamics<T>(m, B, q, qd, u, qdd, Minv_out, stream);                                     \
+  }                                                                                                                  \
+  int rbd_fb_forward_dynamics_grad_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* u,    \
+                                         T* qdd_dq, T* qdd_dqd, T* qdd_out, void* stream) {                          \
+    return launch_fb_forward_dynamics_grad<T>(m, B, q, qd, u, qdd_dq, qdd_dqd, qdd_out, stream);                     \
   }
 
 RBD_FB_DEFINE(f64, double)

@@ -137,8 +137,8 @@ class RBDReference:
     def _fixed_only(self, what: str):
         if self.floating_base:
             raise NotImplementedError(
-                "%s: no floating-base path (rnea, rnea_grad and minv are the floating-base entry points, "
-                "SURVEY.md 8f rank 3)" % what)
+                "%s: no floating-base path (rnea, rnea_grad, minv, forward_dynamics and forward_dynamics_grad "
+                "are the floating-base entry points, SURVEY.md 8f rank 3)" % what)
 
     def _call(self, name: str, ctx: "_Ctx", *args, handle=None):
         if ctx.B == 0:
@@ -322,22 +322,21 @@ class RBDReference:
     def forward_dynamics(self, q, qd, u):
         """RBDReference.py:1369-1372: Minv @ (u - c) with c = rnea(q, qd) (qdd omitted upstream).
         rnea + minv + one fused (u - c) / matrix-vector kernel, all inside the C library."""
-        self._fixed_only("forward_dynamics")
         ctx = self._Ctx(self, q, 1)
         n = self.n
-        dq, dqd, du = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(u, (n,), "u")
+        dq, dqd, du = ctx.dev(q, (self.nq,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(u, (n,), "u")
         qdd = ctx.empty(n)
-        self._call("forward_dynamics", ctx, dq, dqd, du, qdd, None)
+        self._call("fb_forward_dynamics" if self.floating_base else "forward_dynamics", ctx, dq, dqd, du, qdd, None)
         return ctx.ret(qdd)
 
     def forward_dynamics_grad(self, q, qd, u):
         """RBDReference.py:1374-1384 -> (qdd_dq, qdd_dqd) = (-Minv dc_dq, -Minv dc_dqd)."""
-        self._fixed_only("forward_dynamics_grad")
         ctx = self._Ctx(self, q, 1)
         n = self.n
-        dq, dqd, du = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(u, (n,), "u")
+        dq, dqd, du = ctx.dev(q, (self.nq,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(u, (n,), "u")
         o1, o2 = ctx.empty(n, n), ctx.empty(n, n)
-        self._call("forward_dynamics_grad", ctx, dq, dqd, du, o1, o2, None)
+        self._call("fb_forward_dynamics_grad" if self.floating_base else "forward_dynamics_grad", ctx, dq, dqd, du,
+                   o1, o2, None)
         return ctx.ret(o1), ctx.ret(o2)
 
     def aba(self, q, qd, tau, f_ext=None, GRAVITY=-9.81):

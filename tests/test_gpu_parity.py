@@ -777,6 +777,17 @@ def test_floating_base_vs_reference_golden(name):
     assert rel_err(e32.rnea(q, qd, qdd)[0], g["c"]) < TOL_F32
     assert rel_err(e32.rnea_grad(q, qd, qdd), g["dc_du"]) < TOL_F32
     assert rel_err(e32.minv(q), g["Minv"]) < 5 * TOL_F32
+    # compositions (RBDReference.py:1369-1384); conditioning of Minv enters, as for the fixed base
+    assert rel_err(eng.forward_dynamics(q, qd, g["u"]), g["fd_qdd"]) < 10 * TOL_F64
+    d1, d2 = eng.forward_dynamics_grad(q, qd, g["u"])
+    assert rel_err(d1, g["fd_dq"]) < 10 * TOL_F64 and rel_err(d2, g["fd_dqd"]) < 10 * TOL_F64
+    from rbdreference_b200 import RBDReference
+    RBDReference.set_kernel_variant(1)            # register-tiled product instead of the FP64 tensor-core one
+    try:
+        t1, t2 = eng.forward_dynamics_grad(q, qd, g["u"])
+        assert rel_err(t1, g["fd_dq"]) < 10 * TOL_F64 and rel_err(t2, g["fd_dqd"]) < 10 * TOL_F64
+    finally:
+        RBDReference.set_kernel_variant(0)
     with pytest.raises(NotImplementedError):
         eng.crba(q)
 

@@ -139,6 +139,9 @@ def test_floating_base_oracle_vs_golden(name):
         assert rel_err(so.rnea_grad(q, qd), g["dc_du_noqdd"][k]) < PIN
         assert rel_err(so.minv(q), g["Minv"][k]) < PIN
         assert rel_err(so.minv(q, output_dense=False), g["Minv_sparse"][k]) < PIN
+        assert rel_err(so.forward_dynamics(q, qd, g["u"][k]), g["fd_qdd"][k]) < PIN
+        r1, r2 = so.forward_dynamics_grad(q, qd, g["u"][k])
+        assert rel_err(r1, g["fd_dq"][k]) < 10 * PIN and rel_err(r2, g["fd_dqd"][k]) < 10 * PIN
 
 
 def test_floating_base_identities():
