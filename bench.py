@@ -475,11 +475,14 @@ def measure_e2e(args, eng, torch, dist, dev, rank, world, n, B, tdtype, itemsize
 
 
 def measure_cpu_baseline(args, n):
+    """The reference on the host cores over a bounded sample sized for 10-20 s of wall time."""
     cpu = CpuReference(args.robot, args.op)
-    per = per_eval_cpu_seconds(args.robot, args.op)
-    sample = int(max(cpu.cores, min(16384, round(12.0 * cpu.cores / per))))   # ~12 s of wall time
-    q, qd, qdd = synth_host(n, sample, 0xB200, args.robot)
+    ncal = 16 * cpu.cores
+    q, qd, qdd = synth_host(n, ncal, 0xB201, args.robot)
     cpu.run(q[: cpu.cores], qd[: cpu.cores], qdd[: cpu.cores])                # warm the workers
+    rate = ncal / cpu.run(q, qd, qdd)                                         # calibration: evals/s on all cores
+    sample = int(max(cpu.cores, min(1 << 20, round(16.0 * rate))))
+    q, qd, qdd = synth_host(n, sample, 0xB200, args.robot)
     t = cpu.run(q, qd, qdd)
     cpu.close()
     return {"value": sample / t, "unit": "evals/s", "cores": cpu.cores, "kind": cpu.kind,
