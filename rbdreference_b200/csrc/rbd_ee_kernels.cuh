@@ -26,6 +26,7 @@ struct EeModel {
   int kind[RBD_MAX_DOF];                      // 0: cos/sin basis, 1: affine in q
   int chain_len[RBD_MAX_EE];
   unsigned char chain[RBD_MAX_EE][RBD_MAX_DOF];  // joint ids base -> leaf
+  signed char chain_pos[RBD_MAX_EE][RBD_MAX_DOF]; // position of joint j in chain e, -1 when off the chain
   T off[4];                                   // ee_offsets[0] = (x, y, z, w)   (:248, :335)
   T TA[RBD_MAX_DOF][12], TB[RBD_MAX_DOF][12], TC[RBD_MAX_DOF][12];   // rows 0..2 of T_k(q)
   T DA[RBD_MAX_DOF][12], DB[RBD_MAX_DOF][12], DC[RBD_MAX_DOF][12];   // rows 0..2 of dT_k/dq
@@ -66,13 +67,19 @@ __device__ __forceinline__ T darctan2(T y, T x, T yp, T xp) { return (-xp * y + 
 template <typename T, bool GRAD, bool COEF_SMEM>
 __global__ void __launch_bounds__(kEeMaxWarps * 32)
 ee_pose_kernel(const __grid_constant__ EeModel<T> m, int64_t B, const T* __restrict__ q, T* __restrict__ pose_out,
-               T* __restrict__ grad_out, int grad_pitch) {
+               T* __restrict__ grad_out, int grad_pitch, int compact) {
   extern __shared__ __align__(16) unsigned char ee_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int n = m.n, n_ee = m.n_ee;
   // joint coefficients: [n][72] = TA | TB | TC | DA | DB | DC.  The joint index comes from the chain
   // table at run time; indexed constant-bank loads stalled the FMA chain (ncu: short scoreboard), a
   // broadcast shared-memory load does not.
+  // compact tile ([lane][6][len], several end effectors): the copy-out looks the chain position of
+  // every column up with a lane-dependent index - shared memory, not the constant bank
+  __shared__ signed char s_chain_pos[RBD_MAX_EE][RBD_MAX_DOF];
+  if (GRAD && compact)
+    for (int k = threadIdx.x; k < RBD_MAX_EE * RBD_MAX_DOF; k += blockDim.x)
+      s_chain_pos[k / RBD_MAX_DOF][k % RBD_MAX_DOF] = m.chain_pos[k / RBD_MAX_DOF][k % RBD_MAX_DOF];
   T* coef = reinterpret_cast<T*>(ee_smem_raw);
   if (COEF_SMEM) {
     for (int k = threadIdx.x; k < n * 72; k += blockDim.x) {
@@ -80,8 +87,8 @@ ee_pose_kernel(const __grid_constant__ EeModel<T> m, int64_t B, const T* __restr
       const T* src = which == 0 ? m.TA[j] : which == 1 ? m.TB[j] : which == 2 ? m.TC[j] : which == 3 ? m.DA[j] : which == 4 ? m.DB[j] : m.DC[j];
       coef[k] = src[idx];
     }
-    __syncthreads();
   }
+  __syncthreads();
   const int pose_vals = 32 * n_ee * 6;
   const int per_warp = pose_vals + (GRAD ? 32 * grad_pitch : 0);
   T* pose_tile = coef + (COEF_SMEM ? ((n * 72 + 1) & ~1) : 0) + (size_t)warp * per_warp;
@@ -126,8 +133,10 @@ ee_pose_kernel(const __grid_constant__ EeModel<T> m, int64_t B, const T* __restr
         pt[5] = atan2_t(M[4], M[0]);
       }
       if (GRAD) {
-        T* gt = grad_tile + lane * grad_pitch;
-        for (int k = 0; k < 6 * n; ++k) gt[k] = T(0);          // columns off the chain stay zero (:359-361)
+        T* gt = grad_tile + lane * grad_pitch;                 // dense [6][n] or compact [6][len]
+        const int gld = compact ? len : n;
+        if (!compact)
+          for (int k = 0; k < 6 * n; ++k) gt[k] = T(0);        // columns off the chain stay zero (:359-361)
         T P[12] = {T(1), T(0), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(0), T(1), T(0)};
         for (int t = 0; t < len; ++t) {
           const int j = m.chain[e][t];
@@ -146,11 +155,12 @@ ee_pose_kernel(const __grid_constant__ EeModel<T> m, int64_t B, const T* __restr
           // one gradient column (:327-351)
 #pragma unroll
           for (int r = 0; r < 3; ++r)
-            gt[r * n + j] = fma_t(dX[4 * r + 3], m.off[3], fma_t(dX[4 * r + 2], m.off[2], fma_t(dX[4 * r + 1], m.off[1], dX[4 * r] * m.off[0])));
-          gt[3 * n + j] = darctan2(M[9], M[10], dX[9], dX[10]);
+            gt[r * gld + (compact ? t : j)] = fma_t(dX[4 * r + 3], m.off[3], fma_t(dX[4 * r + 2], m.off[2], fma_t(dX[4 * r + 1], m.off[1], dX[4 * r] * m.off[0])));
+          const int gc = compact ? t : j;
+          gt[3 * gld + gc] = darctan2(M[9], M[10], dX[9], dX[10]);
           const T dsq = (M[10] * dX[10] + M[9] * dX[9]) / sq;
-          gt[4 * n + j] = darctan2(-M[8], sq, -dX[8], dsq);
-          gt[5 * n + j] = darctan2(M[4], M[0], dX[4], dX[0]);
+          gt[4 * gld + gc] = darctan2(-M[8], sq, -dX[8], dsq);
+          gt[5 * gld + gc] = darctan2(M[4], M[0], dX[4], dX[0]);
           mul34(P, Tk, T(1), W);
 #pragma unroll
           for (int k = 0; k < 12; ++k) P[k] = W[k];
@@ -168,6 +178,26 @@ ee_pose_kernel(const __grid_constant__ EeModel<T> m, int64_t B, const T* __restr
             __stcs(dst + k, grad_tile[r * grad_pitch + c]);
             c += 32;
             while (c >= row) { c -= row; ++r; }
+          }
+        } else if (compact) {
+          // where element k = lane + 32 it of a (6, n) block comes from in the compact tile (-1: a zero
+          // column, :359-361); the same for every knot point, so the divisions are done once per task
+          int src[6];
+#pragma unroll
+          for (int it = 0; it < 6; ++it) {
+            const int k = lane + 32 * it;
+            src[it] = -2;
+            if (k < row) {
+              const int comp = k / n, j = k - comp * n, pos = s_chain_pos[e][j];
+              src[it] = pos >= 0 ? comp * len + pos : -1;
+            }
+          }
+          for (int r = 0; r < nlive; ++r) {
+            T* dst = grad_out + ((b0 + r) * n_ee + e) * (int64_t)row;
+            const T* tl = grad_tile + r * grad_pitch;
+#pragma unroll
+            for (int it = 0; it < 6; ++it)
+              if (src[it] > -2) __stcs(dst + lane + 32 * it, src[it] >= 0 ? tl[src[it]] : T(0));
           }
         } else {
           for (int r = 0; r < nlive; ++r) {

@@ -34,7 +34,11 @@ void fill_ee(const RbdEeDesc* d, EeModel<T>& out) {
     int tmp[RBD_MAX_DOF], len = 0;
     for (int j = d->ee_joint[e]; j >= 0; j = d->parent[j]) tmp[len++] = j;     // leaf -> base (:238-242)
     out.chain_len[e] = len;
-    for (int t = 0; t < len; ++t) out.chain[e][t] = (unsigned char)tmp[len - 1 - t];
+    for (int j = 0; j < RBD_MAX_DOF; ++j) out.chain_pos[e][j] = -1;
+    for (int t = 0; t < len; ++t) {
+      out.chain[e][t] = (unsigned char)tmp[len - 1 - t];
+      out.chain_pos[e][tmp[len - 1 - t]] = (signed char)t;
+    }
     for (int k = 0; k < 12; ++k) out.fin[e][k] = (T)d->ee_final[12 * e + k];
   }
 }
@@ -45,7 +49,12 @@ int launch_ee(const rbd_ee_model* m, int64_t B, const T* q, T* pose, T* grad, vo
   if (B == 0) return 0;
   const EeModel<T>& em = pick_ee<T>(m);
   const int n = em.n, n_ee = em.n_ee;
-  const int pitch = (6 * n) | 1;                                  // odd pitch: lanes hit distinct banks
+  // several end effectors: the tile holds only the chain's columns and the copy-out expands them (Atlas: 46 KB
+  // -> 16 KB per warp); one end effector: dense tile, the warp's slab leaves in one linear pass
+  const int compact = n_ee > 1 ? 1 : 0;
+  int maxlen = 1;
+  for (int e = 0; e < n_ee; ++e) maxlen = em.chain_len[e] > maxlen ? em.chain_len[e] : maxlen;
+  const int pitch = (6 * (compact ? maxlen : n)) | 1;             // odd pitch: lanes hit distinct banks
   const size_t per_warp = ((size_t)32 * n_ee * 6 + (GRAD ? (size_t)32 * pitch : 0)) * sizeof(T);
   // joint coefficients in shared memory for small robots (iiwa14: +13 % FP64, +52 % FP32); for large ones the
   // 72 n values per CTA cost more occupancy than the constant-bank stalls they remove (Atlas FP64: -33 %)
@@ -55,13 +64,13 @@ int launch_ee(const rbd_ee_model* m, int64_t B, const T* q, T* pose, T* grad, vo
   // warps per CTA that put the most warps on an SM (227 KB of shared memory, 1 KB reserved per CTA)
   int warps = 1, best = 0, resident_ctas = 1;
   for (int w = 1; w <= kEeMaxWarps; ++w) {
-    const size_t cta = coef_bytes + (size_t)w * per_warp + 1024;
+    const size_t cta = coef_bytes + (size_t)w * per_warp + 2048;          // static chain table + the per-CTA reserve
     if (cta > kMaxDynSmem) break;
     const int resident = (int)((size_t)(228 * 1024) / cta) * w;
     if (resident > best) { best = resident; warps = w; resident_ctas = resident / w; }
   }
   auto kern = coef_smem ? ee_pose_kernel<T, GRAD, true> : ee_pose_kernel<T, GRAD, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(coef_bytes + per_warp * warps));   // + 1 KB static
   if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
   const int64_t ntask = (B + 31) / 32;
   int64_t blocks = (ntask + warps - 1) / warps;
@@ -69,7 +78,7 @@ int launch_ee(const rbd_ee_model* m, int64_t B, const T* q, T* pose, T* grad, vo
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // a few waves of CTAs: exactly one wave (fully persistent) measured 20 % slower on iiwa14 (tail imbalance)
   if (blocks > (int64_t)sms * resident_ctas * 8) blocks = (int64_t)sms * resident_ctas * 8;
-  kern<<<(unsigned)blocks, warps * 32, coef_bytes + per_warp * warps, (cudaStream_t)stream>>>(em, B, q, pose, grad, pitch);
+  kern<<<(unsigned)blocks, warps * 32, coef_bytes + per_warp * warps, (cudaStream_t)stream>>>(em, B, q, pose, grad, pitch, compact);
   return cuda_status(what);
 }
 
