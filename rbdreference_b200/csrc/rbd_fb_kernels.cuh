@@ -29,6 +29,8 @@ struct FbModel {
   int quat_off;         // q[quat_off .. +4] unit quaternion
   int w_first;          // 1: (w, x, y, z), 0: (x, y, z, w)
   int transpose;        // 0: E = R(quat)^T (coordinate transform world -> base), 1: E = R(quat)
+  unsigned store_mask;  // bit i: body i has a child other than i + 1, so its per-column state must be kept in
+                        // local memory; along chains (parent == i - 1) the state travels in registers
 };
 
 // X0 = xrot(E) xlt(p) in the 18-value layout [E | L], L = -E p^x
@@ -188,6 +190,8 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
     const int bc = c < 6 ? 0 : c - 5;
     const int cg = c & 3;
     const unsigned sub = m.d.sub_mask[bc];
+    T pvq[6], paq[6], pvd[6], pad[6];          // the previously visited body's dv / da (d/dq | d/dqd)
+    int prev = -1;
     for (int i = bc; i < NB; ++i) {
       if (!((sub >> i) & 1u)) continue;
       T dvq[6], daq[6], dvd[6], dad[6], t[6], vi[6];
@@ -226,19 +230,14 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
           for (int r = 0; r < 6; ++r) dvd[r] = S[r];                           // :1231
           crm_mul(vi, S, dad);                                                 // :1243
         } else {
-          T pv[6];
+          if (p != prev) {                     // parent is a branch point: its state was kept in local memory
 #pragma unroll
-          for (int r = 0; r < 6; ++r) pv[r] = sdv[p][r];
-          X_apply(X, pv, dvq);
-#pragma unroll
-          for (int r = 0; r < 6; ++r) pv[r] = sda[p][r];
-          X_apply(X, pv, daq);
-#pragma unroll
-          for (int r = 0; r < 6; ++r) pv[r] = sdv[p][6 + r];
-          X_apply(X, pv, dvd);
-#pragma unroll
-          for (int r = 0; r < 6; ++r) pv[r] = sda[p][6 + r];
-          X_apply(X, pv, dad);
+            for (int r = 0; r < 6; ++r) { pvq[r] = sdv[p][r]; paq[r] = sda[p][r]; pvd[r] = sdv[p][6 + r]; pad[r] = sda[p][6 + r]; }
+          }
+          X_apply(X, pvq, dvq);
+          X_apply(X, paq, daq);
+          X_apply(X, pvd, dvd);
+          X_apply(X, pad, dad);
         }
         crm_mul(dvq, S, t);                                                    // :1170
 #pragma unroll
@@ -254,20 +253,33 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
       crf_mul(dvq, Iv, t1);
       crf_mul(vi, Idv, t2);
 #pragma unroll
-      for (int r = 0; r < 6; ++r) { sdv[i][r] = dvq[r]; sda[i][r] = daq[r]; sdf[i][r] = Ida[r] + t1[r] + t2[r]; }
+      for (int r = 0; r < 6; ++r) sdf[i][r] = Ida[r] + t1[r] + t2[r];
       mat6_apply(m.d.I[i], dad, Ida);
       mat6_apply(m.d.I[i], dvd, Idv);
       crf_mul(dvd, Iv, t1);
       crf_mul(vi, Idv, t2);
 #pragma unroll
-      for (int r = 0; r < 6; ++r) { sdv[i][6 + r] = dvd[r]; sda[i][6 + r] = dad[r]; sdf[i][6 + r] = Ida[r] + t1[r] + t2[r]; }
+      for (int r = 0; r < 6; ++r) sdf[i][6 + r] = Ida[r] + t1[r] + t2[r];
+      if ((m.store_mask >> i) & 1u) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { sdv[i][r] = dvq[r]; sda[i][r] = daq[r]; sdv[i][6 + r] = dvd[r]; sda[i][6 + r] = dad[r]; }
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) { pvq[r] = dvq[r]; paq[r] = daq[r]; pvd[r] = dvd[r]; pad[r] = dad[r]; }
+      prev = i;
     }
     // backward over subtree(bc), then up the ancestors of bc to the base
     T Fq[6], Fd[6];
+    T cq[6], cd[6];                             // X^T F of a chain child (parent == child - 1), carried in registers
+    int carry_to = -1;
     for (int i = NB - 1; i >= bc; --i) {
       if (!((sub >> i) & 1u)) continue;
 #pragma unroll
       for (int r = 0; r < 6; ++r) { Fq[r] = sdf[i][r]; Fd[r] = sdf[i][6 + r]; }
+      if (carry_to == i) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { Fq[r] += cq[r]; Fd[r] += cd[r]; }
+      }
       if (i == 0) break;                        // base column: rows 0..5 are written below
       obuf[i + 5][cg] = dot6(m.d.S[i], Fq);                                    // :1284
       obuf[i + 5][4 + cg] = dot6(m.d.S[i], Fd);                                // :1325
@@ -288,8 +300,14 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
         for (int r = 0; r < 6; ++r) { Fq[r] = tq[r]; Fd[r] = td[r]; }
       } else {
         const int p = m.d.parent[i];
+        if (p == i - 1) {
 #pragma unroll
-        for (int r = 0; r < 6; ++r) { sdf[p][r] += tq[r]; sdf[p][6 + r] += td[r]; }
+          for (int r = 0; r < 6; ++r) { cq[r] = tq[r]; cd[r] = td[r]; }
+          carry_to = p;
+        } else {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) { sdf[p][r] += tq[r]; sdf[p][6 + r] += td[r]; }
+        }
       }
     }
     unsigned touched = sub;
@@ -454,17 +472,24 @@ fb_minv_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restr
     }
     // forward pass restricted to column j (:760-781)
 #pragma unroll
-    for (int r = 0; r < 6; ++r) { colF[0][r] = colM[r]; obuf[r][jg] = colM[r]; }     // :779
+    for (int r = 0; r < 6; ++r) { colF[0][r] = colM[r]; obuf[r][jg] = colM[r]; }     // :779 (the base always keeps its F)
+    T Fprev[6];                                  // F of body i - 1, in registers along chains
+#pragma unroll
+    for (int r = 0; r < 6; ++r) Fprev[r] = colM[r];
     for (int i = 1; i < NB; ++i) {
       const int p = m.d.parent[i];
       T X[18], Fp[6], Fi[6];
 #pragma unroll
-      for (int r = 0; r < 6; ++r) Fp[r] = colF[p][r];
+      for (int r = 0; r < 6; ++r) Fp[r] = (p == i - 1) ? Fprev[r] : colF[p][r];
       const T mij = colM[i + 5] - linvD[i] * dot6(lUX[i], Fp);                 // :771-773
       build_X(m.d, i, lb[i][0], lb[i][1], X);
       X_apply(X, Fp, Fi);
 #pragma unroll
-      for (int r = 0; r < 6; ++r) colF[i][r] = fma_t(m.d.S[i][r], mij, Fi[r]); // :774-776
+      for (int r = 0; r < 6; ++r) Fprev[r] = fma_t(m.d.S[i][r], mij, Fi[r]);   // :774-776
+      if ((m.store_mask >> i) & 1u) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) colF[i][r] = Fprev[r];
+      }
       obuf[i + 5][jg] = mij;
     }
     // :799-804 mirrors the leading NB x NB block (range(NB), not nv): Minv[row, col] = Minv[col, row]

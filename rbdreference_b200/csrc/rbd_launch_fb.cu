@@ -39,6 +39,7 @@ void fill_fb(const RbdFbModelDesc* fd, FbModel<T>& out) {
     unsigned anc = 1u << i;
     if (d->parent[i] >= 0) anc |= o.anc_mask[d->parent[i]];
     o.anc_mask[i] = anc;
+    if (i > 0 && d->parent[i] != i - 1) out.store_mask |= 1u << d->parent[i];
   }
   for (int i = n - 1; i >= 0; --i) {
     o.sub_mask[i] |= 1u << i;
