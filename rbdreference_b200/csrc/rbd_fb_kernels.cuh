@@ -20,6 +20,9 @@
 namespace rbd {
 
 constexpr int kFbThreads = 64;
+// resident CTAs the register allocation aims at (measured on B200, 2^18 knot points): minv gains from six
+// (168 registers; Atlas + base 23.9 -> 17.9 ms, eight spills and is slower), rnea_grad does not (4.9 -> 5.1 ms)
+constexpr int kFbMinvMinCtas = 6;
 constexpr int kFbMaxNv = RBD_MAX_DOF + 5;
 
 template <typename T>
@@ -357,7 +360,7 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
 // (:697-726, :686-691) and sweep every body root -> leaves (:760-781, whole rows as upstream).
 // =============================================================================================
 template <typename T>
-__global__ void __launch_bounds__(kFbThreads)
+__global__ void __launch_bounds__(kFbThreads, kFbMinvMinCtas)
 fb_minv_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restrict__ q, int output_dense,
                T* __restrict__ Minv) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -20,3 +20,16 @@ python tools/bench_passes.py --reps 5 --batch 1048576 > gpurun_out/passes.jsonl 
 python tools/bench_passes.py --reps 5 --robot hyq --batch 262144 >> gpurun_out/passes.jsonl 2>/dev/null
 python tools/bench_passes.py --reps 5 --robot atlas --batch 65536 >> gpurun_out/passes.jsonl 2>/dev/null
 ls -la gpurun_out/*.ncu-rep | tail -5
+
+# ---- rows SURVEY.md 8f marks "next": end-effector kinematics and the floating base ------------------
+: > gpurun_out/ee_bench.jsonl; : > gpurun_out/fb_bench.jsonl
+for r in iiwa14 hyq atlas; do for d in f64 f32; do
+  b=1048576; if [ $r = atlas ]; then b=262144; fi
+  python bench.py --op ee_grad --robot $r --dtype $d --batch $b --no-cpu-baseline --steps 20 2>/dev/null | tail -1 >> gpurun_out/ee_bench.jsonl
+done; done
+for r in iiwa14_fb hyq_fb atlas_fb; do for op in rnea rnea_grad minv; do for d in f64 f32; do
+  python bench.py --robot $r --op $op --dtype $d --batch 262144 --steps 10 --no-cpu-baseline 2>/dev/null | tail -1 >> gpurun_out/fb_bench.jsonl
+done; done; done
+ncu --set full --clock-control none --import-source on -k regex:ee_pose_kernel -c 1 -o gpurun_out/prof_ee_iiwa2 python bench.py --op ee_grad --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_ee.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:fb_rnea_grad -c 1 -o gpurun_out/prof_fb_grad_hyq2 python bench.py --robot hyq_fb --op rnea_grad --batch 262144 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_fb.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:fb_minv -c 1 -o gpurun_out/prof_fb_minv_hyq python bench.py --robot hyq_fb --op minv --batch 262144 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_fb2.log 2>&1

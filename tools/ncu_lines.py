@@ -20,7 +20,7 @@ for r in rows:
         def g(h):
             try:
                 return int((r[hdr[h]] or "0").split("(")[0])
-            except (ValueError, IndexError):
+            except (ValueError, IndexError, KeyError):      # optional columns differ between kernels
                 return 0
         lines.append(dict(file=cur_file, line=int(r[0]), src=r[1].strip(), smp=g("# Samples"), inst=g("Instructions Executed"),
                           wait=g("stall_wait"), short=g("stall_short_sb"), long=g("stall_long_sb"), mio=g("stall_mio"),
