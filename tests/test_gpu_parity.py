@@ -869,3 +869,38 @@ def test_end_effector_and_floating_base_calls_are_cuda_graph_capturable_and_stre
         a2 = [feng.rnea_grad(fq, fqd, fqdd) for _ in range(4)]
     torch.cuda.synchronize()
     assert all(torch.equal(x, e_grad) for x in a1) and all(torch.equal(x, g_dc) for x in a2)
+
+
+@requires_cuda
+@pytest.mark.parametrize("kind", ["one", "two", "chain32", "bush32", "stars"])
+def test_edge_topologies_end_effector_and_floating_base(kind):
+    """n = 1, 2 and RBD_MAX_DOF bodies, the deepest chain (one end effector, 32 columns: dense tile)
+    and the flattest trees (many end effectors with one-joint chains: compact tile); the same trees
+    on a floating base (up to 37 velocity coordinates), both precisions."""
+    from oracle.rbd_oracle_fb import FloatingScalarOracle
+    from rbdreference_b200 import robots
+    rb = _edge_robot(kind)
+    eng, e32, bo = _engine(rb), _engine(rb, torch.float32), BatchOracle(rb)
+    B = 97
+    q = np.random.default_rng(9).uniform(-np.pi, np.pi, (B, eng.n))
+    Pref, Gref = bo.end_effector_pose(q, gradient=True)
+    G, P = eng.end_effector_pose_gradient(_t(q), return_pose=True)
+    scale = np.maximum(1.0, np.abs(Gref).max(axis=(1, 2, 3), keepdims=True))     # per knot point (rpy singularities)
+    assert rel_err(P.cpu().numpy(), Pref) < TOL_F64
+    assert np.max(np.abs(G.cpu().numpy() - Gref) / scale) < TOL_F64
+    G32 = e32.end_effector_pose_gradient(_t(q, torch.float32)).cpu().numpy()
+    assert np.max(np.abs(G32 - Gref) / scale) < 20 * TOL_F32
+    if rb.get_num_bodies() < 2:
+        return
+    fb = robots.FloatingBaseRobot(_edge_robot(kind) if rb.get_num_bodies() < 32 else robots.random_tree(31, seed=5, branching=0.3))
+    feng, so = _engine(fb), FloatingScalarOracle(fb)
+    fq, fqd, fqdd = fb.random_state(np.random.default_rng(10), 33)
+    c = feng.rnea(_t(fq), _t(fqd), _t(fqdd), outputs="c").cpu().numpy()
+    M = feng.minv(_t(fq)).cpu().numpy()
+    for k in (0, 32):
+        assert rel_err(c[k], so.rnea(fq[k], fqd[k], fqdd[k])[0]) < TOL_F64
+        assert rel_err(M[k], so.minv(fq[k])) < TOL_F64
+    if fb.get_num_bodies() >= 6:                     # the reference's gradient needs NB >= 6 (:1168)
+        dc = feng.rnea_grad(_t(fq), _t(fqd), _t(fqdd), USE_VELOCITY_DAMPING=True).cpu().numpy()
+        for k in (0, 32):
+            assert rel_err(dc[k], so.rnea_grad(fq[k], fqd[k], fqdd[k], USE_VELOCITY_DAMPING=True)) < TOL_F64
