@@ -60,9 +60,33 @@ __device__ __forceinline__ void fb_base_X(const FbModel<T>& m, const T* __restri
   }
 }
 
-// forward + backward sweep of rnea (:559-621) shared by the rnea and rnea_grad kernels
+// Per-body constants in shared memory: [body][96] = XA(18) XB(18) XC(18) S(6) I(36).  The body index is a run-time
+// value in every sweep, and indexed constant-bank loads (LDC with a register index) stalled the FMA chains
+// (ncu: short scoreboard 12.6 stalls per issue in minv); a broadcast shared-memory load does not.
+constexpr int kFbSmStride = 96;
 template <typename T>
-__device__ __forceinline__ void fb_rnea_state(const FbModel<T>& m, const T* qb, const T* qdb, const T* qddb, T gravity,
+__device__ __forceinline__ void fb_stage_model(const FbModel<T>& m, T* sm) {
+  const int NB = m.d.n;
+  for (int k = threadIdx.x; k < NB * kFbSmStride; k += blockDim.x) {
+    const int i = k / kFbSmStride, w = k - i * kFbSmStride;
+    sm[k] = w < 18 ? m.d.XA[i][w] : w < 36 ? m.d.XB[i][w - 18] : w < 54 ? m.d.XC[i][w - 36] : w < 60 ? m.d.S[i][w - 54] : m.d.I[i][w - 60];
+  }
+  __syncthreads();
+}
+template <typename T>
+__device__ __forceinline__ void fb_build_X(const T* sm, int i, T f1, T f2, T (&X)[18]) {
+  const T* c = sm + i * kFbSmStride;
+#pragma unroll
+  for (int k = 0; k < 18; ++k) X[k] = fma_t(c[36 + k], f2, fma_t(c[18 + k], f1, c[k]));
+}
+template <typename T> __device__ __forceinline__ const T* fb_S(const T* sm, int i) { return sm + i * kFbSmStride + 54; }
+template <typename T> __device__ __forceinline__ const T* fb_I(const T* sm, int i) { return sm + i * kFbSmStride + 60; }
+
+// forward + backward sweep of rnea (:559-621) shared by the rnea and rnea_grad kernels
+// SM: per-body constants from shared memory (rnea_grad) or from the constant bank (rnea: one sweep per knot
+// point does not repay the staging, measured 10-20 % slower)
+template <typename T, bool SM>
+__device__ __forceinline__ void fb_rnea_state(const FbModel<T>& m, const T* sm, const T* qb, const T* qdb, const T* qddb, T gravity,
                                               const T (&X0)[18], T (*lv)[6], T (*la)[6], T (*lf)[6], T (*lb)[2]) {
   const int NB = m.d.n;
   for (int i = 0; i < NB; ++i) {
@@ -77,7 +101,7 @@ __device__ __forceinline__ void fb_rnea_state(const FbModel<T>& m, const T* qb, 
       for (int r = 0; r < 6; ++r) vJ[r] = qdb[r];                              // :585, S = eye(6)
     } else {
       joint_basis(m.d, i, qb[i + 6], lb[i][0], lb[i][1]);
-      build_X(m.d, i, lb[i][0], lb[i][1], X);
+      if (SM) fb_build_X(sm, i, lb[i][0], lb[i][1], X); else build_X(m.d, i, lb[i][0], lb[i][1], X);
       const int p = m.d.parent[i];
 #pragma unroll
       for (int r = 0; r < 6; ++r) par[r] = lv[p][r];
@@ -87,7 +111,7 @@ __device__ __forceinline__ void fb_rnea_state(const FbModel<T>& m, const T* qb, 
       X_apply(X, par, ai);
       const T qdi = qdb[i + 5];
 #pragma unroll
-      for (int r = 0; r < 6; ++r) vJ[r] = m.d.S[i][r] * qdi;
+      for (int r = 0; r < 6; ++r) vJ[r] = (SM ? fb_S(sm, i) : m.d.S[i])[r] * qdi;
     }
 #pragma unroll
     for (int r = 0; r < 6; ++r) vi[r] += vJ[r];
@@ -101,12 +125,12 @@ __device__ __forceinline__ void fb_rnea_state(const FbModel<T>& m, const T* qb, 
       } else {
         const T qddi = qddb[i + 5];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) ai[r] = fma_t(m.d.S[i][r], qddi, ai[r]);
+        for (int r = 0; r < 6; ++r) ai[r] = fma_t((SM ? fb_S(sm, i) : m.d.S[i])[r], qddi, ai[r]);
       }
     }
     T Ia[6], Iv[6], vxIv[6];
-    mat6_apply(m.d.I[i], ai, Ia);
-    mat6_apply(m.d.I[i], vi, Iv);
+    mat6_apply(SM ? fb_I(sm, i) : m.d.I[i], ai, Ia);
+    mat6_apply(SM ? fb_I(sm, i) : m.d.I[i], vi, Iv);
     crf_mul(vi, Iv, vxIv);
 #pragma unroll
     for (int r = 0; r < 6; ++r) { lv[i][r] = vi[r]; la[i][r] = ai[r]; lf[i][r] = Ia[r] + vxIv[r]; }
@@ -115,7 +139,7 @@ __device__ __forceinline__ void fb_rnea_state(const FbModel<T>& m, const T* qb, 
     T X[18], fi[6], t[6];
 #pragma unroll
     for (int r = 0; r < 6; ++r) fi[r] = lf[i][r];
-    build_X(m.d, i, lb[i][0], lb[i][1], X);
+    if (SM) fb_build_X(sm, i, lb[i][0], lb[i][1], X); else build_X(m.d, i, lb[i][0], lb[i][1], X);
     XT_apply(X, fi, t);
     const int p = m.d.parent[i];
 #pragma unroll
@@ -138,7 +162,7 @@ fb_rnea_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restr
   T X0[18];
   fb_base_X(m, qb, X0);
   T lv[RBD_MAX_DOF][6], la[RBD_MAX_DOF][6], lf[RBD_MAX_DOF][6], lb[RBD_MAX_DOF][2];
-  fb_rnea_state(m, qb, qd + b * nv, qdd ? qdd + b * nv : nullptr, gravity, X0, lv, la, lf, lb);
+  fb_rnea_state<T, false>(m, nullptr, qb, qd + b * nv, qdd ? qdd + b * nv : nullptr, gravity, X0, lv, la, lf, lb);
   T* cb = c + b * nv;
 #pragma unroll
   for (int r = 0; r < 6; ++r) cb[r] = lf[0][r];                                // :612 with S = eye(6)
@@ -163,6 +187,9 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
                     const T* __restrict__ qd, const T* __restrict__ qdd, T gravity, int use_damping,
                     T* __restrict__ dc_du, T* __restrict__ c_out) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ __align__(16) unsigned char fb_smem_raw[];
+  T* sm = reinterpret_cast<T*>(fb_smem_raw);
+  fb_stage_model(m, sm);                      // every thread of the CTA takes part (barrier inside)
   if (b >= B) return;
   const int NB = m.d.n, nv = NB + 5, nq = NB + 6;
   const T* qb = q + b * nq;
@@ -170,12 +197,12 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
   T X0[18];
   fb_base_X(m, qb, X0);
   T lv[RBD_MAX_DOF][6], la[RBD_MAX_DOF][6], lf[RBD_MAX_DOF][6], lb[RBD_MAX_DOF][2];
-  fb_rnea_state(m, qb, qdb, qdd ? qdd + b * nv : nullptr, gravity, X0, lv, la, lf, lb);
+  fb_rnea_state<T, true>(m, sm, qb, qdb, qdd ? qdd + b * nv : nullptr, gravity, X0, lv, la, lf, lb);
   if (c_out) {
     T* cb = c_out + b * nv;
 #pragma unroll
     for (int r = 0; r < 6; ++r) cb[r] = lf[0][r];
-    for (int i = 1; i < NB; ++i) cb[i + 5] = dot6(m.d.S[i], lf[i]);
+    for (int i = 1; i < NB; ++i) cb[i + 5] = dot6(fb_S(sm, i), lf[i]);
   }
   T* gout = dc_du + b * (int64_t)2 * nv * nv;
   const int ld = 2 * nv;
@@ -214,11 +241,11 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
         for (int r = 0; r < 6; ++r) dad[r] += t[r];
       } else {
         T X[18], S[6];
-        build_X(m.d, i, lb[i][0], lb[i][1], X);
+        fb_build_X(sm, i, lb[i][0], lb[i][1], X);
         const T qdi = qdb[i + 5];
         const int p = m.d.parent[i];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) S[r] = m.d.S[i][r];
+        for (int r = 0; r < 6; ++r) S[r] = fb_S(sm, i)[r];
         if (i == bc) {
           T par[6], xp[6];
 #pragma unroll
@@ -250,15 +277,15 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
         for (int r = 0; r < 6; ++r) dad[r] = fma_t(qdi, t[r], dad[r]);
       }
       T Iv[6], Ida[6], Idv[6], t1[6], t2[6];
-      mat6_apply(m.d.I[i], vi, Iv);
-      mat6_apply(m.d.I[i], daq, Ida);
-      mat6_apply(m.d.I[i], dvq, Idv);
+      mat6_apply(fb_I(sm, i), vi, Iv);
+      mat6_apply(fb_I(sm, i), daq, Ida);
+      mat6_apply(fb_I(sm, i), dvq, Idv);
       crf_mul(dvq, Iv, t1);
       crf_mul(vi, Idv, t2);
 #pragma unroll
       for (int r = 0; r < 6; ++r) sdf[i][r] = Ida[r] + t1[r] + t2[r];
-      mat6_apply(m.d.I[i], dad, Ida);
-      mat6_apply(m.d.I[i], dvd, Idv);
+      mat6_apply(fb_I(sm, i), dad, Ida);
+      mat6_apply(fb_I(sm, i), dvd, Idv);
       crf_mul(dvd, Iv, t1);
       crf_mul(vi, Idv, t2);
 #pragma unroll
@@ -284,14 +311,14 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
         for (int r = 0; r < 6; ++r) { Fq[r] += cq[r]; Fd[r] += cd[r]; }
       }
       if (i == 0) break;                        // base column: rows 0..5 are written below
-      obuf[i + 5][cg] = dot6(m.d.S[i], Fq);                                    // :1284
-      obuf[i + 5][4 + cg] = dot6(m.d.S[i], Fd);                                // :1325
+      obuf[i + 5][cg] = dot6(fb_S(sm, i), Fq);                                    // :1284
+      obuf[i + 5][4 + cg] = dot6(fb_S(sm, i), Fd);                                // :1325
       T X[18], tq[6], td[6];
-      build_X(m.d, i, lb[i][0], lb[i][1], X);
+      fb_build_X(sm, i, lb[i][0], lb[i][1], X);
       if (i == bc) {                                                           // :1292-1294
         T fi[6], S[6], fxs[6];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) { fi[r] = lf[i][r]; S[r] = m.d.S[i][r]; }
+        for (int r = 0; r < 6; ++r) { fi[r] = lf[i][r]; S[r] = fb_S(sm, i)[r]; }
         crm_mul(fi, S, fxs);
 #pragma unroll
         for (int r = 0; r < 6; ++r) Fq[r] -= fxs[r];
@@ -317,10 +344,10 @@ fb_rnea_grad_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __
     if (bc != 0) {
       for (int j = m.d.parent[bc]; j > 0; j = m.d.parent[j]) {
         touched |= 1u << j;
-        obuf[j + 5][cg] = dot6(m.d.S[j], Fq);
-        obuf[j + 5][4 + cg] = dot6(m.d.S[j], Fd);
+        obuf[j + 5][cg] = dot6(fb_S(sm, j), Fq);
+        obuf[j + 5][4 + cg] = dot6(fb_S(sm, j), Fd);
         T X[18], tq[6], td[6];
-        build_X(m.d, j, lb[j][0], lb[j][1], X);
+        fb_build_X(sm, j, lb[j][0], lb[j][1], X);
         XT_apply(X, Fq, tq);
         XT_apply(X, Fd, td);
 #pragma unroll
@@ -378,6 +405,9 @@ __global__ void __launch_bounds__(kFbThreads, kFbMinvMinCtas)
 fb_minv_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restrict__ q, int output_dense,
                T* __restrict__ Minv) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ __align__(16) unsigned char fb_smem_raw[];
+  T* sm = reinterpret_cast<T*>(fb_smem_raw);
+  fb_stage_model(m, sm);                      // every thread of the CTA takes part (barrier inside)
   if (b >= B) return;
   const int NB = m.d.n, nv = NB + 5, nq = NB + 6;
   const T* qb = q + b * nq;
@@ -386,13 +416,13 @@ fb_minv_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restr
   T lb[RBD_MAX_DOF][2], lU[RBD_MAX_DOF][6], lUX[RBD_MAX_DOF][6], linvD[RBD_MAX_DOF];
   for (int i = 0; i < NB; ++i) {
 #pragma unroll
-    for (int k = 0; k < 36; ++k) IA[i][k] = m.d.I[i][k];
+    for (int k = 0; k < 36; ++k) IA[i][k] = fb_I(sm, i)[k];
     if (i > 0) joint_basis(m.d, i, qb[i + 6], lb[i][0], lb[i][1]);
   }
   for (int i = NB - 1; i >= 1; --i) {
     T S[6], Ui[6], X[18], UX[6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) S[r] = m.d.S[i][r];
+    for (int r = 0; r < 6; ++r) S[r] = fb_S(sm, i)[r];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
       T acc = T(0);
@@ -403,7 +433,7 @@ fb_minv_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restr
     }
     const T invD = T(1) / dot6(S, Ui);                                         // :698
     linvD[i] = invD;
-    build_X(m.d, i, lb[i][0], lb[i][1], X);
+    fb_build_X(sm, i, lb[i][0], lb[i][1], X);
     XT_apply(X, Ui, UX);
 #pragma unroll
     for (int r = 0; r < 6; ++r) lUX[i][r] = UX[r];
@@ -469,12 +499,12 @@ fb_minv_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restr
       T F[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
       for (int i = j - 5; i > 0; i = m.d.parent[i]) {                          // :697-726 restricted to column j
         const T invD = linvD[i];
-        const T mij = (i + 5 == j ? invD : T(0)) - invD * dot6(m.d.S[i], F);
+        const T mij = (i + 5 == j ? invD : T(0)) - invD * dot6(fb_S(sm, i), F);
         colM[i + 5] = mij;
         T X[18], t[6];
 #pragma unroll
         for (int r = 0; r < 6; ++r) F[r] = fma_t(lU[i][r], mij, F[r]);
-        build_X(m.d, i, lb[i][0], lb[i][1], X);
+        fb_build_X(sm, i, lb[i][0], lb[i][1], X);
         XT_apply(X, F, t);
 #pragma unroll
         for (int r = 0; r < 6; ++r) F[r] = t[r];
@@ -499,10 +529,10 @@ fb_minv_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restr
 #pragma unroll
       for (int r = 0; r < 6; ++r) Fp[r] = (p == i - 1) ? Fprev[r] : colF[p][r];
       const T mij = colM[i + 5] - linvD[i] * dot6(lUX[i], Fp);                 // :771-773
-      build_X(m.d, i, lb[i][0], lb[i][1], X);
+      fb_build_X(sm, i, lb[i][0], lb[i][1], X);
       X_apply(X, Fp, Fi);
 #pragma unroll
-      for (int r = 0; r < 6; ++r) Fprev[r] = fma_t(m.d.S[i][r], mij, Fi[r]);   // :774-776
+      for (int r = 0; r < 6; ++r) Fprev[r] = fma_t(fb_S(sm, i)[r], mij, Fi[r]);   // :774-776
       if ((m.store_mask >> i) & 1u) {
 #pragma unroll
         for (int r = 0; r < 6; ++r) colF[i][r] = Fprev[r];

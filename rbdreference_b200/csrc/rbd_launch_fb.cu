@@ -47,6 +47,10 @@ void fill_fb(const RbdFbModelDesc* fd, FbModel<T>& out) {
   }
 }
 
+// dynamic shared memory of the rnea_grad and minv kernels: the per-body constants (rbd_fb_kernels.cuh: fb_stage_model)
+template <typename T>
+size_t fb_smem_bytes(const rbd_fb_model* m) { return (size_t)m->d.d.n * kFbSmStride * sizeof(T); }
+
 template <typename T>
 int launch_fb_rnea(const rbd_fb_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, T* c, T* v, T* a, T* f,
                    void* stream) {
@@ -61,7 +65,7 @@ int launch_fb_rnea_grad(const rbd_fb_model* m, int64_t B, const T* q, const T* q
                         T* c_out, void* stream) {
   RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_fb_rnea_grad: null model/q/qd/dc_du or negative B");
   if (B == 0) return 0;
-  fb_rnea_grad_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, qd, qdd, g, damp,
+  fb_rnea_grad_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, fb_smem_bytes<T>(m), (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, qd, qdd, g, damp,
                                                                                              dc_du, c_out);
   return cuda_status("rbd_fb_rnea_grad");
 }
@@ -70,7 +74,7 @@ template <typename T>
 int launch_fb_minv(const rbd_fb_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && B >= 0, "rbd_fb_minv: null model/q/Minv or negative B");
   if (B == 0) return 0;
-  fb_minv_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, dense, Minv);
+  fb_minv_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, fb_smem_bytes<T>(m), (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, dense, Minv);
   return cuda_status("rbd_fb_minv");
 }
 
