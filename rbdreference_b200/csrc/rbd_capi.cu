@@ -130,8 +130,25 @@ template <typename T>
 int launch_minv_bpass(const rbd_model* m, int64_t B, const T* q, T* Minv, T* F, T* U, T* Dinv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && F && U && Dinv && B >= 0, "rbd_minv_bpass: null argument or negative B");
   if (B == 0) return 0;
-  minv_bpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
-      pick<T>(m), B, q, Minv, F, U, Dinv);
+  if (g_variant.load(std::memory_order_relaxed) == 1) {          // knot point per thread (the first version)
+    minv_bpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
+        pick<T>(m), B, q, Minv, F, U, Dinv);
+    return cuda_status("rbd_minv_bpass");
+  }
+  // one column per lane, articulated inertias shared through shared memory
+  const int n = m->d.n;
+  const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+  const int vals = G == 8 ? minv_bpass_col_warp_vals<8>(n) : (G == 16 ? minv_bpass_col_warp_vals<16>(n) : minv_bpass_col_warp_vals<32>(n));
+  const size_t smem = (size_t)(kPassThreads / 32) * vals * sizeof(T);
+  auto kern = G == 8 ? minv_bpass_col_kernel<T, 8> : (G == 16 ? minv_bpass_col_kernel<T, 16> : minv_bpass_col_kernel<T, 32>);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+  }
+  const int64_t ntask = (B + 32 / G - 1) / (32 / G);
+  int64_t blocks = (ntask + kPassThreads / 32 - 1) / (kPassThreads / 32);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  kern<<<(unsigned)blocks, kPassThreads, smem, (cudaStream_t)stream>>>(pick<T>(m), B, q, Minv, F, U, Dinv);
   return cuda_status("rbd_minv_bpass");
 }
 
@@ -140,8 +157,19 @@ int launch_minv_fpass(const rbd_model* m, int64_t B, const T* q, T* Minv, T* F, 
                       void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && F && U && Dinv && B >= 0, "rbd_minv_fpass: null argument or negative B");
   if (B == 0) return 0;
-  minv_fpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
-      pick<T>(m), B, q, Minv, F, U, Dinv);
+  if (g_variant.load(std::memory_order_relaxed) == 1) {          // knot point per thread (the first version)
+    minv_fpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
+        pick<T>(m), B, q, Minv, F, U, Dinv);
+    return cuda_status("rbd_minv_fpass");
+  }
+  // one column per lane: rows of Minv and F are read and written contiguously
+  const int n = m->d.n;
+  const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+  const int64_t ntask = (B + 32 / G - 1) / (32 / G);
+  int64_t blocks = (ntask + kPassThreads / 32 - 1) / (kPassThreads / 32);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  auto kern = G == 8 ? minv_fpass_col_kernel<T, 8> : (G == 16 ? minv_fpass_col_kernel<T, 16> : minv_fpass_col_kernel<T, 32>);
+  kern<<<(unsigned)blocks, kPassThreads, 0, (cudaStream_t)stream>>>(pick<T>(m), B, q, Minv, F, U, Dinv);
   return cuda_status("rbd_minv_fpass");
 }
 

@@ -382,6 +382,175 @@ minv_fpass_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __r
   }
 }
 
+// ---- minv_bpass, one column per lane ----------------------------------------------------------
+// Lane (g, l) of a warp carries column l of knot point g (G = 8 | 16 | 32 lanes per knot point).
+// Columns never mix in :700-726: column j becomes active at body j and walks to its root, its
+// running F (six registers) is F[i][:, j] of the body it currently belongs to.  Rows of Minv and of
+// F[i][r, :] are stored once, contiguously across the lanes (zeros outside subtree(i)); the
+// knot-point-per-thread version used F in global memory as read-modify-write working storage, 8 bytes
+// per 32-byte sector.  The articulated inertias (:728-733) are shared by the lanes of a knot point
+// through shared memory: IA[body][36], and per body X (as a dense 6x6), U, 1/D and tmp = Ia X; the
+// 36 entries of tmp and of X^T tmp are spread over the G lanes.
+template <int G> __host__ __device__ constexpr int minv_bpass_col_warp_vals(int n) { return (32 / G) * (n * 36 + 36 + 36 + 8); }
+
+template <typename T, int G>
+__global__ void __launch_bounds__(kPassThreads)
+minv_bpass_col_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __restrict__ q,
+                      T* __restrict__ Minv, T* __restrict__ F, T* __restrict__ U, T* __restrict__ Dinv) {
+  extern __shared__ __align__(16) unsigned char bp_smem_raw[];
+  constexpr int IPW = 32 / G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane / G, l = lane % G;
+  const int n = m.n;
+  const int knot_vals = n * 36 + 36 + 36 + 8;
+  T* ws = reinterpret_cast<T*>(bp_smem_raw) + (size_t)warp * IPW * knot_vals + (size_t)g * knot_vals;
+  T* IA = ws;                  // [n][36]
+  T* Xs = IA + n * 36;         // X_i as a dense row-major 6x6
+  T* tmp = Xs + 36;            // Ia X
+  T* Us = tmp + 36;            // U(6), 1/D
+  const int64_t ntask = (B + IPW - 1) / IPW;
+  for (int64_t task = (int64_t)blockIdx.x * nwarps + warp; task < ntask; task += (int64_t)gridDim.x * nwarps) {
+    const int64_t b = task * IPW + g;
+    const bool live = b < B;
+    const bool col = live && l < n;                         // this lane owns a column
+    const int64_t bb = live ? b : task * IPW;               // idle groups shadow a valid knot point (no stores)
+    const T* qb = q + bb * n;
+    T* Mb = Minv + bb * (int64_t)n * n;
+    T* Fb = F + bb * (int64_t)6 * n * n;
+    T* Ub = U + bb * (int64_t)6 * n;
+    T* Db = Dinv + bb * n;
+    for (int e = l; e < n * 36; e += G) IA[e] = m.I[e / 36][e % 36];     // :662
+    __syncwarp();
+    T Frun[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+    for (int i = n - 1; i >= 0; --i) {
+      const int p = m.parent[i];
+      T X[18];
+      if (p >= 0) build_X_from_q(m, i, qb[i], X);
+      // U = IA_i S, D = S . U (:697-698): lane r < 6 computes U[r]
+      if (l < 6) {
+        T acc = T(0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc = fma_t(IA[i * 36 + 6 * l + k], m.S[i][k], acc);
+        Us[l] = acc;
+      }
+      if (l == 0 && p >= 0) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            Xs[6 * r + c] = X[3 * r + c];
+            Xs[6 * r + 3 + c] = T(0);
+            Xs[6 * (3 + r) + c] = X[9 + 3 * r + c];
+            Xs[6 * (3 + r) + 3 + c] = X[3 * r + c];
+          }
+      }
+      __syncwarp();
+      T Ui[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Ui[r] = Us[r];
+      const T D = dot6(m.S[i], Ui);
+      const T invD = T(1) / D;
+      if (live) {
+        if (l < 6) Ub[i * 6 + l] = Ui[l];
+        if (l == 6) Db[i] = D;                               // "Dinv" holds D (:698)
+      }
+      // column l at body i (:700-726)
+      if (col) {
+        const bool mine = (m.sub_mask[i] >> l) & 1u;
+        T mij = T(0), Fout[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+        if (mine) {
+          mij = (l == i ? invD : T(0)) - invD * dot6(m.S[i], Frun);
+#pragma unroll
+          for (int r = 0; r < 6; ++r) Fout[r] = p >= 0 ? fma_t(Ui[r], mij, Frun[r]) : Frun[r];
+          if (p >= 0) XT_apply(X, Fout, Frun);               // now F[p][:, l] (:724-726)
+        }
+        Mb[i * n + l] = mij;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) Fb[(i * 6 + r) * n + l] = Fout[r];
+      }
+      // IA_p += X^T (IA_i - U U^T / D) X (:728-733), entries spread over the G lanes
+      if (p >= 0) {
+        for (int e = l; e < 36; e += G) {
+          const int r = e / 6, c = e - 6 * r;
+          const T ur = Us[r] * invD;
+          T acc = T(0);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) acc = fma_t(IA[i * 36 + 6 * r + k] - ur * Us[k], Xs[6 * k + c], acc);
+          tmp[e] = acc;
+        }
+        __syncwarp();
+        for (int e = l; e < 36; e += G) {
+          const int r = e / 6, c = e - 6 * r;
+          T acc = T(0);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) acc = fma_t(Xs[6 * k + r], tmp[6 * k + c], acc);
+          IA[p * 36 + e] += acc;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ---- minv_fpass, one column per lane ----------------------------------------------------------
+// The forward pass never mixes columns (:771-776 act on whole rows, entry by entry), so lane (g, j)
+// carries column j of knot point g through the bodies: every access to Minv[i, :] and F[i][r, :] is
+// one contiguous row per knot point (the knot-point-per-thread version touched 8 bytes per 32-byte
+// sector), the parent's F stays in registers along chains and is re-read (own store) at branch
+// points.  G = 8 | 16 | 32 lanes per knot point; lanes j >= n idle.
+template <typename T, int G>
+__global__ void __launch_bounds__(kPassThreads)
+minv_fpass_col_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __restrict__ q,
+                      T* __restrict__ Minv, T* __restrict__ F, const T* __restrict__ U,
+                      const T* __restrict__ Dinv) {
+  constexpr int IPW = 32 / G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane / G, j = lane % G;
+  const int n = m.n;
+  const int64_t ntask = (B + IPW - 1) / IPW;
+  for (int64_t task = (int64_t)blockIdx.x * nwarps + warp; task < ntask; task += (int64_t)gridDim.x * nwarps) {
+    const int64_t b = task * IPW + g;
+    if (b >= B || j >= n) continue;
+    const T* qb = q + b * n;
+    T* Mb = Minv + b * (int64_t)n * n;
+    T* Fb = F + b * (int64_t)6 * n * n;
+    const T* Ub = U + b * (int64_t)6 * n;
+    const T* Db = Dinv + b * n;
+    T Fprev[6];
+    int prev = -1;
+    for (int i = 0; i < n; ++i) {
+      const int p = m.parent[i];
+      T mij = Mb[i * n + j];
+      if (p >= 0) {
+        T X[18], Ui[6], UX[6], Fp[6], Fi[6];
+        build_X_from_q(m, i, qb[i], X);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) Ui[r] = Ub[i * 6 + r];
+        XT_apply(X, Ui, UX);                                                   // U^T X = (X^T U)^T
+        const T invD = T(1) / Db[i];
+        if (p == prev) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) Fp[r] = Fprev[r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) Fp[r] = Fb[(p * 6 + r) * n + j];
+        }
+        mij -= invD * dot6(UX, Fp);                                            // :771-773
+        Mb[i * n + j] = mij;
+        X_apply(X, Fp, Fi);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) Fprev[r] = fma_t(m.S[i][r], mij, Fi[r]);   // :774-776
+      } else {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) Fprev[r] = m.S[i][r] * mij;                // :781
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Fb[(i * 6 + r) * n + j] = Fprev[r];
+      prev = i;
+    }
+  }
+}
+
 // ---- minv epilogue (RBDReference.py:799-804): lower <- upper --------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kPassThreads)
