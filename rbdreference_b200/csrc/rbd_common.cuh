@@ -133,4 +133,21 @@ __device__ __forceinline__ T dot6(const T* s, const T* x) {
   return acc;
 }
 
+// Cooperative store of per-lane result blocks: lane k of the warp holds the NV values of knot point b0 + k
+// (in memory order) in `vals` (registers / local memory); dst + (b0 + k) * NV is where they go.  32 values
+// per lane are transposed through `tile` ([32][33]) at a time, so every store instruction writes 256
+// contiguous bytes of one knot point instead of 8 bytes per lane NV * sizeof(T) apart.  All 32 lanes call.
+constexpr int kFlushChunk = 32;
+template <typename T>
+__device__ __forceinline__ void warp_flush_blocks(const T* vals, int NV, T* tile, T* __restrict__ dst, int nlive, int lane) {
+  for (int c0 = 0; c0 < NV; c0 += kFlushChunk) {
+    const int cnt = NV - c0 < kFlushChunk ? NV - c0 : kFlushChunk;
+    for (int k = 0; k < cnt; ++k) tile[lane * (kFlushChunk + 1) + k] = vals[c0 + k];
+    __syncwarp();
+    if (lane < cnt)
+      for (int r = 0; r < nlive; ++r) __stcs(dst + (int64_t)r * NV + c0 + lane, tile[r * (kFlushChunk + 1) + lane]);
+    __syncwarp();
+  }
+}
+
 }  // namespace rbd

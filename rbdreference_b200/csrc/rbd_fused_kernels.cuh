@@ -21,13 +21,18 @@ __global__ void __launch_bounds__(kFusedThreads)
 rnea_fused_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __restrict__ q,
                   const T* __restrict__ qd, const T* __restrict__ qdd, T gravity,
                   T* __restrict__ c, T* __restrict__ v, T* __restrict__ a, T* __restrict__ f) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+  __shared__ T tiles[kFusedThreads / 32][32 * (kFlushChunk + 1)];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane;
+  if (b0 >= B) return;                                     // whole warp past the end
+  const int nlive = (int)(B - b0 < 32 ? B - b0 : 32);
+  const bool live = lane < nlive;
+  const int64_t b = b0 + (live ? lane : 0);                // idle lanes shadow a valid knot point
   const int n = m.n;
   const T* qb = q + b * n;
   const T* qdb = qd + b * n;
   const T* qddb = qdd ? qdd + b * n : nullptr;
-  T lv[RBD_MAX_DOF][6], la[RBD_MAX_DOF][6], lf[RBD_MAX_DOF][6], lb[RBD_MAX_DOF][2];
+  T lv[6 * RBD_MAX_DOF], la[6 * RBD_MAX_DOF], lf[6 * RBD_MAX_DOF], lb[RBD_MAX_DOF][2];   // (6, NB): (r, i) at r*n + i
   for (int i = 0; i < n; ++i) {
     T X[18], f1, f2;
     joint_basis(m, i, qb[i], f1, f2);
@@ -42,10 +47,10 @@ rnea_fused_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __r
       X_apply(X, par, ai);
     } else {
 #pragma unroll
-      for (int r = 0; r < 6; ++r) par[r] = lv[p][r];
+      for (int r = 0; r < 6; ++r) par[r] = lv[r * n + p];
       X_apply(X, par, vi);
 #pragma unroll
-      for (int r = 0; r < 6; ++r) par[r] = la[p][r];
+      for (int r = 0; r < 6; ++r) par[r] = la[r * n + p];
       X_apply(X, par, ai);
     }
     T vJ[6], t[6];
@@ -66,44 +71,30 @@ rnea_fused_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __r
     crf_mul(vi, Iv, vxIv);
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      lv[i][r] = vi[r];
-      la[i][r] = ai[r];
-      lf[i][r] = Ia[r] + vxIv[r];
+      lv[r * n + i] = vi[r];
+      la[r * n + i] = ai[r];
+      lf[r * n + i] = Ia[r] + vxIv[r];
     }
   }
   T* cb = c + b * n;
   for (int i = n - 1; i >= 0; --i) {
     T fi[6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) fi[r] = lf[i][r];
-    cb[i] = dot6(m.S[i], fi);
+    for (int r = 0; r < 6; ++r) fi[r] = lf[r * n + i];
+    if (live) cb[i] = dot6(m.S[i], fi);
     const int p = m.parent[i];
     if (p >= 0) {
       T X[18], t[6];
       build_X(m, i, lb[i][0], lb[i][1], X);
       XT_apply(X, fi, t);
 #pragma unroll
-      for (int r = 0; r < 6; ++r) lf[p][r] += t[r];
+      for (int r = 0; r < 6; ++r) lf[r * n + p] += t[r];
     }
   }
-  if (v) {
-    T* vb = v + b * 6 * n;
-    for (int i = 0; i < n; ++i)
-#pragma unroll
-      for (int r = 0; r < 6; ++r) vb[r * n + i] = lv[i][r];
-  }
-  if (a) {
-    T* ab = a + b * 6 * n;
-    for (int i = 0; i < n; ++i)
-#pragma unroll
-      for (int r = 0; r < 6; ++r) ab[r * n + i] = la[i][r];
-  }
-  if (f) {
-    T* fb = f + b * 6 * n;
-    for (int i = 0; i < n; ++i)
-#pragma unroll
-      for (int r = 0; r < 6; ++r) fb[r * n + i] = lf[i][r];
-  }
+  // v / a / f: coalesced 256-byte rows through a shared-memory transpose (warp_flush_blocks)
+  if (v) warp_flush_blocks(lv, 6 * n, tiles[warp], v + b0 * 6 * n, nlive, lane);
+  if (a) warp_flush_blocks(la, 6 * n, tiles[warp], a + b0 * 6 * n, nlive, lane);
+  if (f) warp_flush_blocks(lf, 6 * n, tiles[warp], f + b0 * 6 * n, nlive, lane);
 }
 
 // =============================================================================================

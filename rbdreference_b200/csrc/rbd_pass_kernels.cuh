@@ -14,20 +14,24 @@ namespace rbd {
 constexpr int kPassThreads = 128;
 
 // ---- rnea_fpass (RBDReference.py:559-598) --------------------------------------------------
+// Generic version (large robots, non-rigid inertias): one knot point per thread, v / a / f kept per thread
+// in memory order and stored through warp_flush_blocks (coalesced 256-byte rows).
 template <typename T>
 __global__ void __launch_bounds__(kPassThreads)
 rnea_fpass_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __restrict__ q,
                   const T* __restrict__ qd, const T* __restrict__ qdd, T gravity,
                   T* __restrict__ v, T* __restrict__ a, T* __restrict__ f) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+  __shared__ T tiles[kPassThreads / 32][32 * (kFlushChunk + 1)];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane;
+  if (b0 >= B) return;                                     // whole warp past the end
+  const int nlive = (int)(B - b0 < 32 ? B - b0 : 32);
+  const int64_t b = b0 + (lane < nlive ? lane : 0);        // idle lanes shadow a valid knot point
   const int n = m.n;
   const T* qb = q + b * n;
   const T* qdb = qd + b * n;
   const T* qddb = qdd ? qdd + b * n : nullptr;
-  T* vb = v + b * 6 * n;   // (6, NB): element (r, i) at r*n + i
-  T* ab = a + b * 6 * n;
-  T* fb = f + b * 6 * n;
+  T lv[6 * RBD_MAX_DOF], la[6 * RBD_MAX_DOF], lf[6 * RBD_MAX_DOF];     // (6, NB): element (r, i) at r*n + i
   for (int i = 0; i < n; ++i) {
     T X[18];
     build_X_from_q(m, i, qb[i], X);
@@ -40,7 +44,7 @@ rnea_fpass_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __r
       X_apply(X, ap, ai);                                // :578
     } else {
 #pragma unroll
-      for (int r = 0; r < 6; ++r) { vp[r] = vb[r * n + p]; ap[r] = ab[r * n + p]; }
+      for (int r = 0; r < 6; ++r) { vp[r] = lv[r * n + p]; ap[r] = la[r * n + p]; }
       X_apply(X, vp, vi);                                // :580
       X_apply(X, ap, ai);                                // :581
     }
@@ -62,11 +66,14 @@ rnea_fpass_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __r
     crf_mul(vi, Iv, vxIv);                                                     // :170-182
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      vb[r * n + i] = vi[r];
-      ab[r * n + i] = ai[r];
-      fb[r * n + i] = Ia[r] + vxIv[r];                                         // :596
+      lv[r * n + i] = vi[r];
+      la[r * n + i] = ai[r];
+      lf[r * n + i] = Ia[r] + vxIv[r];                                         // :596
     }
   }
+  warp_flush_blocks(lv, 6 * n, tiles[warp], v + b0 * 6 * n, nlive, lane);
+  warp_flush_blocks(la, 6 * n, tiles[warp], a + b0 * 6 * n, nlive, lane);
+  warp_flush_blocks(lf, 6 * n, tiles[warp], f + b0 * 6 * n, nlive, lane);
 }
 
 // ---- rnea_bpass (RBDReference.py:600-621) --------------------------------------------------
