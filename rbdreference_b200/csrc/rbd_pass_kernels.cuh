@@ -396,9 +396,9 @@ minv_fpass_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T* __r
 // F[i][r, :] are stored once, contiguously across the lanes (zeros outside subtree(i)); the
 // knot-point-per-thread version used F in global memory as read-modify-write working storage, 8 bytes
 // per 32-byte sector.  The articulated inertias (:728-733) are shared by the lanes of a knot point
-// through shared memory: IA[body][36], and per body X (as a dense 6x6), U, 1/D and tmp = Ia X; the
-// 36 entries of tmp and of X^T tmp are spread over the G lanes.
-template <int G> __host__ __device__ constexpr int minv_bpass_col_warp_vals(int n) { return (32 / G) * (n * 36 + 36 + 36 + 8); }
+// through shared memory (IA[body][36], U): lane c < 6 owns column c of the update - Ia X[:, c] from shared
+// memory, then X^T of it straight from its registers (XT_apply), added to column c of IA_parent.
+template <int G> __host__ __device__ constexpr int minv_bpass_col_warp_vals(int n) { return (32 / G) * (n * 36 + 8); }
 
 template <typename T, int G>
 __global__ void __launch_bounds__(kPassThreads)
@@ -409,12 +409,10 @@ minv_bpass_col_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T*
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane / G, l = lane % G;
   const int n = m.n;
-  const int knot_vals = n * 36 + 36 + 36 + 8;
+  const int knot_vals = n * 36 + 8;
   T* ws = reinterpret_cast<T*>(bp_smem_raw) + (size_t)warp * IPW * knot_vals + (size_t)g * knot_vals;
   T* IA = ws;                  // [n][36]
-  T* Xs = IA + n * 36;         // X_i as a dense row-major 6x6
-  T* tmp = Xs + 36;            // Ia X
-  T* Us = tmp + 36;            // U(6), 1/D
+  T* Us = IA + n * 36;         // U(6)
   const int64_t ntask = (B + IPW - 1) / IPW;
   for (int64_t task = (int64_t)blockIdx.x * nwarps + warp; task < ntask; task += (int64_t)gridDim.x * nwarps) {
     const int64_t b = task * IPW + g;
@@ -440,17 +438,6 @@ minv_bpass_col_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T*
         for (int k = 0; k < 6; ++k) acc = fma_t(IA[i * 36 + 6 * l + k], m.S[i][k], acc);
         Us[l] = acc;
       }
-      if (l == 0 && p >= 0) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            Xs[6 * r + c] = X[3 * r + c];
-            Xs[6 * r + 3 + c] = T(0);
-            Xs[6 * (3 + r) + c] = X[9 + 3 * r + c];
-            Xs[6 * (3 + r) + 3 + c] = X[3 * r + c];
-          }
-      }
       __syncwarp();
       T Ui[6];
 #pragma unroll
@@ -475,24 +462,30 @@ minv_bpass_col_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T*
 #pragma unroll
         for (int r = 0; r < 6; ++r) Fb[(i * 6 + r) * n + l] = Fout[r];
       }
-      // IA_p += X^T (IA_i - U U^T / D) X (:728-733), entries spread over the G lanes
-      if (p >= 0) {
-        for (int e = l; e < 36; e += G) {
-          const int r = e / 6, c = e - 6 * r;
-          const T ur = Us[r] * invD;
+      // IA_p += X^T (IA_i - U U^T / D) X (:728-733): lane c < 6 owns column c
+      if (p >= 0 && l < 6) {
+        // column c of X = [[E, 0], [L, E]] picked out of the lane's registers (c is a run-time value)
+        const int cc = l < 3 ? l : l - 3;
+        T xk[6];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const T e = cc == 0 ? X[3 * r] : (cc == 1 ? X[3 * r + 1] : X[3 * r + 2]);
+          const T lo = cc == 0 ? X[9 + 3 * r] : (cc == 1 ? X[9 + 3 * r + 1] : X[9 + 3 * r + 2]);
+          xk[r] = l < 3 ? e : T(0);
+          xk[3 + r] = l < 3 ? lo : e;
+        }
+        const T ux = invD * dot6(Ui, xk);
+        T colv[6], t[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
           T acc = T(0);
 #pragma unroll
-          for (int k = 0; k < 6; ++k) acc = fma_t(IA[i * 36 + 6 * r + k] - ur * Us[k], Xs[6 * k + c], acc);
-          tmp[e] = acc;
+          for (int k = 0; k < 6; ++k) acc = fma_t(IA[i * 36 + 6 * r + k], xk[k], acc);
+          colv[r] = acc - Ui[r] * ux;
         }
-        __syncwarp();
-        for (int e = l; e < 36; e += G) {
-          const int r = e / 6, c = e - 6 * r;
-          T acc = T(0);
+        XT_apply(X, colv, t);
 #pragma unroll
-          for (int k = 0; k < 6; ++k) acc = fma_t(Xs[6 * k + r], tmp[6 * k + c], acc);
-          IA[p * 36 + e] += acc;
-        }
+        for (int r = 0; r < 6; ++r) IA[p * 36 + 6 * r + l] += t[r];
       }
       __syncwarp();
     }
