@@ -121,7 +121,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -333,10 +333,11 @@ def run_ours(args):
                                            torch.cuda.current_stream(dev).cuda_stream)
     fma_peak_tflops = peak.value / 1e12 if rc == 0 else None
 
+    # started before the warm-up so that nvidia-smi is already streaming when the (short) timed region begins
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = eng.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_wall0 = time.perf_counter()
