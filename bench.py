@@ -482,7 +482,7 @@ def measure_cpu_baseline(args, n):
     q, qd, qdd = synth_host(n, ncal, 0xB201, args.robot)
     cpu.run(q[: cpu.cores], qd[: cpu.cores], qdd[: cpu.cores])                # warm the workers
     rate = ncal / cpu.run(q, qd, qdd)                                         # calibration: evals/s on all cores
-    sample = int(max(cpu.cores, min(1 << 20, round(16.0 * rate))))
+    sample = int(max(cpu.cores, min(1 << 20, round(30.0 * rate))))
     q, qd, qdd = synth_host(n, sample, 0xB200, args.robot)
     t = cpu.run(q, qd, qdd)
     cpu.close()
