@@ -74,9 +74,12 @@ int rbd_model_uses_world_kernels(const rbd_model_t* m);
  * (knot point per lane for the articulated inertias, column per lane for the rows of Minv; other
  * operations behave as 0), 5 = lane minv kernel (knot point per lane in every phase, per-body table
  * and output tile in shared memory; robots too large for it run the generic kernel; other
- * operations behave as 0), 6 = lane2 minv kernel (knot point per lane, per-body table in an L2-resident
- * scratch buffer; for large robots; other operations behave as 0).  Used by the tests and the benchmark to cross-check / compare. */
+ * operations behave as 0), 7 = chain rnea_grad kernel (serial chains, knot point per lane; other robots and
+ * operations behave as 0).  6 is retired.  Used by the tests and the benchmark to cross-check / compare. */
 int rbd_set_kernel_variant(int variant);
+/* The same choice for one handle only (-1 = follow the process-wide setting, the default): calls on
+ * different handles never see each other's choice, so handles stay independent across threads. */
+int rbd_model_set_kernel_variant(rbd_model_t* m, int variant);
 
 /* ---- fused drivers ------------------------------------------------------------------------ */
 /* rnea (RBDReference.py:623-628).  qdd may be NULL (skips the S*qdd term, :589).  v, a, f may

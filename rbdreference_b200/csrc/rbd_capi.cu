@@ -49,6 +49,18 @@ cudaMemPool_t scratch_pool(int dev) {
   return pools[dev];
 }
 
+int sm_count() {
+  static std::atomic<int> cache[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return 148; }
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v <= 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); return 148; }
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 int fail(int code, const char* msg) {
   std::snprintf(g_err, sizeof(g_err), "%s", msg);
   return code;
@@ -67,7 +79,7 @@ int cuda_status(const char* what) {
 // ---- forward dynamics (RBDReference.py:1369-1384): compositions of the fused drivers plus the
 // per-knot-point products of rbd_fd_kernels.cuh; temporaries are stream-ordered pool allocations.
 template <typename T, bool SPLIT>
-int launch_fd_apply(int n, int mcols, int64_t B, const T* A, const T* R1, const T* R2, T alpha, T* out0, T* out1,
+int launch_fd_apply(int variant, int n, int mcols, int64_t B, const T* A, const T* R1, const T* R2, T alpha, T* out0, T* out1,
                     void* stream) {
   const size_t per_knot = (size_t)(n * n + 2 * n * mcols) * sizeof(T);
   // small per-CTA batches: several CTAs per SM keep loads, products and stores of different batches overlapped
@@ -75,7 +87,7 @@ int launch_fd_apply(int n, int mcols, int64_t B, const T* A, const T* R1, const 
   if (KB < 1) KB = 1;
   if (KB > 32) KB = 32;
   const size_t smem = per_knot * KB;
-  if (mcols > 1 && std::is_same<T, double>::value && !R2 && g_variant.load(std::memory_order_relaxed) != 1) {
+  if (mcols > 1 && std::is_same<T, double>::value && !R2 && variant != 1) {
     // FP64 tensor-core product (forward_dynamics_grad)
     const FdMmaShape sh = fd_mma_shape(n, mcols);
     const size_t per_knot_m = (size_t)sh.vals * sizeof(double);
@@ -86,7 +98,7 @@ int launch_fd_apply(int n, int mcols, int64_t B, const T* A, const T* R1, const 
     cudaError_t e = cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
     int64_t blocks = (B + KM - 1) / KM;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > grid_cap()) blocks = grid_cap();
     mk<<<(unsigned)blocks, kFdMmaThreads, per_knot_m * KM, (cudaStream_t)stream>>>(
         n, mcols, KM, B, (const double*)A, (const double*)R1, (double)alpha, (double*)out0, (double*)out1);
     return cuda_status("rbd_forward_dynamics(apply, mma)");
@@ -102,7 +114,7 @@ int launch_fd_apply(int n, int mcols, int64_t B, const T* A, const T* R1, const 
     cudaError_t e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
     int64_t blocks = (B + KT - 1) / KT;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > grid_cap()) blocks = grid_cap();
     tk<<<(unsigned)blocks, kFdTiledThreads, smem_t, (cudaStream_t)stream>>>(n, mcols, KT, B, A, R1, R2, alpha, out0, out1);
     return cuda_status("rbd_forward_dynamics(apply, tiled)");
   }
@@ -110,15 +122,15 @@ int launch_fd_apply(int n, int mcols, int64_t B, const T* A, const T* R1, const 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
   if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
   int64_t blocks = (B + KB - 1) / KB;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > grid_cap()) blocks = grid_cap();
   kern<<<(unsigned)blocks, kFdThreads, smem, (cudaStream_t)stream>>>(n, mcols, KB, B, A, R1, R2, alpha, out0, out1);
   return cuda_status("rbd_forward_dynamics(apply)");
 }
 
-template int launch_fd_apply<double, false>(int, int, int64_t, const double*, const double*, const double*, double, double*, double*, void*);
-template int launch_fd_apply<double, true>(int, int, int64_t, const double*, const double*, const double*, double, double*, double*, void*);
-template int launch_fd_apply<float, false>(int, int, int64_t, const float*, const float*, const float*, float, float*, float*, void*);
-template int launch_fd_apply<float, true>(int, int, int64_t, const float*, const float*, const float*, float, float*, float*, void*);
+template int launch_fd_apply<double, false>(int, int, int, int64_t, const double*, const double*, const double*, double, double*, double*, void*);
+template int launch_fd_apply<double, true>(int, int, int, int64_t, const double*, const double*, const double*, double, double*, double*, void*);
+template int launch_fd_apply<float, false>(int, int, int, int64_t, const float*, const float*, const float*, float, float*, float*, void*);
+template int launch_fd_apply<float, true>(int, int, int, int64_t, const float*, const float*, const float*, float, float*, float*, void*);
 
 }  // namespace rbd_host
 
@@ -130,7 +142,7 @@ template <typename T>
 int launch_minv_bpass(const rbd_model* m, int64_t B, const T* q, T* Minv, T* F, T* U, T* Dinv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && F && U && Dinv && B >= 0, "rbd_minv_bpass: null argument or negative B");
   if (B == 0) return 0;
-  if (g_variant.load(std::memory_order_relaxed) == 1) {          // knot point per thread (the first version)
+  if (variant_of(m) == 1) {          // knot point per thread (the first version)
     minv_bpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
         pick<T>(m), B, q, Minv, F, U, Dinv);
     return cuda_status("rbd_minv_bpass");
@@ -147,7 +159,7 @@ int launch_minv_bpass(const rbd_model* m, int64_t B, const T* q, T* Minv, T* F, 
   }
   const int64_t ntask = (B + 32 / G - 1) / (32 / G);
   int64_t blocks = (ntask + kPassThreads / 32 - 1) / (kPassThreads / 32);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > grid_cap()) blocks = grid_cap();
   kern<<<(unsigned)blocks, kPassThreads, smem, (cudaStream_t)stream>>>(pick<T>(m), B, q, Minv, F, U, Dinv);
   return cuda_status("rbd_minv_bpass");
 }
@@ -157,7 +169,7 @@ int launch_minv_fpass(const rbd_model* m, int64_t B, const T* q, T* Minv, T* F, 
                       void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && F && U && Dinv && B >= 0, "rbd_minv_fpass: null argument or negative B");
   if (B == 0) return 0;
-  if (g_variant.load(std::memory_order_relaxed) == 1) {          // knot point per thread (the first version)
+  if (variant_of(m) == 1) {          // knot point per thread (the first version)
     minv_fpass_kernel<T><<<blocks_for(B, kPassThreads), kPassThreads, 0, (cudaStream_t)stream>>>(
         pick<T>(m), B, q, Minv, F, U, Dinv);
     return cuda_status("rbd_minv_fpass");
@@ -167,7 +179,7 @@ int launch_minv_fpass(const rbd_model* m, int64_t B, const T* q, T* Minv, T* F, 
   const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
   const int64_t ntask = (B + 32 / G - 1) / (32 / G);
   int64_t blocks = (ntask + kPassThreads / 32 - 1) / (kPassThreads / 32);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > grid_cap()) blocks = grid_cap();
   auto kern = G == 8 ? minv_fpass_col_kernel<T, 8> : (G == 16 ? minv_fpass_col_kernel<T, 16> : minv_fpass_col_kernel<T, 32>);
   kern<<<(unsigned)blocks, kPassThreads, 0, (cudaStream_t)stream>>>(pick<T>(m), B, q, Minv, F, U, Dinv);
   return cuda_status("rbd_minv_fpass");
@@ -193,7 +205,7 @@ int launch_forward_dynamics(const rbd_model* m, int64_t B, const T* q, const T* 
   if (rc) return rc;
   rc = launch_minv<T>(m, B, q, 1, Minv, stream);
   if (rc) return rc;
-  return launch_fd_apply<T, false>(n, 1, B, Minv, u, (const T*)c.p, T(1), qdd, nullptr, stream);
+  return launch_fd_apply<T, false>(variant_of(m), n, 1, B, Minv, u, (const T*)c.p, T(1), qdd, nullptr, stream);
 }
 
 template <typename T>
@@ -218,7 +230,7 @@ int launch_forward_dynamics_grad(const rbd_model* m, int64_t B, const T* q, cons
   rc = launch_rnea_grad<T>(m, B, q, qd, qdd, T(-9.81), 0, (T*)dc.p, nullptr, stream);           // :1378
   if (rc) return rc;
   // qdd_dq = -Minv dc_dq, qdd_dqd = -Minv dc_dqd (:1381-1383); the reference recomputes minv (:1381)
-  return launch_fd_apply<T, true>(n, 2 * n, B, (const T*)Mi.p, (const T*)dc.p, nullptr, T(-1), qdd_dq, qdd_dqd, stream);
+  return launch_fd_apply<T, true>(variant_of(m), n, 2 * n, B, (const T*)Mi.p, (const T*)dc.p, nullptr, T(-1), qdd_dq, qdd_dqd, stream);
 }
 
 template <typename T>
@@ -402,6 +414,8 @@ int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out) {
   fill_model<double>(desc, m->d);
   fill_model<float>(desc, m->f);
   m->fast_ok = build_fast_model(desc, m->fd);
+  m->is_chain = true;
+  for (int i = 0; i < desc->n; ++i) m->is_chain = m->is_chain && desc->parent[i] == i - 1;
   narrow_fast_model(m->fd, m->ff);
   m->fast_ok = build_dfs_model(desc, m->fd_dfs, m->plan) && m->fast_ok;
   narrow_fast_model(m->fd_dfs, m->ff_dfs);
@@ -429,26 +443,6 @@ int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out) {
       mp.comp_root[i] = p < 0 ? i : mp.comp_root[p];
       if (i - mp.comp_root[i] + 1 > mp.maxcomp) mp.maxcomp = i - mp.comp_root[i] + 1;
     }
-    // visit lists of the lane2 minv kernel: bodies a phase of a column group has to touch
-    Lane2Plan& lp = m->lane2;
-    std::memset(&lp, 0, sizeof(lp));
-    lp.ngroups = (n + kL2GC - 1) / kL2GC;
-    lp.ok = m->fast_ok && cp.maxdepth < kL2MaxDepth && m->fd_dfs.n_slot_a <= kL2MaxSlots;
-    for (int g = 0; g < lp.ngroups && lp.ok; ++g) {
-      const int j0 = g * kL2GC, jtop = (j0 + kL2GC < n ? j0 + kL2GC : n) - 1;
-      bool firstB = true, firstC = true;
-      for (int a = jtop; a >= 0; --a)
-        if (m->plan.sub_end[a] > j0 && lp.nsteps < kL2MaxSteps) {
-          lp.seq[lp.nsteps++] = (unsigned short)(a | (firstB ? 64 : 0) | (g << 7));
-          firstB = false;
-        }
-      for (int a = mp.comp_root[j0]; a <= jtop; ++a)
-        if (m->plan.comp_end[a] > j0 && lp.nsteps < kL2MaxSteps) {
-          lp.seq[lp.nsteps++] = (unsigned short)(a | 32 | (firstC ? 64 : 0) | (g << 7));
-          firstC = false;
-        }
-      if (lp.nsteps >= kL2MaxSteps) lp.ok = 0;
-    }
   }
   {
     // create the current device's scratch pool now, so that no call made later under CUDA-graph
@@ -468,11 +462,17 @@ int rbd_model_destroy(rbd_model_t* m) {
 
 int rbd_model_num_dof(const rbd_model_t* m) { return m ? m->d.n : RBD_E_INVALID_ARGUMENT; }
 
+static const char* kVariantHelp =
+    "kernel variant: 0 auto, 1 generic, 2 world (thread per knot point), 3 cooperative, 4 hybrid (minv), 5 lane (minv), "
+    "7 chain (rnea_grad, serial chains)";
 int rbd_set_kernel_variant(int variant) {
-  if (variant < 0 || variant > 6)
-    return fail(RBD_E_INVALID_ARGUMENT,
-                "rbd_set_kernel_variant: 0 auto, 1 generic, 2 world (thread per knot point), 3 cooperative, 4 hybrid (minv), 5 lane (minv), 6 lane2 (minv)");
+  if (variant < 0 || variant > 7 || variant == 6) return fail(RBD_E_INVALID_ARGUMENT, kVariantHelp);
   g_variant.store(variant, std::memory_order_relaxed);
+  return 0;
+}
+int rbd_model_set_kernel_variant(rbd_model_t* m, int variant) {
+  if (!m || variant < -1 || variant > 7 || variant == 6) return fail(RBD_E_INVALID_ARGUMENT, kVariantHelp);
+  m->variant.store(variant, std::memory_order_relaxed);
   return 0;
 }
 int rbd_model_uses_world_kernels(const rbd_model_t* m) { return (m && m->fast_ok) ? 1 : 0; }

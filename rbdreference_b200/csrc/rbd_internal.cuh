@@ -22,7 +22,6 @@
 #include "rbd_minv_kernels.cuh"
 #include "rbd_coop_kernels.cuh"
 #include "rbd_coop_minv_kernels.cuh"
-#include "rbd_lane2_minv_kernels.cuh"
 
 struct rbd_model {
   rbd::DevModel<double> d;
@@ -30,18 +29,26 @@ struct rbd_model {
   rbd::FastModel<double> fd;     // world-frame kernels (rigid-body inertias only)
   rbd::FastModel<float> ff;
   bool fast_ok;                  // FastModel valid (rigid inertias, 1-DoF revolute/prismatic joints)
+  bool is_chain;                 // parent[i] == i - 1 for every body (serial chain)
   rbd::FastModel<double> fd_dfs; // the same robot renumbered in depth-first preorder
   rbd::FastModel<float> ff_dfs;
   rbd::DfsPlan plan;
   rbd::CoopPlan coop;
   rbd::CoopMinvPlan coop_minv;
-  rbd::Lane2Plan lane2;
+  mutable std::atomic<int> variant{-1};   // per-handle kernel family (-1: follow rbd_set_kernel_variant)
 };
 
 namespace rbd_host {
 
 constexpr size_t kMaxDynSmem = 227 * 1024;
 extern std::atomic<int> g_variant;      // 0 auto, 1 force the generic body-frame kernels, 2.. see rbd_b200.h
+// kernel family of one call: the handle's own choice (rbd_model_set_kernel_variant) or the process default
+inline int variant_of(const rbd_model* m) {
+  const int v = m ? m->variant.load(std::memory_order_relaxed) : -1;
+  return v >= 0 ? v : g_variant.load(std::memory_order_relaxed);
+}
+int sm_count();                         // SMs of the current device (cudaDevAttrMultiProcessorCount, cached per device)
+inline int64_t grid_cap(int ctas_per_sm = 16) { return (int64_t)sm_count() * ctas_per_sm; }
 size_t smem_limit();                    // shared-memory budget per warp of the world-frame grad kernel
 cudaMemPool_t scratch_pool(int dev);    // private stream-ordered pool for scratch buffers
 int fail(int code, const char* msg);    // records the message for rbd_last_error_string()
@@ -57,6 +64,8 @@ template <typename T> inline const rbd::FastModel<T>& pick_fast(const rbd_model*
 template <> inline const rbd::FastModel<double>& pick_fast<double>(const rbd_model* m) { return m->fd; }
 template <> inline const rbd::FastModel<float>& pick_fast<float>(const rbd_model* m) { return m->ff; }
 
+// below this batch the one-knot-point-per-lane chain kernel leaves SMs idle (32 knot points per warp)
+inline int64_t chain_min_batch(int n) { (void)n; return 16384; }
 inline unsigned blocks_for(int64_t B, int threads) { return (unsigned)((B + threads - 1) / threads); }
 
 #define RBD_CHECK_ARGS(cond, msg) \
@@ -83,7 +92,7 @@ struct PoolBuf {
 // Y = alpha A (R1 - R2) per knot point, the product of forward_dynamics(_grad) (rbd_fd_kernels.cuh); defined and
 // explicitly instantiated in rbd_capi.cu
 template <typename T, bool SPLIT>
-int launch_fd_apply(int n, int mcols, int64_t B, const T* A, const T* R1, const T* R2, T alpha, T* out0, T* out1,
+int launch_fd_apply(int variant, int n, int mcols, int64_t B, const T* A, const T* R1, const T* R2, T alpha, T* out0, T* out1,
                     void* stream);
 
 // fused drivers (defined in rbd_launch_*.cu, explicitly instantiated for double and float)

@@ -74,8 +74,7 @@ int launch_ee(const rbd_ee_model* m, int64_t B, const T* q, T* pose, T* grad, vo
   if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
   const int64_t ntask = (B + 31) / 32;
   int64_t blocks = (ntask + warps - 1) / warps;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = rbd_host::sm_count();
   // a few waves of CTAs: exactly one wave (fully persistent) measured 20 % slower on iiwa14 (tail imbalance)
   if (blocks > (int64_t)sms * resident_ctas * 8) blocks = (int64_t)sms * resident_ctas * 8;
   kern<<<(unsigned)blocks, warps * 32, coef_bytes + per_warp * warps, (cudaStream_t)stream>>>(em, B, q, pose, grad, pitch, compact);

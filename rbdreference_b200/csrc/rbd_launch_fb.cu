@@ -99,7 +99,7 @@ int launch_fb_forward_dynamics(const rbd_fb_model* m, int64_t B, const T* q, con
   if (rc) return rc;
   rc = launch_fb_minv<T>(m, B, q, 1, Minv, stream);                                                       // :1371
   if (rc) return rc;
-  return launch_fd_apply<T, false>(nv, 1, B, Minv, u, (const T*)c.p, T(1), qdd, nullptr, stream);         // :1372
+  return launch_fd_apply<T, false>(g_variant.load(std::memory_order_relaxed), nv, 1, B, Minv, u, (const T*)c.p, T(1), qdd, nullptr, stream);         // :1372
 }
 
 template <typename T>
@@ -123,7 +123,7 @@ int launch_fb_forward_dynamics_grad(const rbd_fb_model* m, int64_t B, const T* q
   if (rc) return rc;
   rc = launch_fb_rnea_grad<T>(m, B, q, qd, qdd, T(-9.81), 0, (T*)dc.p, nullptr, stream);                   // :1378
   if (rc) return rc;
-  return launch_fd_apply<T, true>(nv, 2 * nv, B, (const T*)Mi.p, (const T*)dc.p, nullptr, T(-1), qdd_dq, qdd_dqd, stream);
+  return launch_fd_apply<T, true>(g_variant.load(std::memory_order_relaxed), nv, 2 * nv, B, (const T*)Mi.p, (const T*)dc.p, nullptr, T(-1), qdd_dq, qdd_dqd, stream);
 }
 
 }  // namespace

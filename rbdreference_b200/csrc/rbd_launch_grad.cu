@@ -1,6 +1,7 @@
 // rbd_launch_grad.cu - part of librbd_b200.so (see rbd_internal.cuh); compiled with -DRBD_LAUNCH_T=double|float.
 #include "rbd_internal.cuh"
 #include "rbd_fused_kernels.cuh"
+#include "rbd_chain_grad_kernels.cuh"
 
 #ifndef RBD_LAUNCH_T
 #error "compile with -DRBD_LAUNCH_T=double or -DRBD_LAUNCH_T=float"
@@ -15,8 +16,26 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
                      T* dc_du, T* c_out, void* stream) {
   RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_rnea_grad: null model/q/qd/dc_du or negative B");
   if (B == 0) return 0;
-  int variant = g_variant.load(std::memory_order_relaxed);
-  if (variant >= 4) variant = 0;                       // 4, 5 only select among the minv kernels
+  int variant = variant_of(m);
+  if (variant >= 4 && variant != 7) variant = 0;       // 4, 5 only select among the minv kernels
+  if (m->fast_ok && m->is_chain && (variant == 0 || variant == 7) && B >= chain_min_batch(m->d.n) &&
+      (reinterpret_cast<uintptr_t>(dc_du) & (2 * sizeof(T) - 1)) == 0) {
+    // serial chain, one knot point per lane (rbd_chain_grad_kernels.cuh)
+    void (*kern)(const FastModel<T>, int64_t, const T*, const T*, const T*, T, int, T*, T*) = nullptr;
+    switch (m->d.n) {
+      case 6: kern = rnea_grad_chain_kernel<T, 6>; break;
+      case 7: kern = rnea_grad_chain_kernel<T, 7>; break;
+      default: break;
+    }
+    if (kern) {
+      const size_t smem = chain_grad_smem_pairs(m->d.n) * 32 * 2 * sizeof(T);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+      kern<<<blocks_for(B, 32), 32, smem, (cudaStream_t)stream>>>(pick_fast<T>(m), B, q, qd, qdd, g, damp, dc_du, c_out);
+      return cuda_status("rbd_rnea_grad(chain)");
+    }
+  }
+  if (variant == 7) variant = 0;
   if (m->fast_ok && (variant == 0 || variant == 3)) {
     // warp-cooperative kernel: one body per lane, 32/G knot points per warp
     const FastModel<T>& fm = pick_dfs<T>(m);
@@ -36,7 +55,7 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
       if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
       const int64_t ngroups = (B + ipw - 1) / ipw;
       int64_t blocks = (ngroups + kCoopWarps - 1) / kCoopWarps;
-      const int64_t cap = 148 * 16;
+      const int64_t cap = grid_cap();
       if (blocks > cap) blocks = cap;
       kern<<<(unsigned)blocks, kCoopWarps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, B, q, qd, qdd, g, damp,
                                                                               dc_du, c_out);

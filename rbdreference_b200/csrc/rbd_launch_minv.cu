@@ -15,7 +15,7 @@ template <typename T>
 int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && B >= 0, "rbd_minv: null model/q/Minv or negative B");
   if (B == 0) return 0;
-  int variant = g_variant.load(std::memory_order_relaxed);
+  int variant = variant_of(m);
   if (variant == 0 && m->fast_ok && dense) {
     // automatic choice, measured on B200 (evals/s FP64 | FP32 at the BASELINE batch sizes):
     //   Atlas  n=30: hybrid 1.21e8 | 2.0e8   cooperative 1.19e8 | 1.8e8   thread 5.8e7 | 7.1e7
@@ -23,9 +23,6 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
     //   iiwa14 n=7 : hybrid 8.5e8 | 1.38e9   cooperative 7.8e8 | 1.2e9    thread 1.13e9 | 1.88e9 (body frame)
     const int n = m->d.n;
     //   iiwa14 n=7 : lane 1.49e9 | 2.60e9 (knot point per lane, table + tile in shared memory)
-    //   Atlas       : lane2 (variant 6: knot point per lane, table in an L2 scratch, cp.async ring) 0.97e8 | 1.3e8 -
-    //                 its 8-byte result stores 7.2 KB apart are partial-sector writes (DRAM read-modify-write),
-    //                 which costs more than the idle lanes of the column-per-lane phases it avoids
     variant = n > 16 ? 4 : (n > 8 ? 3 : 5);
     // Small batches (MPC-sized): the knot-point-per-lane kernels process 32 knot points per warp one
     // after the other, so below one wave of tasks their time is the latency of a single task
@@ -59,40 +56,6 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
       if (blocks > (int64_t)sms * ctas) blocks = (int64_t)sms * ctas;
       kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop_minv, B, q, Minv);
       return cuda_status("rbd_minv(lane)");
-    }
-  }
-  if (m->fast_ok && dense && variant == 6 && m->lane2.ok) {
-    // knot point per lane in every phase, per-body table in an L2-resident [body][field][lane] scratch
-    const FastModel<T>& fm = pick_dfs<T>(m);
-    const int n = fm.n;
-    auto kern = fm.has_prismatic ? minv_lane2_kernel<T, true> : minv_lane2_kernel<T, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) {
-      // resident warps per SM: bounded by shared memory and by the L2 budget of the scratch blocks
-      static const long l2_budget_mb = [] { const char* v = std::getenv("RBD_LANE2_L2_MB"); return v ? std::atol(v) : 96L; }();
-      static const int max_warps = [] { const char* v = std::getenv("RBD_LANE2_WARPS"); return v ? std::atoi(v) : kL2MaxWarps; }();
-      const size_t per_warp_smem = (size_t)lane2_warp_vals<T>(m->coop.maxdepth, fm.n_slot_a, fm.n_slot_b) * sizeof(T);
-      const size_t per_warp_scr = lane2_scratch_vals_per_warp<T>(n) * sizeof(T);
-      int warps = max_warps < kL2MaxWarps ? max_warps : kL2MaxWarps;
-      while (warps > 1 && ((size_t)warps * per_warp_smem > kMaxDynSmem ||
-                           (size_t)warps * sms * per_warp_scr > (size_t)l2_budget_mb * 1024 * 1024)) --warps;
-      if (warps >= 1 && (size_t)warps * per_warp_smem <= kMaxDynSmem) {
-        const int64_t ntasks = (B + 31) / 32;
-        int64_t blocks = (ntasks + warps - 1) / warps;
-        if (blocks > sms) blocks = sms;                   // one CTA per SM: the L2 budget counts on it
-        T* scratch = nullptr;
-        cudaMemPool_t pool = scratch_pool(dev);
-        if (!pool) return fail(RBD_E_NO_DEVICE, "rbd_minv: cannot create the scratch memory pool");
-        e = cudaMallocFromPoolAsync((void**)&scratch, (size_t)blocks * warps * per_warp_scr, pool, (cudaStream_t)stream);
-        if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-        kern<<<(unsigned)blocks, warps * 32, warps * per_warp_smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop_minv, m->lane2,
-                                                                                           m->coop.maxdepth, B, q, Minv, scratch);
-        const int rc = cuda_status("rbd_minv(lane2)");
-        cudaFreeAsync(scratch, (cudaStream_t)stream);
-        return rc;
-      }
     }
   }
   if (m->fast_ok && dense && variant == 4) {
@@ -159,7 +122,7 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
       const int ipw = 32 / G;
       const int64_t ngroups = (B + ipw - 1) / ipw;
       int64_t blocks = (ngroups + warps - 1) / warps;
-      const int64_t cap = 148 * 16;
+      const int64_t cap = grid_cap();
       if (blocks > cap) blocks = cap;
       kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, m->coop_minv, B, q, Minv);
       return cuda_status("rbd_minv(coop)");
@@ -197,7 +160,7 @@ template <typename T>
 int launch_crba(const rbd_model* m, int64_t B, const T* q, T* H, void* stream) {
   RBD_CHECK_ARGS(m && q && H && B >= 0, "rbd_crba: null model/q/H or negative B");
   if (B == 0) return 0;
-  const int variant = g_variant.load(std::memory_order_relaxed);
+  const int variant = variant_of(m);
   if (m->fast_ok && variant != 1) {
     const FastModel<T>& fm = pick_dfs<T>(m);
     const int n = fm.n;
@@ -220,7 +183,7 @@ int launch_crba(const rbd_model* m, int64_t B, const T* q, T* H, void* stream) {
       const int ipw = 32 / G;
       const int64_t ngroups = (B + ipw - 1) / ipw;
       int64_t blocks = (ngroups + warps - 1) / warps;
-      const int64_t cap = 148 * 16;
+      const int64_t cap = grid_cap();
       if (blocks > cap) blocks = cap;
       kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, m->coop_minv, B, q, H);
       return cuda_status("rbd_crba(coop)");

@@ -32,8 +32,7 @@ static int cp_geometry(K kern, size_t per_warp, size_t* smem_out, int* ctas_out)
 }
 
 static int64_t cp_blocks(int64_t ngroups, int warps, int ctas) {
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = rbd_host::sm_count();
   int64_t blocks = (ngroups + warps - 1) / warps;
   const int64_t cap = (int64_t)sms * ctas;
   return blocks > cap ? cap : blocks;
@@ -45,7 +44,7 @@ int launch_grad_fpass(const rbd_model* m, int64_t B, const T* q, const T* qd, co
   RBD_CHECK_ARGS(m && q && qd && v && (a || !DQ) && dv && da && df && B >= 0,
                  "rbd_rnea_grad_fpass: null argument or negative B");
   if (B == 0) return 0;
-  if (g_variant.load(std::memory_order_relaxed) != 1) {
+  if (variant_of(m) != 1) {
     // one derivative column per lane, tensors staged through a shared-memory tile
     const int n = m->d.n;
     const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
@@ -70,7 +69,7 @@ int launch_grad_bpass(const rbd_model* m, int64_t B, const T* q, const T* f, T* 
                       void* stream) {
   RBD_CHECK_ARGS(m && q && (f || !DQ) && df && dc && B >= 0, "rbd_rnea_grad_bpass: null argument or negative B");
   if (B == 0) return 0;
-  if (g_variant.load(std::memory_order_relaxed) != 1) {
+  if (variant_of(m) != 1) {
     const int n = m->d.n;
     const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
     auto kern = G == 8 ? grad_bpass_coop_kernel<T, 8, DQ> : (G == 16 ? grad_bpass_coop_kernel<T, 16, DQ> : grad_bpass_coop_kernel<T, 32, DQ>);

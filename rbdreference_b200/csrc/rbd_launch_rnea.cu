@@ -18,7 +18,7 @@ int launch_rnea(const rbd_model* m, int64_t B, const T* q, const T* qd, const T*
                 T* f, void* stream) {
   RBD_CHECK_ARGS(m && q && qd && c && B >= 0, "rbd_rnea: null model/q/qd/c or negative B");
   if (B == 0) return 0;
-  const int variant = g_variant.load(std::memory_order_relaxed);
+  const int variant = variant_of(m);
   const int nd = m->d.n;
   // measured crossovers against the lane kernel: iiwa14 ~16k, Atlas ~4k knot points
   const int64_t small = nd <= 8 ? 16384 : (nd <= 16 ? 8192 : 4096);
@@ -41,7 +41,7 @@ int launch_rnea(const rbd_model* m, int64_t B, const T* q, const T* qd, const T*
       if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
       const int64_t ngroups = (B + ipw - 1) / ipw;
       int64_t blocks = (ngroups + kCoopWarps - 1) / kCoopWarps;
-      if (blocks > 148 * 16) blocks = 148 * 16;
+      if (blocks > grid_cap()) blocks = grid_cap();
       kern<<<(unsigned)blocks, kCoopWarps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, B, q, qd, qdd, g, 0, nullptr, c);
       return cuda_status("rbd_rnea(coop)");
     }
@@ -110,7 +110,7 @@ int launch_rnea_fpass(const rbd_model* m, int64_t B, const T* q, const T* qd, co
                       T* f, void* stream) {
   RBD_CHECK_ARGS(m && q && qd && v && a && f && B >= 0, "rbd_rnea_fpass: null argument or negative B");
   if (B == 0) return 0;
-  if (m->fast_ok && g_variant.load(std::memory_order_relaxed) != 1) {
+  if (m->fast_ok && variant_of(m) != 1) {
     const FastModel<T>& fm = pick_dfs<T>(m);
     const int n = fm.n;
     const size_t per_warp = (size_t)lane_rnea_warp_vals(n, fm.n_slot_a, false, true) * sizeof(T);
@@ -133,7 +133,7 @@ template <typename T>
 int launch_rnea_bpass(const rbd_model* m, int64_t B, const T* q, T* f, T* c, void* stream) {
   RBD_CHECK_ARGS(m && q && f && c && B >= 0, "rbd_rnea_bpass: null argument or negative B");
   if (B == 0) return 0;
-  if (m->fast_ok && g_variant.load(std::memory_order_relaxed) != 1) {
+  if (m->fast_ok && variant_of(m) != 1) {
     const FastModel<T>& fm = pick_dfs<T>(m);
     const int n = fm.n;
     const size_t per_warp = (size_t)lane_rnea_warp_vals(n, fm.n_slot_a, false, false) * sizeof(T);
