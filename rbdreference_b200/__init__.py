@@ -14,7 +14,7 @@ def __getattr__(name):
     if name == "RBDReference":
         from .engine import RBDReference
         return RBDReference
-    if name in ("shard_bounds", "ShardedBatch", "gather_to_all", "gather_to_rank"):
+    if name in ("shard_bounds", "gather_to_all", "gather_to_rank"):
         from . import dist
         return getattr(dist, name)
     raise AttributeError(name)

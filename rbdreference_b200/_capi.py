@@ -15,6 +15,7 @@ PASS_SYMBOLS = ["rnea_fpass", "rnea_bpass", "rnea_grad_fpass_dq", "rnea_grad_fpa
 FUSED_SYMBOLS = ["rnea", "rnea_grad", "minv", "forward_dynamics", "forward_dynamics_grad", "crba", "aba"]
 PLAIN_SYMBOLS = ["rbd_abi_version", "rbd_last_error_string", "rbd_model_create", "rbd_model_destroy",
                  "rbd_model_num_dof", "rbd_model_uses_world_kernels", "rbd_set_kernel_variant",
+                 "rbd_model_set_kernel_variant",
                  "rbd_measure_fma_peak", "rbd_launch_count",
                  "rbd_ee_model_create", "rbd_ee_model_destroy", "rbd_ee_model_num_ee",
                  "rbd_fb_model_create", "rbd_fb_model_destroy", "rbd_fb_model_num_vel"]
@@ -74,6 +75,7 @@ def load_library():
     lib.rbd_model_num_dof.argtypes = [c_void_p]
     lib.rbd_model_uses_world_kernels.argtypes = [c_void_p]
     lib.rbd_set_kernel_variant.argtypes = [c_int]
+    lib.rbd_model_set_kernel_variant.argtypes = [c_void_p, c_int]
     lib.rbd_measure_fma_peak.argtypes = [c_int, POINTER(c_double), POINTER(c_double), c_void_p]
     lib.rbd_launch_count.restype = c_int64
     lib.rbd_ee_model_create.argtypes = [POINTER(RbdEeDesc), POINTER(c_void_p)]

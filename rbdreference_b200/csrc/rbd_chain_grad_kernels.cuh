@@ -4,17 +4,21 @@
 // Same world-frame composite formulation as rbd_grad_kernels.cuh (RBDReference.py:1345-1368 is the
 // object computed), specialised at compile time for parent[i] = i - 1 and N bodies:
 //
-//   * forward sweep (rolled over the bodies): pose, v, a in registers; S_i, Psi_dot_i, Psi_ddot_i and
-//     (cos q_i, sin q_i) of bodies 0 .. N-2 go to a [row][slot][lane] shared-memory table (16-byte
-//     accesses, conflict free); the leaf's stay in registers;
+//   * stage 0: cos / sin of all N joint angles at once (N independent polynomial chains in flight);
+//   * forward sweep (rolled over the bodies): pose, v, a in registers; S_i, Psi_dot_i, Psi_ddot_i of
+//     bodies 1 .. N-2 and S_0 go to a [row][pair][lane] shared-memory table (16-byte accesses,
+//     conflict free).  Psi_dot_0 = 0 and Psi_ddot_0 = a_base x S_0 (the base does not move) are
+//     never stored; the leaf's vectors stay in registers;
 //   * backward sweep (rolled): the pose / velocity / acceleration of the parent are re-derived from
 //     the child's (nothing but the table is stored), composites are a running sum in registers,
 //     F1..F4 of body i meet the table rows of its ancestors in a pair loop unrolled over the
 //     ancestor index (table offsets and result registers are compile-time);
 //   * results: row i of dc_du is complete at body i and leaves straight from registers as 16-byte
 //     stores; the entries body i produces for the rows of its ancestors ([j, i], j < i) wait in the
-//     table row of body i, which nobody reads any more.  Shared memory per knot point is therefore
-//     11 (N - 1) pairs of values (33 KB per warp for N = 7 in FP64): six resident warps per SM.
+//     table row of body i, which nobody reads any more (the leaf has no row: its entries go to
+//     global memory as 8-byte stores into sectors the row stores complete later).
+//     Shared memory per knot point: 10 (N - 2) + 4 pairs of values = 27 KB per warp for N = 7 in
+//     FP64, i.e. eight resident warps per SM (two per scheduler) within 255 registers.
 //
 // The body loops stay rolled on purpose: the straight-line version of the per-knot-point kernel was
 // measured 28 % slower (instruction cache, rbd_launch_grad.cu).
@@ -25,8 +29,12 @@
 namespace rbd {
 
 constexpr int kChainRowPairs = 10;      // S(3) Psi_dot(3) Psi_ddot(3) (cos, sin)(1) pairs per table row
+constexpr int kChainRow0Pairs = 4;      // row 0: S(3) (cos, sin)(1)
 
-__host__ __device__ inline size_t chain_grad_smem_pairs(int n) { return (size_t)(n - 1) * (kChainRowPairs + 1); }
+// rows 1 .. n-2 first, row 0 last
+__host__ __device__ inline size_t chain_grad_smem_pairs(int n) {
+  return (size_t)(n > 2 ? n - 2 : 0) * kChainRowPairs + kChainRow0Pairs;
+}
 
 template <typename T> __device__ __forceinline__ void stcs2(T* p, T x, T y);
 template <> __device__ __forceinline__ void stcs2<double>(double* p, double x, double y) {
@@ -36,15 +44,97 @@ template <> __device__ __forceinline__ void stcs2<float>(float* p, float x, floa
   __stcs(reinterpret_cast<float2*>(p), make_float2(x, y));
 }
 
+// sin / cos of NV angles at once: Cody-Waite reduction by pi/2 (exact products through FMA) and the
+// fdlibm minimax polynomials on [-pi/4, pi/4]; every step loops over the NV values so that NV
+// independent dependency chains are in flight.  |x| > 1e5 (never the case for joint angles) takes
+// the library path.  Max error ~1 ulp.
+static __device__ __noinline__ void sincos_far(const double* x, double* s, double* c, int n) {
+  for (int k = 0; k < n; ++k) sincos(x[k], &s[k], &c[k]);
+}
+template <int NV>
+__device__ __forceinline__ void sincos_batch(const double* x, double* s, double* c) {
+  const double MAGIC = 6755399441055744.0;           // 1.5 * 2^52: round-to-nearest integer in the low word
+  double kd[NV], r[NV], z[NV], ps[NV], pc[NV];
+  int ki[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double t = fma(x[k], 6.36619772367581382433e-01, MAGIC);
+    ki[k] = __double2loint(t);
+    kd[k] = t - MAGIC;
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) r[k] = fma(-kd[k], 1.57079632679489655800e+00, x[k]);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) r[k] = fma(-kd[k], 6.12323399573676603587e-17, r[k]);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) r[k] = fma(-kd[k], -1.49738490485916983e-33, r[k]);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    z[k] = r[k] * r[k];
+    ps[k] = fma(z[k], 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    pc[k] = fma(z[k], -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ps[k] = fma(z[k], ps[k], 2.75573137070700676789e-06);
+    pc[k] = fma(z[k], pc[k], -2.75573143513906633035e-07);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ps[k] = fma(z[k], ps[k], -1.98412698298579493134e-04);
+    pc[k] = fma(z[k], pc[k], 2.48015872894767294178e-05);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ps[k] = fma(z[k], ps[k], 8.33333333332248946124e-03);
+    pc[k] = fma(z[k], pc[k], -1.38888888888741095749e-03);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ps[k] = fma(z[k], ps[k], -1.66666666666666324348e-01);
+    pc[k] = fma(z[k], pc[k], 4.16666666666666019037e-02);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double sv = fma(z[k] * r[k], ps[k], r[k]);
+    const double cv = fma(z[k] * z[k], pc[k], fma(-0.5, z[k], 1.0));
+    const bool swap = ki[k] & 1;
+    double so = swap ? cv : sv, co = swap ? sv : cv;
+    if (ki[k] & 2) so = -so;
+    if ((ki[k] + 1) & 2) co = -co;
+    s[k] = so;
+    c[k] = co;
+  }
+  bool far = false;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) far = far || !(fabs(x[k]) <= 1.0e5);   // also NaN / Inf
+  if (far) {                                                          // cold: arrays live on the stack only here
+    double xs[NV], ss[NV], cs[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) xs[k] = x[k];
+    sincos_far(xs, ss, cs, NV);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { s[k] = ss[k]; c[k] = cs[k]; }
+  }
+}
+template <int NV>
+__device__ __forceinline__ void sincos_batch(const float* x, float* s, float* c) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) sincosf(x[k], &s[k], &c[k]);
+}
+
 template <typename T, int N>
-__global__ void __launch_bounds__(32, 6)
+__global__ void __launch_bounds__(32, 8)
 rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const T* __restrict__ q,
                        const T* __restrict__ qd, const T* __restrict__ qdd, T gravity, int use_damping,
                        T* __restrict__ dc_du, T* __restrict__ c_out) {
+  static_assert(N >= 3, "chain kernel needs at least three bodies");
   typedef typename Vec2<T>::type V2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  V2* tab = reinterpret_cast<V2*>(smem_raw) + threadIdx.x;       // pair k of row r: tab[(r * 10 + k) * 32]
-  constexpr int RS = kChainRowPairs * 32;                          // row stride in pairs
+  V2* tab = reinterpret_cast<V2*>(smem_raw) + threadIdx.x;       // pair k of row r: tab[(rowbase(r) + k) * 32]
+  constexpr int RS = kChainRowPairs * 32;                          // row stride in pairs (rows 1 .. N-2)
+  constexpr int ROW0 = (N - 2) * kChainRowPairs * 32;              // row 0: S pairs 0..2, (cos, sin) pair 3
+  // row r >= 1 starts at (r - 1) * RS; its (cos, sin) pair is pair 9
   int64_t b = (int64_t)blockIdx.x * 32 + threadIdx.x;
   const bool active = b < B;
   if (!active) b = B - 1;                                          // keep the warp convergent; stores are masked
@@ -52,8 +142,26 @@ rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
   const T* qdb = qd + b * N;
   const T* qddb = qdd ? qdd + b * N : nullptr;
 
+  // ------------------------------------------------------------------ stage 0: cos / sin of every joint angle
+  T f1 = T(1), f2 = T(0);                                          // the leaf's (cos, sin) / prismatic (q, 0)
+  {
+    T qv[N], sv[N], cv[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) qv[i] = __ldg(qb + i);
+    sincos_batch<N>(qv, sv, cv);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      V2 t;
+      if (m.kind[i] == 0) { t.x = cv[i]; t.y = sv[i]; }
+      else { t.x = qv[i]; t.y = T(0); }
+      if (i == 0) tab[ROW0 + 3 * 32] = t;
+      else if (i < N - 1) tab[(i - 1) * RS + 9 * 32] = t;
+      else { f1 = t.x; f2 = t.y; }
+    }
+  }
+
   T E[9], p[3], v[6], a[6];
-  T S[6], Pd[6], Pdd[6], f1 = T(1), f2 = T(0);
+  T S[6], Pd[6], Pdd[6];
 #pragma unroll
   for (int k = 0; k < 9; ++k) E[k] = (k % 4 == 0) ? T(1) : T(0);
 #pragma unroll
@@ -63,29 +171,32 @@ rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
   a[5] = -gravity;                                                 // RBDReference.py:566
 
   // ------------------------------------------------------------------ forward sweep
-  T q_nx = __ldg(qb), qd_nx = __ldg(qdb), qdd_nx = qddb ? __ldg(qddb) : T(0);
+  T qd_nx = __ldg(qdb), qdd_nx = qddb ? __ldg(qddb) : T(0);
 #pragma unroll 1
   for (int i = 0; i < N; ++i) {
-    const T qi = q_nx, qdi = qd_nx, qddi = qdd_nx;
+    const T qdi = qd_nx, qddi = qdd_nx;
     if (i + 1 < N) {
-      q_nx = __ldg(qb + i + 1);
       qd_nx = __ldg(qdb + i + 1);
       if (qddb) qdd_nx = __ldg(qddb + i + 1);
     }
+    V2* row = tab + (i == 0 ? ROW0 : (i - 1) * RS);
+    T c1 = f1, c2 = f2;
+    if (i < N - 1) {
+      const V2 t = row[(i == 0 ? 3 : 9) * 32];
+      c1 = t.x; c2 = t.y;
+    }
     const int kind = m.kind[i];
-    if (kind == 0) sincos_t(qi, &f2, &f1);
-    else { f1 = qi; f2 = T(0); }
     {
       T r[3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) r[k] = fma_t(m.rC[i][k], f2, fma_t(m.rB[i][k], f1, m.rA[i][k]));
+      for (int k = 0; k < 3; ++k) r[k] = fma_t(m.rC[i][k], c2, fma_t(m.rB[i][k], c1, m.rA[i][k]));
       // p_i = p_parent + E_parent^T r
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) p[cc] = fma_t(E[6 + cc], r[2], fma_t(E[3 + cc], r[1], fma_t(E[cc], r[0], p[cc])));
       // E_i = Ej E_parent, column by column
       T Ej[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) Ej[k] = fma_t(m.EC[i][k], f2, fma_t(m.EB[i][k], f1, m.EA[i][k]));
+      for (int k = 0; k < 9; ++k) Ej[k] = fma_t(m.EC[i][k], c2, fma_t(m.EB[i][k], c1, m.EA[i][k]));
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {
         const T t0 = E[cc], t1 = E[3 + cc], t2 = E[6 + cc];
@@ -119,16 +230,19 @@ rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
       a[k] = fma_t(Pd[k], qdi, fma_t(S[k], qddi, a[k]));
     }
     if (i < N - 1) {
-      V2* row = tab + i * RS;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         V2 t;
         t.x = S[2 * k]; t.y = S[2 * k + 1]; row[k * 32] = t;
-        t.x = Pd[2 * k]; t.y = Pd[2 * k + 1]; row[(3 + k) * 32] = t;
-        t.x = Pdd[2 * k]; t.y = Pdd[2 * k + 1]; row[(6 + k) * 32] = t;
       }
-      V2 t;
-      t.x = f1; t.y = f2; row[9 * 32] = t;
+      if (i > 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          V2 t;
+          t.x = Pd[2 * k]; t.y = Pd[2 * k + 1]; row[(3 + k) * 32] = t;
+          t.x = Pdd[2 * k]; t.y = Pdd[2 * k + 1]; row[(6 + k) * 32] = t;
+        }
+      }
     }
   }
 
@@ -138,22 +252,34 @@ rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
 #pragma unroll
   for (int k = 0; k < 28; ++k) acc[k] = T(0);
   T* out = dc_du + b * (int64_t)(2 * N * N);
+  const T ag = -gravity;                      // a_base = [0 0 0 0 0 ag]: Psi_ddot_0 = [0; (-ag S0y, ag S0x, 0)]
 
 #pragma unroll 1
   for (int i = N - 1; i >= 0; --i) {
-    V2* rowi = tab + i * RS;                  // own table row; from here on the pending entries [j, i], j < i
+    V2* rowi = tab + (i == 0 ? ROW0 : (i - 1) * RS);   // own table row; then the pending entries [j, i], j < i
     if (i < N - 1) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        V2 t = rowi[k * 32]; S[2 * k] = t.x; S[2 * k + 1] = t.y;
-        t = rowi[(3 + k) * 32]; Pd[2 * k] = t.x; Pd[2 * k + 1] = t.y;
-        t = rowi[(6 + k) * 32]; Pdd[2 * k] = t.x; Pdd[2 * k + 1] = t.y;
+      for (int k = 0; k < 3; ++k) { const V2 t = rowi[k * 32]; S[2 * k] = t.x; S[2 * k + 1] = t.y; }
+      if (i > 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          V2 t = rowi[(3 + k) * 32]; Pd[2 * k] = t.x; Pd[2 * k + 1] = t.y;
+          t = rowi[(6 + k) * 32]; Pdd[2 * k] = t.x; Pdd[2 * k + 1] = t.y;
+        }
+        const V2 t = rowi[9 * 32];
+        f1 = t.x; f2 = t.y;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { Pd[k] = T(0); Pdd[k] = T(0); }
+        Pdd[3] = -ag * S[1];
+        Pdd[4] = ag * S[0];
       }
-      const V2 t = rowi[9 * 32];
-      f1 = t.x; f2 = t.y;
     }
-    const T qdi = __ldg(qdb + i);
-    const T qddi = qddb ? __ldg(qddb + i) : T(0);
+    T qdi = T(0), qddi = T(0);
+    if (i > 0) {
+      qdi = __ldg(qdb + i);
+      if (qddb) qddi = __ldg(qddb + i);
+    }
     // ---- own rigid-body terms in world coordinates, added to the running composites
     {
       const T mi = m.mass[i];
@@ -294,41 +420,68 @@ rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
       }
     }
     // ---- row i of [dc_dq | dc_dqd]: column j < i from the pair (i, j), column i the diagonal,
-    //      column k > i from the entries body k left in its table row
-    T rq[N], rd[N];
+    //      column k > i from the entries body k left in its table row (the leaf's are in HBM already)
+    T rowv[2 * N];
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       if (j < i) {
-        const V2* rowj = tab + j * RS;
-        T Sj[6], Pdj[6], Pddj[6];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          V2 t = rowj[k * 32]; Sj[2 * k] = t.x; Sj[2 * k + 1] = t.y;
-          t = rowj[(3 + k) * 32]; Pdj[2 * k] = t.x; Pdj[2 * k + 1] = t.y;
-          t = rowj[(6 + k) * 32]; Pddj[2 * k] = t.x; Pddj[2 * k + 1] = t.y;
-        }
+        T Sj[6];
         V2 pend;
+        if (j == 0) {
+          const V2* rowj = tab + ROW0;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { const V2 t = rowj[k * 32]; Sj[2 * k] = t.x; Sj[2 * k + 1] = t.y; }
+          // Psi_dot_0 = 0, Psi_ddot_0 = [0; (-ag S0y, ag S0x, 0)]
+          rowv[j] = ag * (F4[4] * Sj[0] - F4[3] * Sj[1]);                        // dc_dq [i, 0]
+          rowv[N + j] = T(2) * dot3s(F3, Sj);                                    // dc_dqd[i, 0]
+        } else {
+          const V2* rowj = tab + (j - 1) * RS;
+          T Pdj[6], Pddj[6];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            V2 t = rowj[k * 32]; Sj[2 * k] = t.x; Sj[2 * k + 1] = t.y;
+            t = rowj[(3 + k) * 32]; Pdj[2 * k] = t.x; Pdj[2 * k + 1] = t.y;
+            t = rowj[(6 + k) * 32]; Pddj[2 * k] = t.x; Pddj[2 * k + 1] = t.y;
+          }
+          rowv[j] = fma_t(T(2), dot3s(F3, Pdj), dot6s(F4, Pddj));                // dc_dq [i, j]
+          rowv[N + j] = T(2) * (dot6s(F4, Pdj) + dot3s(F3, Sj));                 // dc_dqd[i, j]
+        }
         pend.x = dot6s(Sj, F1);                                                  // dc_dq [j, i]
         pend.y = dot6s(Sj, F2);                                                  // dc_dqd[j, i]
-        rowi[j * 32] = pend;
-        rq[j] = fma_t(T(2), dot3s(F3, Pdj), dot6s(F4, Pddj));                    // dc_dq [i, j]
-        rd[j] = T(2) * (dot6s(F4, Pdj) + dot3s(F3, Sj));                         // dc_dqd[i, j]
+        if (i == N - 1) {
+          if (active) { __stcs(out + j * (2 * N) + (N - 1), pend.x); __stcs(out + j * (2 * N) + (2 * N - 1), pend.y); }
+        } else {
+          rowi[j * 32] = pend;
+        }
       } else if (j == i) {
-        rq[j] = dqq;
-        rd[j] = ddd;
+        rowv[j] = dqq;
+        rowv[N + j] = ddd;
+      } else if (j < N - 1) {
+        const V2 pend = tab[(j - 1) * RS + i * 32];
+        rowv[j] = pend.x;
+        rowv[N + j] = pend.y;
       } else {
-        const V2 pend = tab[(j * RS) + i * 32];
-        rq[j] = pend.x;
-        rd[j] = pend.y;
+        rowv[j] = T(0);                       // leaf column of an inner row: already stored by the leaf
+        rowv[N + j] = T(0);
       }
     }
     if (active) {
       T* orow = out + i * (2 * N);
-      T rowv[2 * N];
+      if (i == N - 1) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) { rowv[j] = rq[j]; rowv[N + j] = rd[j]; }
+        for (int k = 0; k < N; ++k) stcs2<T>(orow + 2 * k, rowv[2 * k], rowv[2 * k + 1]);
+      } else {
 #pragma unroll
-      for (int k = 0; k < N; ++k) stcs2<T>(orow + 2 * k, rowv[2 * k], rowv[2 * k + 1]);
+        for (int k = 0; k < N; ++k) {
+          const bool leaf0 = (2 * k == N - 1) || (2 * k == 2 * N - 1);
+          const bool leaf1 = (2 * k + 1 == N - 1) || (2 * k + 1 == 2 * N - 1);
+          if (!leaf0 && !leaf1) stcs2<T>(orow + 2 * k, rowv[2 * k], rowv[2 * k + 1]);
+          else {
+            if (!leaf0) __stcs(orow + 2 * k, rowv[2 * k]);
+            if (!leaf1) __stcs(orow + 2 * k + 1, rowv[2 * k + 1]);
+          }
+        }
+      }
     }
   }
 }

@@ -30,6 +30,7 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
     if (kern) {
       const size_t smem = chain_grad_smem_pairs(m->d.n) * 32 * 2 * sizeof(T);
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
       kern<<<blocks_for(B, 32), 32, smem, (cudaStream_t)stream>>>(pick_fast<T>(m), B, q, qd, qdd, g, damp, dc_du, c_out);
       return cuda_status("rbd_rnea_grad(chain)");

@@ -25,6 +25,7 @@ import numpy as np
 import torch
 
 from . import _capi
+from .hostpipe import HostPipeline, pinned_empty
 from .model import FbModel, RobotModel, compile_ee_model, compile_fb_model, compile_model, select_end_effector_joints
 
 __all__ = ["RBDReference"]
@@ -58,6 +59,7 @@ class RBDReference:
             self._handle = _capi.ModelHandle(self.model)
         self._device = torch.device(device) if device is not None else None
         self._ee_handles = {}                       # (names, offset) -> compiled end-effector handle
+        self._pipes = {}                            # device -> HostPipeline (streams + staging buffers)
 
     # ------------------------------------------------------------------------------------
     # plumbing
@@ -140,6 +142,88 @@ class RBDReference:
                 "%s: no floating-base path (rnea, rnea_grad, minv, forward_dynamics and forward_dynamics_grad "
                 "are the floating-base entry points, SURVEY.md 8f rank 3)" % what)
 
+    # ---- caller-supplied result buffers ---------------------------------------------------------
+    def _check_out(self, t, ctx: "_Ctx", shape, name: str):
+        """`out=` / `c_out=` of a batched CUDA-tensor call: the kernels write through the raw pointer, so
+        anything but a contiguous tensor of the engine dtype, exact shape and compute device is refused."""
+        if t is None:
+            return None
+        if ctx.kind != "torch" or not ctx.batched:
+            raise ValueError("%s: a torch result buffer needs batched torch inputs (numpy calls take a numpy `out`)" % name)
+        if not isinstance(t, torch.Tensor):
+            raise ValueError("%s must be a torch tensor" % name)
+        if not t.is_cuda or t.device != ctx.device:
+            raise ValueError("%s must live on the compute device %s, got %s" % (name, ctx.device, t.device))
+        if t.dtype != self.dtype:
+            raise ValueError("%s must have dtype %s, got %s" % (name, self.dtype, t.dtype))
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous" % name)
+        return t
+
+    # ---- host-buffer path (numpy in, numpy out): chunked, pinned, three streams -------------------
+    @staticmethod
+    def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+        """numpy array in page-locked host memory: the DMA engines read / write it directly, so passing
+        such arrays (inputs and `out=`) to the batched numpy calls skips every host-side copy."""
+        return pinned_empty(shape, dtype)
+
+    def _host_batched(self, lead) -> bool:
+        if isinstance(lead, torch.Tensor) or np.ndim(lead) != 2:
+            return False
+        self._default_device()                      # raises without a CUDA device: there is no CPU path
+        return True
+
+    def _host_in(self, x, tail, name, B=None):
+        if x is None:
+            return None
+        a = np.asarray(x)
+        if a.dtype != self._np_dtype or not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a, dtype=self._np_dtype)
+        if a.ndim != 1 + len(tail) or tuple(a.shape[1:]) != tuple(tail):
+            raise ValueError("%s: expected trailing shape %s, got %s" % (name, tuple(tail), tuple(a.shape[1:])))
+        if B is not None and a.shape[0] != B:
+            raise ValueError("%s: batch size %d does not match %d" % (name, a.shape[0], B))
+        return a
+
+    def _host_out(self, out, B, tail, name):
+        shape = (B,) + tuple(tail)
+        if out is None:
+            return pinned_empty(shape, self._np_dtype)
+        if isinstance(out, torch.Tensor) or not isinstance(out, np.ndarray):
+            raise ValueError("%s: numpy inputs take a numpy result buffer" % name)
+        if out.dtype != self._np_dtype or tuple(out.shape) != shape or not out.flags.c_contiguous or not out.flags.writeable:
+            raise ValueError("%s must be a writable C-contiguous %s array of shape %s" % (name, np.dtype(self._np_dtype), shape))
+        return out
+
+    def _pipeline(self) -> HostPipeline:
+        dev = self._default_device()
+        p = self._pipes.get(dev)
+        if p is None:
+            p = self._pipes[dev] = HostPipeline(dev, self.dtype)
+        return p
+
+    def _host_run(self, name, B, ins, in_tails, outs, out_tails, make_args, handle=None):
+        """Run C-ABI driver `name` over host arrays through the pipeline.  `make_args(dins, douts)` returns
+        the argument list between the batch size and the stream."""
+        fn = getattr(self._lib, "rbd_%s_%s" % (name, self._suffix))
+        h = (handle or self._handle).ptr
+        pipe = self._pipeline()
+
+        def launch(m, dins, douts):
+            args = [a.data_ptr() if isinstance(a, torch.Tensor) else a for a in make_args(dins, douts)]
+            rc = fn(h, m, *args, torch.cuda.current_stream(pipe.device).cuda_stream)
+            _capi.check(rc, "rbd_%s_%s" % (name, self._suffix))
+
+        pipe.run(B, ins, in_tails, outs, out_tails, launch)
+
+    def set_variant(self, variant: int) -> None:
+        """Kernel family for THIS engine's handle only (-1 = follow `set_kernel_variant`)."""
+        if self.floating_base:
+            raise NotImplementedError("kernel variants exist for fixed-base models only")
+        _capi.check(self._lib.rbd_model_set_kernel_variant(self._handle.ptr, int(variant)), "rbd_model_set_kernel_variant")
+
     def _call(self, name: str, ctx: "_Ctx", *args, handle=None):
         if ctx.B == 0:
             return                                   # empty batch: nothing to launch
@@ -183,9 +267,23 @@ class RBDReference:
 
         `outputs="c"` (extension) skips writing v, a, f and returns only c.
         """
-        ctx = self._Ctx(self, q, 1)
         n, NB = self.n, self.NB
         op = "fb_rnea" if self.floating_base else "rnea"
+        if self._host_batched(q):
+            hq = self._host_in(q, (self.nq,), "q")
+            B = hq.shape[0]
+            hqd, hqdd = self._host_in(qd, (n,), "qd", B), self._host_in(qdd, (n,), "qdd", B)
+            g = float(GRAVITY)
+            if outputs == "c":
+                c = self._host_out(None, B, (n,), "c")
+                self._host_run(op, B, [hq, hqd, hqdd], [(self.nq,), (n,), (n,)], [c], [(n,)],
+                               lambda di, do: [di[0], di[1], di[2], g, do[0], None, None, None])
+                return c
+            res = [self._host_out(None, B, t, "out") for t in ((n,), (6, NB), (6, NB), (6, NB))]
+            self._host_run(op, B, [hq, hqd, hqdd], [(self.nq,), (n,), (n,)], res, [(n,), (6, NB), (6, NB), (6, NB)],
+                           lambda di, do: [di[0], di[1], di[2], g, do[0], do[1], do[2], do[3]])
+            return tuple(res)
+        ctx = self._Ctx(self, q, 1)
         dq, dqd, dqdd = ctx.dev(q, (self.nq,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(qdd, (n,), "qdd")
         c = ctx.empty(n)
         if outputs == "c":
@@ -222,11 +320,19 @@ class RBDReference:
 
     def minv(self, q, output_dense=True, out=None):
         """RBDReference.py:785-806 -> Minv (n, n)."""
-        ctx = self._Ctx(self, q, 1)
         n = self.n
+        op = "fb_minv" if self.floating_base else "minv"
+        if self._host_batched(q):
+            hq = self._host_in(q, (self.nq,), "q")
+            B = hq.shape[0]
+            res = self._host_out(out, B, (n, n), "out")
+            dense = 1 if output_dense else 0
+            self._host_run(op, B, [hq], [(self.nq,)], [res], [(n, n)], lambda di, do: [di[0], dense, do[0]])
+            return res
+        ctx = self._Ctx(self, q, 1)
         dq = ctx.dev(q, (self.nq,), "q")
-        Minv = out if (out is not None and ctx.kind == "torch" and ctx.batched) else ctx.empty(n, n)
-        self._call("fb_minv" if self.floating_base else "minv", ctx, dq, 1 if output_dense else 0, Minv)
+        Minv = self._check_out(out, ctx, (ctx.B, n, n), "out") if out is not None else ctx.empty(n, n)
+        self._call(op, ctx, dq, 1 if output_dense else 0, Minv)
         return ctx.ret(Minv)
 
     # ------------------------------------------------------------------------------------
@@ -278,17 +384,30 @@ class RBDReference:
     def rnea_grad(self, q, qd, qdd=None, GRAVITY=-9.81, USE_VELOCITY_DAMPING=False, out=None, c_out=None):
         """RBDReference.py:1345-1368 -> dc_du (n, 2n) = [dc_dq | dc_dqd], one fused launch.
 
-        `out` / `c_out` (extension, batched CUDA tensors only) receive dc_du (B,n,2n) / c (B,n).
+        `out` / `c_out` (extension) receive dc_du (B,n,2n) / c (B,n): CUDA tensors for batched CUDA-tensor
+        calls, numpy arrays for batched numpy calls (pinned ones are filled by DMA directly).
         """
-        ctx = self._Ctx(self, q, 1)
         n = self.n
+        op = "fb_rnea_grad" if self.floating_base else "rnea_grad"
+        if self._host_batched(q):
+            hq = self._host_in(q, (self.nq,), "q")
+            B = hq.shape[0]
+            hqd, hqdd = self._host_in(qd, (n,), "qd", B), self._host_in(qdd, (n,), "qdd", B)
+            res = self._host_out(out, B, (n, 2 * n), "out")
+            g, damp = float(GRAVITY), 1 if USE_VELOCITY_DAMPING else 0
+            if c_out is not None:
+                hc = self._host_out(c_out, B, (n,), "c_out")
+                self._host_run(op, B, [hq, hqd, hqdd], [(self.nq,), (n,), (n,)], [res, hc], [(n, 2 * n), (n,)],
+                               lambda di, do: [di[0], di[1], di[2], g, damp, do[0], do[1]])
+            else:
+                self._host_run(op, B, [hq, hqd, hqdd], [(self.nq,), (n,), (n,)], [res], [(n, 2 * n)],
+                               lambda di, do: [di[0], di[1], di[2], g, damp, do[0], None])
+            return res
+        ctx = self._Ctx(self, q, 1)
         dq, dqd, dqdd = ctx.dev(q, (self.nq,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(qdd, (n,), "qdd")
-        use_out = out is not None and ctx.kind == "torch" and ctx.batched
-        dc_du = out if use_out else ctx.empty(n, 2 * n)
-        if use_out and (tuple(out.shape) != (ctx.B, n, 2 * n) or out.dtype != self.dtype or not out.is_contiguous()):
-            raise ValueError("out must be a contiguous (B, n, 2n) tensor of the engine dtype")
-        self._call("fb_rnea_grad" if self.floating_base else "rnea_grad", ctx, dq, dqd, dqdd, float(GRAVITY),
-                   1 if USE_VELOCITY_DAMPING else 0, dc_du, c_out)
+        dc_du = self._check_out(out, ctx, (ctx.B, n, 2 * n), "out") if out is not None else ctx.empty(n, 2 * n)
+        c_out = self._check_out(c_out, ctx, (ctx.B, n), "c_out")
+        self._call(op, ctx, dq, dqd, dqdd, float(GRAVITY), 1 if USE_VELOCITY_DAMPING else 0, dc_du, c_out)
         return ctx.ret(dc_du)
 
     def rnea_grad_passes(self, q, qd, qdd=None, GRAVITY=-9.81, USE_VELOCITY_DAMPING=False):
@@ -353,10 +472,16 @@ class RBDReference:
     def crba(self, q, out=None):
         """RBDReference.py:1026-1124 (fixed-base branch) -> joint-space inertia matrix H (n, n)."""
         self._fixed_only("crba")
-        ctx = self._Ctx(self, q, 1)
         n = self.n
+        if self._host_batched(q):
+            hq = self._host_in(q, (n,), "q")
+            B = hq.shape[0]
+            res = self._host_out(out, B, (n, n), "out")
+            self._host_run("crba", B, [hq], [(n,)], [res], [(n, n)], lambda di, do: [di[0], do[0]])
+            return res
+        ctx = self._Ctx(self, q, 1)
         dq = ctx.dev(q, (n,), "q")
-        H = out if (out is not None and ctx.kind == "torch" and ctx.batched) else ctx.empty(n, n)
+        H = self._check_out(out, ctx, (ctx.B, n, n), "out") if out is not None else ctx.empty(n, n)
         self._call("crba", ctx, dq, H)
         return ctx.ret(H)
 
@@ -425,7 +550,8 @@ class RBDReference:
 
     @staticmethod
     def set_kernel_variant(variant: int) -> None:
-        """0 = automatic kernel choice (default); 1 = force the generic body-frame kernels."""
+        """Process-wide default: 0 = automatic kernel choice; 1 = force the generic body-frame kernels; 2.. see
+        include/rbd_b200.h.  `set_variant` overrides it for one engine."""
         lib = _capi.load_library()
         _capi.check(lib.rbd_set_kernel_variant(int(variant)), "rbd_set_kernel_variant")
 
