@@ -373,6 +373,149 @@ bool build_dfs_model(const RbdModelDesc* d, FastModel<double>& out, DfsPlan& pla
   return ok;
 }
 
+
+// Schedule of the tile minv kernel (rbd_tile_minv_kernels.cuh): chains of the depth-first numbering with their
+// dependency levels and hand-off slots, per-warp work lists, and the step tables of the column groups.
+void build_tile_plan(const FastModel<double>& fm, const DfsPlan& plan, const CoopMinvPlan& mp, int maxdepth, TilePlan& tp) {
+  std::memset(&tp, 0, sizeof(tp));
+  const int n = fm.n;
+  int chain_of[RBD_MAX_DOF], flevel[RBD_MAX_DOF] = {0}, blevel[RBD_MAX_DOF] = {0};
+  for (int i = 0; i < n; ++i) {
+    if (i == 0 || fm.parent[i] != i - 1) { tp.chain_begin[tp.nchain] = i; ++tp.nchain; }
+    chain_of[i] = tp.nchain - 1;
+    tp.chain_end[tp.nchain - 1] = i + 1;
+  }
+  const int nch = tp.nchain;
+  for (int c = 0; c < nch; ++c) {
+    const int p = fm.parent[tp.chain_begin[c]];
+    flevel[c] = p < 0 ? 0 : flevel[chain_of[p]] + 1;
+    if (flevel[c] + 1 > tp.nflevel) tp.nflevel = flevel[c] + 1;
+    tp.out_slot[c] = p < 0 ? -1 : tp.nslot++;
+  }
+  // forward sweep as late as possible (a root chain nobody waits for runs next to the deepest level)
+  for (int c = nch - 1; c >= 0; --c) {
+    int lv = tp.nflevel - 1;
+    for (int d = c + 1; d < nch; ++d) {
+      const int p = fm.parent[tp.chain_begin[d]];
+      if (p >= 0 && chain_of[p] == c && flevel[d] - 1 < lv) lv = flevel[d] - 1;
+    }
+    flevel[c] = lv;
+  }
+  for (int c = nch - 1; c >= 0; --c) {                    // chains hanging off c have larger indices: final before use
+    const int p = fm.parent[tp.chain_begin[c]];
+    if (p >= 0 && blevel[chain_of[p]] < blevel[c] + 1) blevel[chain_of[p]] = blevel[c] + 1;
+    if (blevel[c] + 1 > tp.nblevel) tp.nblevel = blevel[c] + 1;
+  }
+  int cnt = 0;
+  for (int i = 0; i < n; ++i) {
+    tp.in_begin[i] = cnt;
+    for (int c = 0; c < nch; ++c)
+      if (fm.parent[tp.chain_begin[c]] == i) tp.in_slot[cnt++] = tp.out_slot[c];
+  }
+  tp.in_begin[n] = cnt;
+  tp.maxdepth = maxdepth;
+  tp.nslot_g = fm.n_slot_a;
+  // warps per CTA: as many as the FP64 shared-memory budget allows (the FP32 kernel uses the same schedule)
+  int w = kTmMaxWarps;
+  while (w > 1 && tile_minv_smem_vals(n, tp.nslot, maxdepth, tp.nslot_g, w) * sizeof(double) > rbd_host::kMaxDynSmem - 1024) --w;
+  tp.nwarps = w;
+  tp.ok = maxdepth < 16 && fm.n_slot_a < 15 &&
+          tile_minv_smem_vals(n, tp.nslot, maxdepth, tp.nslot_g, w) * sizeof(double) <= rbd_host::kMaxDynSmem - 1024;
+  // per-(level, warp) chain lists: longest chains first, each to the least loaded warp of its level
+  auto fill = [&](const int* level, int nlevel, int* begin, int* item) {
+    int pos = 0;
+    for (int lv = 0; lv < nlevel; ++lv) {
+      int load[kTmMaxWarps] = {0}, owner[RBD_MAX_DOF];
+      bool used[RBD_MAX_DOF] = {false};
+      for (int c = 0; c < nch; ++c) owner[c] = -1;
+      for (;;) {
+        int best = -1;
+        for (int c = 0; c < nch; ++c)
+          if (level[c] == lv && !used[c] && (best < 0 || tp.chain_end[c] - tp.chain_begin[c] > tp.chain_end[best] - tp.chain_begin[best])) best = c;
+        if (best < 0) break;
+        int ww = 0;
+        for (int x = 1; x < w; ++x)
+          if (load[x] < load[ww]) ww = x;
+        used[best] = true;
+        owner[best] = ww;
+        load[ww] += tp.chain_end[best] - tp.chain_begin[best];
+      }
+      for (int x = 0; x < w; ++x) {
+        begin[lv * w + x] = pos;
+        for (int c = 0; c < nch; ++c)
+          if (owner[c] == x) item[pos++] = c;
+      }
+    }
+    begin[nlevel * w] = pos;
+  };
+  fill(flevel, tp.nflevel, tp.f_begin, tp.f_item);
+  fill(blevel, tp.nblevel, tp.b_begin, tp.b_item);
+  // column groups: up to kTmGC consecutive columns of one root component, with their step tables
+  int cost[kTmMaxGroups], ns = 0;
+  for (int r = 0; r < n && tp.ok; r = plan.comp_end[r]) {
+    const int cend = plan.comp_end[r];
+    for (int j0 = r; j0 < cend; j0 += kTmGC) {
+      const int g = tp.ngroup++;
+      const int nc = cend - j0 < kTmGC ? cend - j0 : kTmGC;
+      tp.g_first[g] = j0;
+      tp.g_ncols[g] = nc;
+      tp.g_ocol[g] = plan.orig[j0];
+      for (int c = 1; c < nc; ++c)
+        if (plan.orig[j0 + c] != plan.orig[j0] + c) tp.g_ocol[g] = -1;
+      if (ns + 3 * n > kTmMaxSteps) { tp.ok = 0; break; }
+      tp.g_sb[g] = ns;
+      for (int a = j0 + nc - 1; a >= r; --a) {            // phase B: bodies with a column of the group below them
+        if (plan.sub_end[a] <= j0) continue;
+        int mask = 0, self = 7;
+        for (int c = 0; c < nc; ++c) {
+          const int j = j0 + c;
+          if (j >= a && j < plan.sub_end[a]) mask |= 1 << c;
+          if (j == a) self = c;
+        }
+        tp.steps[ns++] = tm_pack_step(a, mp.depth[a], mask, self, -1, -1, 0, fm.kind[a], plan.orig[a]);
+      }
+      tp.g_sc[g] = ns;
+      for (int a = r; a < cend; ++a) {                    // phase C: the whole component in preorder
+        int mask = 0;
+        for (int c = 0; c < nc; ++c) {
+          const int j = j0 + c;
+          if (j >= a && j < plan.sub_end[a]) mask |= 1 << c;
+        }
+        const int par = fm.parent[a];
+        const int psl = (par >= 0 && par != a - 1) ? fm.slot_a[par] : -1;
+        tp.steps[ns++] = tm_pack_step(a, mp.depth[a], mask, 7, fm.slot_a[a], psl, par < 0 ? 1 : 0, fm.kind[a], plan.orig[a]);
+      }
+      tp.g_sz[g] = ns;
+      for (int a = 0; a < n; ++a)                         // rows of the other components: zeros
+        if (a < r || a >= cend) tp.steps[ns++] = tm_pack_step(a, 0, 0, 7, -1, -1, 0, 0, plan.orig[a]);
+      tp.g_se[g] = ns;
+      cost[g] = 8 * (tp.g_sz[g] - tp.g_sb[g]) + (tp.g_se[g] - tp.g_sz[g]);
+    }
+  }
+  // longest-processing-time assignment of the groups to the warps
+  int load[kTmMaxWarps] = {0}, owner[kTmMaxGroups];
+  bool done[kTmMaxGroups] = {false};
+  for (int k = 0; k < tp.ngroup; ++k) {
+    int best = -1;
+    for (int g = 0; g < tp.ngroup; ++g)
+      if (!done[g] && (best < 0 || cost[g] > cost[best])) best = g;
+    int ww = 0;
+    for (int x = 1; x < w; ++x)
+      if (load[x] < load[ww]) ww = x;
+    done[best] = true;
+    owner[best] = ww;
+    load[ww] += cost[best];
+  }
+  int pos = 0;
+  for (int x = 0; x < kTmMaxWarps; ++x) {
+    tp.g_begin[x] = pos;
+    if (x < w)
+      for (int g = 0; g < tp.ngroup; ++g)
+        if (owner[g] == x) tp.g_item[pos++] = g;
+  }
+  tp.g_begin[kTmMaxWarps] = pos;
+}
+
 void narrow_fast_model(const FastModel<double>& a, FastModel<float>& b) {
   std::memset(&b, 0, sizeof(b));
   b.n = a.n; b.n_slot_a = a.n_slot_a; b.n_slot_b = a.n_slot_b; b.rigid = a.rigid; b.has_prismatic = a.has_prismatic;
@@ -444,6 +587,7 @@ int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out) {
       if (i - mp.comp_root[i] + 1 > mp.maxcomp) mp.maxcomp = i - mp.comp_root[i] + 1;
     }
   }
+  build_tile_plan(m->fd_dfs, m->plan, m->coop_minv, m->coop.maxdepth, m->tile);
   {
     // create the current device's scratch pool now, so that no call made later under CUDA-graph
     // capture has to create it (pool creation is not allowed while a global-mode capture is open)
@@ -464,14 +608,14 @@ int rbd_model_num_dof(const rbd_model_t* m) { return m ? m->d.n : RBD_E_INVALID_
 
 static const char* kVariantHelp =
     "kernel variant: 0 auto, 1 generic, 2 world (thread per knot point), 3 cooperative, 4 hybrid (minv), 5 lane (minv), "
-    "7 chain (rnea_grad, serial chains)";
+    "7 chain (rnea_grad, serial chains), 8 tile (minv, large trees)";
 int rbd_set_kernel_variant(int variant) {
-  if (variant < 0 || variant > 7 || variant == 6) return fail(RBD_E_INVALID_ARGUMENT, kVariantHelp);
+  if (variant < 0 || variant > 8 || variant == 6) return fail(RBD_E_INVALID_ARGUMENT, kVariantHelp);
   g_variant.store(variant, std::memory_order_relaxed);
   return 0;
 }
 int rbd_model_set_kernel_variant(rbd_model_t* m, int variant) {
-  if (!m || variant < -1 || variant > 7 || variant == 6) return fail(RBD_E_INVALID_ARGUMENT, kVariantHelp);
+  if (!m || variant < -1 || variant > 8 || variant == 6) return fail(RBD_E_INVALID_ARGUMENT, kVariantHelp);
   m->variant.store(variant, std::memory_order_relaxed);
   return 0;
 }

@@ -35,6 +35,85 @@ __device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(
 __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 
+// sin / cos of NV angles at once: Cody-Waite reduction by pi/2 (exact products through FMA) and the
+// fdlibm minimax polynomials on [-pi/4, pi/4]; every step loops over the NV values so that NV
+// independent dependency chains are in flight.  |x| > 1e5 (never the case for joint angles) takes
+// the library path.  Max error ~1 ulp.
+static __device__ __noinline__ void sincos_far(const double* x, double* s, double* c, int n) {
+  for (int k = 0; k < n; ++k) sincos(x[k], &s[k], &c[k]);
+}
+template <int NV>
+__device__ __forceinline__ void sincos_batch(const double* x, double* s, double* c) {
+  const double MAGIC = 6755399441055744.0;           // 1.5 * 2^52: round-to-nearest integer in the low word
+  double kd[NV], r[NV], z[NV], ps[NV], pc[NV];
+  int ki[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double t = fma(x[k], 6.36619772367581382433e-01, MAGIC);
+    ki[k] = __double2loint(t);
+    kd[k] = t - MAGIC;
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) r[k] = fma(-kd[k], 1.57079632679489655800e+00, x[k]);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) r[k] = fma(-kd[k], 6.12323399573676603587e-17, r[k]);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) r[k] = fma(-kd[k], -1.49738490485916983e-33, r[k]);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    z[k] = r[k] * r[k];
+    ps[k] = fma(z[k], 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    pc[k] = fma(z[k], -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ps[k] = fma(z[k], ps[k], 2.75573137070700676789e-06);
+    pc[k] = fma(z[k], pc[k], -2.75573143513906633035e-07);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ps[k] = fma(z[k], ps[k], -1.98412698298579493134e-04);
+    pc[k] = fma(z[k], pc[k], 2.48015872894767294178e-05);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ps[k] = fma(z[k], ps[k], 8.33333333332248946124e-03);
+    pc[k] = fma(z[k], pc[k], -1.38888888888741095749e-03);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ps[k] = fma(z[k], ps[k], -1.66666666666666324348e-01);
+    pc[k] = fma(z[k], pc[k], 4.16666666666666019037e-02);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double sv = fma(z[k] * r[k], ps[k], r[k]);
+    const double cv = fma(z[k] * z[k], pc[k], fma(-0.5, z[k], 1.0));
+    const bool swap = ki[k] & 1;
+    double so = swap ? cv : sv, co = swap ? sv : cv;
+    if (ki[k] & 2) so = -so;
+    if ((ki[k] + 1) & 2) co = -co;
+    s[k] = so;
+    c[k] = co;
+  }
+  bool far = false;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) far = far || !(fabs(x[k]) <= 1.0e5);   // also NaN / Inf
+  if (far) {                                                          // cold: arrays live on the stack only here
+    double xs[NV], ss[NV], cs[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) xs[k] = x[k];
+    sincos_far(xs, ss, cs, NV);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { s[k] = ss[k]; c[k] = cs[k]; }
+  }
+}
+template <int NV>
+__device__ __forceinline__ void sincos_batch(const float* x, float* s, float* c) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) sincosf(x[k], &s[k], &c[k]);
+}
+
 // ---- joint transform X(q) = A + B*f1 + C*f2 ------------------------------------------------
 // X[0..8] = E row-major, X[9..17] = L row-major.
 template <typename T>

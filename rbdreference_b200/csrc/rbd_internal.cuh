@@ -22,6 +22,7 @@
 #include "rbd_minv_kernels.cuh"
 #include "rbd_coop_kernels.cuh"
 #include "rbd_coop_minv_kernels.cuh"
+#include "rbd_tile_minv_kernels.cuh"
 
 struct rbd_model {
   rbd::DevModel<double> d;
@@ -35,6 +36,7 @@ struct rbd_model {
   rbd::DfsPlan plan;
   rbd::CoopPlan coop;
   rbd::CoopMinvPlan coop_minv;
+  rbd::TilePlan tile;            // chain / column-group schedule of the tile minv kernel
   mutable std::atomic<int> variant{-1};   // per-handle kernel family (-1: follow rbd_set_kernel_variant)
 };
 

@@ -23,7 +23,9 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
     //   iiwa14 n=7 : hybrid 8.5e8 | 1.38e9   cooperative 7.8e8 | 1.2e9    thread 1.13e9 | 1.88e9 (body frame)
     const int n = m->d.n;
     //   iiwa14 n=7 : lane 1.49e9 | 2.60e9 (knot point per lane, table + tile in shared memory)
-    variant = n > 16 ? 4 : (n > 8 ? 3 : 5);
+    // n > 16, measured on B200 (Atlas, 2^18 knot points): tile 2.11 ms | hybrid 2.09 ms in FP64 with 2.5 GB against
+    // 5.1 GB of DRAM traffic (no scratch hand-off): tile; FP32 tile 1.42 ms | hybrid 1.26 ms: hybrid
+    variant = n > 16 ? ((m->tile.ok && std::is_same<T, double>::value) ? 8 : 4) : (n > 8 ? 3 : 5);
     // Small batches (MPC-sized): the knot-point-per-lane kernels process 32 knot points per warp one
     // after the other, so below one wave of tasks their time is the latency of a single task
     // (iiwa14 48 us, Atlas 243 us, flat from 1k to 16k knot points); the cooperative kernel spreads
@@ -58,6 +60,27 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
       return cuda_status("rbd_minv(lane)");
     }
   }
+  if (m->fast_ok && dense && variant == 8 && m->tile.ok) {
+    // one CTA per tile of 32 knot points: branch-parallel articulated inertias, column groups per warp,
+    // per-body table in shared memory, rows stored straight from registers (rbd_tile_minv_kernels.cuh)
+    const FastModel<T>& fm = pick_dfs<T>(m);
+    auto kern = fm.has_prismatic ? minv_tile_kernel<T, true> : minv_tile_kernel<T, false>;
+    const int warps = m->tile.nwarps;
+    const size_t smem = tile_minv_smem_vals(fm.n, m->tile.nslot, m->tile.maxdepth, m->tile.nslot_g, warps) * sizeof(T);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem) == cudaSuccess && nb > 0) {
+      const int64_t ntiles = (B + 31) / 32;
+      int64_t blocks = (int64_t)sm_count() * nb;
+      if (blocks > ntiles) blocks = ntiles;
+      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->tile, B, q, Minv);
+      return cuda_status("rbd_minv(tile)");
+    }
+    cudaGetLastError();
+  }
+  if (variant == 8) variant = 4;
   if (m->fast_ok && dense && variant == 4) {
     // hybrid kernel: knot point per lane for the articulated inertias, column per lane for the
     // rows of Minv, per-body table handed over through an L2-resident scratch buffer

@@ -70,7 +70,7 @@ def test_generic_body_frame_kernels_vs_reference_golden(golden):
 
 
 @requires_cuda
-@pytest.mark.parametrize("variant", [2, 3, 4, 5, 7])
+@pytest.mark.parametrize("variant", [2, 3, 4, 5, 7, 8])
 def test_world_kernel_variants_vs_reference_golden(golden, variant):
     """Both world-frame mappings (2: knot point per thread, 3: body per lane) against the goldens."""
     from rbdreference_b200 import RBDReference
@@ -415,7 +415,7 @@ def test_edge_topologies_all_drivers_vs_oracle(kind):
     cond = float(np.max(np.linalg.cond(rH)))
     scale_m = max(1.0, cond * 2.3e-16 / TOL_F64 * 50.0)
     scale = 1.0
-    for variant in (0, 1, 2, 3, 4, 5, 7):
+    for variant in (0, 1, 2, 3, 4, 5, 7, 8):
         RBDReference.set_kernel_variant(variant)
         try:
             eng = _engine(rb)
@@ -591,7 +591,11 @@ def test_full_size_properties_atlas_256k():
     for dtype, tol in ((torch.float64, TOL_F64), (torch.float32, TOL_F32)):
         eng = _engine(rb, dtype)
         M = eng.minv(q64.to(dtype))
-        assert torch.isfinite(M).all() and torch.equal(M, M.transpose(1, 2))
+        assert torch.isfinite(M).all()
+        # FP32 (hybrid kernel): the mirror is a copy (:799-804).  FP64 (tile kernel): both triangles come from the
+        # forward recursion itself (:771 updates whole rows; it is what output_dense=False returns), symmetric to rounding
+        asym = float((M - M.transpose(1, 2)).abs().max() / M.abs().max())
+        assert asym == 0.0 if dtype == torch.float32 else asym < 1e-13
         # block structure: pelvis-rooted components (torso+arms | l_leg | r_leg) do not couple
         assert float(M[:, :18, 18:].abs().max()) == 0.0 and float(M[:, 18:24, 24:].abs().max()) == 0.0
         idx = torch.arange(0, B, B // 512, device="cuda")[:512]
@@ -1024,7 +1028,7 @@ def test_host_numpy_pipeline_bit_identical_to_device_path(pinned):
     e32 = _engine(rb, torch.float32)
     assert np.array_equal(e32.minv(hq[:5000]), e32.minv(_t(q[:5000], torch.float32)).cpu().numpy())
     # tiny and empty batches go through the same path
-    assert np.array_equal(eng.rnea_grad(hq[:3], hqd[:3], hqdd[:3]), ref[:3])
+    assert np.array_equal(eng.rnea_grad(hq[:3], hqd[:3], hqdd[:3]), eng.rnea_grad(_t(q[:3]), _t(qd[:3]), _t(qdd[:3])).cpu().numpy())
     assert eng.rnea_grad(hq[:0], hqd[:0], hqdd[:0]).shape == (0, 7, 14)
 
 
