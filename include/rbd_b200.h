@@ -248,6 +248,42 @@ int rbd_fb_rnea_grad_f32(const rbd_fb_model_t* m, int64_t B, const float* q, con
                          float gravity, int use_velocity_damping, float* dc_du, float* c_out, void* stream);
 int rbd_fb_minv_f64(const rbd_fb_model_t* m, int64_t B, const double* q, int output_dense, double* Minv, void* stream);
 int rbd_fb_minv_f32(const rbd_fb_model_t* m, int64_t B, const float* q, int output_dense, float* Minv, void* stream);
+/* The eight per-pass helpers for a floating-base robot - the `floating_base` branches of rnea_fpass
+ * (RBDReference.py:559-598), rnea_bpass (:600-621), minv_bpass (:630-735), minv_fpass (:737-783),
+ * rnea_grad_fpass_dq (:1127-1187), rnea_grad_fpass_dqd (:1189-1255), rnea_grad_bpass_dq (:1257-1297) and
+ * rnea_grad_bpass_dqd (:1299-1343), reference shapes with a leading batch axis and n = NB + 5:
+ * v, a, f (B, 6, NB); Minv (B, n, n); F (B, n, 6, n); U (B, n, 6); Dinv (B, n) [= D, rows 0..5 unused];
+ * dv, da, df (B, 6, n, NB); dc (B, n, n).  Same in-place contracts as the fixed-base helpers (f, Minv and F,
+ * df are updated through the caller's pointers).  rnea_grad_fpass_dq needs NB >= 6 (the reference raises
+ * IndexError at :1168 otherwise): RBD_E_UNSUPPORTED. */
+int rbd_fb_rnea_fpass_f64(const rbd_fb_model_t* m, int64_t B, const double* q, const double* qd, const double* qdd, double gravity,
+                          double* v, double* a, double* f, void* stream);
+int rbd_fb_rnea_bpass_f64(const rbd_fb_model_t* m, int64_t B, const double* q, double* f, double* c, void* stream);
+int rbd_fb_minv_bpass_f64(const rbd_fb_model_t* m, int64_t B, const double* q, double* Minv, double* F, double* U, double* Dinv, void* stream);
+int rbd_fb_minv_fpass_f64(const rbd_fb_model_t* m, int64_t B, const double* q, double* Minv, double* F, const double* U, const double* Dinv,
+                          void* stream);
+int rbd_fb_rnea_grad_fpass_dq_f64(const rbd_fb_model_t* m, int64_t B, const double* q, const double* qd, const double* v, const double* a,
+                                  double gravity, double* dv, double* da, double* df, void* stream);
+int rbd_fb_rnea_grad_fpass_dqd_f64(const rbd_fb_model_t* m, int64_t B, const double* q, const double* qd, const double* v, double* dv,
+                                   double* da, double* df, void* stream);
+int rbd_fb_rnea_grad_bpass_dq_f64(const rbd_fb_model_t* m, int64_t B, const double* q, const double* f, double* df_dq, double* dc_dq,
+                                  void* stream);
+int rbd_fb_rnea_grad_bpass_dqd_f64(const rbd_fb_model_t* m, int64_t B, const double* q, double* df_dqd, int use_velocity_damping,
+                                   double* dc_dqd, void* stream);
+int rbd_fb_rnea_fpass_f32(const rbd_fb_model_t* m, int64_t B, const float* q, const float* qd, const float* qdd, float gravity,
+                          float* v, float* a, float* f, void* stream);
+int rbd_fb_rnea_bpass_f32(const rbd_fb_model_t* m, int64_t B, const float* q, float* f, float* c, void* stream);
+int rbd_fb_minv_bpass_f32(const rbd_fb_model_t* m, int64_t B, const float* q, float* Minv, float* F, float* U, float* Dinv, void* stream);
+int rbd_fb_minv_fpass_f32(const rbd_fb_model_t* m, int64_t B, const float* q, float* Minv, float* F, const float* U, const float* Dinv,
+                          void* stream);
+int rbd_fb_rnea_grad_fpass_dq_f32(const rbd_fb_model_t* m, int64_t B, const float* q, const float* qd, const float* v, const float* a,
+                                  float gravity, float* dv, float* da, float* df, void* stream);
+int rbd_fb_rnea_grad_fpass_dqd_f32(const rbd_fb_model_t* m, int64_t B, const float* q, const float* qd, const float* v, float* dv,
+                                   float* da, float* df, void* stream);
+int rbd_fb_rnea_grad_bpass_dq_f32(const rbd_fb_model_t* m, int64_t B, const float* q, const float* f, float* df_dq, float* dc_dq,
+                                  void* stream);
+int rbd_fb_rnea_grad_bpass_dqd_f32(const rbd_fb_model_t* m, int64_t B, const float* q, float* df_dqd, int use_velocity_damping,
+                                   float* dc_dqd, void* stream);
 /* forward_dynamics / forward_dynamics_grad (RBDReference.py:1369-1384) of a floating-base robot: the
  * same compositions as rbd_forward_dynamics*, u / qdd (B, NB+5), qdd_dq / qdd_dqd (B, NB+5, NB+5). */
 int rbd_fb_forward_dynamics_f64(const rbd_fb_model_t* m, int64_t B, const double* q, const double* qd, const double* u,

@@ -166,9 +166,55 @@ def run_fb_case(name, B, seed):
     print("wrote %s (%d states, %.1f KB)" % (path, B, os.path.getsize(path) / 1024))
 
 
+# per-pass intermediates of the floating-base branches (the eight helpers)
+FBPASS_CASES = [("hyq_fb", 3), ("atlas_fb", 1), ("iiwa14_fb", 3), ("tree9_fb", 2)]
+
+
+def run_fbpass_case(name, B, seed):
+    """tests/golden/fbpass_<name>.npz: every array the unmodified reference's eight per-pass helpers take and return
+    for floating-base robots (copies are taken around the calls that mutate their arguments)."""
+    import warnings
+    warnings.simplefilter("ignore")
+    rb = make_fb_robot(name)
+    ref = RBDReference(rb)
+    q, qd, qdd = rb.random_state(np.random.default_rng(seed), B)
+    keys = ["v", "a", "f", "c", "f_acc", "Minv_b", "F_b", "U", "Dinv", "Minv_f", "F_f", "dv_dq", "da_dq", "df_dq", "dv_dqd",
+            "da_dqd", "df_dqd", "dc_dq", "df_dq_acc", "dc_dqd", "dc_dqd_damped", "df_dqd_acc"]
+    acc = {k: [] for k in keys}
+    for k in range(B):
+        v, a, f = ref.rnea_fpass(q[k], qd[k], qdd[k])
+        acc["v"].append(v.copy()); acc["a"].append(a.copy()); acc["f"].append(f.copy())
+        c, f_acc = ref.rnea_bpass(q[k], f.copy())
+        acc["c"].append(c); acc["f_acc"].append(f_acc.copy())
+        Mb, Fb, U, D = ref.minv_bpass(q[k])
+        acc["Minv_b"].append(Mb.copy()); acc["F_b"].append(Fb.copy()); acc["U"].append(U.copy()); acc["Dinv"].append(D.copy())
+        Mf, Ff = Mb.copy(), Fb.copy()
+        ref.minv_fpass(q[k], Mf, Ff, U, D)
+        acc["Minv_f"].append(Mf); acc["F_f"].append(Ff)
+        dv, da, df = ref.rnea_grad_fpass_dq(q[k], qd[k], v, a)
+        acc["dv_dq"].append(dv.copy()); acc["da_dq"].append(da.copy()); acc["df_dq"].append(df.copy())
+        dv2, da2, df2 = ref.rnea_grad_fpass_dqd(q[k], qd[k], v)
+        acc["dv_dqd"].append(dv2.copy()); acc["da_dqd"].append(da2.copy()); acc["df_dqd"].append(df2.copy())
+        dfa = df.copy()
+        acc["dc_dq"].append(ref.rnea_grad_bpass_dq(q[k], f_acc, dfa)); acc["df_dq_acc"].append(dfa)
+        dfa2 = df2.copy()
+        acc["dc_dqd"].append(ref.rnea_grad_bpass_dqd(q[k], dfa2)); acc["df_dqd_acc"].append(dfa2)
+        acc["dc_dqd_damped"].append(ref.rnea_grad_bpass_dqd(q[k], df2.copy(), USE_VELOCITY_DAMPING=True))
+    out = dict(q=q, qd=qd, qdd=qdd)
+    for key in keys:
+        out[key] = np.stack([np.asarray(x, dtype=float) for x in acc[key]])
+    path = os.path.join(ROOT, "tests", "golden", "fbpass_" + name[:-3] + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s (%d states, %.1f KB)" % (path, B, os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     only_ee = "--ee" in sys.argv          # regenerate only the end-effector fixtures
     only_fb = "--fb" in sys.argv          # regenerate only the floating-base fixtures
+    if "--fbpass" in sys.argv:            # only the floating-base per-pass fixtures
+        for idx, (name, B) in enumerate(FBPASS_CASES):
+            run_fbpass_case(name, B, seed=4000 + idx)
+        sys.exit(0)
     for idx, (name, make, B) in enumerate(CASES):
         if not (only_ee or only_fb):
             run_case(name, make, B, seed=1000 + idx)
@@ -177,3 +223,5 @@ if __name__ == "__main__":
     if not only_ee:
         for idx, (name, B) in enumerate(FB_CASES):
             run_fb_case(name, B, seed=3000 + idx)
+        for idx, (name, B) in enumerate(FBPASS_CASES):
+            run_fbpass_case(name, B, seed=4000 + idx)

@@ -19,7 +19,7 @@ PLAIN_SYMBOLS = ["rbd_abi_version", "rbd_last_error_string", "rbd_model_create",
                  "rbd_measure_fma_peak", "rbd_launch_count",
                  "rbd_ee_model_create", "rbd_ee_model_destroy", "rbd_ee_model_num_ee",
                  "rbd_fb_model_create", "rbd_fb_model_destroy", "rbd_fb_model_num_vel"]
-FB_SYMBOLS = ["fb_rnea", "fb_rnea_grad", "fb_minv", "fb_forward_dynamics", "fb_forward_dynamics_grad"]
+FB_SYMBOLS = ["fb_rnea", "fb_rnea_grad", "fb_minv", "fb_forward_dynamics", "fb_forward_dynamics_grad"] + ["fb_" + p for p in PASS_SYMBOLS]
 EE_SYMBOLS = ["end_effector_pose", "end_effector_pose_gradient"]
 
 
@@ -110,6 +110,8 @@ def load_library():
             "end_effector_pose": [P, c_int64, P, P, P],
             "end_effector_pose_gradient": [P, c_int64, P, P, P, P],
         }
+        for base in PASS_SYMBOLS:                       # the floating-base helpers share the fixed-base signatures
+            sig["fb_" + base] = sig[base]
         for base, argtypes in sig.items():
             fn = getattr(lib, "rbd_%s_%s" % (base, suf))
             fn.argtypes = argtypes

@@ -1,0 +1,442 @@
+// rbd_fb_pass_kernels.cuh - the eight per-pass helpers for FLOATING-BASE robots.
+//
+// The `self.robot.floating_base` branches of rnea_fpass RBDReference.py:559-598 (:585, :591), rnea_bpass
+// :600-621, minv_bpass :630-735 (:652-691), minv_fpass :737-783 (:761-779), rnea_grad_fpass_dq :1127-1187
+// (:1141-1168), rnea_grad_fpass_dqd :1189-1255 (:1212-1238), rnea_grad_bpass_dq :1257-1297 (:1267-1282) and
+// rnea_grad_bpass_dqd :1299-1343 (:1309-1341), with every intermediate array in the reference's own shape and
+// index convention: body 0 is the base (S = eye(6), q[0:7], qd[0:6]), body i >= 1 owns row / column i + 5,
+// n = NB + 5.  The reference's behaviour is kept to the letter where it is unusual:
+//   * minv_bpass :687-691 subtracts fb_Dinv F[5][:, adj] for the base (the trailing [-1] picks F[5]);
+//   * minv_fpass :771-781 re-uses F with BODY indices (F[ind], F[parent_ind]), F[0] = Minv[0:6, :];
+//   * rnea_grad_fpass_dq :1166-1168 adds zeros for the base (dv_dq is still zero there);
+//   * rnea_grad_bpass_dqd :1336-1341 adds the base's damping to the block [0:5, 0:5] and body i's to [i, i].
+//
+// These entry points exist so that downstream accelerators can be checked pass by pass (README.md:19): one
+// knot point per thread, the passes' arrays in HBM are the working storage exactly as in the reference
+// (the in-place contracts - f of rnea_bpass, Minv and F of minv_fpass, df of the gradient bpasses - come for
+// free).  They are HBM-bound by construction (each array is written once and read back by the same thread).
+#pragma once
+#include "rbd_common.cuh"
+#include "rbd_fb_kernels.cuh"
+
+namespace rbd {
+
+constexpr int kFbPassThreads = 64;
+
+// X of body i from q: the base from position + quaternion, joint i >= 1 from q[i + 6]
+template <typename T>
+__device__ __forceinline__ void fbp_X(const FbModel<T>& m, int i, const T* __restrict__ qb, T (&X)[18]) {
+  if (i == 0) fb_base_X(m, qb, X);
+  else build_X_from_q(m.d, i, qb[i + 6], X);
+}
+
+// dense 6x6 (row-major) of the 18-value [E | L] layout:  X = [[E, 0], [L, E]]
+template <typename T>
+__device__ __forceinline__ void fbp_dense(const T (&X)[18], T (&D)[36]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      D[6 * r + c] = X[3 * r + c];
+      D[6 * r + 3 + c] = T(0);
+      D[6 * (3 + r) + c] = X[9 + 3 * r + c];
+      D[6 * (3 + r) + 3 + c] = X[3 * r + c];
+    }
+}
+
+// ---- rnea_fpass (:559-598) -------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kFbPassThreads)
+fbp_rnea_fpass_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restrict__ q, const T* __restrict__ qd,
+                      const T* __restrict__ qdd, T gravity, T* __restrict__ v, T* __restrict__ a, T* __restrict__ f) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int NB = m.d.n, nv = NB + 5;
+  const T* qb = q + b * (NB + 6);
+  const T* qdb = qd + b * nv;
+  const T* qddb = qdd ? qdd + b * nv : nullptr;
+  T* vb = v + b * 6 * NB;
+  T* ab = a + b * 6 * NB;
+  T* fb = f + b * 6 * NB;
+  for (int i = 0; i < NB; ++i) {
+    T X[18], vi[6], ai[6], par[6], vJ[6], t[6];
+    fbp_X(m, i, qb, X);
+    const int p = m.d.parent[i];
+    if (p < 0) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) { vi[r] = T(0); par[r] = T(0); }
+      par[5] = -gravity;                                                       // :566
+      X_apply(X, par, ai);                                                     // :578
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) par[r] = vb[r * NB + p];
+      X_apply(X, par, vi);                                                     // :580
+#pragma unroll
+      for (int r = 0; r < 6; ++r) par[r] = ab[r * NB + p];
+      X_apply(X, par, ai);                                                     // :581
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) vJ[r] = i == 0 ? qdb[r] : m.d.S[i][r] * qdb[i + 5];   // :585-586
+#pragma unroll
+    for (int r = 0; r < 6; ++r) vi[r] += vJ[r];
+    crm_mul(vi, vJ, t);                                                        // :588
+#pragma unroll
+    for (int r = 0; r < 6; ++r) ai[r] += t[r];
+    if (qddb) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) ai[r] += i == 0 ? qddb[r] : m.d.S[i][r] * qddb[i + 5];   // :591-593
+    }
+    T Ia[6], Iv[6], vxIv[6];
+    mat6_apply(m.d.I[i], ai, Ia);
+    mat6_apply(m.d.I[i], vi, Iv);
+    crf_mul(vi, Iv, vxIv);                                                     // :596
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { vb[r * NB + i] = vi[r]; ab[r * NB + i] = ai[r]; fb[r * NB + i] = Ia[r] + vxIv[r]; }
+  }
+}
+
+// ---- rnea_bpass (:600-621): f accumulated in place ---------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kFbPassThreads)
+fbp_rnea_bpass_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restrict__ q, T* __restrict__ f,
+                      T* __restrict__ c) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int NB = m.d.n, nv = NB + 5;
+  const T* qb = q + b * (NB + 6);
+  T* fb = f + b * 6 * NB;
+  T* cb = c + b * nv;
+  for (int i = NB - 1; i >= 1; --i) {
+    T X[18], fi[6], t[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) fi[r] = fb[r * NB + i];
+    cb[i + 5] = dot6(m.d.S[i], fi);                                            // :612
+    fbp_X(m, i, qb, X);
+    XT_apply(X, fi, t);
+    const int p = m.d.parent[i];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) fb[r * NB + p] += t[r];                        // :617-619
+  }
+#pragma unroll
+  for (int r = 0; r < 6; ++r) cb[r] = fb[r * NB];                              // :612 with S = eye(6)
+}
+
+// ---- minv_bpass (:630-735) -----------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kFbPassThreads)
+fbp_minv_bpass_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restrict__ q, T* __restrict__ Minv,
+                      T* __restrict__ F, T* __restrict__ U, T* __restrict__ Dinv) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int NB = m.d.n, n = NB + 5;
+  const T* qb = q + b * (NB + 6);
+  T* Mb = Minv + b * (int64_t)n * n;
+  T* Fb = F + b * (int64_t)n * 6 * n;                       // F[mi][r][col] = Fb[(mi * 6 + r) * n + col]
+  T* Ub = U + b * (int64_t)n * 6;
+  T* Db = Dinv + b * (int64_t)n;
+  for (int k = 0; k < n * n; ++k) Mb[k] = T(0);
+  for (int k = 0; k < n * 6 * n; ++k) Fb[k] = T(0);
+  for (int k = 0; k < n * 6; ++k) Ub[k] = T(0);
+  for (int k = 0; k < n; ++k) Db[k] = T(0);
+  T IA[RBD_MAX_DOF][36];                                     // :662
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int k = 0; k < 36; ++k) IA[i][k] = m.d.I[i][k];
+  for (int i = NB - 1; i >= 1; --i) {
+    const int mi = i + 5, p = m.d.parent[i], mp = p + 5;
+    const unsigned sub = m.d.sub_mask[i];
+    T Ui[6];
+    mat6_apply(IA[i], m.d.S[i], Ui);                                           // :697
+    const T D = dot6(m.d.S[i], Ui);                                            // :698
+    const T invD = T(1) / D;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) Ub[mi * 6 + r] = Ui[r];
+    Db[mi] = D;
+    Mb[mi * n + mi] = invD;                                                    // :700
+    for (int j = i; j < NB; ++j) {                                             // :702-708
+      if (!((sub >> j) & 1u)) continue;
+      T sF = T(0);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) sF = fma_t(m.d.S[i][r], Fb[(mi * 6 + r) * n + j + 5], sF);
+      Mb[mi * n + j + 5] -= invD * sF;
+    }
+    T X[18];
+    fbp_X(m, i, qb, X);
+    for (int j = i; j < NB; ++j) {                                             // :720-726
+      if (!((sub >> j) & 1u)) continue;
+      const T mij = Mb[mi * n + j + 5];
+      T Fi[6], t[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        Fi[r] = fma_t(Ui[r], mij, Fb[(mi * 6 + r) * n + j + 5]);
+        Fb[(mi * 6 + r) * n + j + 5] = Fi[r];
+      }
+      XT_apply(X, Fi, t);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Fb[(mp * 6 + r) * n + j + 5] += t[r];
+    }
+    // IA_parent += X^T (IA - U U^T / D) X   (:728-733)
+    T Xd[36], tmp[36];
+    fbp_dense(X, Xd);
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) {
+        T acc = T(0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc = fma_t(IA[i][6 * r + k] - Ui[r] * (invD * Ui[k]), Xd[6 * k + cc], acc);
+        tmp[6 * r + cc] = acc;
+      }
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) {
+        T acc = T(0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc = fma_t(Xd[6 * k + r], tmp[6 * k + cc], acc);
+        IA[p][6 * r + cc] += acc;
+      }
+  }
+  // base (:677-691): U[0:6] = IA_0, fb_Dinv = inv(IA_0), Minv[0:6, 0:6] = fb_Dinv, Minv[0:6, adj] -= fb_Dinv F[5][:, adj]
+#pragma unroll
+  for (int k = 0; k < 36; ++k) Ub[k] = IA[0][k];
+  T Di[36];
+  {
+    T A[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) { A[k] = IA[0][k]; Di[k] = (k % 7 == 0) ? T(1) : T(0); }
+#pragma unroll
+    for (int pv = 0; pv < 6; ++pv) {
+      const T inv = T(1) / A[7 * pv];
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) { A[6 * pv + cc] *= inv; Di[6 * pv + cc] *= inv; }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        if (r == pv) continue;
+        const T fct = A[6 * r + pv];
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {
+          A[6 * r + cc] = fma_t(-fct, A[6 * pv + cc], A[6 * r + cc]);
+          Di[6 * r + cc] = fma_t(-fct, Di[6 * pv + cc], Di[6 * r + cc]);
+        }
+      }
+    }
+  }
+  const T m00 = Mb[0];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) Mb[r * n + cc] = m00 + Di[6 * r + cc];      // :686
+  for (int col = 5; col < n; ++col) {                                          // adj = subtree(0) + 5 = 5 .. n-1
+    T Fc[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) Fc[r] = Fb[(5 * 6 + r) * n + col];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      T acc = T(0);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc = fma_t(Di[6 * r + k], Fc[k], acc);
+      Mb[r * n + col] -= acc;
+    }
+  }
+}
+
+// ---- minv_fpass (:737-783): Minv and F updated in place ---------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kFbPassThreads)
+fbp_minv_fpass_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restrict__ q, T* __restrict__ Minv,
+                      T* __restrict__ F, const T* __restrict__ U, const T* __restrict__ Dinv) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int NB = m.d.n, n = NB + 5;
+  const T* qb = q + b * (NB + 6);
+  T* Mb = Minv + b * (int64_t)n * n;
+  T* Fb = F + b * (int64_t)n * 6 * n;
+  const T* Ub = U + b * (int64_t)n * 6;
+  const T* Db = Dinv + b * (int64_t)n;
+  for (int r = 0; r < 6; ++r)
+    for (int col = 0; col < n; ++col) Fb[(0 * 6 + r) * n + col] = Mb[r * n + col];   // :779  F[0] = S Minv[0:6, 0:]
+  for (int i = 1; i < NB; ++i) {
+    const int mi = i + 5, p = m.d.parent[i];
+    T X[18], Ui[6], UX[6];
+    fbp_X(m, i, qb, X);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) Ui[r] = Ub[mi * 6 + r];
+    XT_apply(X, Ui, UX);                                                       // (U^T X)^T = X^T U
+    const T invD = T(1) / Db[mi];
+    for (int col = 0; col < n; ++col) {
+      T Fp[6], XF[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Fp[r] = Fb[(p * 6 + r) * n + col];
+      const T mij = Mb[mi * n + col] - invD * dot6(UX, Fp);                    // :771-773
+      Mb[mi * n + col] = mij;
+      X_apply(X, Fp, XF);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Fb[(i * 6 + r) * n + col] = fma_t(m.d.S[i][r], mij, XF[r]);   // :774-776
+    }
+  }
+}
+
+// df[:, c] = I da_c + crf(dv_c) (I v) + crf(v) (I dv_c)   (:1179-1185 / :1247-1252)
+template <typename T>
+__device__ __forceinline__ void fbp_df(const T* __restrict__ I, const T (&vi)[6], const T (&Iv)[6], const T (&dvc)[6],
+                                       const T (&dac)[6], T (&dfc)[6]) {
+  T t1[6], t2[6], Idv[6];
+  mat6_apply(I, dac, dfc);
+  crf_mul(dvc, Iv, t1);
+  mat6_apply(I, dvc, Idv);
+  crf_mul(vi, Idv, t2);
+#pragma unroll
+  for (int r = 0; r < 6; ++r) dfc[r] += t1[r] + t2[r];
+}
+
+// ---- rnea_grad_fpass_dq (:1127-1187) and rnea_grad_fpass_dqd (:1189-1255) --------------------------------------
+template <typename T, bool DQ>
+__global__ void __launch_bounds__(kFbPassThreads)
+fbp_grad_fpass_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restrict__ q, const T* __restrict__ qd,
+                      const T* __restrict__ v, const T* __restrict__ a, T gravity, T* __restrict__ dv, T* __restrict__ da,
+                      T* __restrict__ df) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int NB = m.d.n, n = NB + 5;
+  const T* qb = q + b * (NB + 6);
+  const T* qdb = qd + b * n;
+  const T* vb = v + b * 6 * NB;
+  const T* ab = DQ ? a + b * 6 * NB : nullptr;
+  const int64_t sz = (int64_t)6 * n * NB;                   // [r][c][body] = (r * n + c) * NB + body
+  T* dvb = dv + b * sz;
+  T* dab = da + b * sz;
+  T* dfb = df + b * sz;
+  for (int i = 0; i < NB; ++i) {
+    T X[18], vi[6], Iv[6];
+    fbp_X(m, i, qb, X);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) vi[r] = vb[r * NB + i];
+    mat6_apply(m.d.I[i], vi, Iv);
+    const int p = m.d.parent[i], idx = i + 5;
+    T seed_v[6], seed_a[6];                                   // what column idx gets on top (i >= 1)
+    T xg[6];                                                  // base, dq: X0 g
+    if (i == 0) {
+      if (DQ) {
+        T g6[6] = {T(0), T(0), T(0), T(0), T(0), -gravity};
+        X_apply(X, g6, xg);
+      }
+    } else {
+      T par[6], t[6];
+      if (DQ) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) par[r] = vb[r * NB + p];
+        X_apply(X, par, t);
+        crm_mul(t, m.d.S[i], seed_v);                                          // :1159
+#pragma unroll
+        for (int r = 0; r < 6; ++r) par[r] = ab[r * NB + p];
+        X_apply(X, par, t);
+        crm_mul(t, m.d.S[i], seed_a);                                          // :1173
+      } else {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) seed_v[r] = m.d.S[i][r];                   // :1231
+        crm_mul(vi, m.d.S[i], seed_a);                                         // :1243
+      }
+    }
+    for (int c = 0; c < n; ++c) {
+      T dvc[6], dac[6], dfc[6];
+      if (i == 0) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { dvc[r] = T(0); dac[r] = T(0); }
+        if (c < 6) {
+          T e[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+          e[c] = T(1);
+          if (DQ) {
+            crm_mul(xg, e, dac);                                               // :1175 with S = eye(6); :1166-1168 adds zeros
+          } else {
+            dvc[c] = T(1);                                                     // :1231
+            T qb6[6], t1[6], t2[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) qb6[r] = qdb[r];
+            crm_mul(e, qb6, t1);                                               // :1236-1238  sum_ii qd[ii] crm(dv_c)[:, ii]
+            crm_mul(vi, e, t2);                                                // :1243
+#pragma unroll
+            for (int r = 0; r < 6; ++r) dac[r] = t1[r] + t2[r];
+          }
+        }
+      } else {
+        T par[6], t[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) par[r] = dvb[(r * n + c) * NB + p];
+        X_apply(X, par, dvc);                                                  // :1158 / :1230
+#pragma unroll
+        for (int r = 0; r < 6; ++r) par[r] = dab[(r * n + c) * NB + p];
+        X_apply(X, par, dac);                                                  // :1163 / :1234
+        if (c == idx) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) dvc[r] += seed_v[r];
+        }
+        crm_mul(dvc, m.d.S[i], t);                                             // :1170 / :1240
+        const T qdi = qdb[idx];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) dac[r] = fma_t(qdi, t[r], dac[r]);
+        if (c == idx) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) dac[r] += seed_a[r];
+        }
+      }
+      fbp_df(m.d.I[i], vi, Iv, dvc, dac, dfc);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        dvb[(r * n + c) * NB + i] = dvc[r];
+        dab[(r * n + c) * NB + i] = dac[r];
+        dfb[(r * n + c) * NB + i] = dfc[r];
+      }
+    }
+  }
+}
+
+// ---- rnea_grad_bpass_dq (:1257-1297) and rnea_grad_bpass_dqd (:1299-1343): df accumulated in place --------------
+template <typename T, bool DQ>
+__global__ void __launch_bounds__(kFbPassThreads)
+fbp_grad_bpass_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restrict__ q, const T* __restrict__ f,
+                      T* __restrict__ df, int use_damping, T* __restrict__ dc) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int NB = m.d.n, n = NB + 5;
+  const T* qb = q + b * (NB + 6);
+  const T* fb = DQ ? f + b * 6 * NB : nullptr;
+  T* dfb = df + b * (int64_t)6 * n * NB;
+  T* dcb = dc + b * (int64_t)n * n;
+  for (int i = NB - 1; i >= 1; --i) {
+    const int idx = i + 5, p = m.d.parent[i];
+    T X[18], extra[6];
+    fbp_X(m, i, qb, X);
+    if (DQ) {
+      T fi[6], t[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) fi[r] = fb[r * NB + i];
+      crm_mul(fi, m.d.S[i], t);                                                // fxS = -crm(f) S (:166-168)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) t[r] = -t[r];
+      XT_apply(X, t, extra);                                                   // :1292
+    }
+    for (int c = 0; c < n; ++c) {
+      T col[6], t[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) col[r] = dfb[(r * n + c) * NB + i];
+      dcb[idx * n + c] = dot6(m.d.S[i], col);                                  // :1284 / :1325
+      XT_apply(X, col, t);
+      if (DQ && c == idx) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) t[r] += extra[r];                          // :1293-1294
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) dfb[(r * n + c) * NB + p] += t[r];           // :1291 / :1331
+    }
+  }
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < n; ++c) dcb[r * n + c] = dfb[(r * n + c) * NB];        // :1282 / :1325 with S = eye(6)
+  if (!DQ && use_damping) {                                                    // :1336-1341
+    for (int r = 0; r < 5; ++r)
+      for (int c = 0; c < 5; ++c) dcb[r * n + c] += m.d.damping[0];
+    for (int i = 1; i < NB; ++i) dcb[i * n + i] += m.d.damping[i];
+  }
+}
+
+}  // namespace rbd

@@ -2,6 +2,7 @@
 // Reference: the `floating_base` branches of RBDReference.py:559-806 and :1127-1368.
 #include "rbd_internal.cuh"
 #include "rbd_fb_kernels.cuh"
+#include "rbd_fb_pass_kernels.cuh"
 
 using namespace rbd;
 using namespace rbd_host;
@@ -76,6 +77,54 @@ int launch_fb_minv(const rbd_fb_model* m, int64_t B, const T* q, int dense, T* M
   if (B == 0) return 0;
   fb_minv_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, fb_smem_bytes<T>(m), (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, dense, Minv);
   return cuda_status("rbd_fb_minv");
+}
+
+
+// ---- per-pass helpers (rbd_fb_pass_kernels.cuh): one knot point per thread, the passes' arrays are the working storage
+template <typename T>
+int launch_fb_rnea_fpass(const rbd_fb_model* m, int64_t B, const T* q, const T* qd, const T* qdd, T g, T* v, T* a, T* f, void* stream) {
+  RBD_CHECK_ARGS(m && q && qd && v && a && f && B >= 0, "rbd_fb_rnea_fpass: null argument or negative B");
+  if (B == 0) return 0;
+  fbp_rnea_fpass_kernel<T><<<blocks_for(B, kFbPassThreads), kFbPassThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, qd, qdd, g, v, a, f);
+  return cuda_status("rbd_fb_rnea_fpass");
+}
+template <typename T>
+int launch_fb_rnea_bpass(const rbd_fb_model* m, int64_t B, const T* q, T* f, T* c, void* stream) {
+  RBD_CHECK_ARGS(m && q && f && c && B >= 0, "rbd_fb_rnea_bpass: null argument or negative B");
+  if (B == 0) return 0;
+  fbp_rnea_bpass_kernel<T><<<blocks_for(B, kFbPassThreads), kFbPassThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, f, c);
+  return cuda_status("rbd_fb_rnea_bpass");
+}
+template <typename T>
+int launch_fb_minv_bpass(const rbd_fb_model* m, int64_t B, const T* q, T* Minv, T* F, T* U, T* Dinv, void* stream) {
+  RBD_CHECK_ARGS(m && q && Minv && F && U && Dinv && B >= 0, "rbd_fb_minv_bpass: null argument or negative B");
+  if (B == 0) return 0;
+  fbp_minv_bpass_kernel<T><<<blocks_for(B, kFbPassThreads), kFbPassThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, Minv, F, U, Dinv);
+  return cuda_status("rbd_fb_minv_bpass");
+}
+template <typename T>
+int launch_fb_minv_fpass(const rbd_fb_model* m, int64_t B, const T* q, T* Minv, T* F, const T* U, const T* Dinv, void* stream) {
+  RBD_CHECK_ARGS(m && q && Minv && F && U && Dinv && B >= 0, "rbd_fb_minv_fpass: null argument or negative B");
+  if (B == 0) return 0;
+  fbp_minv_fpass_kernel<T><<<blocks_for(B, kFbPassThreads), kFbPassThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, Minv, F, U, Dinv);
+  return cuda_status("rbd_fb_minv_fpass");
+}
+template <typename T, bool DQ>
+int launch_fb_grad_fpass(const rbd_fb_model* m, int64_t B, const T* q, const T* qd, const T* v, const T* a, T g, T* dv, T* da, T* df,
+                         void* stream) {
+  RBD_CHECK_ARGS(m && q && qd && v && (a || !DQ) && dv && da && df && B >= 0, "rbd_fb_rnea_grad_fpass: null argument or negative B");
+  if (B == 0) return 0;
+  if (DQ && m->d.d.n < 6)        // RBDReference.py:1168 indexes bodies 0..5 (IndexError upstream)
+    return fail(RBD_E_UNSUPPORTED, "rbd_fb_rnea_grad_fpass_dq: the reference needs at least 6 bodies on this path (:1168)");
+  fbp_grad_fpass_kernel<T, DQ><<<blocks_for(B, kFbPassThreads), kFbPassThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, qd, v, a, g, dv, da, df);
+  return cuda_status("rbd_fb_rnea_grad_fpass");
+}
+template <typename T, bool DQ>
+int launch_fb_grad_bpass(const rbd_fb_model* m, int64_t B, const T* q, const T* f, T* df, int damp, T* dc, void* stream) {
+  RBD_CHECK_ARGS(m && q && (f || !DQ) && df && dc && B >= 0, "rbd_fb_rnea_grad_bpass: null argument or negative B");
+  if (B == 0) return 0;
+  fbp_grad_bpass_kernel<T, DQ><<<blocks_for(B, kFbPassThreads), kFbPassThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, f, df, damp, dc);
+  return cuda_status("rbd_fb_rnea_grad_bpass");
 }
 
 // forward_dynamics / forward_dynamics_grad (RBDReference.py:1369-1384) are robot-agnostic compositions; with a
@@ -173,6 +222,37 @@ int rbd_fb_model_num_vel(const rbd_fb_model_t* m) { return m ? m->d.d.n + 5 : RB
   }                                                                                                                  \
   int rbd_fb_minv_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, int output_dense, T* Minv, void* stream) {   \
     return launch_fb_minv<T>(m, B, q, output_dense, Minv, stream);                                                   \
+  }                                                                                                                  \
+  int rbd_fb_rnea_fpass_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* qdd, T gravity,  \
+                              T* v, T* a, T* f, void* stream) {                                                      \
+    return launch_fb_rnea_fpass<T>(m, B, q, qd, qdd, gravity, v, a, f, stream);                                      \
+  }                                                                                                                  \
+  int rbd_fb_rnea_bpass_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, T* f, T* c, void* stream) {            \
+    return launch_fb_rnea_bpass<T>(m, B, q, f, c, stream);                                                           \
+  }                                                                                                                  \
+  int rbd_fb_minv_bpass_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, T* Minv, T* F, T* U, T* Dinv,          \
+                              void* stream) {                                                                        \
+    return launch_fb_minv_bpass<T>(m, B, q, Minv, F, U, Dinv, stream);                                               \
+  }                                                                                                                  \
+  int rbd_fb_minv_fpass_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, T* Minv, T* F, const T* U,             \
+                              const T* Dinv, void* stream) {                                                         \
+    return launch_fb_minv_fpass<T>(m, B, q, Minv, F, U, Dinv, stream);                                               \
+  }                                                                                                                  \
+  int rbd_fb_rnea_grad_fpass_dq_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* v,       \
+                                      const T* a, T gravity, T* dv, T* da, T* df, void* stream) {                    \
+    return launch_fb_grad_fpass<T, true>(m, B, q, qd, v, a, gravity, dv, da, df, stream);                            \
+  }                                                                                                                  \
+  int rbd_fb_rnea_grad_fpass_dqd_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* v,      \
+                                       T* dv, T* da, T* df, void* stream) {                                          \
+    return launch_fb_grad_fpass<T, false>(m, B, q, qd, v, nullptr, T(0), dv, da, df, stream);                        \
+  }                                                                                                                  \
+  int rbd_fb_rnea_grad_bpass_dq_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* f, T* df_dq,          \
+                                      T* dc_dq, void* stream) {                                                      \
+    return launch_fb_grad_bpass<T, true>(m, B, q, f, df_dq, 0, dc_dq, stream);                                       \
+  }                                                                                                                  \
+  int rbd_fb_rnea_grad_bpass_dqd_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, T* df_dqd,                    \
+                                       int use_velocity_damping, T* dc_dqd, void* stream) {                          \
+    return launch_fb_grad_bpass<T, false>(m, B, q, nullptr, df_dqd, use_velocity_damping, dc_dqd, stream);           \
   }                                                                                                                  \
   int rbd_fb_forward_dynamics_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* u, T* qdd, \
                                     T* Minv_out, void* stream) {                                                     \

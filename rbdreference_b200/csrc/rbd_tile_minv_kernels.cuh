@@ -87,16 +87,17 @@ __host__ __device__ inline size_t tile_minv_smem_vals(int n, int nslot, int maxd
   return (size_t)n * kTmTab * 32 + (s1 > s2 ? s1 : s2);
 }
 
-// Minv[row][j0 .. j0 + nc) <- v[0 .. nc)   (p points at column j0; `even`: p is 2-value aligned)
+// Minv[row][j0 .. j0 + nc) <- v[0 .. nc)   (p points at column j0; par = 0: p is 2-value aligned, 1: p + 1 is,
+// 2: nothing is known - the result's n*n is odd or its base is not 2-value aligned)
 template <typename T>
-__device__ __forceinline__ void tm_store_row(T* p, const T* v, int nc, bool even) {
+__device__ __forceinline__ void tm_store_row(T* p, const T* v, int nc, int par) {
   typedef typename Vec2<T>::type V2;
-  if (nc == kTmGC && even) {
+  if (nc == kTmGC && par == 0) {
     V2 a, b;
     a.x = v[0]; a.y = v[1]; b.x = v[2]; b.y = v[3];
     __stcs(reinterpret_cast<V2*>(p), a);
     __stcs(reinterpret_cast<V2*>(p) + 1, b);
-  } else if (nc == kTmGC) {
+  } else if (nc == kTmGC && par == 1) {
     V2 a;
     a.x = v[1]; a.y = v[2];
     __stcs(p, v[0]);
@@ -407,7 +408,7 @@ minv_tile_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
         // column j of Minv at row a == row j at column a (:799-804): a whole row segment per lane
         if (live) {
           const int orow = (st >> 26) & 31;
-          if (ocol >= 0) tm_store_row<T>(outk + orow * n + ocol, mij, nc, vec_ok && (((orow * n + ocol) & 1) == 0));
+          if (ocol >= 0) tm_store_row<T>(outk + orow * n + ocol, mij, nc, vec_ok ? ((orow * n + ocol) & 1) : 2);
           else {
 #pragma unroll
             for (int c = 0; c < GC; ++c)
@@ -423,7 +424,7 @@ minv_tile_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
 #pragma unroll 1
         for (int s = tp.g_sz[g]; s < tp.g_se[g]; ++s) {
           const int orow = (tp.steps[s] >> 26) & 31;
-          if (ocol >= 0) tm_store_row<T>(outk + orow * n + ocol, z, nc, vec_ok && (((orow * n + ocol) & 1) == 0));
+          if (ocol >= 0) tm_store_row<T>(outk + orow * n + ocol, z, nc, vec_ok ? ((orow * n + ocol) & 1) : 2);
           else {
 #pragma unroll
             for (int c = 0; c < GC; ++c)

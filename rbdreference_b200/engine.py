@@ -57,6 +57,7 @@ class RBDReference:
             self.model = robotObj if isinstance(robotObj, RobotModel) else compile_model(robotObj)
             self.n = self.nq = self.NB = self.model.n
             self._handle = _capi.ModelHandle(self.model)
+        self._fb = "fb_" if self.floating_base else ""       # C-ABI prefix of the per-pass helpers
         self._device = torch.device(device) if device is not None else None
         self._ee_handles = {}                       # (names, offset) -> compiled end-effector handle
         self._pipes = {}                            # device -> HostPipeline (streams + staging buffers)
@@ -139,8 +140,8 @@ class RBDReference:
     def _fixed_only(self, what: str):
         if self.floating_base:
             raise NotImplementedError(
-                "%s: no floating-base path (rnea, rnea_grad, minv, forward_dynamics and forward_dynamics_grad "
-                "are the floating-base entry points, SURVEY.md 8f rank 3)" % what)
+                "%s: no floating-base path (rnea, rnea_grad, minv, their eight per-pass helpers, forward_dynamics and "
+                "forward_dynamics_grad are the floating-base entry points, SURVEY.md 8f rank 3)" % what)
 
     # ---- caller-supplied result buffers ---------------------------------------------------------
     def _check_out(self, t, ctx: "_Ctx", shape, name: str):
@@ -244,22 +245,20 @@ class RBDReference:
     # ------------------------------------------------------------------------------------
     def rnea_fpass(self, q, qd, qdd=None, GRAVITY=-9.81):
         """RBDReference.py:559-598 -> (v, a, f), each (6, NB)."""
-        self._fixed_only("rnea_fpass")
         ctx = self._Ctx(self, q, 1)
-        n = self.n
-        dq, dqd, dqdd = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(qdd, (n,), "qdd")
-        v, a, f = ctx.empty(6, n), ctx.empty(6, n), ctx.empty(6, n)
-        self._call("rnea_fpass", ctx, dq, dqd, dqdd, float(GRAVITY), v, a, f)
+        n, NB = self.n, self.NB
+        dq, dqd, dqdd = ctx.dev(q, (self.nq,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(qdd, (n,), "qdd")
+        v, a, f = ctx.empty(6, NB), ctx.empty(6, NB), ctx.empty(6, NB)
+        self._call(self._fb + "rnea_fpass", ctx, dq, dqd, dqdd, float(GRAVITY), v, a, f)
         return ctx.ret(v), ctx.ret(a), ctx.ret(f)
 
     def rnea_bpass(self, q, f):
         """RBDReference.py:600-621 -> (c, f); `f` is accumulated in place and returned."""
-        self._fixed_only("rnea_bpass")
         ctx = self._Ctx(self, q, 1)
         n = self.n
-        dq, df = ctx.dev(q, (n,), "q"), ctx.dev(f, (6, n), "f")
+        dq, df = ctx.dev(q, (self.nq,), "q"), ctx.dev(f, (6, self.NB), "f")
         c = ctx.empty(n)
-        self._call("rnea_bpass", ctx, dq, df, c)
+        self._call(self._fb + "rnea_bpass", ctx, dq, df, c)
         return ctx.ret(c), ctx.write_back(f, df)
 
     def rnea(self, q, qd, qdd=None, GRAVITY=-9.81, f_ext=None, outputs="all"):
@@ -298,23 +297,21 @@ class RBDReference:
     # ------------------------------------------------------------------------------------
     def minv_bpass(self, q):
         """RBDReference.py:630-735 -> (Minv, F, U, Dinv) with Dinv = D (:698)."""
-        self._fixed_only("minv_bpass")
         ctx = self._Ctx(self, q, 1)
         n = self.n
-        dq = ctx.dev(q, (n,), "q")
+        dq = ctx.dev(q, (self.nq,), "q")
         Minv, F, U, D = ctx.empty(n, n), ctx.empty(n, 6, n), ctx.empty(n, 6), ctx.empty(n)
-        self._call("minv_bpass", ctx, dq, Minv, F, U, D)
+        self._call(self._fb + "minv_bpass", ctx, dq, Minv, F, U, D)
         return ctx.ret(Minv), ctx.ret(F), ctx.ret(U), ctx.ret(D)
 
     def minv_fpass(self, q, Minv, F, U, Dinv):
         """RBDReference.py:737-783 -> Minv (the caller's array, updated in place; F is rewritten)."""
-        self._fixed_only("minv_fpass")
         ctx = self._Ctx(self, q, 1)
         n = self.n
-        dq = ctx.dev(q, (n,), "q")
+        dq = ctx.dev(q, (self.nq,), "q")
         dM, dF = ctx.dev(Minv, (n, n), "Minv"), ctx.dev(F, (n, 6, n), "F")
         dU, dD = ctx.dev(U, (n, 6), "U"), ctx.dev(Dinv, (n,), "Dinv")
-        self._call("minv_fpass", ctx, dq, dM, dF, dU, dD)
+        self._call(self._fb + "minv_fpass", ctx, dq, dM, dF, dU, dD)
         ctx.write_back(F, dF)
         return ctx.write_back(Minv, dM)
 
@@ -340,44 +337,40 @@ class RBDReference:
     # ------------------------------------------------------------------------------------
     def rnea_grad_fpass_dq(self, q, qd, v, a, GRAVITY=-9.81):
         """RBDReference.py:1127-1187 -> (dv_dq, da_dq, df_dq), each (6, n, NB)."""
-        self._fixed_only("rnea_grad_fpass_dq")
         ctx = self._Ctx(self, q, 1)
-        n = self.n
-        dq, dqd = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd")
-        dv_, da_ = ctx.dev(v, (6, n), "v"), ctx.dev(a, (6, n), "a")
-        dv, da, df = ctx.empty(6, n, n), ctx.empty(6, n, n), ctx.empty(6, n, n)
-        self._call("rnea_grad_fpass_dq", ctx, dq, dqd, dv_, da_, float(GRAVITY), dv, da, df)
+        n, NB = self.n, self.NB
+        dq, dqd = ctx.dev(q, (self.nq,), "q"), ctx.dev(qd, (n,), "qd")
+        dv_, da_ = ctx.dev(v, (6, NB), "v"), ctx.dev(a, (6, NB), "a")
+        dv, da, df = ctx.empty(6, n, NB), ctx.empty(6, n, NB), ctx.empty(6, n, NB)
+        self._call(self._fb + "rnea_grad_fpass_dq", ctx, dq, dqd, dv_, da_, float(GRAVITY), dv, da, df)
         return ctx.ret(dv), ctx.ret(da), ctx.ret(df)
 
     def rnea_grad_fpass_dqd(self, q, qd, v):
         """RBDReference.py:1189-1255 -> (dv_dqd, da_dqd, df_dqd)."""
-        self._fixed_only("rnea_grad_fpass_dqd")
         ctx = self._Ctx(self, q, 1)
-        n = self.n
-        dq, dqd, dv_ = ctx.dev(q, (n,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(v, (6, n), "v")
-        dv, da, df = ctx.empty(6, n, n), ctx.empty(6, n, n), ctx.empty(6, n, n)
-        self._call("rnea_grad_fpass_dqd", ctx, dq, dqd, dv_, dv, da, df)
+        n, NB = self.n, self.NB
+        dq, dqd, dv_ = ctx.dev(q, (self.nq,), "q"), ctx.dev(qd, (n,), "qd"), ctx.dev(v, (6, NB), "v")
+        dv, da, df = ctx.empty(6, n, NB), ctx.empty(6, n, NB), ctx.empty(6, n, NB)
+        self._call(self._fb + "rnea_grad_fpass_dqd", ctx, dq, dqd, dv_, dv, da, df)
         return ctx.ret(dv), ctx.ret(da), ctx.ret(df)
 
     def rnea_grad_bpass_dq(self, q, f, df_dq):
         """RBDReference.py:1257-1297 -> dc_dq (n, n); `df_dq` is accumulated in place."""
-        self._fixed_only("rnea_grad_bpass_dq")
         ctx = self._Ctx(self, q, 1)
-        n = self.n
-        dq, df_, ddf = ctx.dev(q, (n,), "q"), ctx.dev(f, (6, n), "f"), ctx.dev(df_dq, (6, n, n), "df_dq")
+        n, NB = self.n, self.NB
+        dq, df_, ddf = ctx.dev(q, (self.nq,), "q"), ctx.dev(f, (6, NB), "f"), ctx.dev(df_dq, (6, n, NB), "df_dq")
         dc = ctx.empty(n, n)
-        self._call("rnea_grad_bpass_dq", ctx, dq, df_, ddf, dc)
+        self._call(self._fb + "rnea_grad_bpass_dq", ctx, dq, df_, ddf, dc)
         ctx.write_back(df_dq, ddf)
         return ctx.ret(dc)
 
     def rnea_grad_bpass_dqd(self, q, df_dqd, USE_VELOCITY_DAMPING=False):
         """RBDReference.py:1299-1343 -> dc_dqd (n, n); `df_dqd` is accumulated in place."""
-        self._fixed_only("rnea_grad_bpass_dqd")
         ctx = self._Ctx(self, q, 1)
-        n = self.n
-        dq, ddf = ctx.dev(q, (n,), "q"), ctx.dev(df_dqd, (6, n, n), "df_dqd")
+        n, NB = self.n, self.NB
+        dq, ddf = ctx.dev(q, (self.nq,), "q"), ctx.dev(df_dqd, (6, n, NB), "df_dqd")
         dc = ctx.empty(n, n)
-        self._call("rnea_grad_bpass_dqd", ctx, dq, ddf, 1 if USE_VELOCITY_DAMPING else 0, dc)
+        self._call(self._fb + "rnea_grad_bpass_dqd", ctx, dq, ddf, 1 if USE_VELOCITY_DAMPING else 0, dc)
         ctx.write_back(df_dqd, ddf)
         return ctx.ret(dc)
 
@@ -427,7 +420,7 @@ class RBDReference:
         Minv, F, U, D = self.minv_bpass(q)
         Minv = self.minv_fpass(q, Minv, F, U, D)
         if output_dense:
-            n = self.n
+            n = self.NB                                 # :799-804 loops over range(NB): with a floating base only that block
             iu = np.triu_indices(n, 1)
             if isinstance(Minv, torch.Tensor):
                 Minv[..., iu[1], iu[0]] = Minv[..., iu[0], iu[1]]

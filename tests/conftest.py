@@ -63,6 +63,12 @@ def load_fb_golden(name):
     return dict(np.load(os.path.join(GOLDEN_DIR, "fb_" + name + ".npz")))
 
 
+def load_fbpass_golden(name):
+    """tests/golden/fbpass_<name>.npz (oracle/make_golden.py --fbpass): every array the unmodified reference's eight
+    per-pass helpers take and return for floating-base robots."""
+    return dict(np.load(os.path.join(GOLDEN_DIR, "fbpass_" + name + ".npz")))
+
+
 def load_ee_golden(name):
     """tests/golden/ee_<name>.npz (oracle/make_golden.py --ee): the unmodified reference's
     end_effector_pose / end_effector_pose_gradient.  -> (q, [(names, offset, pose, grad), ...])"""

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FB_CASES, GOLDEN_CASES, TOL_F32, TOL_F64, load_ee_golden, load_fb_golden, make_fb_robot, make_robot, random_states, rel_err
+from conftest import FB_CASES, GOLDEN_CASES, TOL_F32, TOL_F64, load_ee_golden, load_fb_golden, load_fbpass_golden, make_fb_robot, make_robot, random_states, rel_err
 from oracle.rbd_oracle import BatchOracle
 
 pytestmark = pytest.mark.gpu
@@ -801,6 +801,74 @@ def test_floating_base_vs_reference_golden(name):
         RBDReference.set_kernel_variant(0)
     with pytest.raises(NotImplementedError):
         eng.crba(q)
+
+
+@requires_cuda
+@pytest.mark.parametrize("name", FB_CASES)
+def test_floating_base_pass_helpers_vs_reference_golden(name):
+    """The eight per-pass entry points of a floating-base robot against arrays of the unmodified reference: batched
+    (numpy and CUDA tensors), one knot point with reference shapes, in-place contracts, both precisions, and the
+    reference's own call sequence composed from the helpers."""
+    rb = make_fb_robot(name)
+    g = load_fbpass_golden(name)
+    q, qd, qdd = g["q"], g["qd"], g["qdd"]
+    for dtype, tol in ((torch.float64, TOL_F64), (torch.float32, TOL_F32)):
+        eng = _engine(rb, dtype)
+        v, a, f = eng.rnea_fpass(q, qd, qdd)
+        for got, key in ((v, "v"), (a, "a"), (f, "f")):
+            assert rel_err(got, g[key]) < tol, key
+        fa = _t(g["f"], dtype)
+        c, fr = eng.rnea_bpass(_t(q, dtype), fa)
+        assert fr is fa and rel_err(c.cpu().numpy(), g["c"]) < tol and rel_err(fa.cpu().numpy(), g["f_acc"]) < tol
+        Mb, Fb, U, D = eng.minv_bpass(q)
+        for got, key in ((Mb, "Minv_b"), (Fb, "F_b"), (U, "U"), (D, "Dinv")):
+            assert rel_err(got, g[key]) < tol * (5 if dtype == torch.float32 else 1), key
+        Mf, Ff = _t(g["Minv_b"], dtype), _t(g["F_b"], dtype)
+        out = eng.minv_fpass(_t(q, dtype), Mf, Ff, _t(g["U"], dtype), _t(g["Dinv"], dtype))
+        assert out is Mf
+        assert rel_err(Mf.cpu().numpy(), g["Minv_f"]) < tol * (5 if dtype == torch.float32 else 1)
+        assert rel_err(Ff.cpu().numpy(), g["F_f"]) < tol * (5 if dtype == torch.float32 else 1)
+        dv, da, df = eng.rnea_grad_fpass_dq(q, qd, g["v"], g["a"])
+        for got, key in ((dv, "dv_dq"), (da, "da_dq"), (df, "df_dq")):
+            assert rel_err(got, g[key]) < tol, key
+        dv, da, df = eng.rnea_grad_fpass_dqd(q, qd, g["v"])
+        for got, key in ((dv, "dv_dqd"), (da, "da_dqd"), (df, "df_dqd")):
+            assert rel_err(got, g[key]) < tol, key
+        dfa = _t(g["df_dq"], dtype)
+        dc = eng.rnea_grad_bpass_dq(_t(q, dtype), _t(g["f_acc"], dtype), dfa)
+        assert rel_err(dc.cpu().numpy(), g["dc_dq"]) < tol and rel_err(dfa.cpu().numpy(), g["df_dq_acc"]) < tol
+        dfa = _t(g["df_dqd"], dtype)
+        dc = eng.rnea_grad_bpass_dqd(_t(q, dtype), dfa)
+        assert rel_err(dc.cpu().numpy(), g["dc_dqd"]) < tol and rel_err(dfa.cpu().numpy(), g["df_dqd_acc"]) < tol
+        assert rel_err(eng.rnea_grad_bpass_dqd(q, g["df_dqd"].copy(), USE_VELOCITY_DAMPING=True), g["dc_dqd_damped"]) < tol
+    eng = _engine(rb)
+    # one knot point, reference shapes, numpy in place
+    f0 = g["f"][0].copy()
+    c0, fr0 = eng.rnea_bpass(q[0], f0)
+    assert fr0 is f0 and c0.shape == (eng.n,) and rel_err(f0, g["f_acc"][0]) < TOL_F64
+    M0, F0, U0, D0 = eng.minv_bpass(q[0])
+    assert M0.shape == (eng.n, eng.n) and F0.shape == (eng.n, 6, eng.n) and U0.shape == (eng.n, 6) and D0.shape == (eng.n,)
+    assert eng.minv_fpass(q[0], M0, F0, U0, D0) is M0 and rel_err(M0, g["Minv_f"][0]) < TOL_F64
+    # the reference's own call sequences (:1353-1367, :793-804) composed from the helpers equal the fused drivers
+    fb = load_fb_golden(name)
+    assert rel_err(eng.rnea_grad_passes(fb["q"], fb["qd"], fb["qdd"]), fb["dc_du"]) < TOL_F64
+    assert rel_err(eng.rnea_grad_passes(fb["q"], fb["qd"], fb["qdd"], USE_VELOCITY_DAMPING=True), fb["dc_du_damped"]) < TOL_F64
+    assert rel_err(eng.minv_passes(fb["q"]), fb["Minv"]) < TOL_F64
+    assert rel_err(eng.minv_passes(fb["q"], output_dense=False), fb["Minv_sparse"]) < TOL_F64
+
+
+@requires_cuda
+def test_floating_base_grad_fpass_dq_needs_six_bodies():
+    """RBDReference.py:1168 indexes bodies 0..5: the reference raises IndexError for smaller robots, the library refuses."""
+    from rbdreference_b200 import robots
+    from rbdreference_b200._capi import RbdError
+    rb = robots.FloatingBaseRobot(robots.random_tree(3, seed=4), name="tiny_fb")
+    eng = _engine(rb)
+    q, qd, qdd = rb.random_state(np.random.default_rng(0), 4)
+    v, a, f = eng.rnea_fpass(q, qd, qdd)
+    with pytest.raises(RbdError):
+        eng.rnea_grad_fpass_dq(q, qd, v, a)
+    eng.rnea_grad_fpass_dqd(q, qd, v)
 
 
 @requires_cuda

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import FB_CASES, GOLDEN_CASES, load_ee_golden, load_fb_golden, make_fb_robot, rel_err, random_states, make_robot
+from conftest import FB_CASES, GOLDEN_CASES, load_ee_golden, load_fb_golden, load_fbpass_golden, make_fb_robot, rel_err, random_states, make_robot
 from oracle.rbd_oracle import BatchOracle, ScalarOracle
 from oracle import build_ref
 
@@ -142,6 +142,43 @@ def test_floating_base_oracle_vs_golden(name):
         assert rel_err(so.forward_dynamics(q, qd, g["u"][k]), g["fd_qdd"][k]) < PIN
         r1, r2 = so.forward_dynamics_grad(q, qd, g["u"][k])
         assert rel_err(r1, g["fd_dq"][k]) < 10 * PIN and rel_err(r2, g["fd_dqd"][k]) < 10 * PIN
+
+
+@pytest.mark.parametrize("name", FB_CASES)
+def test_floating_base_pass_oracle_vs_reference_golden(name):
+    """The eight floating-base per-pass restatements against arrays of the unmodified reference, including the
+    in-place behaviour (f, Minv and F, df are updated through the caller's arrays)."""
+    from oracle.rbd_oracle_fb import FloatingScalarOracle
+    rb = make_fb_robot(name)
+    so = FloatingScalarOracle(rb)
+    g = load_fbpass_golden(name)
+    tol = 1e-11
+    for k in range(g["q"].shape[0]):
+        q, qd, qdd = g["q"][k], g["qd"][k], g["qdd"][k]
+        v, a, f = so.rnea_fpass(q, qd, qdd)
+        for got, key in ((v, "v"), (a, "a"), (f, "f")):
+            assert rel_err(got, g[key][k]) < tol, key
+        fa = g["f"][k].copy()
+        c, fr = so.rnea_bpass(q, fa)
+        assert fr is fa and rel_err(c, g["c"][k]) < tol and rel_err(fa, g["f_acc"][k]) < tol
+        Mb, Fb, U, D = so.minv_bpass(q)
+        for got, key in ((Mb, "Minv_b"), (Fb, "F_b"), (U, "U"), (D, "Dinv")):
+            assert rel_err(got, g[key][k]) < tol, key
+        Mf, Ff = g["Minv_b"][k].copy(), g["F_b"][k].copy()
+        assert so.minv_fpass(q, Mf, Ff, g["U"][k], g["Dinv"][k]) is Mf
+        assert rel_err(Mf, g["Minv_f"][k]) < tol and rel_err(Ff, g["F_f"][k]) < tol
+        dv, da, df = so.rnea_grad_fpass_dq(q, qd, g["v"][k], g["a"][k])
+        for got, key in ((dv, "dv_dq"), (da, "da_dq"), (df, "df_dq")):
+            assert rel_err(got, g[key][k]) < tol, key
+        dv, da, df = so.rnea_grad_fpass_dqd(q, qd, g["v"][k])
+        for got, key in ((dv, "dv_dqd"), (da, "da_dqd"), (df, "df_dqd")):
+            assert rel_err(got, g[key][k]) < tol, key
+        dfa = g["df_dq"][k].copy()
+        assert rel_err(so.rnea_grad_bpass_dq(q, g["f_acc"][k], dfa), g["dc_dq"][k]) < tol
+        assert rel_err(dfa, g["df_dq_acc"][k]) < tol
+        dfa = g["df_dqd"][k].copy()
+        assert rel_err(so.rnea_grad_bpass_dqd(q, dfa), g["dc_dqd"][k]) < tol and rel_err(dfa, g["df_dqd_acc"][k]) < tol
+        assert rel_err(so.rnea_grad_bpass_dqd(q, g["df_dqd"][k].copy(), USE_VELOCITY_DAMPING=True), g["dc_dqd_damped"][k]) < tol
 
 
 def test_floating_base_identities():
