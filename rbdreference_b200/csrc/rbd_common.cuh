@@ -212,6 +212,66 @@ __device__ __forceinline__ T dot6(const T* s, const T* x) {
   return acc;
 }
 
+// ---- 1-D bulk copies (TMA engine, cp.async.bulk) between a warp's shared-memory tile and its contiguous slab in HBM ----
+// A tile that has the exact layout of the slab moves with ONE instruction issued by one lane instead of count / 32
+// load + store pairs per lane: the LSU issue slots stay free for the arithmetic and the copy engine works in the
+// background.  Requirements of the instruction: both addresses 16-byte aligned, size a multiple of 16 bytes - checked
+// at run time (warp-uniform); `false` tells the caller to fall back to its element loop.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// shared -> global.  Every lane calls (the fence orders each lane's own generic-proxy writes to the tile before the
+// async proxy reads them); completion is awaited with warp_bulk_store_wait before the tile is written again.
+template <typename T>
+__device__ __forceinline__ bool warp_bulk_store(T* __restrict__ gdst, const T* ssrc, int count, int lane) {
+  const unsigned bytes = (unsigned)count * (unsigned)sizeof(T);
+  if (((bytes | (unsigned)(uintptr_t)gdst | smem_u32(ssrc)) & 15u) != 0u || bytes == 0u) return false;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  return true;
+}
+// the bulk stores this warp issued have finished READING shared memory (the tile may be rewritten)
+__device__ __forceinline__ void warp_bulk_store_wait(int lane) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+}
+
+// global -> shared with mbarrier completion.  `bar` is an 8-byte shared-memory word owned by the warp, initialised
+// once with warp_bulk_bar_init; `phase` is the warp's phase bit (flipped by the caller after every wait).
+__device__ __forceinline__ void warp_bulk_bar_init(unsigned long long* bar, int lane) {
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+}
+template <typename T>
+__device__ __forceinline__ bool warp_bulk_load(T* sdst, const T* __restrict__ gsrc, int count, unsigned long long* bar, int lane) {
+  const unsigned bytes = (unsigned)count * (unsigned)sizeof(T);
+  if (((bytes | (unsigned)(uintptr_t)gsrc | smem_u32(sdst)) & 15u) != 0u || bytes == 0u) return false;
+  __syncwarp();                                          // nobody still reads the tile
+  if (lane == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+  }
+  return true;
+}
+__device__ __forceinline__ void warp_bulk_load_wait(unsigned long long* bar, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+
 // Cooperative store of per-lane result blocks: lane k of the warp holds the NV values of knot point b0 + k
 // (in memory order) in `vals` (registers / local memory); dst + (b0 + k) * NV is where they go.  32 values
 // per lane are transposed through `tile` ([32][33]) at a time, so every store instruction writes 256

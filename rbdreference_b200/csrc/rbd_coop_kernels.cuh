@@ -308,6 +308,7 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
     // knot point of the warp, and every body reads back PS(i) - PS(subtree_end(i)).
     {
       constexpr int K0 = CONLY ? 22 : 0;                      // rnea only needs the force composite (22..27)
+      if (!CONLY) warp_bulk_store_wait(lane);                 // the previous slab has left the tile
       T* cs = tile;                                           // [32][29], the tile is not live yet
       T* mine = cs + lane * kCoopScanStride;
 #pragma unroll
@@ -452,7 +453,9 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
         const int64_t first = grp * IPW;
         const int nk = (int)((B - first) < IPW ? (B - first) : IPW);
         T* dst = dc_du + first * n * n2;
-        if (!SPLIT) {
+        if (!SPLIT && warp_bulk_store(dst, tile, nk * n * n2, lane)) {
+          // one cp.async.bulk for the warp's slab (awaited before the tile is written again)
+        } else if (!SPLIT) {
           typedef typename Vec2<T>::type V2;
           const int count = nk * n * n2;
           if (((IPW * n * n2) & 1) == 0 && nk == IPW && (reinterpret_cast<uintptr_t>(dc_du) & (sizeof(V2) - 1)) == 0) {
@@ -472,6 +475,7 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
       __syncwarp();
     }
   }
+  if (!CONLY) warp_bulk_store_wait(lane);                     // shared memory must outlive the copies
 }
 
 }  // namespace rbd

@@ -183,7 +183,9 @@ __device__ __forceinline__ void minv_column_phases(int n, int maxdepth, int maxc
   // ------------------------------------------------------------------ coalesced slab write
   {
     const int count = nknots * nn;
-    if (pair_ok && count == tile_vals && (reinterpret_cast<uintptr_t>(dst) & (sizeof(V2) - 1)) == 0) {
+    if (warp_bulk_store(dst, tile, count, lane)) {
+      warp_bulk_store_wait(lane);                         // the caller rewrites the tile right away
+    } else if (pair_ok && count == tile_vals && (reinterpret_cast<uintptr_t>(dst) & (sizeof(V2) - 1)) == 0) {
       for (int k = lane; k < (tile_vals >> 1); k += 32) __stcs(reinterpret_cast<V2*>(dst) + k, reinterpret_cast<const V2*>(tile)[k]);
     } else {
       for (int k = lane; k < count; k += 32) __stcs(dst + k, tile[k]);

@@ -21,11 +21,12 @@ __host__ __device__ inline int cp_pitch(int n) { return n | 1; }
 // values of T per warp
 __host__ __device__ inline int cp_fpass_warp_vals(int n, int G) {
   const int ipw = 32 / G;
-  return ipw * (3 * 6 * n * cp_pitch(n) + 12 * n + 3 * n);      // dv da df tiles | v a rows | f1 f2 qd
+  return (ipw * (3 * 6 * n * cp_pitch(n) + 12 * n + 3 * n) + 3) & ~3;      // dv da df tiles | v a rows | f1 f2 qd
 }
 __host__ __device__ inline int cp_bpass_warp_vals(int n, int G) {
   const int ipw = 32 / G;
-  return ipw * (6 * n * cp_pitch(n) + n * n + 6 * n + 2 * n);   // df tile | dc tile | f rows | f1 f2
+  // df tile | dc tile | f rows | f1 f2 | mbarrier of the bulk load (last two values), rounded to 16 / 32 bytes
+  return (ipw * (6 * n * cp_pitch(n) + n * n + 6 * n + 2 * n) + 2 + 3) & ~3;
 }
 
 __device__ __forceinline__ void cp_async_val(double* dst, const double* src) {
@@ -35,6 +36,9 @@ __device__ __forceinline__ void cp_async_val(float* dst, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
+// Tiles of an odd n are dense (pitch = n): they have the exact layout of the warp's slab in HBM and move with one
+// cp.async.bulk per tensor (warp_bulk_store / warp_bulk_load, rbd_common.cuh); padded tiles (even n) and slabs the
+// instruction cannot take (16-byte rule) go through cp_copy:
 // copy `count` values of a [rows][n] slab between global memory and a tile of pitch cp_pitch(n).
 // Global -> shared uses cp.async: all of a lane's copies are in flight at once (a load + store per
 // iteration keeps one load per lane in flight and is latency-bound); the caller's __syncwarp follows
@@ -95,7 +99,7 @@ grad_fpass_coop_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T
       sv[e] = ok ? v[first * 6 * n + e] : T(0);
       if (DQ) sa[e] = ok ? a[first * 6 * n + e] : T(0);
     }
-    __syncwarp();
+    warp_bulk_store_wait(lane);                           // the previous pass's tiles have left (includes __syncwarp)
     if (valid) {
       T* mv = tv + g * tvals + c * np;                    // element (r, c, i) at (r n + c) np + i
       T* ma = ta + g * tvals + c * np;
@@ -167,11 +171,15 @@ grad_fpass_coop_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T
       }
     }
     __syncwarp();
-    cp_copy<T, false>(tv, dv + first * slab, n, nk * 6 * n * n, IPW * 6 * n * n, lane);
-    cp_copy<T, false>(ta, da + first * slab, n, nk * 6 * n * n, IPW * 6 * n * n, lane);
-    cp_copy<T, false>(tf, df + first * slab, n, nk * 6 * n * n, IPW * 6 * n * n, lane);
+    {
+      const int cnt = nk * 6 * n * n;
+      if (!(np == n && warp_bulk_store(dv + first * slab, tv, cnt, lane))) cp_copy<T, false>(tv, dv + first * slab, n, cnt, IPW * 6 * n * n, lane);
+      if (!(np == n && warp_bulk_store(da + first * slab, ta, cnt, lane))) cp_copy<T, false>(ta, da + first * slab, n, cnt, IPW * 6 * n * n, lane);
+      if (!(np == n && warp_bulk_store(df + first * slab, tf, cnt, lane))) cp_copy<T, false>(tf, df + first * slab, n, cnt, IPW * 6 * n * n, lane);
+    }
     __syncwarp();
   }
+  warp_bulk_store_wait(lane);                             // shared memory must outlive the copies
 }
 
 // ---- rnea_grad_bpass_dq / _dqd (:1257-1297, :1299-1343) --------------------------------------
@@ -192,11 +200,16 @@ grad_bpass_coop_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T
   T* tc = td + IPW * tvals;                               // [IPW][n][n]
   T* sf = tc + IPW * nn;                                  // [IPW][6][n]
   T* sj = sf + IPW * 6 * n;                               // [IPW][n][2]
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(ws + cp_bpass_warp_vals(n, G) - 2);
+  unsigned phase = 0;
+  warp_bulk_bar_init(bar, lane);
   const int64_t slab = (int64_t)6 * n * n;
   const int64_t ngroups = (B + IPW - 1) / IPW;
   for (int64_t grp = (int64_t)blockIdx.x * nwarps + warp; grp < ngroups; grp += (int64_t)gridDim.x * nwarps) {
     const int64_t first = grp * IPW;
     const int nk = (int)((B - first) < IPW ? (B - first) : IPW);
+    warp_bulk_store_wait(lane);                           // the previous pass's tiles have left
+    const bool bulk_in = np == n && warp_bulk_load(td, df + first * slab, nk * 6 * n * n, bar, lane);
     if (valid) {
       int64_t b = first + g;
       if (b >= B) b = B - 1;
@@ -207,7 +220,12 @@ grad_bpass_coop_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T
     if (DQ) {
       for (int e = lane; e < IPW * 6 * n; e += 32) sf[e] = e < nk * 6 * n ? f[first * 6 * n + e] : T(0);
     }
-    cp_copy<T, true>(td, df + first * slab, n, nk * 6 * n * n, IPW * 6 * n * n, lane);
+    if (bulk_in) {
+      warp_bulk_load_wait(bar, phase);
+      phase ^= 1u;
+    } else {
+      cp_copy<T, true>(td, df + first * slab, n, nk * 6 * n * n, IPW * 6 * n * n, lane);
+    }
     __syncwarp();
     if (valid) {
       T* md = td + g * tvals + c * np;
@@ -242,10 +260,13 @@ grad_bpass_coop_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T
       }
     }
     __syncwarp();
-    cp_copy<T, false>(td, df + first * slab, n, nk * 6 * n * n, IPW * 6 * n * n, lane);
-    for (int e = lane; e < nk * nn; e += 32) __stcs(dc + first * nn + e, tc[e]);
+    if (!(np == n && warp_bulk_store(df + first * slab, td, nk * 6 * n * n, lane)))
+      cp_copy<T, false>(td, df + first * slab, n, nk * 6 * n * n, IPW * 6 * n * n, lane);
+    if (!warp_bulk_store(dc + first * nn, tc, nk * nn, lane))
+      for (int e = lane; e < nk * nn; e += 32) __stcs(dc + first * nn + e, tc[e]);
     __syncwarp();
   }
+  warp_bulk_store_wait(lane);                             // shared memory must outlive the copies
 }
 
 }  // namespace rbd

@@ -57,17 +57,32 @@ def gather_to_all(local: torch.Tensor, B: int, group=None) -> torch.Tensor:
 
 
 def gather_to_rank(local: torch.Tensor, B: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
-    """Gather result slices onto rank `dst` only (other ranks get None)."""
+    """Gather result slices onto rank `dst` of `group` only (other ranks get None).
+
+    `dst` and the slice owners are ranks INSIDE `group`; point-to-point calls take global ranks, so they are
+    translated with `dist.get_global_rank` (a sub-group whose members are not ranks 0..k-1 would otherwise
+    talk to the wrong peers or dead-lock)."""
     rank, world = _world(group)
     if world == 1:
         return local
+    if not (0 <= dst < world):
+        raise ValueError("dst %d outside the group of size %d" % (dst, world))
     sizes = [shard_bounds(B, r, world)[1] - shard_bounds(B, r, world)[0] for r in range(world)]
+    if local.shape[0] != sizes[rank]:
+        raise ValueError("local slice has %d rows, expected %d" % (local.shape[0], sizes[rank]))
+
+    def to_global(r: int) -> int:
+        return dist.get_global_rank(group, r) if group is not None else r
+
     if rank == dst:
-        parts = [torch.empty((s,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for s in sizes]
-        parts[dst] = local.contiguous()
-        reqs = [dist.irecv(parts[r], src=r, group=group) for r in range(world) if r != dst]
+        out = torch.empty((B,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        offs = [shard_bounds(B, r, world)[0] for r in range(world)]
+        out[offs[dst]: offs[dst] + sizes[dst]] = local
+        reqs = [dist.irecv(out[offs[r]: offs[r] + sizes[r]], src=to_global(r), group=group)
+                for r in range(world) if r != dst and sizes[r] > 0]
         for r in reqs:
             r.wait()
-        return torch.cat(parts, dim=0)
-    dist.send(local.contiguous(), dst=dst, group=group)
+        return out
+    if sizes[rank] > 0:
+        dist.send(local.contiguous(), dst=to_global(dst), group=group)
     return None

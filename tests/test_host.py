@@ -209,28 +209,45 @@ import torch, torch.distributed as dist
 from rbdreference_b200.dist import shard_bounds, gather_to_all, gather_to_rank
 dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 rank, world = dist.get_rank(), dist.get_world_size()
-for B in (10, 7):
+for B in (10, 7, 1):                      # even, ragged, fewer knot points than ranks
     full = torch.arange(B * 3, dtype=torch.float64).reshape(B, 3)
     lo, hi = shard_bounds(B, rank, world)
     local = full[lo:hi].clone()
     assert torch.equal(gather_to_all(local, B), full)
-    got = gather_to_rank(local, B, dst=0)
-    assert (got is None) == (rank != 0)
-    if rank == 0:
-        assert torch.equal(got, full)
+    for dst in range(world):
+        got = gather_to_rank(local, B, dst=dst)
+        assert (got is None) == (rank != dst)
+        if rank == dst:
+            assert torch.equal(got, full)
+if world >= 3:                            # a sub-group that does not start at global rank 0: group ranks != global ranks
+    members = list(range(1, world))
+    grp = dist.new_group(members)
+    if rank in members:
+        gr, gw = dist.get_rank(grp), len(members)
+        for B in (9, 4):
+            full = torch.arange(B * 2, dtype=torch.float64).reshape(B, 2)
+            lo, hi = shard_bounds(B, gr, gw)
+            local = full[lo:hi].clone()
+            assert torch.equal(gather_to_all(local, B, group=grp), full)
+            got = gather_to_rank(local, B, dst=gw - 1, group=grp)
+            assert (got is None) == (gr != gw - 1)
+            if gr == gw - 1:
+                assert torch.equal(got, full)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
 
 
-def test_two_rank_gloo_gather(tmp_path):
-    """world_size-2 run of the sharding + gather plumbing on CPU (gloo)."""
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_gather(tmp_path, world):
+    """world_size-2 and -3 runs of the sharding + gather plumbing on CPU (gloo): ragged batches, every destination
+    rank, and (world 3) a sub-group whose group ranks differ from the global ranks."""
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER)
-    env = dict(os.environ, RBD_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", WORLD_SIZE="2")
+    env = dict(os.environ, RBD_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29613 + world), WORLD_SIZE=str(world))
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
-                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(world)]
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
