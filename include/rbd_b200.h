@@ -295,6 +295,18 @@ int rbd_fb_forward_dynamics_grad_f64(const rbd_fb_model_t* m, int64_t B, const d
 int rbd_fb_forward_dynamics_grad_f32(const rbd_fb_model_t* m, int64_t B, const float* q, const float* qd, const float* u,
                                      float* qdd_dq, float* qdd_dqd, float* qdd_out, void* stream);
 
+/* ---- scratch memory ------------------------------------------------------------------------------ */
+/* forward_dynamics(_grad) and the hybrid minv kernel take stream-ordered temporaries from one private memory pool per
+ * device that KEEPS what it has allocated (no driver call on the steady-state path; the memory is invisible to
+ * the caller's own allocator: Atlas forward_dynamics_grad on 2^20 knot points holds 23 GB).
+ * rbd_trim_scratch returns everything above keep_bytes of the CURRENT device's pool to the driver (call it after a
+ * large one-off batch; synchronise the streams that used the library first).
+ * rbd_prepare_device creates the pool of `device` ahead of time: the first call that needs it must not happen
+ * under CUDA-graph capture (pool creation is not capturable); rbd_model_create prepares the device that is
+ * current at creation. */
+int rbd_trim_scratch(int64_t keep_bytes);
+int rbd_prepare_device(int device);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
 /* Runs a dependent-chain FMA micro-benchmark on `stream`'s device and returns the achieved
  * FLOP/s (2 per FMA) in *flops_per_s; is_f64 selects DFMA or FFMA.  Used only to put a measured

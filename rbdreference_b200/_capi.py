@@ -16,7 +16,7 @@ FUSED_SYMBOLS = ["rnea", "rnea_grad", "minv", "forward_dynamics", "forward_dynam
 PLAIN_SYMBOLS = ["rbd_abi_version", "rbd_last_error_string", "rbd_model_create", "rbd_model_destroy",
                  "rbd_model_num_dof", "rbd_model_uses_world_kernels", "rbd_set_kernel_variant",
                  "rbd_model_set_kernel_variant",
-                 "rbd_measure_fma_peak", "rbd_launch_count",
+                 "rbd_measure_fma_peak", "rbd_launch_count", "rbd_trim_scratch", "rbd_prepare_device",
                  "rbd_ee_model_create", "rbd_ee_model_destroy", "rbd_ee_model_num_ee",
                  "rbd_fb_model_create", "rbd_fb_model_destroy", "rbd_fb_model_num_vel"]
 FB_SYMBOLS = ["fb_rnea", "fb_rnea_grad", "fb_minv", "fb_forward_dynamics", "fb_forward_dynamics_grad"] + ["fb_" + p for p in PASS_SYMBOLS]
@@ -78,6 +78,8 @@ def load_library():
     lib.rbd_model_set_kernel_variant.argtypes = [c_void_p, c_int]
     lib.rbd_measure_fma_peak.argtypes = [c_int, POINTER(c_double), POINTER(c_double), c_void_p]
     lib.rbd_launch_count.restype = c_int64
+    lib.rbd_trim_scratch.argtypes = [c_int64]
+    lib.rbd_prepare_device.argtypes = [c_int]
     lib.rbd_ee_model_create.argtypes = [POINTER(RbdEeDesc), POINTER(c_void_p)]
     lib.rbd_ee_model_destroy.argtypes = [c_void_p]
     lib.rbd_ee_model_num_ee.argtypes = [c_void_p]

@@ -516,6 +516,26 @@ void build_tile_plan(const FastModel<double>& fm, const DfsPlan& plan, const Coo
   tp.g_begin[kTmMaxWarps] = pos;
 }
 
+template <typename T>
+void fill_chain_model(const FastModel<double>& fm, ChainModel<T>& cm) {
+  std::memset(&cm, 0, sizeof(cm));
+  cm.n = fm.n;
+  cm.r_const = 1;
+  for (int i = 0; i < fm.n && i < kChainMaxN; ++i) {
+    cm.kind[i] = fm.kind[i];
+    typename ChainModel<T>::Body& b = cm.b[i];
+    for (int k = 0; k < 9; ++k) { b.EA[k] = (T)fm.EA[i][k]; b.EB[k] = (T)fm.EB[i][k]; b.EC[k] = (T)fm.EC[i][k]; }
+    for (int k = 0; k < 3; ++k) {
+      b.rA[k] = (T)fm.rA[i][k]; b.rB[k] = (T)fm.rB[i][k]; b.rC[k] = (T)fm.rC[i][k];
+      b.axis[k] = (T)fm.axis[i][k]; b.h[k] = (T)fm.h[i][k];
+      if (fm.rB[i][k] != 0.0 || fm.rC[i][k] != 0.0) cm.r_const = 0;
+    }
+    for (int k = 0; k < 6; ++k) b.Ib[k] = (T)fm.Ib[i][k];
+    b.mass = (T)fm.mass[i];
+    b.damping = (T)fm.damping[i];
+  }
+}
+
 void narrow_fast_model(const FastModel<double>& a, FastModel<float>& b) {
   std::memset(&b, 0, sizeof(b));
   b.n = a.n; b.n_slot_a = a.n_slot_a; b.n_slot_b = a.n_slot_b; b.rigid = a.rigid; b.has_prismatic = a.has_prismatic;
@@ -588,6 +608,8 @@ int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out) {
     }
   }
   build_tile_plan(m->fd_dfs, m->plan, m->coop_minv, m->coop.maxdepth, m->tile);
+  fill_chain_model<double>(m->fd, m->chain_d);
+  fill_chain_model<float>(m->fd, m->chain_f);
   {
     // create the current device's scratch pool now, so that no call made later under CUDA-graph
     // capture has to create it (pool creation is not allowed while a global-mode capture is open)
@@ -621,63 +643,82 @@ int rbd_model_set_kernel_variant(rbd_model_t* m, int variant) {
 }
 int rbd_model_uses_world_kernels(const rbd_model_t* m) { return (m && m->fast_ok) ? 1 : 0; }
 
+int rbd_prepare_device(int device) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    cudaGetLastError();
+    return fail(RBD_E_NO_DEVICE, "rbd_prepare_device: no such CUDA device");
+  }
+  return scratch_pool(device) ? 0 : fail(RBD_E_NO_DEVICE, "rbd_prepare_device: cannot create the scratch memory pool");
+}
+
+int rbd_trim_scratch(int64_t keep_bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return fail(RBD_E_NO_DEVICE, "rbd_trim_scratch: no CUDA device"); }
+  cudaMemPool_t pool = scratch_pool(dev);
+  if (!pool) return fail(RBD_E_NO_DEVICE, "rbd_trim_scratch: cannot create the scratch memory pool");
+  cudaError_t e = cudaMemPoolTrimTo(pool, keep_bytes < 0 ? 0 : (size_t)keep_bytes);
+  if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+  return 0;
+}
+
 #define RBD_DEFINE(SUF, T)                                                                                           \
   int rbd_rnea_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* qd, const T* qdd, T gravity, T* c, T* v,  \
                      T* a, T* f, void* stream) {                                                                     \
-    return launch_rnea<T>(m, B, q, qd, qdd, gravity, c, v, a, f, stream);                                            \
+    RBD_NVTX(__func__); return launch_rnea<T>(m, B, q, qd, qdd, gravity, c, v, a, f, stream);                                            \
   }                                                                                                                  \
   int rbd_rnea_grad_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* qd, const T* qdd, T gravity,         \
                           int use_velocity_damping, T* dc_du, T* c_out, void* stream) {                              \
-    return launch_rnea_grad<T>(m, B, q, qd, qdd, gravity, use_velocity_damping, dc_du, c_out, stream);               \
+    RBD_NVTX(__func__); return launch_rnea_grad<T>(m, B, q, qd, qdd, gravity, use_velocity_damping, dc_du, c_out, stream);               \
   }                                                                                                                  \
   int rbd_minv_##SUF(const rbd_model_t* m, int64_t B, const T* q, int output_dense, T* Minv, void* stream) {         \
-    return launch_minv<T>(m, B, q, output_dense, Minv, stream);                                                      \
+    RBD_NVTX(__func__); return launch_minv<T>(m, B, q, output_dense, Minv, stream);                                                      \
   }                                                                                                                  \
   int rbd_crba_##SUF(const rbd_model_t* m, int64_t B, const T* q, T* H, void* stream) {                              \
-    return launch_crba<T>(m, B, q, H, stream);                                                                       \
+    RBD_NVTX(__func__); return launch_crba<T>(m, B, q, H, stream);                                                                       \
   }                                                                                                                  \
   int rbd_aba_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* qd, const T* tau, T gravity, T* qdd,       \
                     void* stream) {                                                                                  \
-    return launch_aba<T>(m, B, q, qd, tau, gravity, qdd, stream);                                                    \
+    RBD_NVTX(__func__); return launch_aba<T>(m, B, q, qd, tau, gravity, qdd, stream);                                                    \
   }                                                                                                                  \
   int rbd_rnea_fpass_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* qd, const T* qdd, T gravity, T* v,  \
                            T* a, T* f, void* stream) {                                                               \
-    return launch_rnea_fpass<T>(m, B, q, qd, qdd, gravity, v, a, f, stream);                                         \
+    RBD_NVTX(__func__); return launch_rnea_fpass<T>(m, B, q, qd, qdd, gravity, v, a, f, stream);                                         \
   }                                                                                                                  \
   int rbd_rnea_bpass_##SUF(const rbd_model_t* m, int64_t B, const T* q, T* f, T* c, void* stream) {                  \
-    return launch_rnea_bpass<T>(m, B, q, f, c, stream);                                                              \
+    RBD_NVTX(__func__); return launch_rnea_bpass<T>(m, B, q, f, c, stream);                                                              \
   }                                                                                                                  \
   int rbd_rnea_grad_fpass_dq_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* qd, const T* v,             \
                                    const T* a, T gravity, T* dv, T* da, T* df, void* stream) {                       \
-    return launch_grad_fpass<T, true>(m, B, q, qd, v, a, gravity, dv, da, df, stream);                               \
+    RBD_NVTX(__func__); return launch_grad_fpass<T, true>(m, B, q, qd, v, a, gravity, dv, da, df, stream);                               \
   }                                                                                                                  \
   int rbd_rnea_grad_fpass_dqd_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* qd, const T* v, T* dv,     \
                                     T* da, T* df, void* stream) {                                                    \
-    return launch_grad_fpass<T, false>(m, B, q, qd, v, nullptr, T(0), dv, da, df, stream);                           \
+    RBD_NVTX(__func__); return launch_grad_fpass<T, false>(m, B, q, qd, v, nullptr, T(0), dv, da, df, stream);                           \
   }                                                                                                                  \
   int rbd_rnea_grad_bpass_dq_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* f, T* df_dq, T* dc_dq,      \
                                    void* stream) {                                                                   \
-    return launch_grad_bpass<T, true>(m, B, q, f, df_dq, 0, dc_dq, stream);                                          \
+    RBD_NVTX(__func__); return launch_grad_bpass<T, true>(m, B, q, f, df_dq, 0, dc_dq, stream);                                          \
   }                                                                                                                  \
   int rbd_rnea_grad_bpass_dqd_##SUF(const rbd_model_t* m, int64_t B, const T* q, T* df_dqd,                          \
                                     int use_velocity_damping, T* dc_dqd, void* stream) {                             \
-    return launch_grad_bpass<T, false>(m, B, q, nullptr, df_dqd, use_velocity_damping, dc_dqd, stream);              \
+    RBD_NVTX(__func__); return launch_grad_bpass<T, false>(m, B, q, nullptr, df_dqd, use_velocity_damping, dc_dqd, stream);              \
   }                                                                                                                  \
   int rbd_minv_bpass_##SUF(const rbd_model_t* m, int64_t B, const T* q, T* Minv, T* F, T* U, T* Dinv,                \
                            void* stream) {                                                                           \
-    return launch_minv_bpass<T>(m, B, q, Minv, F, U, Dinv, stream);                                                  \
+    RBD_NVTX(__func__); return launch_minv_bpass<T>(m, B, q, Minv, F, U, Dinv, stream);                                                  \
   }                                                                                                                  \
   int rbd_minv_fpass_##SUF(const rbd_model_t* m, int64_t B, const T* q, T* Minv, T* F, const T* U, const T* Dinv,    \
                            void* stream) {                                                                           \
-    return launch_minv_fpass<T>(m, B, q, Minv, F, U, Dinv, stream);                                                  \
+    RBD_NVTX(__func__); return launch_minv_fpass<T>(m, B, q, Minv, F, U, Dinv, stream);                                                  \
   }                                                                                                                  \
   int rbd_forward_dynamics_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* qd, const T* u, T* qdd,       \
                                  T* Minv_out, void* stream) {                                                        \
-    return launch_forward_dynamics<T>(m, B, q, qd, u, qdd, Minv_out, stream);                                        \
+    RBD_NVTX(__func__); return launch_forward_dynamics<T>(m, B, q, qd, u, qdd, Minv_out, stream);                                        \
   }                                                                                                                  \
   int rbd_forward_dynamics_grad_##SUF(const rbd_model_t* m, int64_t B, const T* q, const T* qd, const T* u,          \
                                       T* qdd_dq, T* qdd_dqd, T* qdd_out, void* stream) {                             \
-    return launch_forward_dynamics_grad<T>(m, B, q, qd, u, qdd_dq, qdd_dqd, qdd_out, stream);                        \
+    RBD_NVTX(__func__); return launch_forward_dynamics_grad<T>(m, B, q, qd, u, qdd_dq, qdd_dqd, qdd_out, stream);                        \
   }
 
 RBD_DEFINE(f64, double)

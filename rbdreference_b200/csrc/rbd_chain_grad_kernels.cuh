@@ -36,6 +36,25 @@ __host__ __device__ inline size_t chain_grad_smem_pairs(int n) {
   return (size_t)(n > 2 ? n - 2 : 0) * kChainRowPairs + kChainRow0Pairs;
 }
 
+constexpr int kChainMaxN = 8;
+
+// The robot as this kernel reads it: one contiguous record per body (the kernel walks the bodies with a run-time
+// index, so its constant-bank reads are indexed loads; a body's 50 values in 4 consecutive cache lines instead of
+// ten tables 2.3 KB apart keep them in the first-level constant cache - ncu: short-scoreboard stalls on the FMAs
+// that consume them).
+template <typename T>
+struct ChainModel {
+  int n;
+  int r_const;                    // rB = rC = 0 for every body: r(q) = rA (revolute joints through the child's origin)
+  int kind[kChainMaxN];
+  struct Body {
+    T EA[9], EB[9], EC[9];        // E_J(q) = EA + EB f1 + EC f2
+    T rA[3], rB[3], rC[3];
+    T axis[3];
+    T mass, h[3], Ib[6], damping;
+  } b[kChainMaxN];
+};
+
 template <typename T> __device__ __forceinline__ void stcs2(T* p, T x, T y);
 template <> __device__ __forceinline__ void stcs2<double>(double* p, double x, double y) {
   __stcs(reinterpret_cast<double2*>(p), make_double2(x, y));
@@ -46,9 +65,9 @@ template <> __device__ __forceinline__ void stcs2<float>(float* p, float x, floa
 
 template <typename T, int N>
 __global__ void __launch_bounds__(32, 8)
-rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const T* __restrict__ q,
+rnea_grad_chain_kernel(const __grid_constant__ ChainModel<T> m, int64_t B, const T* __restrict__ q,
                        const T* __restrict__ qd, const T* __restrict__ qdd, T gravity, int use_damping,
-                       T* __restrict__ dc_du, T* __restrict__ c_out) {
+                       T* __restrict__ dc_du, T* __restrict__ c_out, int ahead) {
   static_assert(N >= 3, "chain kernel needs at least three bodies");
   typedef typename Vec2<T>::type V2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -63,17 +82,30 @@ rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
   const T* qdb = qd + b * N;
   const T* qddb = qdd ? qdd + b * N : nullptr;
 
+  // the inputs of the CTA that will run in this slot next (`ahead` = resident CTAs of the grid) -> L2
+  {
+    const int64_t nxt = (int64_t)blockIdx.x + ahead;
+    constexpr int kBytes = 32 * N * (int)sizeof(T);
+    if ((nxt + 1) * 32 <= B && (int)threadIdx.x * 128 < kBytes + 127) {
+      const size_t off = (size_t)nxt * kBytes + threadIdx.x * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(q) + off));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(qd) + off));
+      if (qdd) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(qdd) + off));
+    }
+  }
   // ------------------------------------------------------------------ stage 0: cos / sin of every joint angle
   T f1 = T(1), f2 = T(0);                                          // the leaf's (cos, sin) / prismatic (q, 0)
   {
     T qv[N], sv[N], cv[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) qv[i] = __ldg(qb + i);
-    sincos_batch<N>(qv, sv, cv);
+    // FP64: N polynomial chains in flight.  FP32: sincosf is evaluated inside the (rolled) forward sweep instead -
+    // N inlined copies of it made the straight-line stage larger than the instruction cache likes (0.35 -> 0.39 ms)
+    if (sizeof(T) == 8) sincos_batch<N>(qv, sv, cv);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       V2 t;
-      if (m.kind[i] == 0) { t.x = cv[i]; t.y = sv[i]; }
+      if (sizeof(T) == 8 && m.kind[i] == 0) { t.x = cv[i]; t.y = sv[i]; }
       else { t.x = qv[i]; t.y = T(0); }
       if (i == 0) tab[ROW0 + 3 * 32] = t;
       else if (i < N - 1) tab[(i - 1) * RS + 9 * 32] = t;
@@ -95,6 +127,7 @@ rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
   T qd_nx = __ldg(qdb), qdd_nx = qddb ? __ldg(qddb) : T(0);
 #pragma unroll 1
   for (int i = 0; i < N; ++i) {
+    const typename ChainModel<T>::Body& mb = m.b[i];
     const T qdi = qd_nx, qddi = qdd_nx;
     if (i + 1 < N) {
       qd_nx = __ldg(qdb + i + 1);
@@ -107,17 +140,22 @@ rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
       c1 = t.x; c2 = t.y;
     }
     const int kind = m.kind[i];
+    if (sizeof(T) == 4 && kind == 0) {                    // FP32: (q, 0) was staged; the pair is rewritten for the way back
+      sincos_t(c1, &c2, &c1);
+      if (i < N - 1) { V2 t; t.x = c1; t.y = c2; row[(i == 0 ? 3 : 9) * 32] = t; }
+      else { f1 = c1; f2 = c2; }
+    }
     {
       T r[3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) r[k] = fma_t(m.rC[i][k], c2, fma_t(m.rB[i][k], c1, m.rA[i][k]));
+      for (int k = 0; k < 3; ++k) r[k] = m.r_const ? mb.rA[k] : fma_t(mb.rC[k], c2, fma_t(mb.rB[k], c1, mb.rA[k]));
       // p_i = p_parent + E_parent^T r
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) p[cc] = fma_t(E[6 + cc], r[2], fma_t(E[3 + cc], r[1], fma_t(E[cc], r[0], p[cc])));
       // E_i = Ej E_parent, column by column
       T Ej[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) Ej[k] = fma_t(m.EC[i][k], c2, fma_t(m.EB[i][k], c1, m.EA[i][k]));
+      for (int k = 0; k < 9; ++k) Ej[k] = fma_t(mb.EC[k], c2, fma_t(mb.EB[k], c1, mb.EA[k]));
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {
         const T t0 = E[cc], t1 = E[3 + cc], t2 = E[6 + cc];
@@ -128,7 +166,7 @@ rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
     {
       T w[3];
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc) w[cc] = E[cc] * m.axis[i][0] + E[3 + cc] * m.axis[i][1] + E[6 + cc] * m.axis[i][2];
+      for (int cc = 0; cc < 3; ++cc) w[cc] = E[cc] * mb.axis[0] + E[3 + cc] * mb.axis[1] + E[6 + cc] * mb.axis[2];
       if (kind == 0) {
         S[0] = w[0]; S[1] = w[1]; S[2] = w[2];
         cross3(p, w, S + 3);
@@ -177,6 +215,7 @@ rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
 
 #pragma unroll 1
   for (int i = N - 1; i >= 0; --i) {
+    const typename ChainModel<T>::Body& mb = m.b[i];
     V2* rowi = tab + (i == 0 ? ROW0 : (i - 1) * RS);   // own table row; then the pending entries [j, i], j < i
     if (i < N - 1) {
 #pragma unroll
@@ -203,16 +242,16 @@ rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
     }
     // ---- own rigid-body terms in world coordinates, added to the running composites
     {
-      const T mi = m.mass[i];
+      const T mi = mb.mass;
       T hr[3], hw[3];
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {
-        hr[cc] = E[cc] * m.h[i][0] + E[3 + cc] * m.h[i][1] + E[6 + cc] * m.h[i][2];
+        hr[cc] = E[cc] * mb.h[0] + E[3 + cc] * mb.h[1] + E[6 + cc] * mb.h[2];
         hw[cc] = fma_t(mi, p[cc], hr[cc]);
       }
       T IbE[9];
       {
-        const T xx = m.Ib[i][0], xy = m.Ib[i][1], xz = m.Ib[i][2], yy = m.Ib[i][3], yz = m.Ib[i][4], zz = m.Ib[i][5];
+        const T xx = mb.Ib[0], xy = mb.Ib[1], xz = mb.Ib[2], yy = mb.Ib[3], yz = mb.Ib[4], zz = mb.Ib[5];
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
           IbE[cc] = xx * E[cc] + xy * E[3 + cc] + xz * E[6 + cc];
@@ -306,7 +345,7 @@ rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
     if (c_out && active) c_out[b * N + i] = dot6s(S, fC);                       // :613
     T dqq = dot6s(S, F1);
     T ddd = dot6s(S, F2);
-    if (use_damping) ddd += m.damping[i];                                        // :1341
+    if (use_damping) ddd += mb.damping;                                        // :1341
     if (kind == 1) {
       // reference quirk for prismatic joints: X^T(-crm(f)S) instead of X^T(S x* f) (:1292); needs p_i
       T nrot[3], dl[3], da[3], t3[3];
@@ -323,9 +362,9 @@ rnea_grad_chain_kernel(const __grid_constant__ FastModel<T> m, int64_t B, const 
     if (i > 0) {
       T r[3], Ej[9];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) r[k] = fma_t(m.rC[i][k], f2, fma_t(m.rB[i][k], f1, m.rA[i][k]));
+      for (int k = 0; k < 3; ++k) r[k] = m.r_const ? mb.rA[k] : fma_t(mb.rC[k], f2, fma_t(mb.rB[k], f1, mb.rA[k]));
 #pragma unroll
-      for (int k = 0; k < 9; ++k) Ej[k] = fma_t(m.EC[i][k], f2, fma_t(m.EB[i][k], f1, m.EA[i][k]));
+      for (int k = 0; k < 9; ++k) Ej[k] = fma_t(mb.EC[k], f2, fma_t(mb.EB[k], f1, mb.EA[k]));
       // E_parent = Ej^T E_i, column by column; p_parent = p_i - E_parent^T r
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {

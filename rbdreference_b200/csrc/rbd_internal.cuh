@@ -16,6 +16,8 @@
 #include <mutex>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/rbd_b200.h"
 #include "rbd_common.cuh"
 #include "rbd_grad_kernels.cuh"
@@ -23,6 +25,7 @@
 #include "rbd_coop_kernels.cuh"
 #include "rbd_coop_minv_kernels.cuh"
 #include "rbd_tile_minv_kernels.cuh"
+#include "rbd_chain_grad_kernels.cuh"
 
 struct rbd_model {
   rbd::DevModel<double> d;
@@ -31,6 +34,8 @@ struct rbd_model {
   rbd::FastModel<float> ff;
   bool fast_ok;                  // FastModel valid (rigid inertias, 1-DoF revolute/prismatic joints)
   bool is_chain;                 // parent[i] == i - 1 for every body (serial chain)
+  rbd::ChainModel<double> chain_d;   // per-body records of the chain rnea_grad kernel (is_chain && n <= kChainMaxN)
+  rbd::ChainModel<float> chain_f;
   rbd::FastModel<double> fd_dfs; // the same robot renumbered in depth-first preorder
   rbd::FastModel<float> ff_dfs;
   rbd::DfsPlan plan;
@@ -41,6 +46,15 @@ struct rbd_model {
 };
 
 namespace rbd_host {
+
+// NVTX range around one C-ABI call (header-only nvtx3: a no-op unless a profiler is attached)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define RBD_NVTX(name) ::rbd_host::NvtxRange rbd_nvtx_range_(name)
 
 constexpr size_t kMaxDynSmem = 227 * 1024;
 extern std::atomic<int> g_variant;      // 0 auto, 1 force the generic body-frame kernels, 2.. see rbd_b200.h
@@ -62,6 +76,9 @@ template <> inline const rbd::DevModel<float>& pick<float>(const rbd_model* m) {
 template <typename T> inline const rbd::FastModel<T>& pick_dfs(const rbd_model* m);
 template <> inline const rbd::FastModel<double>& pick_dfs<double>(const rbd_model* m) { return m->fd_dfs; }
 template <> inline const rbd::FastModel<float>& pick_dfs<float>(const rbd_model* m) { return m->ff_dfs; }
+template <typename T> inline const rbd::ChainModel<T>& pick_chain(const rbd_model* m);
+template <> inline const rbd::ChainModel<double>& pick_chain<double>(const rbd_model* m) { return m->chain_d; }
+template <> inline const rbd::ChainModel<float>& pick_chain<float>(const rbd_model* m) { return m->chain_f; }
 template <typename T> inline const rbd::FastModel<T>& pick_fast(const rbd_model* m);
 template <> inline const rbd::FastModel<double>& pick_fast<double>(const rbd_model* m) { return m->fd; }
 template <> inline const rbd::FastModel<float>& pick_fast<float>(const rbd_model* m) { return m->ff; }

@@ -114,18 +114,18 @@ int rbd_ee_model_destroy(rbd_ee_model_t* m) {
 int rbd_ee_model_num_ee(const rbd_ee_model_t* m) { return m ? m->d.n_ee : RBD_E_INVALID_ARGUMENT; }
 
 int rbd_end_effector_pose_f64(const rbd_ee_model_t* m, int64_t B, const double* q, double* pose, void* stream) {
-  return launch_ee<double, false>(m, B, q, pose, nullptr, stream, "rbd_end_effector_pose");
+  RBD_NVTX(__func__); return launch_ee<double, false>(m, B, q, pose, nullptr, stream, "rbd_end_effector_pose");
 }
 int rbd_end_effector_pose_f32(const rbd_ee_model_t* m, int64_t B, const float* q, float* pose, void* stream) {
-  return launch_ee<float, false>(m, B, q, pose, nullptr, stream, "rbd_end_effector_pose");
+  RBD_NVTX(__func__); return launch_ee<float, false>(m, B, q, pose, nullptr, stream, "rbd_end_effector_pose");
 }
 int rbd_end_effector_pose_gradient_f64(const rbd_ee_model_t* m, int64_t B, const double* q, double* dpose,
                                        double* pose, void* stream) {
-  return launch_ee<double, true>(m, B, q, pose, dpose, stream, "rbd_end_effector_pose_gradient");
+  RBD_NVTX(__func__); return launch_ee<double, true>(m, B, q, pose, dpose, stream, "rbd_end_effector_pose_gradient");
 }
 int rbd_end_effector_pose_gradient_f32(const rbd_ee_model_t* m, int64_t B, const float* q, float* dpose, float* pose,
                                        void* stream) {
-  return launch_ee<float, true>(m, B, q, pose, dpose, stream, "rbd_end_effector_pose_gradient");
+  RBD_NVTX(__func__); return launch_ee<float, true>(m, B, q, pose, dpose, stream, "rbd_end_effector_pose_gradient");
 }
 
 }  // extern "C"

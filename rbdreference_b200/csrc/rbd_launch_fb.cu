@@ -214,53 +214,53 @@ int rbd_fb_model_num_vel(const rbd_fb_model_t* m) { return m ? m->d.d.n + 5 : RB
 #define RBD_FB_DEFINE(SUF, T)                                                                                        \
   int rbd_fb_rnea_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* qdd, T gravity, T* c,  \
                         T* v, T* a, T* f, void* stream) {                                                            \
-    return launch_fb_rnea<T>(m, B, q, qd, qdd, gravity, c, v, a, f, stream);                                         \
+    RBD_NVTX(__func__); return launch_fb_rnea<T>(m, B, q, qd, qdd, gravity, c, v, a, f, stream);                                         \
   }                                                                                                                  \
   int rbd_fb_rnea_grad_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* qdd, T gravity,   \
                              int use_velocity_damping, T* dc_du, T* c_out, void* stream) {                           \
-    return launch_fb_rnea_grad<T>(m, B, q, qd, qdd, gravity, use_velocity_damping, dc_du, c_out, stream);            \
+    RBD_NVTX(__func__); return launch_fb_rnea_grad<T>(m, B, q, qd, qdd, gravity, use_velocity_damping, dc_du, c_out, stream);            \
   }                                                                                                                  \
   int rbd_fb_minv_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, int output_dense, T* Minv, void* stream) {   \
-    return launch_fb_minv<T>(m, B, q, output_dense, Minv, stream);                                                   \
+    RBD_NVTX(__func__); return launch_fb_minv<T>(m, B, q, output_dense, Minv, stream);                                                   \
   }                                                                                                                  \
   int rbd_fb_rnea_fpass_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* qdd, T gravity,  \
                               T* v, T* a, T* f, void* stream) {                                                      \
-    return launch_fb_rnea_fpass<T>(m, B, q, qd, qdd, gravity, v, a, f, stream);                                      \
+    RBD_NVTX(__func__); return launch_fb_rnea_fpass<T>(m, B, q, qd, qdd, gravity, v, a, f, stream);                                      \
   }                                                                                                                  \
   int rbd_fb_rnea_bpass_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, T* f, T* c, void* stream) {            \
-    return launch_fb_rnea_bpass<T>(m, B, q, f, c, stream);                                                           \
+    RBD_NVTX(__func__); return launch_fb_rnea_bpass<T>(m, B, q, f, c, stream);                                                           \
   }                                                                                                                  \
   int rbd_fb_minv_bpass_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, T* Minv, T* F, T* U, T* Dinv,          \
                               void* stream) {                                                                        \
-    return launch_fb_minv_bpass<T>(m, B, q, Minv, F, U, Dinv, stream);                                               \
+    RBD_NVTX(__func__); return launch_fb_minv_bpass<T>(m, B, q, Minv, F, U, Dinv, stream);                                               \
   }                                                                                                                  \
   int rbd_fb_minv_fpass_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, T* Minv, T* F, const T* U,             \
                               const T* Dinv, void* stream) {                                                         \
-    return launch_fb_minv_fpass<T>(m, B, q, Minv, F, U, Dinv, stream);                                               \
+    RBD_NVTX(__func__); return launch_fb_minv_fpass<T>(m, B, q, Minv, F, U, Dinv, stream);                                               \
   }                                                                                                                  \
   int rbd_fb_rnea_grad_fpass_dq_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* v,       \
                                       const T* a, T gravity, T* dv, T* da, T* df, void* stream) {                    \
-    return launch_fb_grad_fpass<T, true>(m, B, q, qd, v, a, gravity, dv, da, df, stream);                            \
+    RBD_NVTX(__func__); return launch_fb_grad_fpass<T, true>(m, B, q, qd, v, a, gravity, dv, da, df, stream);                            \
   }                                                                                                                  \
   int rbd_fb_rnea_grad_fpass_dqd_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* v,      \
                                        T* dv, T* da, T* df, void* stream) {                                          \
-    return launch_fb_grad_fpass<T, false>(m, B, q, qd, v, nullptr, T(0), dv, da, df, stream);                        \
+    RBD_NVTX(__func__); return launch_fb_grad_fpass<T, false>(m, B, q, qd, v, nullptr, T(0), dv, da, df, stream);                        \
   }                                                                                                                  \
   int rbd_fb_rnea_grad_bpass_dq_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* f, T* df_dq,          \
                                       T* dc_dq, void* stream) {                                                      \
-    return launch_fb_grad_bpass<T, true>(m, B, q, f, df_dq, 0, dc_dq, stream);                                       \
+    RBD_NVTX(__func__); return launch_fb_grad_bpass<T, true>(m, B, q, f, df_dq, 0, dc_dq, stream);                                       \
   }                                                                                                                  \
   int rbd_fb_rnea_grad_bpass_dqd_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, T* df_dqd,                    \
                                        int use_velocity_damping, T* dc_dqd, void* stream) {                          \
-    return launch_fb_grad_bpass<T, false>(m, B, q, nullptr, df_dqd, use_velocity_damping, dc_dqd, stream);           \
+    RBD_NVTX(__func__); return launch_fb_grad_bpass<T, false>(m, B, q, nullptr, df_dqd, use_velocity_damping, dc_dqd, stream);           \
   }                                                                                                                  \
   int rbd_fb_forward_dynamics_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* u, T* qdd, \
                                     T* Minv_out, void* stream) {                                                     \
-    return launch_fb_forward_dynamics<T>(m, B, q, qd, u, qdd, Minv_out, stream);                                     \
+    RBD_NVTX(__func__); return launch_fb_forward_dynamics<T>(m, B, q, qd, u, qdd, Minv_out, stream);                                     \
   }                                                                                                                  \
   int rbd_fb_forward_dynamics_grad_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* u,    \
                                          T* qdd_dq, T* qdd_dqd, T* qdd_out, void* stream) {                          \
-    return launch_fb_forward_dynamics_grad<T>(m, B, q, qd, u, qdd_dq, qdd_dqd, qdd_out, stream);                     \
+    RBD_NVTX(__func__); return launch_fb_forward_dynamics_grad<T>(m, B, q, qd, u, qdd_dq, qdd_dqd, qdd_out, stream);                     \
   }
 
 RBD_FB_DEFINE(f64, double)

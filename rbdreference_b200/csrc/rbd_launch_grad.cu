@@ -1,7 +1,6 @@
 // rbd_launch_grad.cu - part of librbd_b200.so (see rbd_internal.cuh); compiled with -DRBD_LAUNCH_T=double|float.
 #include "rbd_internal.cuh"
 #include "rbd_fused_kernels.cuh"
-#include "rbd_chain_grad_kernels.cuh"
 
 #ifndef RBD_LAUNCH_T
 #error "compile with -DRBD_LAUNCH_T=double or -DRBD_LAUNCH_T=float"
@@ -21,7 +20,7 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
   if (m->fast_ok && m->is_chain && (variant == 0 || variant == 7) && B >= chain_min_batch(m->d.n) &&
       (reinterpret_cast<uintptr_t>(dc_du) & (2 * sizeof(T) - 1)) == 0) {
     // serial chain, one knot point per lane (rbd_chain_grad_kernels.cuh)
-    void (*kern)(const FastModel<T>, int64_t, const T*, const T*, const T*, T, int, T*, T*) = nullptr;
+    void (*kern)(const ChainModel<T>, int64_t, const T*, const T*, const T*, T, int, T*, T*, int) = nullptr;
     switch (m->d.n) {
       case 6: kern = rnea_grad_chain_kernel<T, 6>; break;
       case 7: kern = rnea_grad_chain_kernel<T, 7>; break;
@@ -32,7 +31,10 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
-      kern<<<blocks_for(B, 32), 32, smem, (cudaStream_t)stream>>>(pick_fast<T>(m), B, q, qd, qdd, g, damp, dc_du, c_out);
+      int nb = 8;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, smem) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 8; }
+      kern<<<blocks_for(B, 32), 32, smem, (cudaStream_t)stream>>>(pick_chain<T>(m), B, q, qd, qdd, g, damp, dc_du, c_out,
+                                                                  sm_count() * nb);
       return cuda_status("rbd_rnea_grad(chain)");
     }
   }

@@ -59,6 +59,10 @@ class RBDReference:
             self._handle = _capi.ModelHandle(self.model)
         self._fb = "fb_" if self.floating_base else ""       # C-ABI prefix of the per-pass helpers
         self._device = torch.device(device) if device is not None else None
+        if self._device is not None and self._device.type == "cuda" and torch.cuda.is_available():
+            # the scratch pool of an explicitly requested device exists before any (possibly captured) call needs it
+            idx = self._device.index if self._device.index is not None else torch.cuda.current_device()
+            _capi.check(self._lib.rbd_prepare_device(int(idx)), "rbd_prepare_device")
         self._ee_handles = {}                       # (names, offset) -> compiled end-effector handle
         self._pipes = {}                            # device -> HostPipeline (streams + staging buffers)
 
@@ -547,6 +551,14 @@ class RBDReference:
         include/rbd_b200.h.  `set_variant` overrides it for one engine."""
         lib = _capi.load_library()
         _capi.check(lib.rbd_set_kernel_variant(int(variant)), "rbd_set_kernel_variant")
+
+    def trim_scratch(self, keep_bytes: int = 0) -> None:
+        """Return the library's cached scratch memory on this engine's device to the driver (forward_dynamics(_grad)
+        and the hybrid minv kernel keep their temporaries in a private pool; see include/rbd_b200.h)."""
+        dev = self._default_device()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.device(dev):
+            _capi.check(self._lib.rbd_trim_scratch(int(keep_bytes)), "rbd_trim_scratch")
 
     def launch_count(self) -> int:
         return int(self._lib.rbd_launch_count())
