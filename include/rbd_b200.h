@@ -75,8 +75,9 @@ int rbd_model_uses_world_kernels(const rbd_model_t* m);
  * operations behave as 0), 5 = lane minv kernel (knot point per lane in every phase, per-body table
  * and output tile in shared memory; robots too large for it run the generic kernel; other
  * operations behave as 0), 7 = chain rnea_grad kernel (serial chains, knot point per lane; other robots and
- * operations behave as 0), 8 = tile minv kernel (one CTA per 32 knot points, branch-parallel, table in shared
- * memory; the automatic choice for n > 16; other operations behave as 0).  6 is retired.  Used by the tests and the benchmark to cross-check / compare. */
+ * operations behave as 0), 8 / 9 = tile minv kernel (one CTA per 32 knot points, branch-parallel, table in shared
+ * memory) with 4-column groups and 8 warps / 2-column groups and 16 warps per CTA (9 is the automatic choice for
+ * n > 16; other operations behave as 0).  6 is retired.  Used by the tests and the benchmark to cross-check / compare. */
 int rbd_set_kernel_variant(int variant);
 /* The same choice for one handle only (-1 = follow the process-wide setting, the default): calls on
  * different handles never see each other's choice, so handles stay independent across threads. */

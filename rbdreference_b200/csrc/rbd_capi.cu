@@ -376,8 +376,10 @@ bool build_dfs_model(const RbdModelDesc* d, FastModel<double>& out, DfsPlan& pla
 
 // Schedule of the tile minv kernel (rbd_tile_minv_kernels.cuh): chains of the depth-first numbering with their
 // dependency levels and hand-off slots, per-warp work lists, and the step tables of the column groups.
-void build_tile_plan(const FastModel<double>& fm, const DfsPlan& plan, const CoopMinvPlan& mp, int maxdepth, TilePlan& tp) {
+void build_tile_plan(const FastModel<double>& fm, const DfsPlan& plan, const CoopMinvPlan& mp, int maxdepth, int gc, int maxwarps,
+                     TilePlan& tp) {
   std::memset(&tp, 0, sizeof(tp));
+  tp.gc = gc;
   const int n = fm.n;
   int chain_of[RBD_MAX_DOF], flevel[RBD_MAX_DOF] = {0}, blevel[RBD_MAX_DOF] = {0};
   for (int i = 0; i < n; ++i) {
@@ -416,11 +418,11 @@ void build_tile_plan(const FastModel<double>& fm, const DfsPlan& plan, const Coo
   tp.maxdepth = maxdepth;
   tp.nslot_g = fm.n_slot_a;
   // warps per CTA: as many as the FP64 shared-memory budget allows (the FP32 kernel uses the same schedule)
-  int w = kTmMaxWarps;
-  while (w > 1 && tile_minv_smem_vals(n, tp.nslot, maxdepth, tp.nslot_g, w) * sizeof(double) > rbd_host::kMaxDynSmem - 1024) --w;
+  int w = maxwarps;
+  while (w > 1 && tile_minv_smem_vals(n, tp.nslot, maxdepth, tp.nslot_g, w, gc) * sizeof(double) > rbd_host::kMaxDynSmem - 1024) --w;
   tp.nwarps = w;
   tp.ok = maxdepth < 16 && fm.n_slot_a < 15 &&
-          tile_minv_smem_vals(n, tp.nslot, maxdepth, tp.nslot_g, w) * sizeof(double) <= rbd_host::kMaxDynSmem - 1024;
+          tile_minv_smem_vals(n, tp.nslot, maxdepth, tp.nslot_g, w, gc) * sizeof(double) <= rbd_host::kMaxDynSmem - 1024;
   // per-(level, warp) chain lists: longest chains first, each to the least loaded warp of its level
   auto fill = [&](const int* level, int nlevel, int* begin, int* item) {
     int pos = 0;
@@ -454,9 +456,9 @@ void build_tile_plan(const FastModel<double>& fm, const DfsPlan& plan, const Coo
   int cost[kTmMaxGroups], ns = 0;
   for (int r = 0; r < n && tp.ok; r = plan.comp_end[r]) {
     const int cend = plan.comp_end[r];
-    for (int j0 = r; j0 < cend; j0 += kTmGC) {
+    for (int j0 = r; j0 < cend; j0 += gc) {
       const int g = tp.ngroup++;
-      const int nc = cend - j0 < kTmGC ? cend - j0 : kTmGC;
+      const int nc = cend - j0 < gc ? cend - j0 : gc;
       tp.g_first[g] = j0;
       tp.g_ncols[g] = nc;
       tp.g_ocol[g] = plan.orig[j0];
@@ -607,7 +609,8 @@ int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out) {
       if (i - mp.comp_root[i] + 1 > mp.maxcomp) mp.maxcomp = i - mp.comp_root[i] + 1;
     }
   }
-  build_tile_plan(m->fd_dfs, m->plan, m->coop_minv, m->coop.maxdepth, m->tile);
+  build_tile_plan(m->fd_dfs, m->plan, m->coop_minv, m->coop.maxdepth, 4, 8, m->tile);
+  build_tile_plan(m->fd_dfs, m->plan, m->coop_minv, m->coop.maxdepth, 2, 16, m->tile2);
   fill_chain_model<double>(m->fd, m->chain_d);
   fill_chain_model<float>(m->fd, m->chain_f);
   {
@@ -630,14 +633,14 @@ int rbd_model_num_dof(const rbd_model_t* m) { return m ? m->d.n : RBD_E_INVALID_
 
 static const char* kVariantHelp =
     "kernel variant: 0 auto, 1 generic, 2 world (thread per knot point), 3 cooperative, 4 hybrid (minv), 5 lane (minv), "
-    "7 chain (rnea_grad, serial chains), 8 tile (minv, large trees)";
+    "7 chain (rnea_grad, serial chains), 8 tile (minv, large trees), 9 tile with 2-column groups / 16 warps";
 int rbd_set_kernel_variant(int variant) {
-  if (variant < 0 || variant > 8 || variant == 6) return fail(RBD_E_INVALID_ARGUMENT, kVariantHelp);
+  if (variant < 0 || variant > 9 || variant == 6) return fail(RBD_E_INVALID_ARGUMENT, kVariantHelp);
   g_variant.store(variant, std::memory_order_relaxed);
   return 0;
 }
 int rbd_model_set_kernel_variant(rbd_model_t* m, int variant) {
-  if (!m || variant < -1 || variant > 8 || variant == 6) return fail(RBD_E_INVALID_ARGUMENT, kVariantHelp);
+  if (!m || variant < -1 || variant > 9 || variant == 6) return fail(RBD_E_INVALID_ARGUMENT, kVariantHelp);
   m->variant.store(variant, std::memory_order_relaxed);
   return 0;
 }

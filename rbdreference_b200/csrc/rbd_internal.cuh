@@ -41,7 +41,8 @@ struct rbd_model {
   rbd::DfsPlan plan;
   rbd::CoopPlan coop;
   rbd::CoopMinvPlan coop_minv;
-  rbd::TilePlan tile;            // chain / column-group schedule of the tile minv kernel
+  rbd::TilePlan tile;            // chain / column-group schedule of the tile minv kernel (4-column groups, 8 warps)
+  rbd::TilePlan tile2;           // the same with 2-column groups and 16 warps per CTA
   mutable std::atomic<int> variant{-1};   // per-handle kernel family (-1: follow rbd_set_kernel_variant)
 };
 

@@ -23,9 +23,10 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
     //   iiwa14 n=7 : hybrid 8.5e8 | 1.38e9   cooperative 7.8e8 | 1.2e9    thread 1.13e9 | 1.88e9 (body frame)
     const int n = m->d.n;
     //   iiwa14 n=7 : lane 1.49e9 | 2.60e9 (knot point per lane, table + tile in shared memory)
-    // n > 16, measured on B200 (Atlas, 2^18 knot points): tile 2.11 ms | hybrid 2.09 ms in FP64 with 2.5 GB against
-    // 5.1 GB of DRAM traffic (no scratch hand-off): tile; FP32 tile 1.42 ms | hybrid 1.26 ms: hybrid
-    variant = n > 16 ? ((m->tile.ok && std::is_same<T, double>::value) ? 8 : 4) : (n > 8 ? 3 : 5);
+    // n > 16, measured on B200 (Atlas, 2^18 knot points, FP64 | FP32 ms): tile with 2-column groups and 16 warps
+    // (variant 9) 1.88 | 1.23, tile with 4-column groups and 8 warps (variant 8) 1.98 | 1.34, hybrid 2.02 | 1.25; the
+    // tile kernels move 2.5 GB of DRAM traffic where the hybrid kernel's scratch hand-off moves 5.1 GB
+    variant = n > 16 ? (m->tile2.ok ? 9 : (m->tile.ok ? 8 : 4)) : (n > 8 ? 3 : 5);
     // Small batches (MPC-sized): the knot-point-per-lane kernels process 32 knot points per warp one
     // after the other, so below one wave of tasks their time is the latency of a single task
     // (iiwa14 48 us, Atlas 243 us, flat from 1k to 16k knot points); the cooperative kernel spreads
@@ -60,27 +61,33 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
       return cuda_status("rbd_minv(lane)");
     }
   }
-  if (m->fast_ok && dense && variant == 8 && m->tile.ok) {
+  if (m->fast_ok && dense && (variant == 8 || variant == 9) && (variant == 8 ? m->tile.ok : m->tile2.ok)) {
     // one CTA per tile of 32 knot points: branch-parallel articulated inertias, column groups per warp,
     // per-body table in shared memory, rows stored straight from registers (rbd_tile_minv_kernels.cuh)
     const FastModel<T>& fm = pick_dfs<T>(m);
-    auto kern = fm.has_prismatic ? minv_tile_kernel<T, true> : minv_tile_kernel<T, false>;
-    const int warps = m->tile.nwarps;
-    const size_t smem = tile_minv_smem_vals(fm.n, m->tile.nslot, m->tile.maxdepth, m->tile.nslot_g, warps) * sizeof(T);
+    const TilePlan& tp = variant == 8 ? m->tile : m->tile2;
+    void (*kern)(const FastModel<T>, const DfsPlan, const TilePlan, int64_t, const T*, T*, int);
+    if (variant == 8) kern = fm.has_prismatic ? minv_tile_kernel<T, true, 4> : minv_tile_kernel<T, false, 4>;
+    else kern = fm.has_prismatic ? minv_tile_kernel<T, true, 2> : minv_tile_kernel<T, false, 2>;
+    const int warps = tp.nwarps;
+    const size_t smem = tile_minv_smem_vals(fm.n, tp.nslot, tp.maxdepth, tp.nslot_g, warps, tp.gc) * sizeof(T);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem) == cudaSuccess && nb > 0) {
+    cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem);
+    if (std::getenv("RBD_DEBUG")) std::fprintf(stderr, "[rbd] tile minv: gc %d warps %d smem %zu occupancy %d (%s)\n", tp.gc, warps, smem, nb, cudaGetErrorString(eo));
+    if (eo == cudaSuccess && nb > 0) {
+      static const int dbg_skip = [] { const char* v = std::getenv("RBD_TILE_SKIP"); return v ? std::atoi(v) : 0; }();
       const int64_t ntiles = (B + 31) / 32;
       int64_t blocks = (int64_t)sm_count() * nb;
       if (blocks > ntiles) blocks = ntiles;
-      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->tile, B, q, Minv);
+      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, tp, B, q, Minv, dbg_skip);
       return cuda_status("rbd_minv(tile)");
     }
     cudaGetLastError();
   }
-  if (variant == 8) variant = 4;
+  if (variant == 8 || variant == 9) variant = 4;
   if (m->fast_ok && dense && variant == 4) {
     // hybrid kernel: knot point per lane for the articulated inertias, column per lane for the
     // rows of Minv, per-body table handed over through an L2-resident scratch buffer

@@ -31,11 +31,11 @@
 namespace rbd {
 
 constexpr int kTmTab = 13;           // w(3) invD U(6) r(3); stage 1 keeps q / E rows 0, 1 in the invD / U slots
-constexpr int kTmGC = 4;             // columns per group
-constexpr int kTmMaxWarps = 8;
+constexpr int kTmMaxGC = 4;          // columns per group: 4 (8 warps per CTA) or 2 (16 warps per CTA)
+constexpr int kTmMaxWarps = 16;
 constexpr int kTmMaxGroups = RBD_MAX_DOF;
 
-constexpr int kTmMaxSteps = 12 * RBD_MAX_DOF;   // step words of all column groups
+constexpr int kTmMaxSteps = 30 * RBD_MAX_DOF;   // step words of all column groups
 
 // One step of a column group, packed by the host (rbd_capi.cu build_tile_plan):
 //   bits 0..4 body a | 5..8 depth(a) | 9..12 columns of the group that hang below a (a is the column or an
@@ -49,6 +49,7 @@ __host__ __device__ inline int tm_pack_step(int a, int depth, int mask, int self
 struct TilePlan {
   int ok;                            // 0: the robot does not fit this kernel (too many slots / deep trees)
   int nwarps;                        // warps per CTA the work lists were built for
+  int gc;                            // columns per group the step tables were built for
   int nchain;
   int chain_begin[RBD_MAX_DOF];      // bodies [begin, end) in depth-first numbering
   int chain_end[RBD_MAX_DOF];
@@ -78,53 +79,77 @@ struct TilePlan {
 };
 
 // shared memory of one CTA, in values of T:  table | max(stage-1 slots, stage-2 per-warp scratch)
-__host__ __device__ inline int tile_minv_warp_vals(int maxdepth, int nslot_g) {
-  return ((maxdepth + 1) * kTmGC + nslot_g * kTmGC * 6) * 32;           // mb | G stashes
+__host__ __device__ inline int tile_minv_warp_vals(int maxdepth, int nslot_g, int gc) {
+  return ((maxdepth + 1) * gc + nslot_g * gc * 6) * 32;                 // mb | G stashes
 }
-__host__ __device__ inline size_t tile_minv_smem_vals(int n, int nslot, int maxdepth, int nslot_g, int nwarps) {
+constexpr int kTmMdl = 52;           // per-body constants in shared memory: EA EB EC (27) rA rB rC (9) axis (3) m h (4) Ib (6), padded
+__host__ __device__ inline size_t tile_minv_smem_vals(int n, int nslot, int maxdepth, int nslot_g, int nwarps, int gc) {
   const size_t s1 = (size_t)nslot * 21 * 32;
-  const size_t s2 = (size_t)nwarps * tile_minv_warp_vals(maxdepth, nslot_g);
-  return (size_t)n * kTmTab * 32 + (s1 > s2 ? s1 : s2);
+  const size_t s2 = (size_t)nwarps * tile_minv_warp_vals(maxdepth, nslot_g, gc);
+  return (size_t)n * kTmMdl + (size_t)n * kTmTab * 32 + (s1 > s2 ? s1 : s2);
 }
 
 // Minv[row][j0 .. j0 + nc) <- v[0 .. nc)   (p points at column j0; par = 0: p is 2-value aligned, 1: p + 1 is,
 // 2: nothing is known - the result's n*n is odd or its base is not 2-value aligned)
-template <typename T>
+template <typename T, int GC>
 __device__ __forceinline__ void tm_store_row(T* p, const T* v, int nc, int par) {
   typedef typename Vec2<T>::type V2;
-  if (nc == kTmGC && par == 0) {
+  if (GC == 4 && nc == 4 && par == 0) {
     V2 a, b;
-    a.x = v[0]; a.y = v[1]; b.x = v[2]; b.y = v[3];
+    a.x = v[0]; a.y = v[1]; b.x = v[GC - 2]; b.y = v[GC - 1];
     __stcs(reinterpret_cast<V2*>(p), a);
     __stcs(reinterpret_cast<V2*>(p) + 1, b);
-  } else if (nc == kTmGC && par == 1) {
+  } else if (GC == 4 && nc == 4 && par == 1) {
     V2 a;
-    a.x = v[1]; a.y = v[2];
+    a.x = v[1]; a.y = v[GC - 2];
     __stcs(p, v[0]);
     __stcs(reinterpret_cast<V2*>(p + 1), a);
-    __stcs(p + 3, v[3]);
+    __stcs(p + 3, v[GC - 1]);
+  } else if (GC == 2 && nc == 2 && par == 0) {
+    V2 a;
+    a.x = v[0]; a.y = v[1];
+    __stcs(reinterpret_cast<V2*>(p), a);
   } else {
 #pragma unroll
-    for (int c = 0; c < kTmGC; ++c)
+    for (int c = 0; c < GC; ++c)
       if (c < nc) __stcs(p + c, v[c]);
   }
 }
 
-template <typename T, bool PRISM>
-__global__ void __launch_bounds__(kTmMaxWarps * 32)
+template <typename T, bool PRISM, int GC>
+__global__ void __launch_bounds__(GC == 4 ? 256 : 512)
 minv_tile_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__ DfsPlan plan,
                  const __grid_constant__ TilePlan tp, int64_t B,
-                 const T* __restrict__ q, T* __restrict__ Minv) {
-  constexpr int GC = kTmGC;
+                 const T* __restrict__ q, T* __restrict__ Minv, int dbg_skip) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = m.n;
   const int nn = n * n;
   const int nwarps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T* tab = reinterpret_cast<T*>(smem_raw);                // [n][13][32]
+  // The robot's constants: indexed constant-bank reads (a run-time body index per warp, several warps on different
+  // bodies) miss the small first-level constant cache and serialise the dependent FMAs; a broadcast shared-memory
+  // load does not.
+  T* mdl = reinterpret_cast<T*>(smem_raw);                // [n][52]
+  T* tab = mdl + (size_t)n * kTmMdl;                      // [n][13][32]
   T* big = tab + (size_t)n * kTmTab * 32;
+  for (int idx = threadIdx.x; idx < n * kTmMdl; idx += blockDim.x) {
+    const int i = idx / kTmMdl, k = idx - i * kTmMdl;
+    T val = T(0);
+    if (k < 9) val = m.EA[i][k];
+    else if (k < 18) val = m.EB[i][k - 9];
+    else if (k < 27) val = m.EC[i][k - 18];
+    else if (k < 30) val = m.rA[i][k - 27];
+    else if (k < 33) val = m.rB[i][k - 30];
+    else if (k < 36) val = m.rC[i][k - 33];
+    else if (k < 39) val = m.axis[i][k - 36];
+    else if (k == 39) val = m.mass[i];
+    else if (k < 43) val = m.h[i][k - 40];
+    else if (k < 49) val = m.Ib[i][k - 43];
+    mdl[idx] = val;
+  }
+  __syncthreads();
   T* slots = big;                                         // stage 1: [nslot][21][32]
-  T* mbw = big + (size_t)warp * tile_minv_warp_vals(tp.maxdepth, tp.nslot_g);   // stage 2: [depth][GC][32]
+  T* mbw = big + (size_t)warp * tile_minv_warp_vals(tp.maxdepth, tp.nslot_g, GC);   // stage 2: [depth][GC][32]
   T* gst = mbw + (tp.maxdepth + 1) * GC * 32;             //          [slot][GC][6][32]
 #define TTAB(i, k) tab[((i) * kTmTab + (k)) * 32 + lane]
 #define TSLOT(s, k) slots[((s) * 21 + (k)) * 32 + lane]
@@ -175,11 +200,12 @@ minv_tile_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
 #pragma unroll 1
         for (int i = cb; i < ce; ++i) {
           const T f1 = TTAB(i, 3), f2 = TTAB(i, 0);
+          const T* mb = mdl + i * kTmMdl;
           T Ej[9], r[3];
 #pragma unroll
-          for (int k = 0; k < 9; ++k) Ej[k] = fma_t(m.EC[i][k], f2, fma_t(m.EB[i][k], f1, m.EA[i][k]));
+          for (int k = 0; k < 9; ++k) Ej[k] = fma_t(mb[18 + k], f2, fma_t(mb[9 + k], f1, mb[k]));
 #pragma unroll
-          for (int k = 0; k < 3; ++k) r[k] = fma_t(m.rC[i][k], f2, fma_t(m.rB[i][k], f1, m.rA[i][k]));
+          for (int k = 0; k < 3; ++k) r[k] = fma_t(mb[33 + k], f2, fma_t(mb[30 + k], f1, mb[27 + k]));
           // r_i = p_i - p_parent in world axes = E_parent^T r
 #pragma unroll
           for (int cc = 0; cc < 3; ++cc) TTAB(i, 10 + cc) = E[cc] * r[0] + E[3 + cc] * r[1] + E[6 + cc] * r[2];
@@ -192,7 +218,7 @@ minv_tile_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
           }
 #pragma unroll
           for (int cc = 0; cc < 3; ++cc)
-            TTAB(i, cc) = E[cc] * m.axis[i][0] + E[3 + cc] * m.axis[i][1] + E[6 + cc] * m.axis[i][2];   // world joint axis
+            TTAB(i, cc) = E[cc] * mb[36] + E[3 + cc] * mb[37] + E[6 + cc] * mb[38];   // world joint axis
 #pragma unroll
           for (int k = 0; k < 6; ++k) TTAB(i, 4 + k) = E[k];
         }
@@ -200,7 +226,7 @@ minv_tile_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
       __syncthreads();
     }
     // ================================================================ stage 1b: articulated inertias, leaf -> root
-    for (int lvl = 0; lvl < tp.nblevel; ++lvl) {
+    for (int lvl = 0; lvl < ((dbg_skip & 2) ? 0 : tp.nblevel); ++lvl) {
       for (int it = tp.b_begin[lvl * nwarps + warp]; it < tp.b_begin[lvl * nwarps + warp + 1]; ++it) {
         const int c = tp.b_item[it];
         const int cb = tp.chain_begin[c], ce = tp.chain_end[c];
@@ -217,12 +243,13 @@ minv_tile_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
           const int kind = PRISM ? m.kind[i] : 0;
           // own rigid inertia about p_i, world-aligned axes
           {
-            const T mi = m.mass[i];
+            const T* mb = mdl + i * kTmMdl;
+            const T mi = mb[39];
             T hr[3];
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) hr[cc] = E[cc] * m.h[i][0] + E[3 + cc] * m.h[i][1] + E[6 + cc] * m.h[i][2];
+            for (int cc = 0; cc < 3; ++cc) hr[cc] = E[cc] * mb[40] + E[3 + cc] * mb[41] + E[6 + cc] * mb[42];
             T IbE[9];
-            const T xx = m.Ib[i][0], xy = m.Ib[i][1], xz = m.Ib[i][2], yy = m.Ib[i][3], yz = m.Ib[i][4], zz = m.Ib[i][5];
+            const T xx = mb[43], xy = mb[44], xz = mb[45], yy = mb[46], yz = mb[47], zz = mb[48];
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) {
               IbE[cc] = xx * E[cc] + xy * E[3 + cc] + xz * E[6 + cc];
@@ -318,8 +345,8 @@ minv_tile_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
     }
     // ================================================================ stage 2: column groups (scratch aliases the slots)
     T* outk = Minv + (first + (lane < nk ? lane : 0)) * (int64_t)nn;
-    const bool live = lane < nk;
-    for (int gi = tp.g_begin[warp]; gi < tp.g_begin[warp + 1]; ++gi) {
+    const bool live = lane < nk && !(dbg_skip & 4);
+    for (int gi = tp.g_begin[warp]; gi < ((dbg_skip & 1) ? 0 : tp.g_begin[warp + 1]); ++gi) {
       const int g = tp.g_item[gi];
       const int j0 = tp.g_first[g], nc = tp.g_ncols[g];
       const int ocol = tp.g_ocol[g];
@@ -408,7 +435,7 @@ minv_tile_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
         // column j of Minv at row a == row j at column a (:799-804): a whole row segment per lane
         if (live) {
           const int orow = (st >> 26) & 31;
-          if (ocol >= 0) tm_store_row<T>(outk + orow * n + ocol, mij, nc, vec_ok ? ((orow * n + ocol) & 1) : 2);
+          if (ocol >= 0) tm_store_row<T, GC>(outk + orow * n + ocol, mij, nc, vec_ok ? ((orow * n + ocol) & 1) : 2);
           else {
 #pragma unroll
             for (int c = 0; c < GC; ++c)
@@ -424,7 +451,7 @@ minv_tile_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
 #pragma unroll 1
         for (int s = tp.g_sz[g]; s < tp.g_se[g]; ++s) {
           const int orow = (tp.steps[s] >> 26) & 31;
-          if (ocol >= 0) tm_store_row<T>(outk + orow * n + ocol, z, nc, vec_ok ? ((orow * n + ocol) & 1) : 2);
+          if (ocol >= 0) tm_store_row<T, GC>(outk + orow * n + ocol, z, nc, vec_ok ? ((orow * n + ocol) & 1) : 2);
           else {
 #pragma unroll
             for (int c = 0; c < GC; ++c)

@@ -70,7 +70,7 @@ def test_generic_body_frame_kernels_vs_reference_golden(golden):
 
 
 @requires_cuda
-@pytest.mark.parametrize("variant", [2, 3, 4, 5, 7, 8])
+@pytest.mark.parametrize("variant", [2, 3, 4, 5, 7, 8, 9])
 def test_world_kernel_variants_vs_reference_golden(golden, variant):
     """Both world-frame mappings (2: knot point per thread, 3: body per lane) against the goldens."""
     from rbdreference_b200 import RBDReference
@@ -415,7 +415,7 @@ def test_edge_topologies_all_drivers_vs_oracle(kind):
     cond = float(np.max(np.linalg.cond(rH)))
     scale_m = max(1.0, cond * 2.3e-16 / TOL_F64 * 50.0)
     scale = 1.0
-    for variant in (0, 1, 2, 3, 4, 5, 7, 8):
+    for variant in (0, 1, 2, 3, 4, 5, 7, 8, 9):
         RBDReference.set_kernel_variant(variant)
         try:
             eng = _engine(rb)
@@ -592,10 +592,10 @@ def test_full_size_properties_atlas_256k():
         eng = _engine(rb, dtype)
         M = eng.minv(q64.to(dtype))
         assert torch.isfinite(M).all()
-        # FP32 (hybrid kernel): the mirror is a copy (:799-804).  FP64 (tile kernel): both triangles come from the
-        # forward recursion itself (:771 updates whole rows; it is what output_dense=False returns), symmetric to rounding
+        # tile kernel: both triangles come from the forward recursion itself (:771 updates whole rows; it is what
+        # output_dense=False returns) instead of the copy of :799-804 - symmetric to rounding
         asym = float((M - M.transpose(1, 2)).abs().max() / M.abs().max())
-        assert asym == 0.0 if dtype == torch.float32 else asym < 1e-13
+        assert asym < (1e-13 if dtype == torch.float64 else 1e-5)
         # block structure: pelvis-rooted components (torso+arms | l_leg | r_leg) do not couple
         assert float(M[:, :18, 18:].abs().max()) == 0.0 and float(M[:, 18:24, 24:].abs().max()) == 0.0
         idx = torch.arange(0, B, B // 512, device="cuda")[:512]

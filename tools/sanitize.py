@@ -73,7 +73,7 @@ def main():
             for B in (33, 1000):
                 q, qd, qdd = (ar.inp(rng.uniform(-1, 1, (B, n))) for _ in range(3))
                 tag = "%s %s B=%d" % (name, dtype, B)
-                for variant in (0, 1, 2, 3, 4, 5, 7, 8):
+                for variant in (0, 1, 2, 3, 4, 5, 7, 8, 9):
                     eng.set_variant(variant)
                     twice(lambda: eng.rnea_grad(q, qd, qdd, out=ar.out(B, n, 2 * n), c_out=ar.out(B, n)), tag + " rnea_grad v%d" % variant)
                     twice(lambda: eng.minv(q, out=ar.out(B, n, n)), tag + " minv v%d" % variant)

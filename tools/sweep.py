@@ -6,7 +6,9 @@ and Atlas, B = 2^10 .. 2^24 knot points on ONE GPU (the multi-GPU points come fr
     python tools/sweep.py [--ops rnea_grad,minv] [--robots iiwa14,atlas] [--dtype f64] [--max-gb 120]
 
 One JSON line per (robot, op, B): ms per launch (median of `--reps`, CUDA events, inputs resident),
-evals/s, algorithmic GB/s and TFLOP/s.  Batches whose dense inputs + outputs exceed --max-gb are
+evals/s, algorithmic GB/s and TFLOP/s, and the SM clock / throttle reasons sampled (NVML, bench.ClockSampler) while
+that point ran.  A 256 MB buffer is rewritten between launches whenever one launch's inputs + outputs are not
+clearly larger than the 126 MB L2.  Batches whose dense inputs + outputs exceed --max-gb are
 skipped (16M Atlas rnea_grad results are 242 GB - more than one B200 holds).
 """
 import argparse
@@ -30,10 +32,14 @@ def main():
     ap.add_argument("--min-log2", type=int, default=10)
     ap.add_argument("--max-log2", type=int, default=24)
     args = ap.parse_args()
+    import time
     import torch
     from rbdreference_b200 import RBDReference, robots
+    from bench import ClockSampler
 
     dev = torch.device("cuda", 0)
+    sampler = ClockSampler(0)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.set_device(dev)
     td = torch.float64 if args.dtype == "f64" else torch.float32
     isz = 8 if args.dtype == "f64" else 4
@@ -68,19 +74,27 @@ def main():
                     fn()
                 torch.cuda.synchronize()
                 ts = []
-                for _ in range(args.reps):
+                flush = B * nbytes <= 2 * 126e6
+                reps = args.reps if B * nbytes > 32e6 else max(args.reps, 40)      # short launches: more samples under the clock sampler
+                t0 = time.perf_counter()
+                for k in range(reps):
+                    if flush:
+                        flush_buf.fill_(k & 1)
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                     fn()
                     e1.record()
                     torch.cuda.synchronize()
                     ts.append(e0.elapsed_time(e1))
+                t1 = time.perf_counter()
                 ms = float(np.median(ts))
                 print(json.dumps({"robot": rname, "op": op, "dtype": args.dtype, "batch": B, "ms": ms,
                                   "evals_per_s": B / (ms * 1e-3), "alg_gb_per_s": nbytes * B / (ms * 1e-3) / 1e9,
-                                  "alg_tflop_per_s": flops * B / (ms * 1e-3) / 1e12}), flush=True)
+                                  "alg_tflop_per_s": flops * B / (ms * 1e-3) / 1e12, "l2_flushed": bool(flush),
+                                  "clocks": sampler.window(t0, t1)}), flush=True)
                 del q, qd, qdd, out
                 torch.cuda.empty_cache()
+    sampler.stop()
 
 
 if __name__ == "__main__":
