@@ -151,7 +151,7 @@ class ClockSampler:
                         self.samples.append((time.perf_counter(), clk, pw, {k for k, v in bits.items() if r & v}))
                     except Exception:
                         pass
-                    time.sleep(0.002)
+                    time.sleep(0.001)
 
             self.thread = threading.Thread(target=poll, daemon=True)
             self.thread.start()
@@ -227,12 +227,26 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_from_profile(robot, op, dtype):
-    """dram bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+def traffic_from_profile(robot, op, dtype, batch=None):
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, if any (the Atlas summaries were
+    taken on 2^18 knot points; the stored figure is scaled to 2^20 and rescaled here to the batch of the run)."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
         d = json.load(open(path))
-        return d.get("%s/%s/%s" % (robot, op, dtype))
+        t = d.get("%s/%s/%s" % (robot, op, dtype))
+        if t is not None and batch is not None:
+            t = int(t * (batch / float(1 << 20)))
+        return t
+    except Exception:
+        return None
+
+
+def executed_from_profile(robot, op, dtype):
+    """What the dominant kernel's pipes actually did (ncu, committed under profiles/): the equivalent-work fraction can
+    exceed 1 because the kernels execute fewer flops than the reference's recursion."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        return json.load(open(path)).get("executed", {}).get("%s/%s/%s" % (robot, op, dtype))
     except Exception:
         return None
 
@@ -399,14 +413,14 @@ def rooflines(w, kernel_ms, fma_peak_tflops, robot, op, dtype):
     hbm_peak, hbm_src = measured_peaks()
     ach_tflops = w.flops * w.B / (kernel_ms * 1e-3) / 1e12
     ach_gbs = w.io_bytes * w.B / (kernel_ms * 1e-3) / 1e9
-    traffic = traffic_from_profile(robot, op, dtype)
+    traffic = traffic_from_profile(robot, op, dtype, w.B)
     roofline = {
         "bound": "fp64_fma" if dtype == "f64" else "fp32_fma",
         "achieved": ach_tflops, "peak": fma_peak_tflops, "unit": "TFLOP/s",
         "frac": (ach_tflops / fma_peak_tflops) if fma_peak_tflops else None,
         "traffic": traffic,
         "peak_source": "FMA micro-benchmark (rbd_measure_fma_peak) on this GPU just before the timed region",
-        "flops_per_eval": w.flops, "kernel_ms": kernel_ms,
+        "flops_per_eval": w.flops, "kernel_ms": kernel_ms, "executed": executed_from_profile(robot, op, dtype),
         "note": "achieved = SURVEY.md 8d algorithmic flops x evals / kernel time (equivalent work: the kernels execute "
                 "fewer flops than the reference's recursion; executed-pipe utilisation is in profiles/); tensor cores are not applicable",
     }

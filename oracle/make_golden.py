@@ -123,6 +123,24 @@ def run_ee_case(name, make, B, seed):
     print("wrote %s (%d states, %.1f KB)" % (path, B, os.path.getsize(path) / 1024))
 
 
+def run_wide_case(name, make, B, seed):
+    """tests/golden/wide_<name>.npz: the fused drivers' outputs (c, dc_du, Minv) of the unmodified reference on MANY
+    states - breadth for the headline operations, next to the depth (every intermediate) of <name>.npz."""
+    rb = make()
+    ref = RBDReference(rb)
+    n = rb.get_num_vel()
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(-np.pi, np.pi, (B, n))
+    qd = rng.uniform(-1.0, 1.0, (B, n))
+    qdd = rng.uniform(-1.0, 1.0, (B, n))
+    c = np.stack([ref.rnea(q[k], qd[k], qdd[k])[0] for k in range(B)])
+    dc = np.stack([ref.rnea_grad(q[k], qd[k], qdd[k]) for k in range(B)])
+    M = np.stack([ref.minv(q[k]) for k in range(B)])
+    path = os.path.join(ROOT, "tests", "golden", "wide_" + name + ".npz")
+    np.savez_compressed(path, q=q, qd=qd, qdd=qdd, c=c, dc_du=dc, Minv=M)
+    print("wrote %s (%d states, %.1f KB)" % (path, B, os.path.getsize(path) / 1024))
+
+
 # floating-base branches (SURVEY.md 8f rank 3): the wrapped robots of rbdreference_b200.robots
 FB_CASES = [("hyq_fb", 5), ("atlas_fb", 3), ("iiwa14_fb", 5), ("tree9_fb", 4)]
 
@@ -211,6 +229,10 @@ def run_fbpass_case(name, B, seed):
 if __name__ == "__main__":
     only_ee = "--ee" in sys.argv          # regenerate only the end-effector fixtures
     only_fb = "--fb" in sys.argv          # regenerate only the floating-base fixtures
+    if "--wide" in sys.argv:              # only the many-state fixtures of the fused drivers
+        run_wide_case("iiwa14", lambda: robots.iiwa14(), 256, seed=5000)
+        run_wide_case("atlas", lambda: robots.atlas(), 24, seed=5001)
+        sys.exit(0)
     if "--fbpass" in sys.argv:            # only the floating-base per-pass fixtures
         for idx, (name, B) in enumerate(FBPASS_CASES):
             run_fbpass_case(name, B, seed=4000 + idx)

@@ -182,6 +182,173 @@ grad_fpass_coop_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T
   warp_bulk_store_wait(lane);                             // shared memory must outlive the copies
 }
 
+// ---- rnea_grad_fpass_dq / _dqd for LARGE robots (n > 16): no tiles ------------------------------------------------
+// With n = 30 the three (6, n, NB) tiles of ONE knot point take 134 KB: one resident warp per SM, 5 % of the HBM
+// peak.  The recursion only needs the parent's dv_c, da_c: they travel in registers from body i - 1 to body i and
+// through a small stash ([slot][12][lane]) for bodies whose children are not their successor, so shared memory
+// is the stash + the staged inputs (a few KB per warp, 16 resident warps).  Column c of lane c is a run of
+// consecutive bodies in HBM ((r n + c) n + i): two bodies are collected in registers and leave as one 16-byte
+// store per row.
+constexpr int kCpMdl = 96;
+__host__ __device__ inline int cp_stream_warp_vals(int n, int nslot) {
+  return (12 * n + 3 * n + nslot * 12 * 32 + 3) & ~3;       // v a rows | f1 f2 qd | stash
+}
+
+template <typename T, bool DQ>
+__global__ void __launch_bounds__(128, 2)
+grad_fpass_stream_kernel(const __grid_constant__ DevModel<T> m, int nslot, int64_t B, const T* __restrict__ q,
+                         const T* __restrict__ qd, const T* __restrict__ v, const T* __restrict__ a, T gravity,
+                         T* __restrict__ dv, T* __restrict__ da, T* __restrict__ df) {
+  typedef typename Vec2<T>::type V2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = m.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int c = lane;
+  const bool valid = c < n;
+  int* slot_of = reinterpret_cast<int*>(smem_raw);                         // [n]: stash slot of body i or -1
+  // per-body constants [body][96] = XA(18) XB(18) XC(18) S(6) I(36): the body index is a run-time value and warps
+  // of one SM sit on different bodies - indexed constant-bank reads of the 25 KB model serialised the kernel
+  // (23 -> 16 ms with 12x the resident warps, i.e. not occupancy-bound); broadcast shared-memory loads do not
+  T* mdl = reinterpret_cast<T*>(smem_raw + ((n * sizeof(int) + 15) & ~(size_t)15));
+  T* ws = mdl + (size_t)n * kCpMdl + (size_t)warp * cp_stream_warp_vals(n, nslot);
+  for (int k = threadIdx.x; k < n * kCpMdl; k += blockDim.x) {
+    const int i = k / kCpMdl, w = k - i * kCpMdl;
+    mdl[k] = w < 18 ? m.XA[i][w] : w < 36 ? m.XB[i][w - 18] : w < 54 ? m.XC[i][w - 36] : w < 60 ? m.S[i][w - 54] : m.I[i][w - 60];
+  }
+  T* sv = ws;                                              // [6][n]
+  T* sa = sv + 6 * n;
+  T* sj = sa + 6 * n;                                      // [n][3]: f1 f2 qd
+  T* stash = sj + 3 * n;                                   // [slot][12][32]
+  if (threadIdx.x == 0) {
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) {
+      bool need = false;                                   // a child that is not body i + 1 reads body i's columns later
+      for (int k = i + 2; k < n; ++k) need = need || m.parent[k] == i;
+      slot_of[i] = need ? cnt++ : -1;
+    }
+  }
+  __syncthreads();
+  const int64_t slab = (int64_t)6 * n * n;
+  const bool vec_ok = (n & 1) == 0 && ((reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(df)) & (2 * sizeof(T) - 1)) == 0;
+  for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
+    if (valid) {
+      T f1, f2;
+      joint_basis(m, c, q[b * n + c], f1, f2);
+      sj[c * 3] = f1; sj[c * 3 + 1] = f2; sj[c * 3 + 2] = qd[b * n + c];
+    }
+    for (int e = lane; e < 6 * n; e += 32) {
+      sv[e] = v[b * 6 * n + e];
+      if (DQ) sa[e] = a[b * 6 * n + e];
+    }
+    __syncwarp();
+    if (valid) {
+      T* odv = dv + b * slab + (int64_t)c * n;             // + r n n + i
+      T* oda = da + b * slab + (int64_t)c * n;
+      T* odf = df + b * slab + (int64_t)c * n;
+      const int rstride = n * n;
+      T pdv[6], pda[6];                                     // columns of body i - 1
+      T hv[6], ha[6], hf[6];                                // the even body of the current pair, waiting for the odd one
+#pragma unroll
+      for (int r = 0; r < 6; ++r) { pdv[r] = T(0); pda[r] = T(0); hv[r] = T(0); ha[r] = T(0); hf[r] = T(0); }
+#pragma unroll 1
+      for (int i = 0; i < n; ++i) {
+        const T* ji = sj + i * 3;
+        const T* mc = mdl + i * kCpMdl;
+        const T* Imat = mc + 60;
+        T X[18];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) X[k] = fma_t(mc[36 + k], ji[1], fma_t(mc[18 + k], ji[0], mc[k]));
+        const T qdi = ji[2];
+        const int p = m.parent[i];
+        T S[6], vi[6], Iv[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { S[r] = mc[54 + r]; vi[r] = sv[r * n + i]; }
+        mat6_apply(Imat, vi, Iv);                                              // :1180 / :1248
+        T dvc[6], dac[6];
+        if (p >= 0) {
+          T pv[6], pa[6];
+          if (p == i - 1) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { pv[r] = pdv[r]; pa[r] = pda[r]; }
+          } else {
+            const T* st = stash + (size_t)slot_of[p] * 12 * 32 + lane;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { pv[r] = st[r * 32]; pa[r] = st[(6 + r) * 32]; }
+          }
+          X_apply(X, pv, dvc);                                                 // :1158 / :1230
+          X_apply(X, pa, dac);                                                 // :1163 / :1234
+        } else {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) { dvc[r] = T(0); dac[r] = T(0); }
+        }
+        T seed_a[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+        if (c == i) {
+          if (DQ) {
+            T par[6], t[6], seed_v[6];
+            if (p >= 0) {
+#pragma unroll
+              for (int r = 0; r < 6; ++r) par[r] = sv[r * n + p];
+              X_apply(X, par, t);
+              crm_mul(t, S, seed_v);                                           // :1159
+#pragma unroll
+              for (int r = 0; r < 6; ++r) { dvc[r] += seed_v[r]; par[r] = sa[r * n + p]; }
+            } else {
+#pragma unroll
+              for (int r = 0; r < 6; ++r) par[r] = T(0);
+              par[5] = -gravity;                                               // :1137
+            }
+            X_apply(X, par, t);
+            crm_mul(t, S, seed_a);                                             // :1173 / :1175
+          } else {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) dvc[r] += S[r];                        // :1231
+            crm_mul(vi, S, seed_a);                                            // :1243
+          }
+        }
+        T t[6];
+        crm_mul(dvc, S, t);                                                    // :1170 / :1240
+#pragma unroll
+        for (int r = 0; r < 6; ++r) dac[r] = fma_t(qdi, t[r], dac[r]) + seed_a[r];
+        T Ida[6], Idv[6], t1[6], t2[6], dfc[6];
+        mat6_apply(Imat, dac, Ida);                                          // :1179 / :1247
+        mat6_apply(Imat, dvc, Idv);
+        crf_mul(dvc, Iv, t1);                                                  // :1184 / :1251
+        crf_mul(vi, Idv, t2);                                                  // :1185 / :1252
+#pragma unroll
+        for (int r = 0; r < 6; ++r) dfc[r] = Ida[r] + t1[r] + t2[r];
+        const int sl = slot_of[i];
+        if (sl >= 0) {
+          T* st = stash + (size_t)sl * 12 * 32 + lane;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) { st[r * 32] = dvc[r]; st[(6 + r) * 32] = dac[r]; }
+        }
+        if (vec_ok && (i & 1) == 0 && i + 1 < n) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) { hv[r] = dvc[r]; ha[r] = dac[r]; hf[r] = dfc[r]; }
+        } else if (vec_ok && (i & 1) == 1) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            V2 x;
+            x.x = hv[r]; x.y = dvc[r]; *reinterpret_cast<V2*>(odv + r * rstride + i - 1) = x;
+            x.x = ha[r]; x.y = dac[r]; *reinterpret_cast<V2*>(oda + r * rstride + i - 1) = x;
+            x.x = hf[r]; x.y = dfc[r]; *reinterpret_cast<V2*>(odf + r * rstride + i - 1) = x;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            odv[r * rstride + i] = dvc[r];
+            oda[r * rstride + i] = dac[r];
+            odf[r * rstride + i] = dfc[r];
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { pdv[r] = dvc[r]; pda[r] = dac[r]; }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // ---- rnea_grad_bpass_dq / _dqd (:1257-1297, :1299-1343) --------------------------------------
 // df arrives from the caller (arbitrary contents), is accumulated IN PLACE and written back.
 template <typename T, int G, bool DQ>

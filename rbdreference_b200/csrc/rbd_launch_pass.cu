@@ -44,6 +44,32 @@ int launch_grad_fpass(const rbd_model* m, int64_t B, const T* q, const T* qd, co
   RBD_CHECK_ARGS(m && q && qd && v && (a || !DQ) && dv && da && df && B >= 0,
                  "rbd_rnea_grad_fpass: null argument or negative B");
   if (B == 0) return 0;
+  if (variant_of(m) != 1 && variant_of(m) != 3 && m->d.n > 16) {
+    // large robots: one derivative column per lane without tiles (rbd_coop_pass_kernels.cuh: grad_fpass_stream_kernel)
+    const int n = m->d.n;
+    int nslot = 0;
+    for (int i = 0; i < n; ++i) {
+      bool need = false;
+      for (int k = i + 2; k < n; ++k) need = need || m->d.parent[k] == i;
+      nslot += need ? 1 : 0;
+    }
+    auto kern = grad_fpass_stream_kernel<T, DQ>;
+    const size_t head = (((size_t)n * sizeof(int) + 15) & ~(size_t)15) + (size_t)n * kCpMdl * sizeof(T);
+    const size_t per_warp = (size_t)cp_stream_warp_vals(n, nslot) * sizeof(T);
+    const int warps = 4;
+    const size_t smem = head + per_warp * warps;
+    if (smem <= kMaxDynSmem && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem) == cudaSuccess && nb > 0) {
+        int64_t blocks = (B + warps - 1) / warps;
+        const int64_t cap = (int64_t)sm_count() * nb * 4;
+        if (blocks > cap) blocks = cap;
+        kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(pick<T>(m), nslot, B, q, qd, v, a, g, dv, da, df);
+        return cuda_status("rbd_rnea_grad_fpass(stream)");
+      }
+    }
+    cudaGetLastError();
+  }
   if (variant_of(m) != 1) {
     // one derivative column per lane, tensors staged through a shared-memory tile
     const int n = m->d.n;

@@ -29,6 +29,20 @@ def rel_err(x, ref):
     return float(np.max(np.abs(x - ref))) / scale
 
 
+def row_scaled_err(x, ref):
+    """max over rows (last axis) of max|x - ref| / max|ref| of that row.  `rel_err` scales by the largest entry of the
+    whole tensor; rows of Minv span 1e-3 .. 1e4 (light distal links) and small rows would never be checked by it.
+    Rows whose reference is identically zero (structural zeros) must be exactly zero."""
+    x = np.asarray(x, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert x.shape == ref.shape
+    scale = np.max(np.abs(ref), axis=-1)
+    err = np.max(np.abs(x - ref), axis=-1)
+    zero = scale == 0.0
+    assert np.all(err[zero] == 0.0), "structural-zero row is not zero"
+    return float(np.max(err[~zero] / scale[~zero])) if np.any(~zero) else 0.0
+
+
 def make_robot(name):
     from rbdreference_b200 import robots
     if name == "tree9":

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FB_CASES, GOLDEN_CASES, TOL_F32, TOL_F64, load_ee_golden, load_fb_golden, load_fbpass_golden, make_fb_robot, make_robot, random_states, rel_err
+from conftest import GOLDEN_DIR, row_scaled_err, FB_CASES, GOLDEN_CASES, TOL_F32, TOL_F64, load_ee_golden, load_fb_golden, load_fbpass_golden, make_fb_robot, make_robot, random_states, rel_err
 from oracle.rbd_oracle import BatchOracle
 
 pytestmark = pytest.mark.gpu
@@ -1127,3 +1127,27 @@ def test_result_buffers_are_validated():
         eng.rnea_grad(q.cpu().numpy(), qd.cpu().numpy(), qdd.cpu().numpy(), out=good)   # numpy call with a torch out
     with pytest.raises(ValueError):
         eng.minv(q.cpu().numpy(), out=np.empty((16, 7, 7), dtype=np.float32))      # numpy out of the wrong dtype
+
+
+@requires_cuda
+@pytest.mark.parametrize("name", ["iiwa14", "atlas"])
+def test_fused_drivers_vs_wide_reference_golden(name):
+    """256 iiwa14 / 24 Atlas states of the unmodified reference (tests/golden/wide_*.npz) through every kernel family
+    that serves the robot, with the per-tensor bar AND a per-row bar (rows of Minv / dc_du of light distal links are
+    orders of magnitude below the tensor's largest entry; the row bar is 100x the tensor bar: a row's own scale can
+    sit 1e-2 below the entries it is computed from)."""
+    import os
+    g = np.load(os.path.join(GOLDEN_DIR, "wide_" + name + ".npz"))
+    rb = make_robot(name)
+    q, qd, qdd = g["q"], g["qd"], g["qdd"]
+    for dtype, tol in ((torch.float64, TOL_F64), (torch.float32, TOL_F32)):
+        eng = _engine(rb, dtype)
+        tq, tqd, tqdd = _t(q, dtype), _t(qd, dtype), _t(qdd, dtype)
+        for variant in (0, 1, 2, 3, 4, 5, 7, 8, 9):
+            eng.set_variant(variant)
+            dc = eng.rnea_grad(tq, tqd, tqdd).cpu().numpy()
+            M = eng.minv(tq).cpu().numpy()
+            c = eng.rnea(tq, tqd, tqdd, outputs="c").cpu().numpy()
+            for got, key in ((c, "c"), (dc, "dc_du"), (M, "Minv")):
+                assert rel_err(got, g[key]) < tol, (variant, key)
+                assert row_scaled_err(got, g[key]) < 100 * tol, (variant, key)

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import FB_CASES, GOLDEN_CASES, load_ee_golden, load_fb_golden, load_fbpass_golden, make_fb_robot, rel_err, random_states, make_robot
+from conftest import GOLDEN_DIR, row_scaled_err, FB_CASES, GOLDEN_CASES, load_ee_golden, load_fb_golden, load_fbpass_golden, make_fb_robot, rel_err, random_states, make_robot
 from oracle.rbd_oracle import BatchOracle, ScalarOracle
 from oracle import build_ref
 
@@ -251,3 +251,16 @@ def test_staged_reference_agrees_when_present():
         assert rel_err(so.rnea_grad(q[k], qd[k], qdd[k]), ref.rnea_grad(q[k], qd[k], qdd[k])) < PIN
         assert rel_err(so.minv(q[k]), ref.minv(q[k])) < PIN
         assert rel_err(so.rnea(q[k], qd[k], qdd[k])[0], ref.rnea(q[k], qd[k], qdd[k])[0]) < PIN
+
+
+@pytest.mark.parametrize("name", ["iiwa14", "atlas"])
+def test_batch_oracle_vs_wide_reference_golden(name):
+    """256 (iiwa14) / 24 (Atlas) states of the unmodified reference's fused drivers: per-tensor and per-row bars."""
+    import os
+    from oracle.rbd_oracle import BatchOracle
+    g = np.load(os.path.join(GOLDEN_DIR, "wide_" + name + ".npz"))
+    bo = BatchOracle(make_robot(name))
+    q, qd, qdd = g["q"], g["qd"], g["qdd"]
+    for got, key in ((bo.rnea(q, qd, qdd)[0], "c"), (bo.rnea_grad(q, qd, qdd), "dc_du"), (bo.minv(q), "Minv")):
+        assert rel_err(got, g[key]) < 1e-11, key
+        assert row_scaled_err(got, g[key]) < 1e-9, key

@@ -1,0 +1,31 @@
+# Copies / summarises gpurun_out/r02_* (written by tools/measure_round.sh on the GPU box) into profiles/ (tracked).
+set -u
+G=gpurun_out; P=profiles
+summ() {  # $1 = .ncu-rep stem, $2 = profiles name
+  [ -f $G/$1.ncu-rep ] || return 0
+  python tools/ncu_summary.py $G/$1.ncu-rep $P/$2 > /dev/null 2>&1
+  python tools/ncu_lines.py $G/$1.ncu-rep 2>/dev/null | awk '{ if ($4+0 >= 0.8 || $6+0 >= 0.8) print }' | cut -c1-260 >> $P/$2
+}
+summ r02_prof_chain_iiwa14_f64 r02_grad_chain_iiwa14_f64.txt
+summ r02_prof_minv_tile_atlas_f64 r02_minv_tile_atlas_f64.txt
+summ r02_prof_minv_lane_iiwa14_f64 r02_minv_lane_iiwa14_f64.txt
+summ r02_prof_grad_coop_atlas_f64 r02_grad_coop_atlas_f64.txt
+summ r02_prof_grad_fpass_iiwa14_f64 r02_grad_fpass_coop_iiwa14_f64.txt
+for f in r02_matrix.jsonl r02_passes.jsonl r02_sweep_f64.jsonl r02_ee_bench.jsonl r02_fb_bench.jsonl r02_sanitize.json r02_launches_bench_default.csv; do
+  [ -f $G/$f ] && cp $G/$f $P/$f
+done
+[ -f $G/r02_bench_default.json ] && tail -1 $G/r02_bench_default.json > $P/r02_bench_default.json
+[ -f $G/r02_bench_ref.json ] && tail -1 $G/r02_bench_ref.json > $P/r02_bench_reference_arm.json
+for n in 2 4 8; do [ -f $G/bench_n${n}_r02.json ] && tail -1 $G/bench_n${n}_r02.json > $P/r02_bench_n$n.json; done
+[ -f $G/pcie_n8.json ] && cp $G/pcie_n8.json $P/r02_pcie_probe_n8.json
+[ -f $G/pcie_n2.json ] && cp $G/pcie_n2.json $P/r02_pcie_probe_n2.json
+# SASS evidence of the bulk-copy (TMA) path: opcode counts of the kernels that use it
+{
+  echo "cuobjdump -sass opcode counts (UBLKCP = cp.async.bulk 1-D TMA copies, SYNCS.* = mbarrier, UTMACMDFLUSH = bulk-group commit)";
+  for o in rbd_launch_pass_double rbd_launch_grad_double rbd_launch_minv_double; do
+    echo "== $o.o"; cuobjdump -sass rbdreference_b200/csrc/_build/$o.o | grep -E "UBLKCP|SYNCS|UTMA" | awk '{ i=2; if ($2 ~ /^@/) i=3; print $i }' | sed 's/;//' | sort | uniq -c | sort -rn
+  done
+  echo "== per kernel (UBLKCP count)"
+  cuobjdump -sass rbdreference_b200/csrc/_build/rbd_launch_pass_double.o rbdreference_b200/csrc/_build/rbd_launch_grad_double.o rbdreference_b200/csrc/_build/rbd_launch_minv_double.o | awk '/Function :/ { f=$3 } /UBLKCP/ { c[f]++ } END { for (k in c) print c[k], k }' | sort -rn | c++filt | cut -c1-160
+} > $P/r02_sass_bulk_copy.txt
+ls -la $P | grep r02
