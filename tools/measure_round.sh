@@ -6,7 +6,7 @@ python bench.py --impl reference --steps 5 --warmup 1 > $O/r02_bench_ref.json 2>
 : > $O/r02_matrix.jsonl
 for r in iiwa14 hyq atlas; do for op in rnea_grad minv rnea crba fd fd_grad; do for dt in f64 f32; do
   b=1048576; if [ $r = atlas ]; then b=262144; fi
-  python bench.py --robot $r --op $op --dtype $dt --batch $b --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --no-quadrants 2>/dev/null | tail -1 >> $O/r02_matrix.jsonl
+  python bench.py --robot $r --op $op --dtype $dt --batch $b --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --no-quadrants 2>/dev/null | tail -1 >> $O/r02_matrix.jsonl
 done; done; done
 python - <<'PY'
 import json
