@@ -22,8 +22,11 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
     // serial chain, one knot point per lane (rbd_chain_grad_kernels.cuh)
     void (*kern)(const ChainModel<T>, int64_t, const T*, const T*, const T*, T, int, T*, T*, int) = nullptr;
     switch (m->d.n) {
+      case 4: kern = rnea_grad_chain_kernel<T, 4>; break;
+      case 5: kern = rnea_grad_chain_kernel<T, 5>; break;
       case 6: kern = rnea_grad_chain_kernel<T, 6>; break;
       case 7: kern = rnea_grad_chain_kernel<T, 7>; break;
+      case 8: kern = rnea_grad_chain_kernel<T, 8>; break;
       default: break;
     }
     if (kern) {

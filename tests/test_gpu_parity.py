@@ -1000,12 +1000,13 @@ def _chain_robot(n, prismatic_at=()):
 
 
 @requires_cuda
-@pytest.mark.parametrize("case", ["iiwa14", "chain6", "chain7_prismatic"])
+@pytest.mark.parametrize("case", ["iiwa14", "chain4", "chain5", "chain6", "chain8", "chain7_prismatic"])
 def test_chain_kernel_vs_oracle(case):
     """variant 7 (one knot point per lane, serial chains): ragged batch, damping, qdd=None, alternate gravity, c_out,
     both precisions; prismatic joints exercise the reference's :1292 quirk path of the kernel."""
     from rbdreference_b200 import RBDReference, robots
-    rb = robots.iiwa14() if case == "iiwa14" else (_chain_robot(6) if case == "chain6" else _chain_robot(7, prismatic_at=(0, 3, 6)))
+    rb = robots.iiwa14() if case == "iiwa14" else (_chain_robot(7, prismatic_at=(0, 3, 6)) if case == "chain7_prismatic"
+                                                   else _chain_robot(int(case[5:])))
     bo = BatchOracle(rb)
     n = rb.get_num_vel()
     B = 32 * 5 + 13

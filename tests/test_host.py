@@ -251,3 +251,22 @@ def test_gloo_gather(tmp_path, world):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_reference_arm_prints_the_contract_line_with_our_config():
+    """`bench.py --impl reference` (CPU only): one JSON line with impl / cpu_baseline / e2e, and the same `config`
+    dict our arm prints for the same workload (the driver compares them)."""
+    import json
+    import bench
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "evals/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+
+    class A:
+        robot, op, dtype, batch = "iiwa14", "rnea_grad", "f64", 1 << 20
+    assert line["config"] == bench.config_for(A, 7)
+    assert line["config"]["n_dof"] == 7 and line["config"]["batch_per_gpu"] == 1 << 20

@@ -25,7 +25,9 @@ for n in 2 4 8; do [ -f $G/bench_n${n}_r02.json ] && tail -1 $G/bench_n${n}_r02.
   for o in rbd_launch_pass_double rbd_launch_grad_double rbd_launch_minv_double; do
     echo "== $o.o"; cuobjdump -sass rbdreference_b200/csrc/_build/$o.o | grep -E "UBLKCP|SYNCS|UTMA" | awk '{ i=2; if ($2 ~ /^@/) i=3; print $i }' | sed 's/;//' | sort | uniq -c | sort -rn
   done
-  echo "== per kernel (UBLKCP count)"
-  cuobjdump -sass rbdreference_b200/csrc/_build/rbd_launch_pass_double.o rbdreference_b200/csrc/_build/rbd_launch_grad_double.o rbdreference_b200/csrc/_build/rbd_launch_minv_double.o | awk '/Function :/ { f=$3 } /UBLKCP/ { c[f]++ } END { for (k in c) print c[k], k }' | sort -rn | c++filt | cut -c1-160
+  echo "== UBLKCP instructions per kernel"
+  for o in rbd_launch_pass_double rbd_launch_grad_double rbd_launch_minv_double; do
+    cuobjdump -sass rbdreference_b200/csrc/_build/$o.o | grep -E "Function|UBLKCP" | awk '/Function/ { f=$3 } /UBLKCP/ { c[f]++ } END { for (k in c) print c[k], k }' | c++filt | sed 's/(.*//' | sort -k2
+  done
 } > $P/r02_sass_bulk_copy.txt
 ls -la $P | grep r02
