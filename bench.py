@@ -603,9 +603,30 @@ def measure_e2e(args, eng, torch, dist, dev, rank, world, n, B):
     h2d = n_in * n * itemsize * B
     d2h = int(np.prod(out_tail)) * itemsize * B
     secs = float(t.item()) / steps
+    # what the link gives a lone copy in the dominant direction on this box, measured right here (all ranks at once when
+    # N > 1, as in the e2e step): the denominator of `frac_of_pcie`
+    big_dir = "d2h" if d2h >= h2d else "h2d"
+    probe_h = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+    probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    copy = (lambda: probe_h.copy_(probe_d, non_blocking=True)) if big_dir == "d2h" else (lambda: probe_d.copy_(probe_h, non_blocking=True))
+    copy()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    p0 = time.perf_counter()
+    for _ in range(4):
+        copy()
+    torch.cuda.synchronize(dev)
+    tp = torch.tensor([time.perf_counter() - p0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    link = 4 * (256 << 20) / float(tp.item()) / 1e9
     return {"value": world * B / secs, "unit": "evals/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": 1e3 * secs,
             "pcie_gbs": {"h2d": h2d / secs / 1e9, "d2h": d2h / secs / 1e9},
+            "pcie_probe": {"direction": big_dir, "gbs_per_gpu": link,
+                           "note": "plain 256 MB pinned copy, every rank at once, measured after the e2e steps"},
+            "frac_of_pcie": (max(h2d, d2h) / secs / 1e9) / link,
             "api": "RBDReference.%s(numpy, ..., out=numpy) on pinned host arrays; chunked 3-stream pipeline inside the engine" % args.op}
 
 
