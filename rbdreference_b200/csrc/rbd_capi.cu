@@ -259,6 +259,10 @@ void fill_model(const RbdModelDesc* d, DevModel<T>& out) {
   }
 }
 
+}  // namespace
+
+namespace rbd_host {
+
 // ---- FastModel: rigid-body parameters, r(q) coefficients, stash-slot plan ---------------------
 bool build_fast_model(const RbdModelDesc* d, FastModel<double>& out) {
   std::memset(&out, 0, sizeof(out));
@@ -372,6 +376,52 @@ bool build_dfs_model(const RbdModelDesc* d, FastModel<double>& out, DfsPlan& pla
   }
   return ok;
 }
+
+// Index tables of the warp-cooperative kernels for a robot in depth-first numbering: pointer-jumping ancestor
+// table, root components, depths.
+void build_coop_plans(const FastModel<double>& dfs, CoopPlan& cp, CoopMinvPlan& mp) {
+  std::memset(&cp, 0, sizeof(cp));
+  std::memset(&mp, 0, sizeof(mp));
+  const int n = dfs.n;
+  int depth[RBD_MAX_DOF];
+  for (int i = 0; i < n; ++i) {
+    const int p = dfs.parent[i];
+    cp.jump[0][i] = p;
+    if (p < 0) cp.comp_begin[cp.ncomp++] = i;
+    depth[i] = p < 0 ? 0 : depth[p] + 1;
+    if (depth[i] > cp.maxdepth) cp.maxdepth = depth[i];
+  }
+  for (int s = 1; s < 5; ++s)
+    for (int i = 0; i < n; ++i) cp.jump[s][i] = cp.jump[s - 1][i] < 0 ? -1 : cp.jump[s - 1][cp.jump[s - 1][i]];
+  while ((1 << cp.nsteps) < cp.maxdepth + 1) ++cp.nsteps;
+  cp.comp_begin[cp.ncomp] = n;
+  for (int i = 0; i < n; ++i) {
+    const int p = dfs.parent[i];
+    mp.depth[i] = depth[i];
+    mp.comp_root[i] = p < 0 ? i : mp.comp_root[p];
+    if (i - mp.comp_root[i] + 1 > mp.maxcomp) mp.maxcomp = i - mp.comp_root[i] + 1;
+  }
+}
+
+void narrow_fast_model(const FastModel<double>& a, FastModel<float>& b) {
+  std::memset(&b, 0, sizeof(b));
+  b.n = a.n; b.n_slot_a = a.n_slot_a; b.n_slot_b = a.n_slot_b; b.rigid = a.rigid; b.has_prismatic = a.has_prismatic;
+  for (int i = 0; i < RBD_MAX_DOF; ++i) {
+    b.parent[i] = a.parent[i]; b.kind[i] = a.kind[i]; b.slot_a[i] = a.slot_a[i]; b.slot_b[i] = a.slot_b[i];
+    b.anc_mask[i] = a.anc_mask[i]; b.sub_mask[i] = a.sub_mask[i];
+    b.damping[i] = (float)a.damping[i]; b.mass[i] = (float)a.mass[i];
+    for (int k = 0; k < 9; ++k) { b.EA[i][k] = (float)a.EA[i][k]; b.EB[i][k] = (float)a.EB[i][k]; b.EC[i][k] = (float)a.EC[i][k]; }
+    for (int k = 0; k < 3; ++k) {
+      b.rA[i][k] = (float)a.rA[i][k]; b.rB[i][k] = (float)a.rB[i][k]; b.rC[i][k] = (float)a.rC[i][k];
+      b.axis[i][k] = (float)a.axis[i][k]; b.h[i][k] = (float)a.h[i][k];
+    }
+    for (int k = 0; k < 6; ++k) b.Ib[i][k] = (float)a.Ib[i][k];
+  }
+}
+
+}  // namespace rbd_host
+
+namespace {
 
 
 // Schedule of the tile minv kernel (rbd_tile_minv_kernels.cuh): chains of the depth-first numbering with their
@@ -538,22 +588,6 @@ void fill_chain_model(const FastModel<double>& fm, ChainModel<T>& cm) {
   }
 }
 
-void narrow_fast_model(const FastModel<double>& a, FastModel<float>& b) {
-  std::memset(&b, 0, sizeof(b));
-  b.n = a.n; b.n_slot_a = a.n_slot_a; b.n_slot_b = a.n_slot_b; b.rigid = a.rigid; b.has_prismatic = a.has_prismatic;
-  for (int i = 0; i < RBD_MAX_DOF; ++i) {
-    b.parent[i] = a.parent[i]; b.kind[i] = a.kind[i]; b.slot_a[i] = a.slot_a[i]; b.slot_b[i] = a.slot_b[i];
-    b.anc_mask[i] = a.anc_mask[i]; b.sub_mask[i] = a.sub_mask[i];
-    b.damping[i] = (float)a.damping[i]; b.mass[i] = (float)a.mass[i];
-    for (int k = 0; k < 9; ++k) { b.EA[i][k] = (float)a.EA[i][k]; b.EB[i][k] = (float)a.EB[i][k]; b.EC[i][k] = (float)a.EC[i][k]; }
-    for (int k = 0; k < 3; ++k) {
-      b.rA[i][k] = (float)a.rA[i][k]; b.rB[i][k] = (float)a.rB[i][k]; b.rC[i][k] = (float)a.rC[i][k];
-      b.axis[i][k] = (float)a.axis[i][k]; b.h[i][k] = (float)a.h[i][k];
-    }
-    for (int k = 0; k < 6; ++k) b.Ib[i][k] = (float)a.Ib[i][k];
-  }
-}
-
 }  // namespace
 
 extern "C" {
@@ -584,31 +618,7 @@ int rbd_model_create(const RbdModelDesc* desc, rbd_model_t** out) {
   narrow_fast_model(m->fd, m->ff);
   m->fast_ok = build_dfs_model(desc, m->fd_dfs, m->plan) && m->fast_ok;
   narrow_fast_model(m->fd_dfs, m->ff_dfs);
-  {
-    CoopPlan& cp = m->coop;
-    std::memset(&cp, 0, sizeof(cp));
-    const int n = desc->n;
-    int depth[RBD_MAX_DOF];
-    for (int i = 0; i < n; ++i) {
-      const int p = m->fd_dfs.parent[i];
-      cp.jump[0][i] = p;
-      if (p < 0) cp.comp_begin[cp.ncomp++] = i;
-      depth[i] = p < 0 ? 0 : depth[p] + 1;
-      if (depth[i] > cp.maxdepth) cp.maxdepth = depth[i];
-    }
-    for (int s = 1; s < 5; ++s)
-      for (int i = 0; i < n; ++i) cp.jump[s][i] = cp.jump[s - 1][i] < 0 ? -1 : cp.jump[s - 1][cp.jump[s - 1][i]];
-    while ((1 << cp.nsteps) < cp.maxdepth + 1) ++cp.nsteps;
-    cp.comp_begin[cp.ncomp] = n;
-    CoopMinvPlan& mp = m->coop_minv;
-    std::memset(&mp, 0, sizeof(mp));
-    for (int i = 0; i < n; ++i) {
-      const int p = m->fd_dfs.parent[i];
-      mp.depth[i] = depth[i];
-      mp.comp_root[i] = p < 0 ? i : mp.comp_root[p];
-      if (i - mp.comp_root[i] + 1 > mp.maxcomp) mp.maxcomp = i - mp.comp_root[i] + 1;
-    }
-  }
+  build_coop_plans(m->fd_dfs, m->coop, m->coop_minv);
   build_tile_plan(m->fd_dfs, m->plan, m->coop_minv, m->coop.maxdepth, 4, 8, m->tile);
   build_tile_plan(m->fd_dfs, m->plan, m->coop_minv, m->coop.maxdepth, 2, 16, m->tile2);
   fill_chain_model<double>(m->fd, m->chain_d);

@@ -212,6 +212,11 @@ __device__ __forceinline__ T dot6(const T* s, const T* x) {
   return acc;
 }
 
+// request the cache line holding p into L2 (no register, no wait)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ---- 1-D bulk copies (TMA engine, cp.async.bulk) between a warp's shared-memory tile and its contiguous slab in HBM ----
 // A tile that has the exact layout of the slab moves with ONE instruction issued by one lane instead of count / 32
 // load + store pairs per lane: the LSU issue slots stay free for the arithmetic and the copy engine works in the

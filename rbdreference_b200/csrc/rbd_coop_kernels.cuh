@@ -35,6 +35,19 @@ struct CoopPlan {
   int jump[5][RBD_MAX_DOF];            // jump[s][i] = ancestor of i at distance 2^s (DFS ids) or -1
 };
 
+// Floating base (FB = true; RBDReference.py :585/:591, :1141-1168, :1212-1238, :1267-1282,
+// :1309-1341): body 0 of the model is the base, a 6-DoF joint with S = eye(6); body i >= 1 reads q[i + 6], qd[i + 5] and
+// owns row / column i + 5.  The kernel then works in BASE coordinates instead of world coordinates: the base's pose only
+// enters through the direction of gravity (X_0 a_grav), its motion subspace is the unit vectors, its own velocity and
+// acceleration (qd[0:6], X_0 a_grav + qdd[0:6]) seed the root-path sums, and it is one more lane of the group whose
+// subtree composite is the whole robot.  Columns 0..5 are derivatives along unit twists of the base in base
+// coordinates (Psi_dot = 0, Psi_ddot = (X_0 a_grav) x e_k, S_dot = v_0 x e_k).
+struct FbBaseLayout {
+  int quat_off;                        // q[quat_off .. +4] unit quaternion
+  int w_first;                         // 1: (w, x, y, z), 0: (x, y, z, w)
+  int transpose;                       // 0: E = R(quat)^T, 1: E = R(quat)
+};
+
 template <typename T>
 __device__ __forceinline__ T shfl_t(T x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 
@@ -47,20 +60,23 @@ __host__ __device__ inline int coop_grad_tile_stride(int n, int ipw, bool split)
 // CONLY = true: rnea only (c into c_out; dc_du is not touched): the forward scans, the composite
 // force f^C by a 6-value segmented scan and c_i = S_i . f^C_i.  Used for small (MPC-sized) batches,
 // where the knot-point-per-lane rnea kernel is bound by the latency of one 32-knot-point task.
-template <typename T, int G, bool SPLIT, bool CONLY = false>
+template <typename T, int G, bool SPLIT, bool CONLY = false, bool FB = false>
 __global__ void __launch_bounds__(kCoopWarps * 32)
 rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__ DfsPlan plan,
                       const __grid_constant__ CoopPlan cp, int64_t B, const T* __restrict__ q,
                       const T* __restrict__ qd, const T* __restrict__ qdd, T gravity, int use_damping,
-                      T* __restrict__ dc_du, T* __restrict__ c_out) {
+                      T* __restrict__ dc_du, T* __restrict__ c_out, const FbBaseLayout fbl) {
+  static_assert(!(FB && CONLY), "the floating-base rnea has its own kernel");
   constexpr int IPW = 32 / G;                          // knot points per warp
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = m.n;
-  const int n2 = 2 * n;
+  const int n = m.n;                                   // bodies (FB: the base is body 0)
+  const int nv = FB ? n + 5 : n;                       // joint-space size: rows of dc_du, entries of qd / qdd / c
+  const int nq = FB ? n + 6 : n;                       // entries of q
+  const int n2 = 2 * nv;
   T* mdl = reinterpret_cast<T*>(smem_raw);                                   // [n][51]
   T* vec_all = mdl + ((n * kCoopMdlStride + 1) & ~1);                        // [warps][32][19]
   T* tile_all = vec_all + kCoopWarps * 32 * kCoopVecStride;                  // [warps][tile_vals (+1)]
-  const int tile_stride = coop_grad_tile_stride(n, IPW, SPLIT);   // also holds the 32 x 29 composite-scan buffer
+  const int tile_stride = coop_grad_tile_stride(nv, IPW, SPLIT);  // also holds the 32 x 29 composite-scan buffer
   int* imdl = reinterpret_cast<int*>(tile_all + kCoopWarps * tile_stride);   // [n][10]
 
   // ---- robot constants -> shared memory (once per CTA)
@@ -104,6 +120,9 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
   const int sub_end = ip[2];
   const bool cut = valid && sub_end < plan.comp_end[ib];   // bodies of the same component follow the subtree
   const int oi = ip[3];
+  const bool base = FB && valid && i == 0;             // the lane of the floating base
+  const int qoff = FB ? oi + 6 : oi;                   // this body's entry of q
+  const int voff = FB ? oi + 5 : oi;                   // ... of qd / qdd / c, and its row / column of dc_du
   T* vec = vec_all + warp * 32 * kCoopVecStride;
   T* tile = tile_all + warp * tile_stride;
   T* myvec = vec + lane * kCoopVecStride;
@@ -119,9 +138,9 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
     if (grp0 < ngroups) {
       int64_t b = grp0 * IPW + g;
       if (b >= B) b = B - 1;
-      q_nx = q[b * n + oi];
-      qd_nx = qd[b * n + oi];
-      qdd_nx = qdd ? qdd[b * n + oi] : T(0);
+      q_nx = q[b * nq + qoff];
+      qd_nx = qd[b * nv + voff];
+      qdd_nx = qdd ? qdd[b * nv + voff] : T(0);
     }
   }
   for (int64_t grp = (int64_t)blockIdx.x * kCoopWarps + warp; grp < ngroups; grp += gstride) {
@@ -138,9 +157,32 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
       if (grp + gstride < ngroups) {
         int64_t bn = (grp + gstride) * IPW + g;
         if (bn >= B) bn = B - 1;
-        q_nx = q[bn * n + oi];
-        qd_nx = qd[bn * n + oi];
-        qdd_nx = qdd ? qdd[bn * n + oi] : T(0);
+        q_nx = q[bn * nq + qoff];
+        qd_nx = qd[bn * nv + voff];
+        qdd_nx = qdd ? qdd[bn * nv + voff] : T(0);
+        if (FB && base) {                                   // the base's 16 inputs of the next knot point -> L2
+          prefetch_l2(q + bn * nq);
+          prefetch_l2(qd + bn * nv);
+          if (qdd) prefetch_l2(qdd + bn * nv);
+        }
+      }
+      if (FB && base) {
+        // v_0 = qd[0:6] (:585, S = eye(6)), X_0 a_grav (:578; only the rotation matters: a_grav is a pure linear
+        // acceleration) and a_0 = X_0 a_grav + qdd[0:6] (:591; crm(v_0) v_0 = 0) go to the base's row of the table
+        const T* qq = q + b * nq + fbl.quat_off;
+        const T qw = fbl.w_first ? qq[0] : qq[3];
+        const T qx = fbl.w_first ? qq[1] : qq[0], qy = fbl.w_first ? qq[2] : qq[1], qz = fbl.w_first ? qq[3] : qq[2];
+        T e2[3];                                            // third column of E: the world's z axis in base coordinates
+        e2[0] = fbl.transpose ? T(2) * (qx * qz + qy * qw) : T(2) * (qx * qz - qy * qw);
+        e2[1] = fbl.transpose ? T(2) * (qy * qz - qx * qw) : T(2) * (qy * qz + qx * qw);
+        e2[2] = T(1) - T(2) * (qx * qx + qy * qy);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const T xg = k < 3 ? T(0) : -gravity * e2[k - 3];
+          myvec[k] = qd[b * nv + k];
+          myvec[6 + k] = xg;
+          myvec[12 + k] = qdd ? xg + qdd[b * nv + k] : xg;
+        }
       }
       T f1, f2;
       if (kind == 0) sincos_t(qi, &f2, &f1);
@@ -186,7 +228,7 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
         S[0] = S[1] = S[2] = T(0);
         S[3] = w[0]; S[4] = w[1]; S[5] = w[2];
       }
-      if (!valid) {
+      if (!valid || base) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) S[k] = T(0);
       }
@@ -194,6 +236,10 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
     // v_i = sum over the root path of S_j qd_j
 #pragma unroll
     for (int k = 0; k < 6; ++k) v[k] = S[k] * qdi;
+    if (FB && base) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v[k] = myvec[k];
+    }
     for (int s = 0; s < nsteps; ++s) {
       const int src = valid ? ip[4 + s] : -1;
       const int sl = gbase + (src >= 0 ? src : 0);
@@ -209,6 +255,10 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
     crm_mul(vl, S, Pd);
 #pragma unroll
     for (int k = 0; k < 6; ++k) a[k] = fma_t(Pd[k], qdi, S[k] * qddi);
+    if (FB && base) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a[k] = myvec[12 + k];
+    }
 #pragma unroll
     for (int k = 0; k < 6; ++k) al[k] = a[k];           // own increment, subtracted back below
     for (int s = 0; s < nsteps; ++s) {
@@ -220,7 +270,7 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
         if (src >= 0) a[k] += t;
       }
     }
-    a[5] -= gravity;                                      // a_base = [0,0,0,0,0,-GRAVITY] (RBDReference.py:566)
+    if (!FB) a[5] -= gravity;                             // a_base = [0,0,0,0,0,-GRAVITY] (RBDReference.py:566); FB: inside a_0
 #pragma unroll
     for (int k = 0; k < 6; ++k) al[k] = a[k] - al[k];
     {
@@ -231,7 +281,7 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
       for (int k = 0; k < 6; ++k) Pdd[k] += t6[k];
     }
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { if (!CONLY) { myvec[k] = S[k]; myvec[6 + k] = Pd[k]; myvec[12 + k] = Pdd[k]; } }
+    for (int k = 0; k < 6; ++k) { if (!CONLY && !(FB && base)) { myvec[k] = S[k]; myvec[6 + k] = Pd[k]; myvec[12 + k] = Pdd[k]; } }
 
     // ------------------------------------------------------------------ own terms -> subtree composites
     // 0 m | 1..3 h | 4..9 Ibar | 10..15 Sym | 16..18 n | 19..21 l | 22..27 f
@@ -382,7 +432,14 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
       for (int k = 0; k < 3; ++k) F2[3 + k] = T(2) * (F2[3 + k] - tl[k]);
     }
     const bool store = valid && (grp * IPW + g) < B;
-    if (c_out && store) c_out[b * n + oi] = dot6s(S, fC);
+    if (c_out && store) {
+      if (FB && base) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c_out[b * nv + k] = fC[k];                      // :612 with S = eye(6)
+      } else {
+        c_out[b * nv + voff] = dot6s(S, fC);
+      }
+    }
     T F1q[6];                                                 // F1 with the prismatic quirk of :1292 folded in
 #pragma unroll
     for (int k = 0; k < 6; ++k) F1q[k] = F1[k];
@@ -401,50 +458,110 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
     // The tile holds dc_du of the warp's knot points (SPLIT = false) or one half of it at a time
     // (SPLIT = true: dc_dq, then dc_dqd - half the shared memory, for large robots).
     constexpr int NPASS = SPLIT ? 2 : 1;
-    const int tw = SPLIT ? n : n2;                            // tile row width
-    const int tvals = IPW * n * tw;
-    T* mytile2 = tile + g * n * tw;
+    const int tw = SPLIT ? nv : n2;                           // tile row width
+    const int tvals = IPW * nv * tw;
+    T* mytile2 = tile + g * nv * tw;
 #pragma unroll
     for (int half = 0; half < NPASS; ++half) {
       const bool do_q = !SPLIT || half == 0, do_qd = !SPLIT || half == 1;
-      const int qd_off = SPLIT ? 0 : n;                       // column offset of the dc_dqd block inside the tile
+      const int qd_off = SPLIT ? 0 : nv;                      // column offset of the dc_dqd block inside the tile
       {
         typedef typename Vec2<T>::type V2;
         V2 z; z.x = T(0); z.y = T(0);
         for (int k = lane; k < ((tvals + 1) >> 1); k += 32) reinterpret_cast<V2*>(tile)[k] = z;   // structural zeros
       }
       __syncwarp();
-      if (valid) {
-        if (do_q) mytile2[oi * tw + oi] = dot6s(S, F1);
+      if (valid && !base) {
+        if (do_q) mytile2[voff * tw + voff] = dot6s(S, F1);
         if (do_qd) {
           T ddd = dot6s(S, F2);
-          if (use_damping) ddd += mb[49];                     // RBDReference.py:1341
-          mytile2[oi * tw + qd_off + oi] = ddd;
+          if (!FB && use_damping) ddd += mb[49];              // RBDReference.py:1341
+          mytile2[voff * tw + qd_off + voff] = ddd;
         }
       }
       // ---------------------------------------------------------------- ancestors of i
       {
         int j = par;
         for (int t = 0; t < cp.maxdepth; ++t) {
-          if (j >= 0) {
+          if (j >= (FB ? 1 : 0)) {                            // FB: the base (body 0) is handled below
             const T* vj = vec + (gbase + j) * kCoopVecStride;
             T Sj[6], Pdj[6];
 #pragma unroll
             for (int k = 0; k < 6; ++k) { Sj[k] = vj[k]; Pdj[k] = vj[6 + k]; }
-            const int oj = imdl[j * kCoopIntStride + 3];
+            const int oj = imdl[j * kCoopIntStride + 3] + (FB ? 5 : 0);
             if (do_q) {
               T Pddj[6];
 #pragma unroll
               for (int k = 0; k < 6; ++k) Pddj[k] = vj[12 + k];
-              mytile2[oj * tw + oi] = dot6s(Sj, F1q);
-              mytile2[oi * tw + oj] = fma_t(T(2), dot3s(F3, Pdj), dot6s(F4, Pddj));
+              mytile2[oj * tw + voff] = dot6s(Sj, F1q);
+              mytile2[voff * tw + oj] = fma_t(T(2), dot3s(F3, Pdj), dot6s(F4, Pddj));
             }
             if (do_qd) {
-              mytile2[oj * tw + qd_off + oi] = dot6s(Sj, F2);
-              mytile2[oi * tw + qd_off + oj] = T(2) * (dot6s(F4, Pdj) + dot3s(F3, Sj));
+              mytile2[oj * tw + qd_off + voff] = dot6s(Sj, F2);
+              mytile2[voff * tw + qd_off + oj] = T(2) * (dot6s(F4, Pdj) + dot3s(F3, Sj));
             }
             j = imdl[j * kCoopIntStride];
           }
+        }
+      }
+      if (FB) {
+        // ---------------------------------------------------------------- the base's six rows and columns
+        const T* vb = vec + gbase * kCoopVecStride;           // the base's row of the table: v_0 | X_0 a_grav
+        T v0[6], xg[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { v0[k] = vb[k]; xg[k] = vb[6 + k]; }
+        if (valid && !base) {
+          // rows 0..5: S_0 = eye(6), so the entries are the components of F1 / F2 (:1282, :1325); columns 0..5:
+          // F4 . (a x e_k) = -(a x* F4)[k] with a = X_0 a_grav (dq: Psi_ddot_0k) or v_0 (dqd: Psi_dot_0k + S_dot_0k)
+          T t6[6];
+          if (do_q) {
+            crf_mul(xg, F4, t6);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { mytile2[k * tw + voff] = F1q[k]; mytile2[voff * tw + k] = -t6[k]; }
+          }
+          if (do_qd) {
+            crf_mul(v0, F4, t6);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+              mytile2[k * tw + qd_off + voff] = F2[k];
+              mytile2[voff * tw + qd_off + k] = k < 3 ? fma_t(T(2), F3[k], -t6[k]) : -t6[k];
+            }
+          }
+        }
+        // base x base block: lane k < 6 of the group owns column k and works on the base's composite
+        T cb[22];
+#pragma unroll
+        for (int k = 0; k < 22; ++k) cb[k] = shfl_t(acc[k], gbase);
+        if (i < 6) {
+          T ek[6], x6[6], y6[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) ek[k] = k == i ? T(1) : T(0);
+          if (do_q) {
+            crm_mul(xg, ek, x6);
+            rigid_mul(cb[0], cb + 1, cb + 4, x6, y6);          // I^C_0 ((X_0 a_grav) x e_k)
+#pragma unroll
+            for (int r = 0; r < 6; ++r) mytile2[r * tw + i] = y6[r];
+          }
+          if (do_qd) {
+            T tb[3], tl[3], tl2[3];
+            crm_mul(v0, ek, x6);
+            rigid_mul(cb[0], cb + 1, cb + 4, x6, y6);          // I^C_0 (v_0 x e_k) + 2 B^C_0 e_k
+            sym3_mul(cb + 10, ek, tb);
+            cross3(cb + 16, ek, tl);
+            cross3(cb + 19, ek, tl2);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { y6[k] += tb[k] - tl[k]; y6[3 + k] -= T(2) * tl2[k]; }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) mytile2[r * tw + qd_off + i] = y6[r];
+          }
+        }
+        if (use_damping && do_qd) {
+          // :1336-1341 to the letter: the base's damping on the whole block [0:5, 0:5], body i's on [i, i] (body
+          // index, not i + 5)
+          __syncwarp();
+          for (int e = i; e < 25; e += G) mytile2[(e / 5) * tw + qd_off + (e % 5)] += mdl[49];
+          __syncwarp();
+          if (valid && !base) mytile2[oi * tw + qd_off + oi] += mb[49];
         }
       }
       __syncwarp();
@@ -452,23 +569,23 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
       {
         const int64_t first = grp * IPW;
         const int nk = (int)((B - first) < IPW ? (B - first) : IPW);
-        T* dst = dc_du + first * n * n2;
-        if (!SPLIT && warp_bulk_store(dst, tile, nk * n * n2, lane)) {
+        T* dst = dc_du + first * nv * n2;
+        if (!SPLIT && warp_bulk_store(dst, tile, nk * nv * n2, lane)) {
           // one cp.async.bulk for the warp's slab (awaited before the tile is written again)
         } else if (!SPLIT) {
           typedef typename Vec2<T>::type V2;
-          const int count = nk * n * n2;
-          if (((IPW * n * n2) & 1) == 0 && nk == IPW && (reinterpret_cast<uintptr_t>(dc_du) & (sizeof(V2) - 1)) == 0) {
+          const int count = nk * nv * n2;
+          if (((IPW * nv * n2) & 1) == 0 && nk == IPW && (reinterpret_cast<uintptr_t>(dc_du) & (sizeof(V2) - 1)) == 0) {
             for (int k = lane; k < (count >> 1); k += 32) __stcs(reinterpret_cast<V2*>(dst) + k, reinterpret_cast<const V2*>(tile)[k]);
           } else {
             for (int k = lane; k < count; k += 32) __stcs(dst + k, tile[k]);
           }
         } else {
           // rows of n values go to columns [half*n, half*n + n) of the (n, 2n) result
-          const int count = nk * n * n;
+          const int count = nk * nv * nv;
           for (int k = lane; k < count; k += 32) {
-            const int r = k / n, c = k - r * n;               // r runs over (knot, row)
-            __stcs(dst + (int64_t)r * n2 + half * n + c, tile[k]);
+            const int r = k / nv, c = k - r * nv;             // r runs over (knot, row)
+            __stcs(dst + (int64_t)r * n2 + half * nv + c, tile[k]);
           }
         }
       }

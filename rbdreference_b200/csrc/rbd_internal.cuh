@@ -68,6 +68,11 @@ int sm_count();                         // SMs of the current device (cudaDevAtt
 inline int64_t grid_cap(int ctas_per_sm = 16) { return (int64_t)sm_count() * ctas_per_sm; }
 size_t smem_limit();                    // shared-memory budget per warp of the world-frame grad kernel
 cudaMemPool_t scratch_pool(int dev);    // private stream-ordered pool for scratch buffers
+// model compilation shared by the fixed-base and the floating-base handles (rbd_capi.cu)
+bool build_fast_model(const RbdModelDesc* d, rbd::FastModel<double>& out);                        // false: not rigid / not 1-DoF
+bool build_dfs_model(const RbdModelDesc* d, rbd::FastModel<double>& out, rbd::DfsPlan& plan);      // depth-first renumbering
+void build_coop_plans(const rbd::FastModel<double>& dfs, rbd::CoopPlan& cp, rbd::CoopMinvPlan& mp);
+void narrow_fast_model(const rbd::FastModel<double>& a, rbd::FastModel<float>& b);
 int fail(int code, const char* msg);    // records the message for rbd_last_error_string()
 int cuda_status(const char* what);      // cudaGetLastError -> status code; counts the launch
 

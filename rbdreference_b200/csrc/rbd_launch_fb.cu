@@ -10,9 +10,46 @@ using namespace rbd_host;
 struct rbd_fb_model {
   FbModel<double> d;
   FbModel<float> f;
+  // warp-cooperative kernels (rbd_coop_kernels.cuh with FB = true): the NB bodies in depth-first numbering, the base
+  // as body 0 with an identity transform; valid when every inertia has rigid-body structure
+  bool fast_ok;
+  FastModel<double> fd_dfs;
+  FastModel<float> ff_dfs;
+  DfsPlan plan;
+  CoopPlan coop;
+  CoopMinvPlan coop_minv;
+  FbBaseLayout layout;
 };
 
 namespace {
+
+template <typename T> const FastModel<T>& pick_fb_dfs(const rbd_fb_model* m);
+template <> const FastModel<double>& pick_fb_dfs<double>(const rbd_fb_model* m) { return m->fd_dfs; }
+template <> const FastModel<float>& pick_fb_dfs<float>(const rbd_fb_model* m) { return m->ff_dfs; }
+
+// The robot as the cooperative kernels see it: body 0 becomes a joint with the identity transform (the kernels work in
+// base coordinates and treat lane 0 as the base), bodies 1.. keep their 1-DoF joints.
+void build_fb_coop(const RbdFbModelDesc* fd, rbd_fb_model* m) {
+  const RbdModelDesc* d = &fd->bodies;
+  const int n = d->n;
+  double S[RBD_MAX_DOF * 6], XA[RBD_MAX_DOF * 18], XB[RBD_MAX_DOF * 18], XC[RBD_MAX_DOF * 18];
+  int32_t kind[RBD_MAX_DOF];
+  std::memcpy(S, d->S, sizeof(double) * 6 * n);
+  std::memcpy(XA, d->XA, sizeof(double) * 18 * n);
+  std::memcpy(XB, d->XB, sizeof(double) * 18 * n);
+  std::memcpy(XC, d->XC, sizeof(double) * 18 * n);
+  std::memcpy(kind, d->kind, sizeof(int32_t) * n);
+  for (int k = 0; k < 6; ++k) S[k] = k == 2 ? 1.0 : 0.0;
+  for (int k = 0; k < 18; ++k) { XA[k] = (k == 0 || k == 4 || k == 8) ? 1.0 : 0.0; XB[k] = 0.0; XC[k] = 0.0; }
+  kind[0] = 0;
+  RbdModelDesc pd = {n, d->parent, kind, S, XA, XB, XC, d->I, d->damping};
+  m->fast_ok = build_dfs_model(&pd, m->fd_dfs, m->plan) && m->plan.orig[0] == 0;
+  narrow_fast_model(m->fd_dfs, m->ff_dfs);
+  build_coop_plans(m->fd_dfs, m->coop, m->coop_minv);
+  m->layout.quat_off = fd->quat_off;
+  m->layout.w_first = fd->w_first;
+  m->layout.transpose = fd->transpose;
+}
 
 template <typename T> const FbModel<T>& pick_fb(const rbd_fb_model* m);
 template <> const FbModel<double>& pick_fb<double>(const rbd_fb_model* m) { return m->d; }
@@ -66,6 +103,29 @@ int launch_fb_rnea_grad(const rbd_fb_model* m, int64_t B, const T* q, const T* q
                         T* c_out, void* stream) {
   RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_fb_rnea_grad: null model/q/qd/dc_du or negative B");
   if (B == 0) return 0;
+  const int variant = g_variant.load(std::memory_order_relaxed);
+  if (m->fast_ok && variant != 1 && variant != 2) {
+    // world-frame composites in base coordinates, one body per lane (rbd_coop_kernels.cuh, FB = true)
+    const FastModel<T>& fm = pick_fb_dfs<T>(m);
+    const int n = fm.n, nv = n + 5;
+    const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+    const int ipw = 32 / G;
+    const int tile_stride = coop_grad_tile_stride(nv, ipw, false);
+    const size_t smem = (size_t)(((n * kCoopMdlStride + 1) & ~1) + kCoopWarps * 32 * kCoopVecStride + kCoopWarps * tile_stride) * sizeof(T) +
+                        (size_t)n * kCoopIntStride * sizeof(int);
+    if (smem <= kMaxDynSmem) {
+      auto kern = G == 8 ? rnea_grad_coop_kernel<T, 8, false, false, true>
+                         : (G == 16 ? rnea_grad_coop_kernel<T, 16, false, false, true> : rnea_grad_coop_kernel<T, 32, false, false, true>);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+      if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+      const int64_t ngroups = (B + ipw - 1) / ipw;
+      int64_t blocks = (ngroups + kCoopWarps - 1) / kCoopWarps;
+      if (blocks > grid_cap()) blocks = grid_cap();
+      kern<<<(unsigned)blocks, kCoopWarps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, B, q, qd, qdd, g, damp, dc_du, c_out,
+                                                                              m->layout);
+      return cuda_status("rbd_fb_rnea_grad(coop)");
+    }
+  }
   fb_rnea_grad_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, fb_smem_bytes<T>(m), (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, qd, qdd, g, damp,
                                                                                              dc_du, c_out);
   return cuda_status("rbd_fb_rnea_grad");
@@ -200,6 +260,7 @@ int rbd_fb_model_create(const RbdFbModelDesc* fd, rbd_fb_model_t** out) {
   if (!m) return fail(RBD_E_INVALID_ARGUMENT, "rbd_fb_model_create: out of host memory");
   fill_fb<double>(fd, m->d);
   fill_fb<float>(fd, m->f);
+  build_fb_coop(fd, m);
   *out = m;
   return 0;
 }

@@ -64,7 +64,7 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
       const int64_t cap = grid_cap();
       if (blocks > cap) blocks = cap;
       kern<<<(unsigned)blocks, kCoopWarps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, B, q, qd, qdd, g, damp,
-                                                                              dc_du, c_out);
+                                                                              dc_du, c_out, FbBaseLayout{});
       return cuda_status("rbd_rnea_grad(coop)");
     }
   }

@@ -42,7 +42,7 @@ int launch_rnea(const rbd_model* m, int64_t B, const T* q, const T* qd, const T*
       const int64_t ngroups = (B + ipw - 1) / ipw;
       int64_t blocks = (ngroups + kCoopWarps - 1) / kCoopWarps;
       if (blocks > grid_cap()) blocks = grid_cap();
-      kern<<<(unsigned)blocks, kCoopWarps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, B, q, qd, qdd, g, 0, nullptr, c);
+      kern<<<(unsigned)blocks, kCoopWarps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, B, q, qd, qdd, g, 0, nullptr, c, FbBaseLayout{});
       return cuda_status("rbd_rnea(coop)");
     }
   }
