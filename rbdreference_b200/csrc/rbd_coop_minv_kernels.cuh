@@ -45,17 +45,48 @@ struct CoopMinvPlan {
 
 // per-warp shared memory, in values of T:  tab | mb | big, where `big` holds the children's
 // inertias in phase A and is re-used for the G stashes and the output tile in phase C
+// fb: floating base - the matrix has n + 5 rows and the warp keeps the inverse of the base's articulated inertia
+// (21 values per knot point, kCmDinvStride apart) after `big`
+constexpr int kCmDinvStride = 24;     // (a multiple of four values: the next warp's table stays 16-byte aligned in FP32)
 template <typename T>
-__host__ __device__ inline int coop_minv_warp_vals(int n, int G, int maxdepth, int nslot) {
+__host__ __device__ inline int coop_minv_warp_vals(int n, int G, int maxdepth, int nslot, bool fb = false) {
   const int ipw = 32 / G;
+  const int nvv = fb ? n + 5 : n;
   const int a = 32 * kCmIaStride;
-  const int c = 6 * nslot * 32 + ((ipw * n * n + 3) & ~3);
-  return 32 * kCmTabStride + (maxdepth + 1) * 32 + (a > c ? a : c);
+  const int c = 6 * nslot * 32 + ((ipw * nvv * nvv + 3) & ~3);
+  return 32 * kCmTabStride + (maxdepth + 1) * 32 + (a > c ? a : c) + (fb ? ipw * kCmDinvStride : 0);
 }
 template <typename T>
-__host__ __device__ inline size_t coop_minv_smem_bytes(int n, int G, int maxdepth, int nslot, int warps) {
-  return (size_t)(((n * kCoopMdlStride + 3) & ~3) + warps * coop_minv_warp_vals<T>(n, G, maxdepth, nslot)) * sizeof(T) +
+__host__ __device__ inline size_t coop_minv_smem_bytes(int n, int G, int maxdepth, int nslot, int warps, bool fb = false) {
+  return (size_t)(((n * kCoopMdlStride + 3) & ~3) + warps * coop_minv_warp_vals<T>(n, G, maxdepth, nslot, fb)) * sizeof(T) +
          (size_t)n * 4 * sizeof(int);
+}
+
+// index of entry (r, c) of a symmetric 6x6 stored as its upper triangle, row by row (21 values)
+__host__ __device__ constexpr int sym6_idx(int r, int c) { return r <= c ? r * 6 - r * (r - 1) / 2 + (c - r) : c * 6 - c * (c - 1) / 2 + (r - c); }
+
+// s <- inverse of the symmetric positive definite 6x6 s (upper triangle): six symmetric sweeps (each pivot is the
+// diagonal of a Schur complement, positive without pivoting), which leave -inverse
+template <typename T>
+__device__ __forceinline__ void sym6_invert(T (&s)[21]) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const T d = T(1) / s[sym6_idx(k, k)];
+    T bk[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) bk[i] = s[sym6_idx(i, k)] * d;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i; j < 6; ++j)
+        if (i != k && j != k) s[sym6_idx(i, j)] = fma_t(-bk[i], s[sym6_idx(k, j)], s[sym6_idx(i, j)]);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (i != k) s[sym6_idx(i, k)] = bk[i];
+    s[sym6_idx(k, k)] = -d;
+  }
+#pragma unroll
+  for (int k = 0; k < 21; ++k) s[k] = -s[k];
 }
 
 // ---- per-body table entry in shared memory: w(3) invD | U(6) | r(3), stride kCmTabStride ------
@@ -85,14 +116,21 @@ __host__ __device__ inline int cm_pack(int depth, int slot, int pslot, int kind)
 // imdl[a] = {parent, sub_end, orig, cm_pack(...)}.  PRISM = false: every joint is revolute.
 // ZERO = false: the caller zeroed the tile and nothing else touched it since (every entry inside a
 // root component is rewritten on each call, entries between components are never written).
-template <typename T, int G, bool PRISM, bool ZERO = true>
+// FB = true (floating base, :652-691 / :761-779): body 0 is the base, whose "1 / D" is the 6x6 `dinv` of its knot point;
+// lane i >= 1 is column i + 5, the base's rows of that column are -dinv F (:687-691), its columns come from the mirror
+// (the reference fills both triangles with the same numbers up to rounding) and lanes 0..5 write dinv itself (:686).
+template <typename T, int G, bool PRISM, bool ZERO = true, bool FB = false>
 __device__ __forceinline__ void minv_column_phases(int n, int maxdepth, int maxcomp, int nslot, bool valid, int i, int gbase,
                                                    int lane, int oi, int comp_root, const int4* imdl, const T* tab, T* mbw,
-                                                   T* big, T* __restrict__ dst, int nknots) {
+                                                   T* big, T* __restrict__ dst, int nknots, const T* dinv = nullptr) {
   constexpr int IPW = 32 / G;
   typedef typename Vec2<T>::type V2;
-  const int nn = n * n;
+  const int nvv = FB ? n + 5 : n;                         // rows of the matrix
+  const int nn = nvv * nvv;
   const int g = lane / G;
+  const int col = FB ? oi + 5 : oi;                       // this lane's column
+  const bool colv = valid && !(FB && i == 0);             // the lane owns a joint's column
+  T m0[6];                                                // FB: the base's rows of the column
   T* tile = big + 6 * nslot * 32;                         // [IPW][n][n]
   T* mytile = tile + g * nn;
   const int tile_vals = IPW * nn;
@@ -109,9 +147,9 @@ __device__ __forceinline__ void minv_column_phases(int n, int maxdepth, int maxc
   // ------------------------------------------------------------------ phase B: walk to the root
   {
     T F[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-    int a = valid ? i : -1;
+    int a = colv ? i : -1;
     for (int t = 0; t <= maxdepth; ++t) {
-      if (a >= 0) {
+      if (a >= (FB ? 1 : 0)) {
         TabEntry<T> e;
         tab_load(tab + (gbase + a) * kCmTabStride, e);
         const int4 ia = imdl[a];
@@ -125,13 +163,36 @@ __device__ __forceinline__ void minv_column_phases(int n, int maxdepth, int maxc
         a = ia.x;
       }
     }
+    if (FB) {
+      const T* dg = dinv + g * kCmDinvStride;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        T acc = T(0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc = fma_t(dg[sym6_idx(r, k)], F[k], acc);
+        m0[r] = -acc;                                                          // :687-691
+      }
+    }
   }
   __syncwarp();
   // ------------------------------------------------------------------ phase C: preorder sweep
-  if (valid) {
+  if (colv) {
     T Gv[6];
-    const int oin = oi * n;
-    {
+    const int oin = col * nvv;
+    if (FB) {
+      // the base: G_0 = S_0 Minv[0:6, j] with S_0 = eye(6) (:778-781)
+      const int4 ia = imdl[0];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Gv[k] = m0[k];
+      const int sl = ((ia.w >> 8) & 0xff) - 1;
+      if (sl >= 0) {
+        T* gs = big + (sl * 6) * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gs[k * 32] = Gv[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { mytile[k * nvv + col] = m0[k]; mytile[oin + k] = m0[k]; }
+    } else {
       // the root of the component: no parent term (:778-781)
       const int a = comp_root;
       TabEntry<T> e;
@@ -151,6 +212,7 @@ __device__ __forceinline__ void minv_column_phases(int n, int maxdepth, int maxc
       mytile[oin + ia.z] = mij;
     }
     for (int a = comp_root + 1; a <= i; ++a) {
+      const int ra = FB ? imdl[a].z + 5 : imdl[a].z;      // row of body a
       TabEntry<T> e;
       tab_load(tab + (gbase + a) * kCmTabStride, e);
       const int4 ia = imdl[a];
@@ -175,9 +237,14 @@ __device__ __forceinline__ void minv_column_phases(int n, int maxdepth, int maxc
 #pragma unroll
         for (int k = 0; k < 6; ++k) gs[k * 32] = Gv[k];
       }
-      mytile[ia.z * n + oi] = mij;
-      mytile[oin + ia.z] = mij;                                                // :799-804
+      mytile[ra * nvv + col] = mij;
+      mytile[oin + ra] = mij;                                                  // :799-804
     }
+  }
+  if (FB && i < 6) {
+    const T* dg = dinv + g * kCmDinvStride;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) mytile[r * nvv + i] = dg[sym6_idx(r, i)];      // :686: the base block is inv(IA_0)
   }
   __syncwarp();
   // ------------------------------------------------------------------ coalesced slab write
@@ -243,19 +310,22 @@ __device__ __forceinline__ void crba_column_phase(int n, int maxdepth, bool vali
 
 // CRBA = false: minv (Minv out).  CRBA = true: the joint-space inertia matrix H (same launch
 // geometry and shared-memory layout; phases B and C are replaced by crba_column_phase).
-template <typename T, int G, bool PRISM, bool CRBA = false>
+template <typename T, int G, bool PRISM, bool CRBA = false, bool FB = false>
 __global__ void __launch_bounds__(kCmMaxWarps * 32)
 minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__ DfsPlan plan,
                  const __grid_constant__ CoopPlan cp, const __grid_constant__ CoopMinvPlan mp, int64_t B,
                  const T* __restrict__ q, T* __restrict__ Minv) {
+  static_assert(!(FB && CRBA), "crba has no floating-base branch here");
   constexpr int IPW = 32 / G;
   typedef typename Vec2<T>::type V2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = m.n;
-  const int nn = n * n;
+  const int n = m.n;                                      // bodies (FB: body 0 is the base, identity transform)
+  const int nvv = FB ? n + 5 : n;
+  const int nq = FB ? n + 6 : n;
+  const int nn = nvv * nvv;
   const int maxdepth = cp.maxdepth;
   const int nwarps = blockDim.x >> 5;
-  const int warp_vals = coop_minv_warp_vals<T>(n, G, maxdepth, m.n_slot_a);
+  const int warp_vals = coop_minv_warp_vals<T>(n, G, maxdepth, m.n_slot_a, FB);
   int4* imdl = reinterpret_cast<int4*>(smem_raw);                            // [n]
   T* mdl = reinterpret_cast<T*>(smem_raw + (size_t)n * sizeof(int4));        // [n][51]
   T* warp_all = mdl + ((n * kCoopMdlStride + 3) & ~3);                       // [nwarps][warp_vals]
@@ -302,6 +372,7 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
   T* mbw = tab + 32 * kCmTabStride;                       // [maxdepth+1][32]
   T* big = mbw + (maxdepth + 1) * 32;                     // phase A: [32][22]; phase C: G stashes [slot][6][32] | tile
   T* mytab = tab + lane * kCmTabStride;
+  T* dinv = tab + warp_vals - IPW * kCmDinvStride;        // FB: [IPW][22] inverse of the base's articulated inertia
   const int nsteps = cp.nsteps;
 
   const int64_t ngroups = (B + IPW - 1) / IPW;
@@ -312,7 +383,7 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
     // ------------------------------------------------------------------ phase 0: rotations
     T E[9], rw[3], w[3];
     {
-      const T qi = q[b * n + oi];
+      const T qi = q[b * nq + (FB ? oi + 6 : oi)];         // (the base's lane reads a value it does not use: E = 1)
       T f1, f2;
       if (kind == 0) sincos_t(qi, &f2, &f1);
       else { f1 = qi; f2 = T(0); }
@@ -391,6 +462,22 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < 11; ++k) { const V2 t = src[k]; IA[2 * k] += t.x; IA[2 * k + 1] += t.y; }
         }
+        if (FB && i == 0) {
+          // the base: S = eye(6), D = IA_0, fb_Dinv = inv(IA_0) (:681-684)
+          T s[21];
+          s[sym6_idx(0, 0)] = IA[0]; s[sym6_idx(0, 1)] = IA[1]; s[sym6_idx(0, 2)] = IA[2];
+          s[sym6_idx(1, 1)] = IA[3]; s[sym6_idx(1, 2)] = IA[4]; s[sym6_idx(2, 2)] = IA[5];
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) s[sym6_idx(rr, 3 + cc)] = IA[6 + 3 * rr + cc];
+          s[sym6_idx(3, 3)] = IA[15]; s[sym6_idx(3, 4)] = IA[16]; s[sym6_idx(3, 5)] = IA[17];
+          s[sym6_idx(4, 4)] = IA[18]; s[sym6_idx(4, 5)] = IA[19]; s[sym6_idx(5, 5)] = IA[20];
+          sym6_invert(s);
+          T* dg = dinv + g * kCmDinvStride;
+#pragma unroll
+          for (int k = 0; k < 21; ++k) dg[k] = s[k];
+        } else {
         T U[6];
         if (kind == 0) {
           sym3_mul(IA, w, U);                                                  // A w
@@ -459,6 +546,7 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < 11; ++k) { V2 t; t.x = IA[2 * k]; t.y = IA[2 * k + 1]; dst[k] = t; }
         }
+        }
       }
       __syncwarp();
     }
@@ -466,6 +554,10 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
     if (CRBA)
       crba_column_phase<T, G, PRISM>(n, maxdepth, valid, i, gbase, lane, oi, imdl, tab, big + 6 * m.n_slot_a * 32,
                                      Minv + grp * IPW * (int64_t)nn, (int)((B - grp * IPW) < IPW ? (B - grp * IPW) : IPW));
+    else if (FB)   // every entry of the matrix is written (the base couples all bodies): no zero fill
+      minv_column_phases<T, G, PRISM, false, true>(n, maxdepth, mp.maxcomp, m.n_slot_a, valid, i, gbase, lane, oi, comp_root, imdl, tab,
+                                                   mbw, big, Minv + grp * IPW * (int64_t)nn,
+                                                   (int)((B - grp * IPW) < IPW ? (B - grp * IPW) : IPW), dinv);
     else
       minv_column_phases<T, G, PRISM>(n, maxdepth, mp.maxcomp, m.n_slot_a, valid, i, gbase, lane, oi, comp_root, imdl, tab, mbw, big,
                                       Minv + grp * IPW * (int64_t)nn, (int)((B - grp * IPW) < IPW ? (B - grp * IPW) : IPW));

@@ -135,6 +135,40 @@ template <typename T>
 int launch_fb_minv(const rbd_fb_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && B >= 0, "rbd_fb_minv: null model/q/Minv or negative B");
   if (B == 0) return 0;
+  const int variant = g_variant.load(std::memory_order_relaxed);
+  if (m->fast_ok && variant != 1 && variant != 2) {
+    // warp-cooperative kernel (rbd_coop_minv_kernels.cuh, FB = true).  The reference fills both triangles of a
+    // floating-base Minv (:761-781 works on whole rows; output_dense then copies the upper triangle of the leading
+    // NB x NB block over the lower one, :799-804), so either setting of output_dense is the full symmetric matrix.
+    (void)dense;
+    const FastModel<T>& fm = pick_fb_dfs<T>(m);
+    const int n = fm.n;
+    const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+    auto kern = fm.has_prismatic
+                    ? (G == 8 ? minv_coop_kernel<T, 8, true, false, true>
+                              : (G == 16 ? minv_coop_kernel<T, 16, true, false, true> : minv_coop_kernel<T, 32, true, false, true>))
+                    : (G == 8 ? minv_coop_kernel<T, 8, false, false, true>
+                              : (G == 16 ? minv_coop_kernel<T, 16, false, false, true> : minv_coop_kernel<T, 32, false, false, true>));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    int warps = 0, best = 0;
+    size_t smem = 0;
+    for (int w = 4; w <= kCmMaxWarps; ++w) {
+      const size_t sz = coop_minv_smem_bytes<T>(n, G, m->coop.maxdepth, fm.n_slot_a, w, true);
+      if (sz > kMaxDynSmem) break;
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, sz) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (nb * w > best) { best = nb * w; warps = w; smem = sz; }
+    }
+    if (warps > 0) {
+      const int ipw = 32 / G;
+      const int64_t ngroups = (B + ipw - 1) / ipw;
+      int64_t blocks = (ngroups + warps - 1) / warps;
+      if (blocks > grid_cap()) blocks = grid_cap();
+      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, m->coop_minv, B, q, Minv);
+      return cuda_status("rbd_fb_minv(coop)");
+    }
+  }
   fb_minv_kernel<T><<<blocks_for(B, kFbThreads), kFbThreads, fb_smem_bytes<T>(m), (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, dense, Minv);
   return cuda_status("rbd_fb_minv");
 }
