@@ -133,6 +133,17 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
   // the inputs of the next knot points are requested one iteration ahead (HBM latency is hidden
   // behind a whole evaluation)
   T q_nx = T(0), qd_nx = T(0), qdd_nx = T(0);
+  // FB: the base's 16 inputs (quaternion, qd[0:6], qdd[0:6]) are fetched by the lanes of the group, NBX each, also one
+  // iteration ahead: input t = i + u G is q[quat_off + t] (t < 4), qd[t - 4] (t < 10) or qdd[t - 10]
+  constexpr int NBX = FB ? (G == 8 ? 2 : 1) : 1;
+  T bx_nx[NBX];
+  auto base_input = [&](int64_t bb, int t) -> T {
+    if (t < 4) return q[bb * nq + fbl.quat_off + t];
+    if (t < 10) return qd[bb * nv + (t - 4)];
+    return (qdd && t < 16) ? qdd[bb * nv + (t - 10)] : T(0);
+  };
+#pragma unroll
+  for (int u = 0; u < NBX; ++u) bx_nx[u] = T(0);
   {
     const int64_t grp0 = (int64_t)blockIdx.x * kCoopWarps + warp;
     if (grp0 < ngroups) {
@@ -141,6 +152,10 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
       q_nx = q[b * nq + qoff];
       qd_nx = qd[b * nv + voff];
       qdd_nx = qdd ? qdd[b * nv + voff] : T(0);
+      if (FB) {
+#pragma unroll
+        for (int u = 0; u < NBX; ++u) bx_nx[u] = base_input(b, i + u * G);
+      }
     }
   }
   for (int64_t grp = (int64_t)blockIdx.x * kCoopWarps + warp; grp < ngroups; grp += gstride) {
@@ -160,16 +175,31 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
         q_nx = q[bn * nq + qoff];
         qd_nx = qd[bn * nv + voff];
         qdd_nx = qdd ? qdd[bn * nv + voff] : T(0);
-        if (FB && base) {                                   // the base's 16 inputs of the next knot point -> L2
-          prefetch_l2(q + bn * nq);
-          prefetch_l2(qd + bn * nv);
-          if (qdd) prefetch_l2(qdd + bn * nv);
+      }
+      if (FB) {
+        // raw inputs of the base -> its row of the table: qd[0:6] at 0..5 (= v_0, :585 with S = eye(6)), the
+        // quaternion at 6..9, qdd[0:6] at 12..17
+        T* vb = vec + gbase * kCoopVecStride;
+        T bx[NBX];
+#pragma unroll
+        for (int u = 0; u < NBX; ++u) bx[u] = bx_nx[u];
+        if (grp + gstride < ngroups) {
+          int64_t bn = (grp + gstride) * IPW + g;
+          if (bn >= B) bn = B - 1;
+#pragma unroll
+          for (int u = 0; u < NBX; ++u) bx_nx[u] = base_input(bn, i + u * G);
         }
+#pragma unroll
+        for (int u = 0; u < NBX; ++u) {
+          const int t = i + u * G;
+          if (t < 16) vb[t < 4 ? 6 + t : (t < 10 ? t - 4 : t + 2)] = bx[u];
+        }
+        __syncwarp();
       }
       if (FB && base) {
-        // v_0 = qd[0:6] (:585, S = eye(6)), X_0 a_grav (:578; only the rotation matters: a_grav is a pure linear
-        // acceleration) and a_0 = X_0 a_grav + qdd[0:6] (:591; crm(v_0) v_0 = 0) go to the base's row of the table
-        const T* qq = q + b * nq + fbl.quat_off;
+        // X_0 a_grav (:578; only the rotation matters: a_grav is a pure linear acceleration) and
+        // a_0 = X_0 a_grav + qdd[0:6] (:591; crm(v_0) v_0 = 0) replace the raw values
+        const T* qq = myvec + 6;
         const T qw = fbl.w_first ? qq[0] : qq[3];
         const T qx = fbl.w_first ? qq[1] : qq[0], qy = fbl.w_first ? qq[2] : qq[1], qz = fbl.w_first ? qq[3] : qq[2];
         T e2[3];                                            // third column of E: the world's z axis in base coordinates
@@ -179,9 +209,8 @@ rnea_grad_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_const
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
           const T xg = k < 3 ? T(0) : -gravity * e2[k - 3];
-          myvec[k] = qd[b * nv + k];
           myvec[6 + k] = xg;
-          myvec[12 + k] = qdd ? xg + qdd[b * nv + k] : xg;
+          myvec[12 + k] += xg;
         }
       }
       T f1, f2;

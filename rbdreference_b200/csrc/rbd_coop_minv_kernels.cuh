@@ -376,14 +376,31 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
   const int nsteps = cp.nsteps;
 
   const int64_t ngroups = (B + IPW - 1) / IPW;
-  for (int64_t grp = (int64_t)blockIdx.x * nwarps + warp; grp < ngroups; grp += (int64_t)gridDim.x * nwarps) {
+  const int64_t gstride = (int64_t)gridDim.x * nwarps;
+  const int qoff = FB ? oi + 6 : oi;                      // (the base's lane reads a value it does not use: E = 1)
+  // the joint position of the next knot point is requested one evaluation ahead
+  T q_nx = T(0);
+  {
+    const int64_t grp0 = (int64_t)blockIdx.x * nwarps + warp;
+    if (grp0 < ngroups) {
+      int64_t b0 = grp0 * IPW + g;
+      if (b0 >= B) b0 = B - 1;
+      q_nx = q[b0 * nq + qoff];
+    }
+  }
+  for (int64_t grp = (int64_t)blockIdx.x * nwarps + warp; grp < ngroups; grp += gstride) {
     int64_t b = grp * IPW + g;
     if (b >= B) b = B - 1;                                // duplicate work, never stored
 
     // ------------------------------------------------------------------ phase 0: rotations
     T E[9], rw[3], w[3];
     {
-      const T qi = q[b * nq + (FB ? oi + 6 : oi)];         // (the base's lane reads a value it does not use: E = 1)
+      const T qi = q_nx;
+      if (grp + gstride < ngroups) {
+        int64_t bn = (grp + gstride) * IPW + g;
+        if (bn >= B) bn = B - 1;
+        q_nx = q[bn * nq + qoff];
+      }
       T f1, f2;
       if (kind == 0) sincos_t(qi, &f2, &f1);
       else { f1 = qi; f2 = T(0); }

@@ -100,14 +100,28 @@ def main():
                 twice(lambda: eng.minv_fpass(q, M.clone(), F.clone(), U, D), tag + " minv_fpass")
                 ar.check(tag + " helpers")
                 stats["guard_checks"] += 1
-    for name in ("hyq_fb", "iiwa14_fb"):
+    # floating base: the cooperative kernels (family 0) and the thread-per-knot-point kernels (family 1)
+    for name in ("hyq_fb", "iiwa14_fb", "atlas_fb"):
         rb = robots.by_name(name)
-        eng = RBDReference(rb)
-        q, qd, qdd = (torch.as_tensor(x, device="cuda") for x in rb.random_state(rng, 33))
-        twice(lambda: eng.rnea_grad(q, qd, qdd), name + " rnea_grad")
-        twice(lambda: eng.minv(q), name + " minv")
-        twice(lambda: eng.rnea_grad_passes(q, qd, qdd), name + " passes")
-        twice(lambda: eng.minv_passes(q), name + " minv passes")
+        for dtype in (torch.float64, torch.float32):
+            eng = RBDReference(rb, dtype=dtype)
+            nv = eng.n
+            ar = Arena(dtype)
+            for B in (33, 1000):
+                q, qd, qdd = (ar.inp(x) for x in rb.random_state(rng, B))
+                tag = "%s %s B=%d" % (name, dtype, B)
+                for family in (0, 1):
+                    RBDReference.set_kernel_variant(family)
+                    twice(lambda: eng.rnea_grad(q, qd, qdd, USE_VELOCITY_DAMPING=True, out=ar.out(B, nv, 2 * nv), c_out=ar.out(B, nv)),
+                          tag + " rnea_grad family %d" % family)
+                    twice(lambda: eng.minv(q, out=ar.out(B, nv, nv)), tag + " minv family %d" % family)
+                    twice(lambda: eng.rnea(q, qd, qdd, outputs="c"), tag + " rnea family %d" % family)
+                    ar.check(tag + " family %d" % family)
+                    stats["guard_checks"] += 1
+                RBDReference.set_kernel_variant(0)
+                if dtype == torch.float64 and B == 33:
+                    twice(lambda: eng.rnea_grad_passes(q, qd, qdd), tag + " passes")
+                    twice(lambda: eng.minv_passes(q), tag + " minv passes")
     torch.cuda.synchronize()
     print(json.dumps(dict(stats, ok=True)))
 
