@@ -11,6 +11,8 @@ summ r02_prof_minv_tile_atlas_f64 r02_minv_tile_atlas_f64.txt
 summ r02_prof_minv_lane_iiwa14_f64 r02_minv_lane_iiwa14_f64.txt
 summ r02_prof_grad_coop_atlas_f64 r02_grad_coop_atlas_f64.txt
 summ r02_prof_grad_fpass_iiwa14_f64 r02_grad_fpass_coop_iiwa14_f64.txt
+summ r02_prof_fb_grad_coop_hyq_f64 r02_fb_grad_coop_hyq_f64.txt
+summ r02_prof_fb_minv_coop_hyq_f64 r02_fb_minv_coop_hyq_f64.txt
 for f in r02_matrix.jsonl r02_passes.jsonl r02_sweep_f64.jsonl r02_ee_bench.jsonl r02_fb_bench.jsonl r02_sanitize.json r02_launches_bench_default.csv; do
   [ -f $G/$f ] && cp $G/$f $P/$f
 done
@@ -22,11 +24,11 @@ for n in 2 4 8; do [ -f $G/bench_n${n}_r02.json ] && tail -1 $G/bench_n${n}_r02.
 # SASS evidence of the bulk-copy (TMA) path: opcode counts of the kernels that use it
 {
   echo "cuobjdump -sass opcode counts (UBLKCP = cp.async.bulk 1-D TMA copies, SYNCS.* = mbarrier, UTMACMDFLUSH = bulk-group commit)";
-  for o in rbd_launch_pass_double rbd_launch_grad_double rbd_launch_minv_double; do
+  for o in rbd_launch_pass_double rbd_launch_grad_double rbd_launch_minv_double rbd_launch_fb; do
     echo "== $o.o"; cuobjdump -sass rbdreference_b200/csrc/_build/$o.o | grep -E "UBLKCP|SYNCS|UTMA" | awk '{ i=2; if ($2 ~ /^@/) i=3; print $i }' | sed 's/;//' | sort | uniq -c | sort -rn
   done
   echo "== UBLKCP instructions per kernel"
-  for o in rbd_launch_pass_double rbd_launch_grad_double rbd_launch_minv_double; do
+  for o in rbd_launch_pass_double rbd_launch_grad_double rbd_launch_minv_double rbd_launch_fb; do
     cuobjdump -sass rbdreference_b200/csrc/_build/$o.o | grep -E "Function|UBLKCP" | awk '/Function/ { f=$3 } /UBLKCP/ { c[f]++ } END { for (k in c) print c[k], k }' | c++filt | sed 's/(.*//' | sort -k2
   done
 } > $P/r02_sass_bulk_copy.txt

@@ -1,3 +1,4 @@
+# Floating-base measurements (one B200; run under gpurun from the repo root, also called by tools/measure_round.sh).
 set -u
 O=gpurun_out
 python tools/sanitize.py > $O/r02_sanitize.json 2> $O/r02_sanitize.err; tail -c 300 $O/r02_sanitize.json; tail -3 $O/r02_sanitize.err

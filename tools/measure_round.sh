@@ -19,15 +19,13 @@ python tools/sweep.py --ops rnea_grad,minv --robots iiwa14,atlas > $O/r02_sweep_
 python tools/bench_passes.py --reps 5 --batch 1048576 >> $O/r02_passes.jsonl 2>/dev/null
 python tools/bench_passes.py --reps 5 --robot hyq --batch 262144 >> $O/r02_passes.jsonl 2>/dev/null
 python tools/bench_passes.py --reps 5 --robot atlas --batch 65536 >> $O/r02_passes.jsonl 2>/dev/null
-: > $O/r02_ee_bench.jsonl; : > $O/r02_fb_bench.jsonl
+: > $O/r02_ee_bench.jsonl
 for r in iiwa14 hyq atlas; do for d in f64 f32; do
   b=1048576; if [ $r = atlas ]; then b=262144; fi
   python bench.py --op ee_grad --robot $r --dtype $d --batch $b --no-cpu-baseline --steps 20 2>/dev/null | tail -1 >> $O/r02_ee_bench.jsonl
 done; done
-for r in iiwa14_fb hyq_fb atlas_fb; do for op in rnea rnea_grad minv; do
-  python bench.py --robot $r --op $op --dtype f64 --batch 262144 --steps 10 --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 >> $O/r02_fb_bench.jsonl
-done; done
-python tools/sanitize.py > $O/r02_sanitize.json 2>&1
+# floating base (bench rows, canary / determinism checker, ncu captures of the two HyQ + base kernels)
+bash tools/measure_fb.sh
 # launch list of the default bench command (cold, serialised per-launch times: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r02_launches_bench_default.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $O/r02_ncu_launch.log 2>&1
 # full captures of the dominant kernels (each after its plain command above has exited 0)
