@@ -239,6 +239,10 @@ typedef struct rbd_fb_model rbd_fb_model_t;
 int rbd_fb_model_create(const RbdFbModelDesc* desc, rbd_fb_model_t** out);
 int rbd_fb_model_destroy(rbd_fb_model_t* m);
 int rbd_fb_model_num_vel(const rbd_fb_model_t* m);
+/* Kernel family of the fused floating-base drivers for THIS handle: -1 follow rbd_set_kernel_variant, 0 automatic
+ * (warp-cooperative kernels in base coordinates when every inertia has rigid-body structure), 1 / 2 one knot point per
+ * thread (the reference's body-frame recursion), 3 cooperative.  Thread-safe; calls in flight keep their choice. */
+int rbd_fb_model_set_kernel_variant(rbd_fb_model_t* m, int variant);
 int rbd_fb_rnea_f64(const rbd_fb_model_t* m, int64_t B, const double* q, const double* qd, const double* qdd,
                     double gravity, double* c, double* v, double* a, double* f, void* stream);
 int rbd_fb_rnea_f32(const rbd_fb_model_t* m, int64_t B, const float* q, const float* qd, const float* qdd,

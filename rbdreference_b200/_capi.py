@@ -18,7 +18,8 @@ PLAIN_SYMBOLS = ["rbd_abi_version", "rbd_last_error_string", "rbd_model_create",
                  "rbd_model_set_kernel_variant",
                  "rbd_measure_fma_peak", "rbd_launch_count", "rbd_trim_scratch", "rbd_prepare_device",
                  "rbd_ee_model_create", "rbd_ee_model_destroy", "rbd_ee_model_num_ee",
-                 "rbd_fb_model_create", "rbd_fb_model_destroy", "rbd_fb_model_num_vel"]
+                 "rbd_fb_model_create", "rbd_fb_model_destroy", "rbd_fb_model_num_vel",
+                 "rbd_fb_model_set_kernel_variant"]
 FB_SYMBOLS = ["fb_rnea", "fb_rnea_grad", "fb_minv", "fb_forward_dynamics", "fb_forward_dynamics_grad"] + ["fb_" + p for p in PASS_SYMBOLS]
 EE_SYMBOLS = ["end_effector_pose", "end_effector_pose_gradient"]
 
@@ -86,6 +87,7 @@ def load_library():
     lib.rbd_fb_model_create.argtypes = [POINTER(RbdFbModelDesc), POINTER(c_void_p)]
     lib.rbd_fb_model_destroy.argtypes = [c_void_p]
     lib.rbd_fb_model_num_vel.argtypes = [c_void_p]
+    lib.rbd_fb_model_set_kernel_variant.argtypes = [c_void_p, c_int]
     P = c_void_p
     for suf, real in (("f64", c_double), ("f32", c_float)):
         sig = {

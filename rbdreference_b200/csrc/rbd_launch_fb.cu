@@ -19,9 +19,16 @@ struct rbd_fb_model {
   CoopPlan coop;
   CoopMinvPlan coop_minv;
   FbBaseLayout layout;
+  mutable std::atomic<int> variant{-1};   // per-handle kernel family (-1: follow rbd_set_kernel_variant)
 };
 
 namespace {
+
+// kernel family of one call: the handle's own choice (rbd_fb_model_set_kernel_variant) or the process default
+inline int fb_variant_of(const rbd_fb_model* m) {
+  const int v = m ? m->variant.load(std::memory_order_relaxed) : -1;
+  return v >= 0 ? v : g_variant.load(std::memory_order_relaxed);
+}
 
 template <typename T> const FastModel<T>& pick_fb_dfs(const rbd_fb_model* m);
 template <> const FastModel<double>& pick_fb_dfs<double>(const rbd_fb_model* m) { return m->fd_dfs; }
@@ -103,7 +110,7 @@ int launch_fb_rnea_grad(const rbd_fb_model* m, int64_t B, const T* q, const T* q
                         T* c_out, void* stream) {
   RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_fb_rnea_grad: null model/q/qd/dc_du or negative B");
   if (B == 0) return 0;
-  const int variant = g_variant.load(std::memory_order_relaxed);
+  const int variant = fb_variant_of(m);
   if (m->fast_ok && variant != 1 && variant != 2) {
     // world-frame composites in base coordinates, one body per lane (rbd_coop_kernels.cuh, FB = true)
     const FastModel<T>& fm = pick_fb_dfs<T>(m);
@@ -135,7 +142,7 @@ template <typename T>
 int launch_fb_minv(const rbd_fb_model* m, int64_t B, const T* q, int dense, T* Minv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && B >= 0, "rbd_fb_minv: null model/q/Minv or negative B");
   if (B == 0) return 0;
-  const int variant = g_variant.load(std::memory_order_relaxed);
+  const int variant = fb_variant_of(m);
   if (m->fast_ok && variant != 1 && variant != 2) {
     // warp-cooperative kernel (rbd_coop_minv_kernels.cuh, FB = true).  The reference fills both triangles of a
     // floating-base Minv (:761-781 works on whole rows; output_dense then copies the upper triangle of the leading
@@ -242,7 +249,7 @@ int launch_fb_forward_dynamics(const rbd_fb_model* m, int64_t B, const T* q, con
   if (rc) return rc;
   rc = launch_fb_minv<T>(m, B, q, 1, Minv, stream);                                                       // :1371
   if (rc) return rc;
-  return launch_fd_apply<T, false>(g_variant.load(std::memory_order_relaxed), nv, 1, B, Minv, u, (const T*)c.p, T(1), qdd, nullptr, stream);         // :1372
+  return launch_fd_apply<T, false>(fb_variant_of(m), nv, 1, B, Minv, u, (const T*)c.p, T(1), qdd, nullptr, stream);         // :1372
 }
 
 template <typename T>
@@ -266,7 +273,7 @@ int launch_fb_forward_dynamics_grad(const rbd_fb_model* m, int64_t B, const T* q
   if (rc) return rc;
   rc = launch_fb_rnea_grad<T>(m, B, q, qd, qdd, T(-9.81), 0, (T*)dc.p, nullptr, stream);                   // :1378
   if (rc) return rc;
-  return launch_fd_apply<T, true>(g_variant.load(std::memory_order_relaxed), nv, 2 * nv, B, (const T*)Mi.p, (const T*)dc.p, nullptr, T(-1), qdd_dq, qdd_dqd, stream);
+  return launch_fd_apply<T, true>(fb_variant_of(m), nv, 2 * nv, B, (const T*)Mi.p, (const T*)dc.p, nullptr, T(-1), qdd_dq, qdd_dqd, stream);
 }
 
 }  // namespace
@@ -305,6 +312,14 @@ int rbd_fb_model_destroy(rbd_fb_model_t* m) {
 }
 
 int rbd_fb_model_num_vel(const rbd_fb_model_t* m) { return m ? m->d.d.n + 5 : RBD_E_INVALID_ARGUMENT; }
+
+int rbd_fb_model_set_kernel_variant(rbd_fb_model_t* m, int variant) {
+  if (!m || variant < -1 || variant > 3)
+    return fail(RBD_E_INVALID_ARGUMENT, "floating-base kernel family: -1 follow the process default, 0 automatic (cooperative), "
+                                        "1 / 2 one knot point per thread, 3 cooperative");
+  m->variant.store(variant, std::memory_order_relaxed);
+  return 0;
+}
 
 #define RBD_FB_DEFINE(SUF, T)                                                                                        \
   int rbd_fb_rnea_##SUF(const rbd_fb_model_t* m, int64_t B, const T* q, const T* qd, const T* qdd, T gravity, T* c,  \

@@ -16,7 +16,7 @@ int launch_rnea_grad(const rbd_model* m, int64_t B, const T* q, const T* qd, con
   RBD_CHECK_ARGS(m && q && qd && dc_du && B >= 0, "rbd_rnea_grad: null model/q/qd/dc_du or negative B");
   if (B == 0) return 0;
   int variant = variant_of(m);
-  if (variant >= 4 && variant != 7) variant = 0;       // 4, 5, 8, 9 only select among the minv kernels       // 4, 5 only select among the minv kernels
+  if (variant >= 4 && variant != 7) variant = 0;       // 4, 5, 8, 9 only select among the minv kernels
   if (m->fast_ok && m->is_chain && (variant == 0 || variant == 7) && B >= chain_min_batch(m->d.n) &&
       (reinterpret_cast<uintptr_t>(dc_du) & (2 * sizeof(T) - 1)) == 0) {
     // serial chain, one knot point per lane (rbd_chain_grad_kernels.cuh)

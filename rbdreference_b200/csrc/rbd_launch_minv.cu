@@ -66,7 +66,7 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
     // per-body table in shared memory, rows stored straight from registers (rbd_tile_minv_kernels.cuh)
     const FastModel<T>& fm = pick_dfs<T>(m);
     const TilePlan& tp = variant == 8 ? m->tile : m->tile2;
-    void (*kern)(const FastModel<T>, const DfsPlan, const TilePlan, int64_t, const T*, T*, int);
+    void (*kern)(const FastModel<T>, const DfsPlan, const TilePlan, int64_t, const T*, T*);
     if (variant == 8) kern = fm.has_prismatic ? minv_tile_kernel<T, true, 4> : minv_tile_kernel<T, false, 4>;
     else kern = fm.has_prismatic ? minv_tile_kernel<T, true, 2> : minv_tile_kernel<T, false, 2>;
     const int warps = tp.nwarps;
@@ -78,11 +78,10 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
     cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem);
     if (std::getenv("RBD_DEBUG")) std::fprintf(stderr, "[rbd] tile minv: gc %d warps %d smem %zu occupancy %d (%s)\n", tp.gc, warps, smem, nb, cudaGetErrorString(eo));
     if (eo == cudaSuccess && nb > 0) {
-      static const int dbg_skip = [] { const char* v = std::getenv("RBD_TILE_SKIP"); return v ? std::atoi(v) : 0; }();
       const int64_t ntiles = (B + 31) / 32;
       int64_t blocks = (int64_t)sm_count() * nb;
       if (blocks > ntiles) blocks = ntiles;
-      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, tp, B, q, Minv, dbg_skip);
+      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, tp, B, q, Minv);
       return cuda_status("rbd_minv(tile)");
     }
     cudaGetLastError();

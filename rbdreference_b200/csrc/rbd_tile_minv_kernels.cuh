@@ -120,7 +120,7 @@ template <typename T, bool PRISM, int GC>
 __global__ void __launch_bounds__(GC == 4 ? 256 : 512)
 minv_tile_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__ DfsPlan plan,
                  const __grid_constant__ TilePlan tp, int64_t B,
-                 const T* __restrict__ q, T* __restrict__ Minv, int dbg_skip) {
+                 const T* __restrict__ q, T* __restrict__ Minv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = m.n;
   const int nn = n * n;
@@ -226,7 +226,7 @@ minv_tile_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
       __syncthreads();
     }
     // ================================================================ stage 1b: articulated inertias, leaf -> root
-    for (int lvl = 0; lvl < ((dbg_skip & 2) ? 0 : tp.nblevel); ++lvl) {
+    for (int lvl = 0; lvl < tp.nblevel; ++lvl) {
       for (int it = tp.b_begin[lvl * nwarps + warp]; it < tp.b_begin[lvl * nwarps + warp + 1]; ++it) {
         const int c = tp.b_item[it];
         const int cb = tp.chain_begin[c], ce = tp.chain_end[c];
@@ -345,8 +345,8 @@ minv_tile_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
     }
     // ================================================================ stage 2: column groups (scratch aliases the slots)
     T* outk = Minv + (first + (lane < nk ? lane : 0)) * (int64_t)nn;
-    const bool live = lane < nk && !(dbg_skip & 4);
-    for (int gi = tp.g_begin[warp]; gi < ((dbg_skip & 1) ? 0 : tp.g_begin[warp + 1]); ++gi) {
+    const bool live = lane < nk;
+    for (int gi = tp.g_begin[warp]; gi < tp.g_begin[warp + 1]; ++gi) {
       const int g = tp.g_item[gi];
       const int j0 = tp.g_first[g], nc = tp.g_ncols[g];
       const int ocol = tp.g_ocol[g];

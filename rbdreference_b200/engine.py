@@ -224,9 +224,11 @@ class RBDReference:
         pipe.run(B, ins, in_tails, outs, out_tails, launch)
 
     def set_variant(self, variant: int) -> None:
-        """Kernel family for THIS engine's handle only (-1 = follow `set_kernel_variant`)."""
+        """Kernel family for THIS engine's handle only (-1 = follow `set_kernel_variant`).  Floating-base robots know
+        two families: 0 / 3 warp-cooperative kernels in base coordinates, 1 / 2 one knot point per thread."""
         if self.floating_base:
-            raise NotImplementedError("kernel variants exist for fixed-base models only")
+            _capi.check(self._lib.rbd_fb_model_set_kernel_variant(self._handle.ptr, int(variant)), "rbd_fb_model_set_kernel_variant")
+            return
         _capi.check(self._lib.rbd_model_set_kernel_variant(self._handle.ptr, int(variant)), "rbd_model_set_kernel_variant")
 
     def _call(self, name: str, ctx: "_Ctx", *args, handle=None):

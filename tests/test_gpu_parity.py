@@ -1077,6 +1077,18 @@ def test_per_handle_variant_is_independent():
     assert np.array_equal(e_a.rnea_grad(_t(q), _t(qd), _t(qdd)).cpu().numpy(), rb_)
     with pytest.raises(Exception):
         e_a.set_variant(6)
+    # floating-base handles: 1 = one knot point per thread, 0 / -1 = cooperative kernels in base coordinates
+    fb = make_fb_robot("hyq")
+    f_a, f_b = _engine(fb), _engine(fb)
+    f_a.set_variant(1)
+    fq, fqd, fqdd = fb.random_state(np.random.default_rng(5), 70)
+    for call in (lambda e: e.rnea_grad(_t(fq), _t(fqd), _t(fqdd)), lambda e: e.minv(_t(fq))):
+        xa, xb = call(f_a).cpu().numpy(), call(f_b).cpu().numpy()
+        assert rel_err(xa, xb) < TOL_F64 and not np.array_equal(xa, xb)
+    f_a.set_variant(-1)
+    assert np.array_equal(f_a.minv(_t(fq)).cpu().numpy(), f_b.minv(_t(fq)).cpu().numpy())
+    with pytest.raises(Exception):
+        f_a.set_variant(7)
 
 
 @requires_cuda
