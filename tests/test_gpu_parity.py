@@ -923,6 +923,32 @@ def test_floating_base_batched_vs_oracle_and_identities(name, B, fb_family):
 
 
 @requires_cuda
+def test_floating_base_with_prismatic_joints_vs_oracle(fb_family):
+    """A branched tree with prismatic joints on a floating base: the reference's prismatic quirk of rnea_grad (:1292)
+    and the prismatic branches of minv, in base coordinates (cooperative family) and in body frames, both precisions,
+    damping on, ragged batch."""
+    from oracle.rbd_oracle_fb import FloatingScalarOracle
+    from rbdreference_b200 import robots
+    tree = robots.random_tree(13, seed=2, branching=0.5, prismatic=0.3)
+    assert any(j.kind == "prismatic" for j in tree.joints)
+    fb = robots.FloatingBaseRobot(tree, name="tree13_fb")
+    eng, e32, so = _engine(fb), _engine(fb, torch.float32), FloatingScalarOracle(fb)
+    B = 75
+    q, qd, qdd = fb.random_state(np.random.default_rng(21), B)
+    dc = eng.rnea_grad(_t(q), _t(qd), _t(qdd), USE_VELOCITY_DAMPING=True).cpu().numpy()
+    M = eng.minv(_t(q)).cpu().numpy()
+    dc32 = e32.rnea_grad(_t(q, torch.float32), _t(qd, torch.float32), _t(qdd, torch.float32), USE_VELOCITY_DAMPING=True).cpu().numpy()
+    M32 = e32.minv(_t(q, torch.float32)).cpu().numpy()
+    for k in (0, 1, 31, 32, 74):
+        ref = np.asarray(so.rnea_grad(q[k], qd[k], qdd[k], USE_VELOCITY_DAMPING=True))
+        Mref = np.asarray(so.minv(q[k]))
+        cond = np.linalg.cond(Mref)
+        assert rel_err(dc[k], ref) < TOL_F64 and rel_err(dc32[k], ref) < TOL_F32
+        assert rel_err(M[k], Mref) < TOL_F64 * max(1.0, cond / 1e4)
+        assert rel_err(M32[k], Mref) < (TOL_F32 if fb_family == 0 else 5 * TOL_F32) * max(1.0, cond / 1e4)
+
+
+@requires_cuda
 def test_end_effector_and_floating_base_calls_are_cuda_graph_capturable_and_stream_safe():
     """The new entry points only enqueue stream-ordered work too: captured in a CUDA graph, replayed on
     new inputs, and issued concurrently on two streams they return what the eager calls return."""
