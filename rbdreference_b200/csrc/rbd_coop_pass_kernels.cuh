@@ -182,170 +182,195 @@ grad_fpass_coop_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T
   warp_bulk_store_wait(lane);                             // shared memory must outlive the copies
 }
 
-// ---- rnea_grad_fpass_dq / _dqd for LARGE robots (n > 16): no tiles ------------------------------------------------
-// With n = 30 the three (6, n, NB) tiles of ONE knot point take 134 KB: one resident warp per SM, 5 % of the HBM
-// peak.  The recursion only needs the parent's dv_c, da_c: they travel in registers from body i - 1 to body i and
-// through a small stash ([slot][12][lane]) for bodies whose children are not their successor, so shared memory
-// is the stash + the staged inputs (a few KB per warp, 16 resident warps).  Column c of lane c is a run of
-// consecutive bodies in HBM ((r n + c) n + i): two bodies are collected in registers and leave as one 16-byte
-// store per row.
-constexpr int kCpMdl = 96;
-__host__ __device__ inline int cp_stream_warp_vals(int n, int nslot) {
-  return (12 * n + 3 * n + nslot * 12 * 32 + 3) & ~3;       // v a rows | f1 f2 qd | stash
+// ---- rnea_grad_fpass_dq / _dqd for LARGE robots (n > 16): one BODY per lane, one ancestor distance per round ------
+// With n = 30 the three (6, n, NB) tensors of ONE knot point take 130 KB, of which 5/6 are structural zeros: column c of
+// body i is non-zero only when c is i or one of its ancestors (150 of Atlas' 900 pairs).  A warp owns one knot point:
+//   * lane i is body i.  In round d the lane works on the pair (c, i) with c = the ancestor of i at distance d: the
+//     recursion dv[c, i] = X_i dv[c, parent(i)] (:1158-1175 / :1230-1243) needs the pair (c, parent(i)), which is what the
+//     parent's lane produced in round d - 1 - twelve values by warp shuffle.  max depth + 1 rounds (10 for Atlas) instead
+//     of n steps over all n columns, and no lane works on a zero;
+//   * the 18 results of a pair wait in shared memory ([tensor row][pair], 22 KB per warp for Atlas);
+//   * the three slabs then leave in ONE coalesced pass of 16-byte stores: a per-CTA table maps every (c, i) of a tensor
+//     row to its pair or to "structural zero".  Every sector is written once (DRAM traffic = the tensors' size; a first
+//     version that zero-filled the slabs and scattered the pairs afterwards wrote 1.4x: with 130 KB per warp in flight
+//     the zeroed lines had left the L2 before their pairs arrived).
+// Shared memory: the per-body constants (one copy per CTA, odd stride: lanes read different bodies), the pair map, and per
+// warp the staged v / a rows and the pair results.
+constexpr int kCpLvlMdl = 97;
+__host__ __device__ inline int cp_level_warp_vals(int n, int npairs) { return (12 * n + 18 * npairs + 3) & ~3; }   // v a rows | results
+__host__ __device__ inline size_t cp_level_head_bytes(int n, size_t tsize) {
+  return (((size_t)n * 4 * sizeof(int) + (size_t)n * n * sizeof(short) + 15) & ~(size_t)15) + (((size_t)n * kCpLvlMdl + 3) & ~(size_t)3) * tsize;
 }
 
 template <typename T, bool DQ>
-__global__ void __launch_bounds__(128, 2)
-grad_fpass_stream_kernel(const __grid_constant__ DevModel<T> m, int nslot, int64_t B, const T* __restrict__ q,
-                         const T* __restrict__ qd, const T* __restrict__ v, const T* __restrict__ a, T gravity,
-                         T* __restrict__ dv, T* __restrict__ da, T* __restrict__ df) {
+__global__ void __launch_bounds__(128)
+grad_fpass_level_kernel(const __grid_constant__ DevModel<T> m, int npairs, int64_t B, const T* __restrict__ q,
+                        const T* __restrict__ qd, const T* __restrict__ v, const T* __restrict__ a, T gravity,
+                        T* __restrict__ dv, T* __restrict__ da, T* __restrict__ df) {
   typedef typename Vec2<T>::type V2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = m.n;
+  const int nn = n * n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int c = lane;
-  const bool valid = c < n;
-  int* slot_of = reinterpret_cast<int*>(smem_raw);                         // [n]: stash slot of body i or -1
-  // per-body constants [body][96] = XA(18) XB(18) XC(18) S(6) I(36): the body index is a run-time value and warps
-  // of one SM sit on different bodies - indexed constant-bank reads of the 25 KB model serialised the kernel
-  // (23 -> 16 ms with 12x the resident warps, i.e. not occupancy-bound); broadcast shared-memory loads do not
-  T* mdl = reinterpret_cast<T*>(smem_raw + ((n * sizeof(int) + 15) & ~(size_t)15));
-  T* ws = mdl + (size_t)n * kCpMdl + (size_t)warp * cp_stream_warp_vals(n, nslot);
-  for (int k = threadIdx.x; k < n * kCpMdl; k += blockDim.x) {
-    const int i = k / kCpMdl, w = k - i * kCpMdl;
-    mdl[k] = w < 18 ? m.XA[i][w] : w < 36 ? m.XB[i][w - 18] : w < 54 ? m.XC[i][w - 36] : w < 60 ? m.S[i][w - 54] : m.I[i][w - 60];
-  }
+  const int i = lane;
+  const bool valid = i < n;
+  int* topo = reinterpret_cast<int*>(smem_raw);                            // [n][4]: parent kind depth first-pair
+  short* pmap = reinterpret_cast<short*>(topo + 4 * n);                     // [n * n]: pair of (c, i) or -1
+  T* mdl = reinterpret_cast<T*>(smem_raw + cp_level_head_bytes(n, 0));     // [n][97]: XA XB XC S I
+  T* ws = mdl + (((size_t)n * kCpLvlMdl + 3) & ~(size_t)3) + (size_t)warp * cp_level_warp_vals(n, npairs);
   T* sv = ws;                                              // [6][n]
   T* sa = sv + 6 * n;
-  T* sj = sa + 6 * n;                                      // [n][3]: f1 f2 qd
-  T* stash = sj + 3 * n;                                   // [slot][12][32]
-  if (threadIdx.x == 0) {
-    int cnt = 0;
-    for (int i = 0; i < n; ++i) {
-      bool need = false;                                   // a child that is not body i + 1 reads body i's columns later
-      for (int k = i + 2; k < n; ++k) need = need || m.parent[k] == i;
-      slot_of[i] = need ? cnt++ : -1;
+  T* res = sa + 6 * n;                                     // [3][6][npairs]
+  for (int k = threadIdx.x; k < n * kCpLvlMdl; k += blockDim.x) {
+    const int b = k / kCpLvlMdl, w = k - b * kCpLvlMdl;
+    mdl[k] = w < 18 ? m.XA[b][w] : w < 36 ? m.XB[b][w - 18] : w < 54 ? m.XC[b][w - 36] : w < 60 ? m.S[b][w - 54] : w < 96 ? m.I[b][w - 60] : T(0);
+  }
+  for (int k = threadIdx.x; k < nn; k += blockDim.x) pmap[k] = (short)-1;
+  int maxdepth = 0;
+  {
+    int first = 0;
+    for (int b = 0; b < n; ++b) {                          // (every thread walks the same entries of the constant bank)
+      int d = 0;
+      for (int p = m.parent[b]; p >= 0; p = m.parent[p]) ++d;
+      if (threadIdx.x == 0) { topo[4 * b] = m.parent[b]; topo[4 * b + 1] = m.kind[b]; topo[4 * b + 2] = d; topo[4 * b + 3] = first; }
+      first += d + 1;
+      maxdepth = d > maxdepth ? d : maxdepth;
     }
   }
   __syncthreads();
-  const int64_t slab = (int64_t)6 * n * n;
-  const bool vec_ok = (n & 1) == 0 && ((reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(df)) & (2 * sizeof(T) - 1)) == 0;
+  if (threadIdx.x < n) {                                   // pairs of body b: (b, b), (parent(b), b), ...
+    const int b = threadIdx.x;
+    int idx = topo[4 * b + 3];
+    for (int c = b; c >= 0; c = topo[4 * c]) pmap[c * n + b] = (short)idx++;
+  }
+  __syncthreads();
+  const int ib = valid ? i : 0;
+  const int par = topo[4 * ib], kind = topo[4 * ib + 1];
+  const int depth = valid ? topo[4 * ib + 2] : -1;
+  const int pair0 = topo[4 * ib + 3];
+  const T* mc = mdl + ib * kCpLvlMdl;
+  // lane = body for the whole kernel: its motion subspace and spatial inertia stay in registers (read from shared
+  // memory in every round, the 72 loads of the two inertia products saturated the memory-instruction queue)
+  T S[6], Im[36];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) S[r] = mc[54 + r];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) Im[k] = mc[60 + k];
+  const int64_t slab = (int64_t)6 * nn;
+  const bool vec_ok = (nn & 1) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(df)) & (2 * sizeof(T) - 1)) == 0;
   for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
-    if (valid) {
-      T f1, f2;
-      joint_basis(m, c, q[b * n + c], f1, f2);
-      sj[c * 3] = f1; sj[c * 3 + 1] = f2; sj[c * 3 + 2] = qd[b * n + c];
-    }
+    // ---- inputs of the knot point
     for (int e = lane; e < 6 * n; e += 32) {
       sv[e] = v[b * 6 * n + e];
       if (DQ) sa[e] = a[b * 6 * n + e];
     }
-    __syncwarp();
-    if (valid) {
-      T* odv = dv + b * slab + (int64_t)c * n;             // + r n n + i
-      T* oda = da + b * slab + (int64_t)c * n;
-      T* odf = df + b * slab + (int64_t)c * n;
-      const int rstride = n * n;
-      T pdv[6], pda[6];                                     // columns of body i - 1
-      T hv[6], ha[6], hf[6];                                // the even body of the current pair, waiting for the odd one
+    T X[18], vi[6], Iv[6], qdi = T(0);
+    {
+      T f1 = T(0), f2 = T(0);
+      if (valid) {
+        const T qi = q[b * n + i];
+        qdi = qd[b * n + i];
+        if (kind == 0) sincos_t(qi, &f2, &f1);
+        else f1 = qi;
+      }
 #pragma unroll
-      for (int r = 0; r < 6; ++r) { pdv[r] = T(0); pda[r] = T(0); hv[r] = T(0); ha[r] = T(0); hf[r] = T(0); }
+      for (int k = 0; k < 18; ++k) X[k] = fma_t(mc[36 + k], f2, fma_t(mc[18 + k], f1, mc[k]));
+    }
+    __syncwarp();                                           // staged rows are in place; the previous slab has been read
+#pragma unroll
+    for (int r = 0; r < 6; ++r) vi[r] = sv[r * n + ib];
+    mat6_apply(Im, vi, Iv);                                                      // :1180 / :1248
+    T cdv[6], cda[6];                                       // dv / da of this lane's pair of the previous round
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { cdv[r] = T(0); cda[r] = T(0); }
 #pragma unroll 1
-      for (int i = 0; i < n; ++i) {
-        const T* ji = sj + i * 3;
-        const T* mc = mdl + i * kCpMdl;
-        const T* Imat = mc + 60;
-        T X[18];
+    for (int d = 0; d <= maxdepth; ++d) {
+      T pv[6], pa[6];
+      const int src = par >= 0 ? par : 0;
 #pragma unroll
-        for (int k = 0; k < 18; ++k) X[k] = fma_t(mc[36 + k], ji[1], fma_t(mc[18 + k], ji[0], mc[k]));
-        const T qdi = ji[2];
-        const int p = m.parent[i];
-        T S[6], vi[6], Iv[6];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) { S[r] = mc[54 + r]; vi[r] = sv[r * n + i]; }
-        mat6_apply(Imat, vi, Iv);                                              // :1180 / :1248
-        T dvc[6], dac[6];
-        if (p >= 0) {
-          T pv[6], pa[6];
-          if (p == i - 1) {
-#pragma unroll
-            for (int r = 0; r < 6; ++r) { pv[r] = pdv[r]; pa[r] = pda[r]; }
-          } else {
-            const T* st = stash + (size_t)slot_of[p] * 12 * 32 + lane;
-#pragma unroll
-            for (int r = 0; r < 6; ++r) { pv[r] = st[r * 32]; pa[r] = st[(6 + r) * 32]; }
-          }
-          X_apply(X, pv, dvc);                                                 // :1158 / :1230
-          X_apply(X, pa, dac);                                                 // :1163 / :1234
-        } else {
-#pragma unroll
-          for (int r = 0; r < 6; ++r) { dvc[r] = T(0); dac[r] = T(0); }
-        }
-        T seed_a[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-        if (c == i) {
+      for (int r = 0; r < 6; ++r) { pv[r] = __shfl_sync(0xffffffffu, cdv[r], src); pa[r] = __shfl_sync(0xffffffffu, cda[r], src); }
+      if (depth >= d) {
+        T dvc[6], dac[6], t[6];
+        if (d == 0) {
+          T seed_a[6];
           if (DQ) {
-            T par[6], t[6], seed_v[6];
-            if (p >= 0) {
+            T pr[6], xp[6];
+            if (par >= 0) {
 #pragma unroll
-              for (int r = 0; r < 6; ++r) par[r] = sv[r * n + p];
-              X_apply(X, par, t);
-              crm_mul(t, S, seed_v);                                           // :1159
+              for (int r = 0; r < 6; ++r) pr[r] = sv[r * n + par];
+              X_apply(X, pr, xp);
+              crm_mul(xp, S, dvc);                                               // :1159
 #pragma unroll
-              for (int r = 0; r < 6; ++r) { dvc[r] += seed_v[r]; par[r] = sa[r * n + p]; }
+              for (int r = 0; r < 6; ++r) pr[r] = sa[r * n + par];
             } else {
 #pragma unroll
-              for (int r = 0; r < 6; ++r) par[r] = T(0);
-              par[5] = -gravity;                                               // :1137
+              for (int r = 0; r < 6; ++r) { dvc[r] = T(0); pr[r] = T(0); }
+              pr[5] = -gravity;                                                  // :1137
             }
-            X_apply(X, par, t);
-            crm_mul(t, S, seed_a);                                             // :1173 / :1175
+            X_apply(X, pr, xp);
+            crm_mul(xp, S, seed_a);                                              // :1173 / :1175
           } else {
 #pragma unroll
-            for (int r = 0; r < 6; ++r) dvc[r] += S[r];                        // :1231
-            crm_mul(vi, S, seed_a);                                            // :1243
+            for (int r = 0; r < 6; ++r) dvc[r] = S[r];                           // :1231
+            crm_mul(vi, S, seed_a);                                              // :1243
           }
-        }
-        T t[6];
-        crm_mul(dvc, S, t);                                                    // :1170 / :1240
+          crm_mul(dvc, S, t);                                                    // :1170 / :1240
 #pragma unroll
-        for (int r = 0; r < 6; ++r) dac[r] = fma_t(qdi, t[r], dac[r]) + seed_a[r];
-        T Ida[6], Idv[6], t1[6], t2[6], dfc[6];
-        mat6_apply(Imat, dac, Ida);                                          // :1179 / :1247
-        mat6_apply(Imat, dvc, Idv);
-        crf_mul(dvc, Iv, t1);                                                  // :1184 / :1251
-        crf_mul(vi, Idv, t2);                                                  // :1185 / :1252
-#pragma unroll
-        for (int r = 0; r < 6; ++r) dfc[r] = Ida[r] + t1[r] + t2[r];
-        const int sl = slot_of[i];
-        if (sl >= 0) {
-          T* st = stash + (size_t)sl * 12 * 32 + lane;
-#pragma unroll
-          for (int r = 0; r < 6; ++r) { st[r * 32] = dvc[r]; st[(6 + r) * 32] = dac[r]; }
-        }
-        if (vec_ok && (i & 1) == 0 && i + 1 < n) {
-#pragma unroll
-          for (int r = 0; r < 6; ++r) { hv[r] = dvc[r]; ha[r] = dac[r]; hf[r] = dfc[r]; }
-        } else if (vec_ok && (i & 1) == 1) {
-#pragma unroll
-          for (int r = 0; r < 6; ++r) {
-            V2 x;
-            x.x = hv[r]; x.y = dvc[r]; *reinterpret_cast<V2*>(odv + r * rstride + i - 1) = x;
-            x.x = ha[r]; x.y = dac[r]; *reinterpret_cast<V2*>(oda + r * rstride + i - 1) = x;
-            x.x = hf[r]; x.y = dfc[r]; *reinterpret_cast<V2*>(odf + r * rstride + i - 1) = x;
-          }
+          for (int r = 0; r < 6; ++r) dac[r] = fma_t(qdi, t[r], seed_a[r]);
         } else {
+          X_apply(X, pv, dvc);                                                   // :1158 / :1230
+          X_apply(X, pa, dac);                                                   // :1163 / :1234
+          crm_mul(dvc, S, t);
 #pragma unroll
-          for (int r = 0; r < 6; ++r) {
-            odv[r * rstride + i] = dvc[r];
-            oda[r * rstride + i] = dac[r];
-            odf[r * rstride + i] = dfc[r];
-          }
+          for (int r = 0; r < 6; ++r) dac[r] = fma_t(qdi, t[r], dac[r]);
         }
+        T Ida[6], Idv[6], t1[6], t2[6];
+        mat6_apply(Im, dac, Ida);                                                // :1179 / :1247
+        mat6_apply(Im, dvc, Idv);
+        crf_mul(dvc, Iv, t1);                                                    // :1184 / :1251
+        crf_mul(vi, Idv, t2);                                                    // :1185 / :1252
+        T* rp = res + pair0 + d;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) { pdv[r] = dvc[r]; pda[r] = dac[r]; }
+        for (int r = 0; r < 6; ++r) {
+          rp[r * npairs] = dvc[r];
+          rp[(6 + r) * npairs] = dac[r];
+          rp[(12 + r) * npairs] = Ida[r] + t1[r] + t2[r];
+          cdv[r] = dvc[r];
+          cda[r] = dac[r];
+        }
       }
     }
     __syncwarp();
+    // ---- the three slabs, every sector once: element f of a slab is row f / nn, entry (c, i) = f % nn
+#pragma unroll 1
+    for (int w = 0; w < 3; ++w) {
+      T* out = (w == 0 ? dv : (w == 1 ? da : df)) + b * slab;
+      const T* rw = res + (size_t)w * 6 * npairs;
+      if (vec_ok) {
+        int e = 2 * lane, r = 0;                            // f = r nn + e
+        while (e >= nn) { e -= nn; ++r; }
+        for (int k = lane; k < 3 * nn; k += 32) {
+          const int p0 = pmap[e], p1 = pmap[e + 1];         // nn is even: both entries lie in row r
+          V2 x;
+          x.x = p0 >= 0 ? rw[r * npairs + p0] : T(0);
+          x.y = p1 >= 0 ? rw[r * npairs + p1] : T(0);
+          __stcs(reinterpret_cast<V2*>(out) + k, x);
+          e += 64;
+          while (e >= nn) { e -= nn; ++r; }
+        }
+      } else {
+        int e = lane, r = 0;
+        while (e >= nn) { e -= nn; ++r; }
+        for (int k = lane; k < 6 * nn; k += 32) {
+          const int p0 = pmap[e];
+          __stcs(out + k, p0 >= 0 ? rw[r * npairs + p0] : T(0));
+          e += 32;
+          while (e >= nn) { e -= nn; ++r; }
+        }
+      }
+    }
+    __syncwarp();                                           // sv / sa / res are rewritten for the next knot point
   }
 }
 

@@ -45,28 +45,24 @@ int launch_grad_fpass(const rbd_model* m, int64_t B, const T* q, const T* qd, co
                  "rbd_rnea_grad_fpass: null argument or negative B");
   if (B == 0) return 0;
   if (variant_of(m) != 1 && variant_of(m) != 3 && m->d.n > 16) {
-    // large robots: one derivative column per lane without tiles (rbd_coop_pass_kernels.cuh: grad_fpass_stream_kernel)
+    // large robots: one body per lane, one ancestor distance per round, slabs written in one coalesced pass
+    // (rbd_coop_pass_kernels.cuh: grad_fpass_level_kernel)
     const int n = m->d.n;
-    int nslot = 0;
-    for (int i = 0; i < n; ++i) {
-      bool need = false;
-      for (int k = i + 2; k < n; ++k) need = need || m->d.parent[k] == i;
-      nslot += need ? 1 : 0;
-    }
-    auto kern = grad_fpass_stream_kernel<T, DQ>;
-    const size_t head = (((size_t)n * sizeof(int) + 15) & ~(size_t)15) + (size_t)n * kCpMdl * sizeof(T);
-    const size_t per_warp = (size_t)cp_stream_warp_vals(n, nslot) * sizeof(T);
-    const int warps = 4;
-    const size_t smem = head + per_warp * warps;
-    if (smem <= kMaxDynSmem && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+    int npairs = 0;
+    for (int i = 0; i < n; ++i)
+      for (int c = i; c >= 0; c = m->d.parent[c]) ++npairs;
+    auto kern = grad_fpass_level_kernel<T, DQ>;
+    for (int warps = 4; warps >= 1; warps >>= 1) {         // deep chains hold more pairs per warp
+      const size_t smem = cp_level_head_bytes(n, sizeof(T)) + (size_t)cp_level_warp_vals(n, npairs) * sizeof(T) * warps;
+      if (smem > kMaxDynSmem) continue;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) break;
       int nb = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem) == cudaSuccess && nb > 0) {
-        int64_t blocks = (B + warps - 1) / warps;
-        const int64_t cap = (int64_t)sm_count() * nb * 4;
-        if (blocks > cap) blocks = cap;
-        kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(pick<T>(m), nslot, B, q, qd, v, a, g, dv, da, df);
-        return cuda_status("rbd_rnea_grad_fpass(stream)");
-      }
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem) != cudaSuccess || nb < 1) break;
+      int64_t blocks = (B + warps - 1) / warps;
+      const int64_t cap = (int64_t)sm_count() * nb * 4;
+      if (blocks > cap) blocks = cap;
+      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(pick<T>(m), npairs, B, q, qd, v, a, g, dv, da, df);
+      return cuda_status("rbd_rnea_grad_fpass(level)");
     }
     cudaGetLastError();
   }
