@@ -182,50 +182,55 @@ grad_fpass_coop_kernel(const __grid_constant__ DevModel<T> m, int64_t B, const T
   warp_bulk_store_wait(lane);                             // shared memory must outlive the copies
 }
 
-// ---- rnea_grad_fpass_dq / _dqd for LARGE robots (n > 16): one BODY per lane, one ancestor distance per round ------
-// With n = 30 the three (6, n, NB) tensors of ONE knot point take 130 KB, of which 5/6 are structural zeros: column c of
-// body i is non-zero only when c is i or one of its ancestors (150 of Atlas' 900 pairs).  A warp owns one knot point:
-//   * lane i is body i.  In round d the lane works on the pair (c, i) with c = the ancestor of i at distance d: the
-//     recursion dv[c, i] = X_i dv[c, parent(i)] (:1158-1175 / :1230-1243) needs the pair (c, parent(i)), which is what the
-//     parent's lane produced in round d - 1 - twelve values by warp shuffle.  max depth + 1 rounds (10 for Atlas) instead
-//     of n steps over all n columns, and no lane works on a zero;
-//   * the 18 results of a pair wait in shared memory ([tensor row][pair], 22 KB per warp for Atlas);
-//   * the three slabs then leave in ONE coalesced pass of 16-byte stores: a per-CTA table maps every (c, i) of a tensor
-//     row to its pair or to "structural zero".  Every sector is written once (DRAM traffic = the tensors' size; a first
-//     version that zero-filled the slabs and scattered the pairs afterwards wrote 1.4x: with 130 KB per warp in flight
-//     the zeroed lines had left the L2 before their pairs arrived).
+// ---- rnea_grad_fpass_dq / _dqd: one BODY per lane, one ancestor distance per round -------------------------------
+// The three (6, n, NB) tensors of a knot point are mostly structural zeros: column c of body i is non-zero only when c
+// is i or one of its ancestors (150 of Atlas' 900 pairs, 28 of iiwa14's 49).  A group of G = 8 / 16 / 32 lanes owns one
+// knot point (32 / G knot points per warp):
+//   * lane i of the group is body i.  In round d the lane works on the pair (c, i) with c = the ancestor of i at
+//     distance d: the recursion dv[c, i] = X_i dv[c, parent(i)] (:1158-1175 / :1230-1243) needs the pair (c, parent(i)),
+//     which is what the parent's lane produced in round d - 1 - twelve values by warp shuffle.  max depth + 1 rounds
+//     (10 for Atlas) instead of n steps over all n columns, and no lane works on a zero;
+//   * the 18 results of a pair wait in shared memory ([tensor row][pair]; 22 KB per knot point for Atlas, 4 KB for iiwa14);
+//   * the warp's slabs (contiguous in HBM: consecutive knot points) then leave in ONE coalesced pass of 16-byte stores:
+//     a per-CTA table maps every (c, i) of a tensor row to its pair or to "structural zero".  Every sector is written
+//     once (DRAM traffic = the tensors' size; a first version that zero-filled the slabs and scattered the pairs
+//     afterwards wrote 1.4x: with 130 KB per warp in flight the zeroed lines had left the L2 before their pairs arrived).
 // Shared memory: the per-body constants (one copy per CTA, odd stride: lanes read different bodies), the pair map, and per
 // warp the staged v / a rows and the pair results.
 constexpr int kCpLvlMdl = 97;
-__host__ __device__ inline int cp_level_warp_vals(int n, int npairs) { return (12 * n + 18 * npairs + 3) & ~3; }   // v a rows | results
-__host__ __device__ inline size_t cp_level_head_bytes(int n, size_t tsize) {
-  return (((size_t)n * 4 * sizeof(int) + (size_t)n * n * sizeof(short) + 15) & ~(size_t)15) + (((size_t)n * kCpLvlMdl + 3) & ~(size_t)3) * tsize;
+__host__ __device__ inline int cp_level_warp_vals(int n, int npairs, int G) { return (32 / G) * ((12 * n + 18 * npairs + 3) & ~3); }   // per knot: v a rows | results
+__host__ __device__ inline size_t cp_level_head_bytes(int n, size_t tsize, int G = 32) {
+  return (((size_t)n * 4 * sizeof(int) + (size_t)(32 / G) * 6 * n * n * sizeof(short) + 15) & ~(size_t)15) + (((size_t)n * kCpLvlMdl + 3) & ~(size_t)3) * tsize;
 }
 
-template <typename T, bool DQ>
+template <typename T, int G, bool DQ>
 __global__ void __launch_bounds__(128)
 grad_fpass_level_kernel(const __grid_constant__ DevModel<T> m, int npairs, int64_t B, const T* __restrict__ q,
                         const T* __restrict__ qd, const T* __restrict__ v, const T* __restrict__ a, T gravity,
                         T* __restrict__ dv, T* __restrict__ da, T* __restrict__ df) {
+  constexpr int IPW = 32 / G;
   typedef typename Vec2<T>::type V2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = m.n;
   const int nn = n * n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int i = lane;
+  const int g = lane / G, i = lane - g * G;
+  const int gbase = g * G;
   const bool valid = i < n;
   int* topo = reinterpret_cast<int*>(smem_raw);                            // [n][4]: parent kind depth first-pair
-  short* pmap = reinterpret_cast<short*>(topo + 4 * n);                     // [n * n]: pair of (c, i) or -1
-  T* mdl = reinterpret_cast<T*>(smem_raw + cp_level_head_bytes(n, 0));     // [n][97]: XA XB XC S I
-  T* ws = mdl + (((size_t)n * kCpLvlMdl + 3) & ~(size_t)3) + (size_t)warp * cp_level_warp_vals(n, npairs);
-  T* sv = ws;                                              // [6][n]
+  short* pmap = reinterpret_cast<short*>(topo + 4 * n);                     // [IPW][6][n * n]: where value f of the warp's slab run waits (offset from the
+                                                                            // first knot point's results), or -1 = structural zero
+  T* mdl = reinterpret_cast<T*>(smem_raw + cp_level_head_bytes(n, 0, G));  // [n][97]: XA XB XC S I
+  const int knot_vals = (12 * n + 18 * npairs + 3) & ~3;
+  T* ws = mdl + (((size_t)n * kCpLvlMdl + 3) & ~(size_t)3) + (size_t)warp * IPW * knot_vals;
+  T* sv = ws + g * knot_vals;                              // [6][n] of this lane's knot point
   T* sa = sv + 6 * n;
   T* res = sa + 6 * n;                                     // [3][6][npairs]
   for (int k = threadIdx.x; k < n * kCpLvlMdl; k += blockDim.x) {
     const int b = k / kCpLvlMdl, w = k - b * kCpLvlMdl;
     mdl[k] = w < 18 ? m.XA[b][w] : w < 36 ? m.XB[b][w - 18] : w < 54 ? m.XC[b][w - 36] : w < 60 ? m.S[b][w - 54] : w < 96 ? m.I[b][w - 60] : T(0);
   }
-  for (int k = threadIdx.x; k < nn; k += blockDim.x) pmap[k] = (short)-1;
+  for (int k = threadIdx.x; k < IPW * 6 * nn; k += blockDim.x) pmap[k] = (short)-1;
   int maxdepth = 0;
   {
     int first = 0;
@@ -241,7 +246,11 @@ grad_fpass_level_kernel(const __grid_constant__ DevModel<T> m, int npairs, int64
   if (threadIdx.x < n) {                                   // pairs of body b: (b, b), (parent(b), b), ...
     const int b = threadIdx.x;
     int idx = topo[4 * b + 3];
-    for (int c = b; c >= 0; c = topo[4 * c]) pmap[c * n + b] = (short)idx++;
+    for (int c = b; c >= 0; c = topo[4 * c]) {
+      for (int kk = 0; kk < IPW; ++kk)
+        for (int r = 0; r < 6; ++r) pmap[(kk * 6 + r) * nn + c * n + b] = (short)(kk * knot_vals + r * npairs + idx);
+      ++idx;
+    }
   }
   __syncthreads();
   const int ib = valid ? i : 0;
@@ -256,12 +265,16 @@ grad_fpass_level_kernel(const __grid_constant__ DevModel<T> m, int npairs, int64
   for (int r = 0; r < 6; ++r) S[r] = mc[54 + r];
 #pragma unroll
   for (int k = 0; k < 36; ++k) Im[k] = mc[60 + k];
-  const int64_t slab = (int64_t)6 * nn;
-  const bool vec_ok = (nn & 1) == 0 &&
-                      ((reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(df)) & (2 * sizeof(T) - 1)) == 0;
-  for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
+  const int slab = 6 * nn;                                  // values of one tensor of one knot point (even)
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(df)) & (2 * sizeof(T) - 1)) == 0;
+  const int64_t ngroups = (B + IPW - 1) / IPW;
+  for (int64_t grp = (int64_t)blockIdx.x * nwarps + warp; grp < ngroups; grp += (int64_t)gridDim.x * nwarps) {
+    const int64_t first = grp * IPW;
+    const int nk = (int)((B - first) < IPW ? (B - first) : IPW);
+    int64_t b = first + g;
+    if (b >= B) b = B - 1;                                  // duplicate work, never stored
     // ---- inputs of the knot point
-    for (int e = lane; e < 6 * n; e += 32) {
+    for (int e = i; e < 6 * n; e += G) {
       sv[e] = v[b * 6 * n + e];
       if (DQ) sa[e] = a[b * 6 * n + e];
     }
@@ -277,7 +290,7 @@ grad_fpass_level_kernel(const __grid_constant__ DevModel<T> m, int npairs, int64
 #pragma unroll
       for (int k = 0; k < 18; ++k) X[k] = fma_t(mc[36 + k], f2, fma_t(mc[18 + k], f1, mc[k]));
     }
-    __syncwarp();                                           // staged rows are in place; the previous slab has been read
+    __syncwarp();                                           // staged rows are in place; the previous slabs have been read
 #pragma unroll
     for (int r = 0; r < 6; ++r) vi[r] = sv[r * n + ib];
     mat6_apply(Im, vi, Iv);                                                      // :1180 / :1248
@@ -287,7 +300,7 @@ grad_fpass_level_kernel(const __grid_constant__ DevModel<T> m, int npairs, int64
 #pragma unroll 1
     for (int d = 0; d <= maxdepth; ++d) {
       T pv[6], pa[6];
-      const int src = par >= 0 ? par : 0;
+      const int src = gbase + (par >= 0 ? par : 0);
 #pragma unroll
       for (int r = 0; r < 6; ++r) { pv[r] = __shfl_sync(0xffffffffu, cdv[r], src); pa[r] = __shfl_sync(0xffffffffu, cda[r], src); }
       if (depth >= d) {
@@ -342,35 +355,29 @@ grad_fpass_level_kernel(const __grid_constant__ DevModel<T> m, int npairs, int64
       }
     }
     __syncwarp();
-    // ---- the three slabs, every sector once: element f of a slab is row f / nn, entry (c, i) = f % nn
+    // ---- the warp's slabs of the three tensors (contiguous: consecutive knot points), every sector once: values
+    //      2 f2, 2 f2 + 1 of the run come from the map (one 32-bit load for the two entries), zero where it says -1
+    const int total = nk * slab;
 #pragma unroll 1
     for (int w = 0; w < 3; ++w) {
-      T* out = (w == 0 ? dv : (w == 1 ? da : df)) + b * slab;
-      const T* rw = res + (size_t)w * 6 * npairs;
+      T* out = (w == 0 ? dv : (w == 1 ? da : df)) + first * slab;
+      const T* rk = ws + 12 * n + (size_t)w * 6 * npairs;   // tensor w of the warp's first knot point
       if (vec_ok) {
-        int e = 2 * lane, r = 0;                            // f = r nn + e
-        while (e >= nn) { e -= nn; ++r; }
-        for (int k = lane; k < 3 * nn; k += 32) {
-          const int p0 = pmap[e], p1 = pmap[e + 1];         // nn is even: both entries lie in row r
+        for (int f2 = lane; f2 < (total >> 1); f2 += 32) {
+          const short2 pp = reinterpret_cast<const short2*>(pmap)[f2];
           V2 x;
-          x.x = p0 >= 0 ? rw[r * npairs + p0] : T(0);
-          x.y = p1 >= 0 ? rw[r * npairs + p1] : T(0);
-          __stcs(reinterpret_cast<V2*>(out) + k, x);
-          e += 64;
-          while (e >= nn) { e -= nn; ++r; }
+          x.x = pp.x >= 0 ? rk[pp.x] : T(0);
+          x.y = pp.y >= 0 ? rk[pp.y] : T(0);
+          __stcs(reinterpret_cast<V2*>(out) + f2, x);
         }
       } else {
-        int e = lane, r = 0;
-        while (e >= nn) { e -= nn; ++r; }
-        for (int k = lane; k < 6 * nn; k += 32) {
-          const int p0 = pmap[e];
-          __stcs(out + k, p0 >= 0 ? rw[r * npairs + p0] : T(0));
-          e += 32;
-          while (e >= nn) { e -= nn; ++r; }
+        for (int f = lane; f < total; f += 32) {
+          const int pp = pmap[f];
+          __stcs(out + f, pp >= 0 ? rk[pp] : T(0));
         }
       }
     }
-    __syncwarp();                                           // sv / sa / res are rewritten for the next knot point
+    __syncwarp();                                           // sv / sa / res are rewritten for the next knot points
   }
 }
 

@@ -44,21 +44,23 @@ int launch_grad_fpass(const rbd_model* m, int64_t B, const T* q, const T* qd, co
   RBD_CHECK_ARGS(m && q && qd && v && (a || !DQ) && dv && da && df && B >= 0,
                  "rbd_rnea_grad_fpass: null argument or negative B");
   if (B == 0) return 0;
-  if (variant_of(m) != 1 && variant_of(m) != 3 && m->d.n > 16) {
-    // large robots: one body per lane, one ancestor distance per round, slabs written in one coalesced pass
+  if (variant_of(m) != 1 && variant_of(m) != 3) {
+    // one body per lane, one ancestor distance per round, slabs written in one coalesced pass
     // (rbd_coop_pass_kernels.cuh: grad_fpass_level_kernel)
     const int n = m->d.n;
+    const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
     int npairs = 0;
     for (int i = 0; i < n; ++i)
       for (int c = i; c >= 0; c = m->d.parent[c]) ++npairs;
-    auto kern = grad_fpass_level_kernel<T, DQ>;
+    auto kern = G == 8 ? grad_fpass_level_kernel<T, 8, DQ> : (G == 16 ? grad_fpass_level_kernel<T, 16, DQ> : grad_fpass_level_kernel<T, 32, DQ>);
     for (int warps = 4; warps >= 1; warps >>= 1) {         // deep chains hold more pairs per warp
-      const size_t smem = cp_level_head_bytes(n, sizeof(T)) + (size_t)cp_level_warp_vals(n, npairs) * sizeof(T) * warps;
+      const size_t smem = cp_level_head_bytes(n, sizeof(T), G) + (size_t)cp_level_warp_vals(n, npairs, G) * sizeof(T) * warps;
       if (smem > kMaxDynSmem) continue;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) break;
       int nb = 0;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem) != cudaSuccess || nb < 1) break;
-      int64_t blocks = (B + warps - 1) / warps;
+      const int64_t ngroups = (B + 32 / G - 1) / (32 / G);
+      int64_t blocks = (ngroups + warps - 1) / warps;
       const int64_t cap = (int64_t)sm_count() * nb * 4;
       if (blocks > cap) blocks = cap;
       kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(pick<T>(m), npairs, B, q, qd, v, a, g, dv, da, df);
