@@ -130,9 +130,10 @@ def test_non_rigid_inertia_falls_back_to_generic_kernels():
 
 
 @requires_cuda
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3])
 def test_pass_helpers_vs_reference_golden(golden, variant):
-    """variant 0: lane / column-per-lane pass kernels; variant 1: the generic knot-point-per-thread ones."""
+    """variant 0: lane / body-per-lane (gradient fpass: one ancestor distance per round) pass kernels; variant 1: the
+    generic knot-point-per-thread ones; variant 3: gradient fpass with one column per lane and shared-memory tiles."""
     from rbdreference_b200 import RBDReference
     RBDReference.set_kernel_variant(variant)
     try:
