@@ -33,5 +33,6 @@ ncu --set full --clock-control none --import-source on -k regex:rnea_grad_chain 
 ncu --set full --clock-control none --import-source on -k regex:minv_tile -c 1 -o $O/r02_prof_minv_tile_atlas_f64 python bench.py --op minv --robot atlas --batch 262144 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $O/r02_ncu2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:minv_lane -c 1 -o $O/r02_prof_minv_lane_iiwa14_f64 python bench.py --op minv --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-quadrants > $O/r02_ncu3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:rnea_grad_coop -c 1 -o $O/r02_prof_grad_coop_atlas_f64 python bench.py --robot atlas --batch 262144 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $O/r02_ncu4.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:grad_fpass_coop -c 1 -o $O/r02_prof_grad_fpass_iiwa14_f64 python tools/bench_passes.py --reps 1 --batch 1048576 > $O/r02_ncu5.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:grad_fpass_level -c 1 -o $O/r02_prof_grad_fpass_level_iiwa14_f64 python tools/bench_passes.py --reps 1 --batch 1048576 > $O/r02_ncu5.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:grad_fpass_level -c 1 -o $O/r02_prof_grad_fpass_level_atlas_f64 python tools/bench_passes.py --reps 1 --robot atlas --batch 65536 > $O/r02_ncu5b.log 2>&1
 ls -la $O/*.ncu-rep | tail -6
