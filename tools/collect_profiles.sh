@@ -1,7 +1,8 @@
 # Copies / summarises gpurun_out/r02_* (written by tools/measure_round.sh on the GPU box) into profiles/ (tracked).
 set -u
 G=gpurun_out; P=profiles
-summ() {  # $1 = .ncu-rep stem, $2 = profiles name
+summ() {  # $1 = capture stem (tools/measure_round.sh summarises on the GPU box: gpurun_out/summ_<stem>.txt), $2 = profiles name
+  if [ -f $G/summ_$1.txt ]; then cp $G/summ_$1.txt $P/$2; return 0; fi
   [ -f $G/$1.ncu-rep ] || return 0
   python tools/ncu_summary.py $G/$1.ncu-rep $P/$2 > /dev/null 2>&1
   python tools/ncu_lines.py $G/$1.ncu-rep 2>/dev/null | awk '{ if ($4+0 >= 0.8 || $6+0 >= 0.8) print }' | cut -c1-260 >> $P/$2
