@@ -203,8 +203,9 @@ __host__ __device__ inline size_t cp_level_head_bytes(int n, size_t tsize, int G
   return (((size_t)n * 4 * sizeof(int) + (size_t)(32 / G) * 6 * n * n * sizeof(short) + 15) & ~(size_t)15) + (((size_t)n * kCpLvlMdl + 3) & ~(size_t)3) * tsize;
 }
 
+constexpr int kCpLvlMaxWarps = 8;
 template <typename T, int G, bool DQ>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kCpLvlMaxWarps * 32)
 grad_fpass_level_kernel(const __grid_constant__ DevModel<T> m, int npairs, int64_t B, const T* __restrict__ q,
                         const T* __restrict__ qd, const T* __restrict__ v, const T* __restrict__ a, T gravity,
                         T* __restrict__ dv, T* __restrict__ da, T* __restrict__ df) {

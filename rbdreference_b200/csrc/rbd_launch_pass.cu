@@ -53,15 +53,23 @@ int launch_grad_fpass(const rbd_model* m, int64_t B, const T* q, const T* qd, co
     for (int i = 0; i < n; ++i)
       for (int c = i; c >= 0; c = m->d.parent[c]) ++npairs;
     auto kern = G == 8 ? grad_fpass_level_kernel<T, 8, DQ> : (G == 16 ? grad_fpass_level_kernel<T, 16, DQ> : grad_fpass_level_kernel<T, 32, DQ>);
-    for (int warps = 4; warps >= 1; warps >>= 1) {         // deep chains hold more pairs per warp
-      const size_t smem = cp_level_head_bytes(n, sizeof(T), G) + (size_t)cp_level_warp_vals(n, npairs, G) * sizeof(T) * warps;
-      if (smem > kMaxDynSmem) continue;
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) break;
-      int nb = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem) != cudaSuccess || nb < 1) break;
+    // warps per CTA: the choice that keeps the most warps resident per SM (the constants and the slab map are per CTA,
+    // the staged inputs and pair results per warp: 25 KB for Atlas, 75 KB for a 32-link chain)
+    int warps = 0, best = 0, ctas = 0;
+    size_t smem = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem) == cudaSuccess) {
+      for (int w = 1; w <= kCpLvlMaxWarps; ++w) {
+        const size_t sz = cp_level_head_bytes(n, sizeof(T), G) + (size_t)cp_level_warp_vals(n, npairs, G) * sizeof(T) * w;
+        if (sz > kMaxDynSmem) break;
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, sz) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (nb * w > best) { best = nb * w; warps = w; smem = sz; ctas = nb; }
+      }
+    }
+    if (warps > 0) {
       const int64_t ngroups = (B + 32 / G - 1) / (32 / G);
       int64_t blocks = (ngroups + warps - 1) / warps;
-      const int64_t cap = (int64_t)sm_count() * nb * 4;
+      const int64_t cap = (int64_t)sm_count() * ctas * 4;
       if (blocks > cap) blocks = cap;
       kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(pick<T>(m), npairs, B, q, qd, v, a, g, dv, da, df);
       return cuda_status("rbd_rnea_grad_fpass(level)");
