@@ -274,10 +274,17 @@ grad_fpass_level_kernel(const __grid_constant__ DevModel<T> m, int npairs, int64
     const int nk = (int)((B - first) < IPW ? (B - first) : IPW);
     int64_t b = first + g;
     if (b >= B) b = B - 1;                                  // duplicate work, never stored
-    // ---- inputs of the knot point
+    // ---- inputs of the knot point (those of the warp's next knot points are requested into L2 meanwhile: the
+    //      loads below were 28 % of the stall samples)
+    int64_t bn = first + (int64_t)gridDim.x * nwarps * IPW + g;
+    const bool more = bn < B;
     for (int e = i; e < 6 * n; e += G) {
       sv[e] = v[b * 6 * n + e];
       if (DQ) sa[e] = a[b * 6 * n + e];
+      if (more) {
+        prefetch_l2(v + bn * 6 * n + e);
+        if (DQ) prefetch_l2(a + bn * 6 * n + e);
+      }
     }
     T X[18], vi[6], Iv[6], qdi = T(0);
     {
@@ -285,6 +292,7 @@ grad_fpass_level_kernel(const __grid_constant__ DevModel<T> m, int npairs, int64
       if (valid) {
         const T qi = q[b * n + i];
         qdi = qd[b * n + i];
+        if (more) { prefetch_l2(q + bn * n + i); prefetch_l2(qd + bn * n + i); }
         if (kind == 0) sincos_t(qi, &f2, &f1);
         else f1 = qi;
       }
