@@ -147,6 +147,41 @@ int launch_minv_bpass(const rbd_model* m, int64_t B, const T* q, T* Minv, T* F, 
         pick<T>(m), B, q, Minv, F, U, Dinv);
     return cuda_status("rbd_minv_bpass");
   }
+  if (m->fast_ok && variant_of(m) != 3) {
+    // rigid-body inertias: phases 0 and A of the cooperative minv kernel (one body per lane, local world-aligned
+    // frames), results rotated into body frames, Minv / F slabs written in one coalesced pass (BPASS = true)
+    const FastModel<T>& fm = pick_dfs<T>(m);
+    const int n = fm.n;
+    const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+    int npairs = 0;
+    for (int i = 0; i < n; ++i) npairs += m->coop_minv.depth[i] + 1;
+    auto kern = fm.has_prismatic
+                    ? (G == 8 ? minv_coop_kernel<T, 8, true, false, false, true>
+                              : (G == 16 ? minv_coop_kernel<T, 16, true, false, false, true> : minv_coop_kernel<T, 32, true, false, false, true>))
+                    : (G == 8 ? minv_coop_kernel<T, 8, false, false, false, true>
+                              : (G == 16 ? minv_coop_kernel<T, 16, false, false, false, true> : minv_coop_kernel<T, 32, false, false, false, true>));
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem) == cudaSuccess) {
+      int warps = 0, best = 0, ctas = 0;
+      size_t smem = 0;
+      for (int w = 1; w <= kCmMaxWarps; ++w) {
+        const size_t sz = coop_minv_smem_bytes<T>(n, G, m->coop.maxdepth, fm.n_slot_a, w, false, npairs);
+        if (sz > kMaxDynSmem) break;
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, sz) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (nb * w > best) { best = nb * w; warps = w; smem = sz; ctas = nb; }
+      }
+      if (warps > 0) {
+        const int ipw = 32 / G;
+        const int64_t ngroups = (B + ipw - 1) / ipw;
+        int64_t blocks = (ngroups + warps - 1) / warps;
+        const int64_t cap = (int64_t)sm_count() * ctas * 4;
+        if (blocks > cap) blocks = cap;
+        kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, m->coop_minv, B, q, Minv, F, U, Dinv, npairs);
+        return cuda_status("rbd_minv_bpass(coop)");
+      }
+    }
+    cudaGetLastError();
+  }
   // one column per lane, articulated inertias shared through shared memory
   const int n = m->d.n;
   const int G = n <= 8 ? 8 : (n <= 16 ? 16 : 32);

@@ -48,18 +48,28 @@ struct CoopMinvPlan {
 // fb: floating base - the matrix has n + 5 rows and the warp keeps the inverse of the base's articulated inertia
 // (21 values per knot point, kCmDinvStride apart) after `big`
 constexpr int kCmDinvStride = 24;     // (a multiple of four values: the next warp's table stays 16-byte aligned in FP32)
+// bpass_pairs > 0: the minv_bpass helper (BPASS = true) - the warp also keeps every body's rotation (12 values per lane)
+// and, per knot point, the seven results (Minv entry, F column) of each (ancestor, column) pair
+__host__ __device__ inline int coop_minv_bpass_stage(int npairs) { return (7 * npairs + 3) & ~3; }
 template <typename T>
-__host__ __device__ inline int coop_minv_warp_vals(int n, int G, int maxdepth, int nslot, bool fb = false) {
+__host__ __device__ inline int coop_minv_warp_vals(int n, int G, int maxdepth, int nslot, bool fb = false, int bpass_pairs = 0) {
   const int ipw = 32 / G;
   const int nvv = fb ? n + 5 : n;
   const int a = 32 * kCmIaStride;
   const int c = 6 * nslot * 32 + ((ipw * nvv * nvv + 3) & ~3);
-  return 32 * kCmTabStride + (maxdepth + 1) * 32 + (a > c ? a : c) + (fb ? ipw * kCmDinvStride : 0);
+  return 32 * kCmTabStride + (maxdepth + 1) * 32 + (a > c ? a : c) + (fb ? ipw * kCmDinvStride : 0) +
+         (bpass_pairs > 0 ? 32 * 12 + ipw * coop_minv_bpass_stage(bpass_pairs) : 0);
+}
+// per-CTA tables of the minv_bpass helper: first pair of every column (n ints) and the maps from every position of
+// the warp's Minv / F slabs to its staged value or -1 (16-bit)
+__host__ __device__ inline size_t coop_minv_bpass_map_bytes(int n, int G) {
+  const int ipw = 32 / G;
+  return (size_t)((n + 3) & ~3) * sizeof(int) + (size_t)(((ipw * n * n + 7) & ~7) + ((ipw * 6 * n * n + 7) & ~7)) * sizeof(short);
 }
 template <typename T>
-__host__ __device__ inline size_t coop_minv_smem_bytes(int n, int G, int maxdepth, int nslot, int warps, bool fb = false) {
-  return (size_t)(((n * kCoopMdlStride + 3) & ~3) + warps * coop_minv_warp_vals<T>(n, G, maxdepth, nslot, fb)) * sizeof(T) +
-         (size_t)n * 4 * sizeof(int);
+__host__ __device__ inline size_t coop_minv_smem_bytes(int n, int G, int maxdepth, int nslot, int warps, bool fb = false, int bpass_pairs = 0) {
+  return (size_t)(((n * kCoopMdlStride + 3) & ~3) + warps * coop_minv_warp_vals<T>(n, G, maxdepth, nslot, fb, bpass_pairs)) * sizeof(T) +
+         (size_t)n * 4 * sizeof(int) + (bpass_pairs > 0 ? coop_minv_bpass_map_bytes(n, G) : 0);
 }
 
 // index of entry (r, c) of a symmetric 6x6 stored as its upper triangle, row by row (21 values)
@@ -310,12 +320,21 @@ __device__ __forceinline__ void crba_column_phase(int n, int maxdepth, bool vali
 
 // CRBA = false: minv (Minv out).  CRBA = true: the joint-space inertia matrix H (same launch
 // geometry and shared-memory layout; phases B and C are replaced by crba_column_phase).
-template <typename T, int G, bool PRISM, bool CRBA = false, bool FB = false>
+// BPASS = true: the minv_bpass helper (RBDReference.py:630-735) on the same phases 0 and A.  The pass returns the
+// reference's arrays in BODY frames: U (n, 6) and Dinv (n; it holds D, :698) leave from phase A (lane = body: a rotation
+// of the lane's own U), and lane j then walks from body j to its root once more, producing for every ancestor a the
+// entry Minv[a, j] (:700-708) and the column F[a][:, j] as the reference leaves it (:721-723: U Minv[a, j] is added only
+// when a has a parent), rotated into a's axes.  The results wait in shared memory and the warp's Minv and F slabs -
+// mostly structural zeros: F[a][:, j] = 0 unless j is in subtree(a) - leave in one coalesced pass through a per-CTA
+// map, every sector written once (the scheme of grad_fpass_level_kernel).
+template <typename T, int G, bool PRISM, bool CRBA = false, bool FB = false, bool BPASS = false>
 __global__ void __launch_bounds__(kCmMaxWarps * 32)
 minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__ DfsPlan plan,
                  const __grid_constant__ CoopPlan cp, const __grid_constant__ CoopMinvPlan mp, int64_t B,
-                 const T* __restrict__ q, T* __restrict__ Minv) {
+                 const T* __restrict__ q, T* __restrict__ Minv, T* __restrict__ Fo, T* __restrict__ Uo,
+                 T* __restrict__ Do, int npairs) {
   static_assert(!(FB && CRBA), "crba has no floating-base branch here");
+  static_assert(!(BPASS && (CRBA || FB)), "the minv_bpass helper is a fixed-base, articulated-inertia mode");
   constexpr int IPW = 32 / G;
   typedef typename Vec2<T>::type V2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -325,7 +344,7 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
   const int nn = nvv * nvv;
   const int maxdepth = cp.maxdepth;
   const int nwarps = blockDim.x >> 5;
-  const int warp_vals = coop_minv_warp_vals<T>(n, G, maxdepth, m.n_slot_a, FB);
+  const int warp_vals = coop_minv_warp_vals<T>(n, G, maxdepth, m.n_slot_a, FB, BPASS ? npairs : 0);
   int4* imdl = reinterpret_cast<int4*>(smem_raw);                            // [n]
   T* mdl = reinterpret_cast<T*>(smem_raw + (size_t)n * sizeof(int4));        // [n][51]
   T* warp_all = mdl + ((n * kCoopMdlStride + 3) & ~3);                       // [nwarps][warp_vals]
@@ -351,6 +370,33 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
     imdl[i] = make_int4(p, plan.sub_end[i], plan.orig[i], cm_pack(mp.depth[i], m.slot_a[i], p >= 0 ? m.slot_a[p] : -1, m.kind[i]));
   }
   __syncthreads();
+  // BPASS: pair tables behind the warps' regions
+  const int stage = coop_minv_bpass_stage(npairs);          // staged values per knot point: [7][npairs]
+  int* pfirst = reinterpret_cast<int*>(warp_all + (size_t)nwarps * warp_vals);                 // [n] first pair of column j
+  short* pmapM = reinterpret_cast<short*>(pfirst + ((n + 3) & ~3));                            // [IPW][n * n]
+  short* pmapF = pmapM + ((IPW * nn + 7) & ~7);                                                // [IPW][n][6][n]
+  if (BPASS) {
+    for (int k = threadIdx.x; k < IPW * nn; k += blockDim.x) pmapM[k] = (short)-1;
+    for (int k = threadIdx.x; k < IPW * 6 * nn; k += blockDim.x) pmapF[k] = (short)-1;
+    if (threadIdx.x == 0) {
+      int first = 0;
+      for (int j = 0; j < n; ++j) { pfirst[j] = first; first += mp.depth[j] + 1; }
+    }
+    __syncthreads();
+    if (threadIdx.x < n) {                                  // pairs of column j: (j, j), (parent(j), j), ...
+      const int j = threadIdx.x, oj = imdl[j].z;
+      int idx = pfirst[j];
+      for (int a = j; a >= 0; a = imdl[a].x) {
+        const int oa = imdl[a].z;
+        for (int kk = 0; kk < IPW; ++kk) {
+          pmapM[kk * nn + oa * n + oj] = (short)(kk * stage + idx);
+          for (int r = 0; r < 6; ++r) pmapF[kk * 6 * nn + (oa * 6 + r) * n + oj] = (short)(kk * stage + (1 + r) * npairs + idx);
+        }
+        ++idx;
+      }
+    }
+    __syncthreads();
+  }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / G, i = lane - g * G;
@@ -373,6 +419,8 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
   T* big = mbw + (maxdepth + 1) * 32;                     // phase A: [32][22]; phase C: G stashes [slot][6][32] | tile
   T* mytab = tab + lane * kCmTabStride;
   T* dinv = tab + warp_vals - IPW * kCmDinvStride;        // FB: [IPW][22] inverse of the base's articulated inertia
+  T* etab = tab + warp_vals - (32 * 12 + IPW * stage);    // BPASS: [32][12] rotation of every body | [IPW][7][npairs] results
+  T* stg = etab + 32 * 12;
   const int nsteps = cp.nsteps;
 
   const int64_t ngroups = (B + IPW - 1) / IPW;
@@ -441,6 +489,10 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
         w[cc] = E[cc] * mb[36] + E[3 + cc] * mb[37] + E[6 + cc] * mb[38];       // joint axis, world axes
       }
     }
+    if (BPASS) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) etab[lane * 12 + k] = E[k];
+    }
 
     // ------------------------------------------------------------------ own rigid inertia about p_i
     // IA = [[A, Bm], [Bm^T, C]] : A sym (0..5: xx xy xz yy yz zz), Bm 3x3 row-major (6..14), C sym (15..20)
@@ -507,6 +559,16 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
         }
         const T D = kind == 0 ? dot3s(w, U) : dot3s(w, U + 3);
         const T invD = T(1) / D;                                               // RBDReference.py:698-700
+        if (BPASS && valid && (grp * IPW + g) < B) {
+          // U (B, n, 6) in body i's axes (same origin: a rotation), Dinv (B, n) = D (:697-698)
+          T* ub = Uo + (b * n + oi) * (int64_t)6;
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr) {
+            ub[rr] = E[3 * rr] * U[0] + E[3 * rr + 1] * U[1] + E[3 * rr + 2] * U[2];
+            ub[3 + rr] = E[3 * rr] * U[3] + E[3 * rr + 1] * U[4] + E[3 * rr + 2] * U[5];
+          }
+          Do[b * n + oi] = D;
+        }
         {
           V2* dst = reinterpret_cast<V2*>(mytab);
           V2 t;
@@ -568,7 +630,62 @@ minv_coop_kernel(const __grid_constant__ FastModel<T> m, const __grid_constant__
       __syncwarp();
     }
 
-    if (CRBA)
+    if (BPASS) {
+      // ---------------------------------------------------------------- lane j: column j up to its root
+      if (valid) {
+        T F[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+        T* sj = stg + g * stage + pfirst[i];
+        int a = i;
+        for (int t = 0; t <= maxdepth; ++t) {
+          if (a >= 0) {
+            TabEntry<T> e;
+            tab_load(tab + (gbase + a) * kCmTabStride, e);
+            const int4 ia = imdl[a];
+            const bool pris = PRISM && ((ia.w >> 24) != 0);
+            const T sF = pris ? dot3s(e.w, F + 3) : dot3s(e.w, F);
+            const T mij = (a == i ? e.invD : T(0)) - e.invD * sF;              // :700-708
+            if (ia.x >= 0) {
+#pragma unroll
+              for (int k = 0; k < 6; ++k) F[k] = fma_t(e.U[k], mij, F[k]);     // :721-723 (only with a parent)
+            }
+            const T* Ea = etab + (gbase + a) * 12;
+            sj[t] = mij;
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+              sj[(1 + rr) * npairs + t] = Ea[3 * rr] * F[0] + Ea[3 * rr + 1] * F[1] + Ea[3 * rr + 2] * F[2];
+              sj[(4 + rr) * npairs + t] = Ea[3 * rr] * F[3] + Ea[3 * rr + 1] * F[4] + Ea[3 * rr + 2] * F[5];
+            }
+            cross3_add(e.r, F + 3, F);                                         // moment about the parent's origin (:724-726)
+            a = ia.x;
+          }
+        }
+      }
+      __syncwarp();
+      // ---------------------------------------------------------------- the warp's Minv and F slabs, every sector once
+      const int64_t first = grp * IPW;
+      const int nk = (int)((B - first) < IPW ? (B - first) : IPW);
+#pragma unroll 1
+      for (int w2 = 0; w2 < 2; ++w2) {
+        const int per = w2 == 0 ? nn : 6 * nn;
+        T* out = (w2 == 0 ? Minv : Fo) + first * per;
+        const short* pm = w2 == 0 ? pmapM : pmapF;
+        const int total = nk * per;
+        if ((total & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & (sizeof(V2) - 1)) == 0) {
+          for (int f2 = lane; f2 < (total >> 1); f2 += 32) {
+            const short2 pp = reinterpret_cast<const short2*>(pm)[f2];
+            V2 x;
+            x.x = pp.x >= 0 ? stg[pp.x] : T(0);
+            x.y = pp.y >= 0 ? stg[pp.y] : T(0);
+            __stcs(reinterpret_cast<V2*>(out) + f2, x);
+          }
+        } else {
+          for (int f = lane; f < total; f += 32) {
+            const int pp = pm[f];
+            __stcs(out + f, pp >= 0 ? stg[pp] : T(0));
+          }
+        }
+      }
+    } else if (CRBA)
       crba_column_phase<T, G, PRISM>(n, maxdepth, valid, i, gbase, lane, oi, imdl, tab, big + 6 * m.n_slot_a * 32,
                                      Minv + grp * IPW * (int64_t)nn, (int)((B - grp * IPW) < IPW ? (B - grp * IPW) : IPW));
     else if (FB)   // every entry of the matrix is written (the base couples all bodies): no zero fill

@@ -172,7 +172,7 @@ int launch_fb_minv(const rbd_fb_model* m, int64_t B, const T* q, int dense, T* M
       const int64_t ngroups = (B + ipw - 1) / ipw;
       int64_t blocks = (ngroups + warps - 1) / warps;
       if (blocks > grid_cap()) blocks = grid_cap();
-      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, m->coop_minv, B, q, Minv);
+      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, m->coop_minv, B, q, Minv, nullptr, nullptr, nullptr, 0);
       return cuda_status("rbd_fb_minv(coop)");
     }
   }

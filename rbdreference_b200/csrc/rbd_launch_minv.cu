@@ -153,7 +153,7 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
       int64_t blocks = (ngroups + warps - 1) / warps;
       const int64_t cap = grid_cap();
       if (blocks > cap) blocks = cap;
-      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, m->coop_minv, B, q, Minv);
+      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, m->coop_minv, B, q, Minv, nullptr, nullptr, nullptr, 0);
       return cuda_status("rbd_minv(coop)");
     }
   }
@@ -214,7 +214,7 @@ int launch_crba(const rbd_model* m, int64_t B, const T* q, T* H, void* stream) {
       int64_t blocks = (ngroups + warps - 1) / warps;
       const int64_t cap = grid_cap();
       if (blocks > cap) blocks = cap;
-      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, m->coop_minv, B, q, H);
+      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(fm, m->plan, m->coop, m->coop_minv, B, q, H, nullptr, nullptr, nullptr, 0);
       return cuda_status("rbd_crba(coop)");
     }
   }
