@@ -1,3 +1,5 @@
+# Per-pass helper measurements (one B200; run under gpurun from the repo root): full -m gpu test run, canary / determinism
+# checker, tools/bench_passes.py for the three robots, ncu captures of the body-per-lane gradient fpass.
 set -u
 O=gpurun_out
 cap() {
@@ -8,10 +10,13 @@ cap() {
   rm -f $O/$stem.ncu-rep
 }
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/sanitize.py > $O/r02_sanitize.json 2> $O/r02_sanitize.err; tail -c 200 $O/r02_sanitize.json; tail -2 $O/r02_sanitize.err
 : > $O/r02_passes.jsonl
 python tools/bench_passes.py --reps 5 --batch 1048576 >> $O/r02_passes.jsonl 2>/dev/null
 python tools/bench_passes.py --reps 5 --robot hyq --batch 262144 >> $O/r02_passes.jsonl 2>/dev/null
 python tools/bench_passes.py --reps 5 --robot atlas --batch 65536 >> $O/r02_passes.jsonl 2>/dev/null
+if [ "${1:-}" = "ncu" ]; then
 cap regex:grad_fpass_level r02_prof_grad_fpass_level_iiwa14_f64 python tools/bench_passes.py --reps 1 --batch 1048576 > $O/r02_ncu5.log 2>&1
 cap regex:grad_fpass_level r02_prof_grad_fpass_level_atlas_f64 python tools/bench_passes.py --reps 1 --robot atlas --batch 65536 > $O/r02_ncu5b.log 2>&1
+fi
 grep -c pass $O/r02_passes.jsonl
