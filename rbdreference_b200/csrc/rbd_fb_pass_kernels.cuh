@@ -18,6 +18,7 @@
 #pragma once
 #include "rbd_common.cuh"
 #include "rbd_fb_kernels.cuh"
+#include "rbd_coop_pass_kernels.cuh"
 
 namespace rbd {
 
@@ -388,6 +389,252 @@ fbp_grad_fpass_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* 
         dfb[(r * n + c) * NB + i] = dfc[r];
       }
     }
+  }
+}
+
+// ---- rnea_grad_fpass_dq / _dqd, one BODY per lane (the scheme of grad_fpass_level_kernel, rbd_coop_pass_kernels.cuh) ----
+// Lane i of a group of G lanes is body i (body 0 = the base).  A body's non-zero columns are those of its joint ancestors
+// (column a + 5 for ancestor body a >= 1, itself included) and the base's six.  Round d handles the ancestor at distance d:
+//   * d < depth(i): one pair, the parent's pair of round d - 1 arrives by warp shuffle (as for a fixed base);
+//   * d = depth(i): the ancestor is the base - six pairs, column k = 0..5.  The base's own lane seeds them (:1175 /
+//     :1231-1243 with S = eye(6)); every other lane reads the parent's six results of the previous round from shared
+//     memory, where all results wait anyway.
+// The three (6, n, NB) slabs then leave in one coalesced pass through a per-CTA map (structural zeros where it says -1).
+__host__ __device__ inline int fbp_level_knot_vals(int NB, int npairs) { return (12 * NB + 18 * npairs + 3) & ~3; }
+__host__ __device__ inline size_t fbp_level_head_bytes(int NB, int G, size_t tsize) {
+  const size_t slab = (size_t)6 * (NB + 5) * NB;
+  return (((size_t)NB * 4 * sizeof(int) + (size_t)(32 / G) * slab * sizeof(short) + 15) & ~(size_t)15) +
+         (((size_t)NB * kCpLvlMdl + 3) & ~(size_t)3) * tsize;
+}
+
+template <typename T, int G, bool DQ>
+__global__ void __launch_bounds__(kCpLvlMaxWarps * 32)
+fbp_grad_fpass_level_kernel(const __grid_constant__ FbModel<T> m, int npairs, int64_t B, const T* __restrict__ q,
+                            const T* __restrict__ qd, const T* __restrict__ v, const T* __restrict__ a, T gravity,
+                            T* __restrict__ dv, T* __restrict__ da, T* __restrict__ df) {
+  constexpr int IPW = 32 / G;
+  typedef typename Vec2<T>::type V2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NB = m.d.n, n = NB + 5, nq = NB + 6;
+  const int cn = n * NB;                                   // entries of one tensor row: [column][body]
+  const int slab = 6 * cn;                                 // values of one tensor of one knot point (even)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane / G, i = lane - g * G;
+  const int gbase = g * G;
+  const bool valid = i < NB;
+  int* topo = reinterpret_cast<int*>(smem_raw);                            // [NB][4]: parent kind depth first-pair
+  short* pmap = reinterpret_cast<short*>(topo + 4 * NB);                    // [IPW][6][n][NB]: where the value waits, or -1
+  T* mdl = reinterpret_cast<T*>(smem_raw + fbp_level_head_bytes(NB, G, 0)); // [NB][97]: XA XB XC S I
+  const int knot_vals = fbp_level_knot_vals(NB, npairs);
+  T* ws = mdl + (((size_t)NB * kCpLvlMdl + 3) & ~(size_t)3) + (size_t)warp * IPW * knot_vals;
+  T* sv = ws + g * knot_vals;                              // [6][NB] of this lane's knot point
+  T* sa = sv + 6 * NB;
+  T* res = sa + 6 * NB;                                    // [3][6][npairs]
+  for (int k = threadIdx.x; k < NB * kCpLvlMdl; k += blockDim.x) {
+    const int b = k / kCpLvlMdl, w = k - b * kCpLvlMdl;
+    mdl[k] = w < 18 ? m.d.XA[b][w] : w < 36 ? m.d.XB[b][w - 18] : w < 54 ? m.d.XC[b][w - 36] : w < 60 ? m.d.S[b][w - 54] : w < 96 ? m.d.I[b][w - 60] : T(0);
+  }
+  for (int k = threadIdx.x; k < IPW * slab; k += blockDim.x) pmap[k] = (short)-1;
+  int maxdepth = 0;
+  {
+    int first = 0;
+    for (int b = 0; b < NB; ++b) {                         // (every thread walks the same entries of the constant bank)
+      int d = 0;
+      for (int p = m.d.parent[b]; p >= 0; p = m.d.parent[p]) ++d;
+      if (threadIdx.x == 0) { topo[4 * b] = m.d.parent[b]; topo[4 * b + 1] = m.d.kind[b]; topo[4 * b + 2] = d; topo[4 * b + 3] = first; }
+      first += d + 6;                                      // d joint ancestors (itself included) + the base's six columns
+      maxdepth = d > maxdepth ? d : maxdepth;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < NB) {
+    const int b = threadIdx.x;
+    int idx = topo[4 * b + 3];
+    for (int c = b; c >= 1; c = topo[4 * c]) {             // joint ancestors: column c + 5
+      for (int kk = 0; kk < IPW; ++kk)
+        for (int r = 0; r < 6; ++r) pmap[(kk * 6 + r) * cn + (c + 5) * NB + b] = (short)(kk * knot_vals + r * npairs + idx);
+      ++idx;
+    }
+    for (int k = 0; k < 6; ++k) {                          // the base's columns
+      for (int kk = 0; kk < IPW; ++kk)
+        for (int r = 0; r < 6; ++r) pmap[(kk * 6 + r) * cn + k * NB + b] = (short)(kk * knot_vals + r * npairs + idx);
+      ++idx;
+    }
+  }
+  __syncthreads();
+  const int ib = valid ? i : 0;
+  const int par = topo[4 * ib], kind = topo[4 * ib + 1];
+  const int depth = valid ? topo[4 * ib + 2] : -1;
+  const int pair0 = topo[4 * ib + 3];
+  const int ppair6 = par >= 0 ? topo[4 * par + 3] + topo[4 * par + 2] : 0;   // the parent's first base pair
+  const T* mc = mdl + ib * kCpLvlMdl;
+  T S[6], Im[36];                                          // lane = body for the whole kernel
+#pragma unroll
+  for (int r = 0; r < 6; ++r) S[r] = mc[54 + r];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) Im[k] = mc[60 + k];
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(df)) & (2 * sizeof(T) - 1)) == 0;
+  const int64_t ngroups = (B + IPW - 1) / IPW;
+  for (int64_t grp = (int64_t)blockIdx.x * nwarps + warp; grp < ngroups; grp += (int64_t)gridDim.x * nwarps) {
+    const int64_t first = grp * IPW;
+    const int nk = (int)((B - first) < IPW ? (B - first) : IPW);
+    int64_t b = first + g;
+    if (b >= B) b = B - 1;                                  // duplicate work, never stored
+    int64_t bn = first + (int64_t)gridDim.x * nwarps * IPW + g;
+    const bool more = bn < B;
+    for (int e = i; e < 6 * NB; e += G) {
+      sv[e] = v[b * 6 * NB + e];
+      if (DQ) sa[e] = a[b * 6 * NB + e];
+      if (more) {
+        prefetch_l2(v + bn * 6 * NB + e);
+        if (DQ) prefetch_l2(a + bn * 6 * NB + e);
+      }
+    }
+    T X[18], vi[6], Iv[6], qdi = T(0);
+    T xg[6], qd0[6];                                        // base lane: X_0 a_grav (dq) / qd[0:6] (dqd)
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { xg[r] = T(0); qd0[r] = T(0); }
+    if (valid && i == 0) {
+      fb_base_X(m, q + b * nq, X);
+      if (DQ) {
+        T g6[6] = {T(0), T(0), T(0), T(0), T(0), -gravity};
+        X_apply(X, g6, xg);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) qd0[r] = qd[b * n + r];
+      }
+    } else {
+      T f1 = T(0), f2 = T(0);
+      if (valid) {
+        const T qi = q[b * nq + i + 6];
+        qdi = qd[b * n + i + 5];
+        if (kind == 0) sincos_t(qi, &f2, &f1);
+        else f1 = qi;
+      }
+#pragma unroll
+      for (int k = 0; k < 18; ++k) X[k] = fma_t(mc[36 + k], f2, fma_t(mc[18 + k], f1, mc[k]));
+    }
+    if (more && valid) { prefetch_l2(q + bn * nq + i + 6); prefetch_l2(qd + bn * n + i + 5); }
+    __syncwarp();                                           // staged rows are in place; the previous slabs have been read
+#pragma unroll
+    for (int r = 0; r < 6; ++r) vi[r] = sv[r * NB + ib];
+    mat6_apply(Im, vi, Iv);                                                      // :1180 / :1248
+    T cdv[6], cda[6];                                       // dv / da of this lane's joint pair of the previous round
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { cdv[r] = T(0); cda[r] = T(0); }
+#pragma unroll 1
+    for (int d = 0; d <= maxdepth; ++d) {
+      T pv[6], pa[6];
+      const int src = gbase + (par >= 0 ? par : 0);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) { pv[r] = __shfl_sync(0xffffffffu, cdv[r], src); pa[r] = __shfl_sync(0xffffffffu, cda[r], src); }
+      if (depth > d) {
+        // ---- a joint ancestor at distance d (d = 0: the body's own column i + 5)
+        T dvc[6], dac[6], t[6];
+        if (d == 0) {
+          T seed_a[6];
+          if (DQ) {
+            T pr[6], xp[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) pr[r] = sv[r * NB + par];
+            X_apply(X, pr, xp);
+            crm_mul(xp, S, dvc);                                                 // :1159
+#pragma unroll
+            for (int r = 0; r < 6; ++r) pr[r] = sa[r * NB + par];
+            X_apply(X, pr, xp);
+            crm_mul(xp, S, seed_a);                                              // :1173
+          } else {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) dvc[r] = S[r];                           // :1231
+            crm_mul(vi, S, seed_a);                                              // :1243
+          }
+          crm_mul(dvc, S, t);                                                    // :1170 / :1240
+#pragma unroll
+          for (int r = 0; r < 6; ++r) dac[r] = fma_t(qdi, t[r], seed_a[r]);
+        } else {
+          X_apply(X, pv, dvc);                                                   // :1158 / :1230
+          X_apply(X, pa, dac);                                                   // :1163 / :1234
+          crm_mul(dvc, S, t);
+#pragma unroll
+          for (int r = 0; r < 6; ++r) dac[r] = fma_t(qdi, t[r], dac[r]);
+        }
+        T dfc[6];
+        fbp_df(Im, vi, Iv, dvc, dac, dfc);
+        T* rp = res + pair0 + d;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          rp[r * npairs] = dvc[r];
+          rp[(6 + r) * npairs] = dac[r];
+          rp[(12 + r) * npairs] = dfc[r];
+          cdv[r] = dvc[r];
+          cda[r] = dac[r];
+        }
+      } else if (depth == d) {
+        // ---- the base's six columns
+#pragma unroll 1
+        for (int k = 0; k < 6; ++k) {
+          T dvc[6], dac[6];
+          if (i == 0) {
+            T e[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { e[r] = r == k ? T(1) : T(0); dvc[r] = T(0); }
+            if (DQ) {
+              crm_mul(xg, e, dac);                                               // :1175 with S = eye(6); :1166-1168 adds zeros
+            } else {
+              T t1[6], t2[6];
+#pragma unroll
+              for (int r = 0; r < 6; ++r) dvc[r] = e[r];                         // :1231
+              crm_mul(e, qd0, t1);                                               // :1236-1238
+              crm_mul(vi, e, t2);                                                // :1243
+#pragma unroll
+              for (int r = 0; r < 6; ++r) dac[r] = t1[r] + t2[r];
+            }
+          } else {
+            T ppv[6], ppa[6], t[6];
+            const T* pr = res + ppair6 + k;                                      // the parent's pair of column k (previous round)
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { ppv[r] = pr[r * npairs]; ppa[r] = pr[(6 + r) * npairs]; }
+            X_apply(X, ppv, dvc);
+            X_apply(X, ppa, dac);
+            crm_mul(dvc, S, t);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) dac[r] = fma_t(qdi, t[r], dac[r]);
+          }
+          T dfc[6];
+          fbp_df(Im, vi, Iv, dvc, dac, dfc);
+          T* rp = res + pair0 + depth + k;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            rp[r * npairs] = dvc[r];
+            rp[(6 + r) * npairs] = dac[r];
+            rp[(12 + r) * npairs] = dfc[r];
+          }
+        }
+      }
+      __syncwarp();                                         // the round's results are visible to the children's base round
+    }
+    // ---- the warp's slabs of the three tensors (contiguous: consecutive knot points), every sector once
+    const int total = nk * slab;
+#pragma unroll 1
+    for (int w = 0; w < 3; ++w) {
+      T* out = (w == 0 ? dv : (w == 1 ? da : df)) + first * slab;
+      const T* rk = ws + 12 * NB + (size_t)w * 6 * npairs;  // tensor w of the warp's first knot point
+      if (vec_ok) {
+        for (int f2 = lane; f2 < (total >> 1); f2 += 32) {
+          const short2 pp = reinterpret_cast<const short2*>(pmap)[f2];
+          V2 x;
+          x.x = pp.x >= 0 ? rk[pp.x] : T(0);
+          x.y = pp.y >= 0 ? rk[pp.y] : T(0);
+          __stcs(reinterpret_cast<V2*>(out) + f2, x);
+        }
+      } else {
+        for (int f = lane; f < total; f += 32) {
+          const int pp = pmap[f];
+          __stcs(out + f, pp >= 0 ? rk[pp] : T(0));
+        }
+      }
+    }
+    __syncwarp();                                           // sv / sa / res are rewritten for the next knot points
   }
 }
 

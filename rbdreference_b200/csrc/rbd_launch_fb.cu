@@ -217,6 +217,39 @@ int launch_fb_grad_fpass(const rbd_fb_model* m, int64_t B, const T* q, const T* 
   if (B == 0) return 0;
   if (DQ && m->d.d.n < 6)        // RBDReference.py:1168 indexes bodies 0..5 (IndexError upstream)
     return fail(RBD_E_UNSUPPORTED, "rbd_fb_rnea_grad_fpass_dq: the reference needs at least 6 bodies on this path (:1168)");
+  if (fb_variant_of(m) != 1) {
+    // one body per lane, one ancestor distance per round, slabs written in one coalesced pass
+    // (rbd_fb_pass_kernels.cuh: fbp_grad_fpass_level_kernel)
+    const int NB = m->d.d.n;
+    const int G = NB <= 8 ? 8 : (NB <= 16 ? 16 : 32);
+    int npairs = 0;
+    for (int i = 0; i < NB; ++i) {
+      npairs += 6;
+      for (int c = i; c >= 1; c = m->d.d.parent[c]) ++npairs;
+    }
+    auto kern = G == 8 ? fbp_grad_fpass_level_kernel<T, 8, DQ>
+                       : (G == 16 ? fbp_grad_fpass_level_kernel<T, 16, DQ> : fbp_grad_fpass_level_kernel<T, 32, DQ>);
+    int warps = 0, best = 0, ctas = 0;
+    size_t smem = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem) == cudaSuccess) {
+      for (int w = 1; w <= kCpLvlMaxWarps; ++w) {
+        const size_t sz = fbp_level_head_bytes(NB, G, sizeof(T)) + (size_t)(32 / G) * fbp_level_knot_vals(NB, npairs) * sizeof(T) * w;
+        if (sz > kMaxDynSmem) break;
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, sz) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (nb * w > best) { best = nb * w; warps = w; smem = sz; ctas = nb; }
+      }
+    }
+    if (warps > 0) {
+      const int64_t ngroups = (B + 32 / G - 1) / (32 / G);
+      int64_t blocks = (ngroups + warps - 1) / warps;
+      const int64_t cap = (int64_t)sm_count() * ctas * 4;
+      if (blocks > cap) blocks = cap;
+      kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(pick_fb<T>(m), npairs, B, q, qd, v, a, g, dv, da, df);
+      return cuda_status("rbd_fb_rnea_grad_fpass(level)");
+    }
+    cudaGetLastError();
+  }
   fbp_grad_fpass_kernel<T, DQ><<<blocks_for(B, kFbPassThreads), kFbPassThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, qd, v, a, g, dv, da, df);
   return cuda_status("rbd_fb_rnea_grad_fpass");
 }

@@ -818,7 +818,7 @@ def test_floating_base_vs_reference_golden(name, fb_family):
 
 @requires_cuda
 @pytest.mark.parametrize("name", FB_CASES)
-def test_floating_base_pass_helpers_vs_reference_golden(name):
+def test_floating_base_pass_helpers_vs_reference_golden(name, fb_family):
     """The eight per-pass entry points of a floating-base robot against arrays of the unmodified reference: batched
     (numpy and CUDA tensors), one knot point with reference shapes, in-place contracts, both precisions, and the
     reference's own call sequence composed from the helpers."""

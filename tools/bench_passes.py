@@ -33,12 +33,19 @@ def main():
     torch.cuda.set_device(dev)
     td = torch.float64 if args.dtype == "f64" else torch.float32
     isz = 8 if args.dtype == "f64" else 4
-    eng = RBDReference(robots.by_name(args.robot), dtype=td)
+    rb = robots.by_name(args.robot)
+    eng = RBDReference(rb, dtype=td)
     n, B = eng.n, args.batch
+    NB = eng.NB                                             # bodies (= n for a fixed base, n - 5 with a floating base)
     gen = torch.Generator(device=dev).manual_seed(0xB200)
-    q = ((torch.rand(B, n, generator=gen, device=dev, dtype=torch.float64) * 2 - 1) * np.pi).to(td)
-    qd = (torch.rand(B, n, generator=gen, device=dev, dtype=torch.float64) * 2 - 1).to(td)
-    qdd = (torch.rand(B, n, generator=gen, device=dev, dtype=torch.float64) * 2 - 1).to(td)
+    if eng.floating_base:                                   # q carries a unit quaternion: 4096 states from the robot, tiled
+        hq, hqd, hqdd = rb.random_state(np.random.default_rng(0xB200), 4096)
+        rep = (B + 4095) // 4096
+        q, qd, qdd = (torch.as_tensor(x, device=dev, dtype=td).repeat(rep, 1)[:B].contiguous() for x in (hq, hqd, hqdd))
+    else:
+        q = ((torch.rand(B, n, generator=gen, device=dev, dtype=torch.float64) * 2 - 1) * np.pi).to(td)
+        qd = (torch.rand(B, n, generator=gen, device=dev, dtype=torch.float64) * 2 - 1).to(td)
+        qdd = (torch.rand(B, n, generator=gen, device=dev, dtype=torch.float64) * 2 - 1).to(td)
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
         src = "MEASURED_PEAKS.json"
@@ -51,10 +58,10 @@ def main():
     fa = f.clone()
     eng.rnea_bpass(q, fa)
     Mb, Fb, U, D = eng.minv_bpass(q)
-    v6, t6, nn, f6 = 6 * n, 6 * n * n, n * n, 6 * n * n
+    v6, t6, nn, f6 = 6 * NB, 6 * n * NB, n * n, 6 * n * NB
     # (name, callable, values read + written per knot point)
     passes = [
-        ("rnea_fpass", lambda: eng.rnea_fpass(q, qd, qdd), 3 * n + 3 * v6),
+        ("rnea_fpass", lambda: eng.rnea_fpass(q, qd, qdd), eng.nq + 2 * n + 3 * v6),
         ("rnea_bpass", lambda: eng.rnea_bpass(q, fa), n + 2 * v6 + n),
         ("rnea_grad_fpass_dq", lambda: eng.rnea_grad_fpass_dq(q, qd, v, a), 2 * n + 2 * v6 + 3 * t6),
         ("rnea_grad_fpass_dqd", lambda: eng.rnea_grad_fpass_dqd(q, qd, v), 2 * n + v6 + 3 * t6),
