@@ -686,4 +686,95 @@ fbp_grad_bpass_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* 
   }
 }
 
+// ---- rnea_grad_bpass_dq / _dqd, one COLUMN per lane (the scheme of grad_bpass_coop_kernel) ------------------------------
+// The pass never mixes columns (:1284-1294 / :1325-1331 act column by column).  A warp owns one knot point: its df slab
+// (6, n, NB) - contiguous in HBM - is pulled into shared memory with one cp.async.bulk (mbarrier completion), lane c
+// carries column c (and c + 32 when n > 32) through the bodies leaf -> base inside the tile, dc (n, n) is assembled next
+// to it, and both leave with bulk stores (element loops where the 16-byte rule of the instruction is not met).  The
+// thread-per-knot-point kernel above used df in HBM as read-modify-write working storage, 8 bytes per 32-byte sector.
+__host__ __device__ inline int fbp_bpass_warp_vals(int NB) {
+  const int n = NB + 5;
+  return (((6 * n * NB + 3) & ~3) + ((n * n + 3) & ~3) + 8 * NB + 2 + 3) & ~3;  // df tile | dc tile | f | (f1, f2) | mbarrier
+}
+
+template <typename T, bool DQ>
+__global__ void __launch_bounds__(kCpMaxWarps * 32)
+fbp_grad_bpass_coop_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restrict__ q, const T* __restrict__ f,
+                           T* __restrict__ df, int use_damping, T* __restrict__ dc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NB = m.d.n, n = NB + 5, nq = NB + 6, nn = n * n;
+  const int slab = 6 * n * NB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  T* ws = reinterpret_cast<T*>(smem_raw) + (size_t)warp * fbp_bpass_warp_vals(NB);
+  T* td = ws;                                              // [6][n][NB]: the slab itself
+  T* tc = td + ((slab + 3) & ~3);                          // [n][n]
+  T* sf = tc + ((nn + 3) & ~3);                            // [6][NB]
+  T* sj = sf + 6 * NB;                                     // [NB][2]
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(ws + fbp_bpass_warp_vals(NB) - 2);
+  unsigned phase = 0;
+  warp_bulk_bar_init(bar, lane);
+  for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
+    T* dfb = df + b * (int64_t)slab;
+    T* dcb = dc + b * (int64_t)nn;
+    warp_bulk_store_wait(lane);                            // the previous knot point's tiles have left
+    const bool bulk_in = warp_bulk_load(td, dfb, slab, bar, lane);
+    if (lane >= 1 && lane < NB) {
+      T f1, f2;
+      joint_basis(m.d, lane, q[b * nq + lane + 6], f1, f2);
+      sj[2 * lane] = f1; sj[2 * lane + 1] = f2;
+    }
+    if (DQ) {
+      for (int e = lane; e < 6 * NB; e += 32) sf[e] = f[b * 6 * NB + e];
+    }
+    if (bulk_in) {
+      warp_bulk_load_wait(bar, phase);
+      phase ^= 1u;
+    } else {
+      for (int e = lane; e < slab; e += 32) td[e] = dfb[e];
+    }
+    __syncwarp();
+    for (int c = lane; c < n; c += 32) {
+      T* md = td + c * NB;                                 // + r n NB + body
+      const int rstride = n * NB;
+      for (int i = NB - 1; i >= 1; --i) {
+        const int p = m.d.parent[i];
+        T col[6], X[18], t[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) col[r] = md[r * rstride + i];
+        tc[(i + 5) * n + c] = dot6(m.d.S[i], col);                             // :1284 / :1325
+        build_X(m.d, i, sj[2 * i], sj[2 * i + 1], X);
+        XT_apply(X, col, t);                                                   // :1291 / :1331
+        if (DQ && c == i + 5) {
+          T fi[6], S[6], fxs[6], t2[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) { fi[r] = sf[r * NB + i]; S[r] = m.d.S[i][r]; }
+          crm_mul(fi, S, fxs);
+#pragma unroll
+          for (int r = 0; r < 6; ++r) fxs[r] = -fxs[r];                        // fxS :166-168
+          XT_apply(X, fxs, t2);                                                // :1292
+#pragma unroll
+          for (int r = 0; r < 6; ++r) t[r] += t2[r];                           // :1293-1294
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) md[r * rstride + p] += t[r];
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) tc[r * n + c] = md[r * rstride];             // :1282 / :1325 with S = eye(6)
+    }
+    __syncwarp();
+    if (!DQ && use_damping) {                                                  // :1336-1341, in the reference's order
+      if (lane < 25) tc[(lane / 5) * n + lane % 5] += m.d.damping[0];
+      __syncwarp();
+      if (lane >= 1 && lane < NB) tc[lane * n + lane] += m.d.damping[lane];
+      __syncwarp();
+    }
+    if (!warp_bulk_store(dfb, td, slab, lane))
+      for (int e = lane; e < slab; e += 32) dfb[e] = td[e];
+    if (!warp_bulk_store(dcb, tc, nn, lane))
+      for (int e = lane; e < nn; e += 32) __stcs(dcb + e, tc[e]);
+    __syncwarp();
+  }
+  warp_bulk_store_wait(lane);                              // shared memory must outlive the copies
+}
+
 }  // namespace rbd

@@ -257,6 +257,29 @@ template <typename T, bool DQ>
 int launch_fb_grad_bpass(const rbd_fb_model* m, int64_t B, const T* q, const T* f, T* df, int damp, T* dc, void* stream) {
   RBD_CHECK_ARGS(m && q && (f || !DQ) && df && dc && B >= 0, "rbd_fb_rnea_grad_bpass: null argument or negative B");
   if (B == 0) return 0;
+  if (fb_variant_of(m) != 1) {
+    // one column per lane, the knot point's df slab in a shared-memory tile (rbd_fb_pass_kernels.cuh: fbp_grad_bpass_coop_kernel)
+    const int NB = m->d.d.n;
+    auto kern = fbp_grad_bpass_coop_kernel<T, DQ>;
+    const size_t per_warp = (size_t)fbp_bpass_warp_vals(NB) * sizeof(T);
+    int warps = 0, best = 0, ctas = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem) == cudaSuccess) {
+      for (int w = 1; w <= kCpMaxWarps; ++w) {
+        if (per_warp * w > kMaxDynSmem) break;
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, w * 32, per_warp * w) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (nb * w > best) { best = nb * w; warps = w; ctas = nb; }
+      }
+    }
+    if (warps > 0) {
+      int64_t blocks = (B + warps - 1) / warps;
+      const int64_t cap = (int64_t)sm_count() * ctas * 4;
+      if (blocks > cap) blocks = cap;
+      kern<<<(unsigned)blocks, warps * 32, per_warp * warps, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, f, df, damp, dc);
+      return cuda_status("rbd_fb_rnea_grad_bpass(coop)");
+    }
+    cudaGetLastError();
+  }
   fbp_grad_bpass_kernel<T, DQ><<<blocks_for(B, kFbPassThreads), kFbPassThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, f, df, damp, dc);
   return cuda_status("rbd_fb_rnea_grad_bpass");
 }
