@@ -19,6 +19,7 @@
 #include "rbd_common.cuh"
 #include "rbd_fb_kernels.cuh"
 #include "rbd_coop_pass_kernels.cuh"
+#include "rbd_pass_kernels.cuh"
 
 namespace rbd {
 
@@ -775,6 +776,67 @@ fbp_grad_bpass_coop_kernel(const __grid_constant__ FbModel<T> m, int64_t B, cons
     __syncwarp();
   }
   warp_bulk_store_wait(lane);                              // shared memory must outlive the copies
+}
+
+// ---- minv_fpass, one COLUMN per lane (the scheme of minv_fpass_col_kernel, rbd_pass_kernels.cuh) -----------------------
+// The forward pass never mixes columns (:771-776 act on whole rows, entry by entry).  A warp owns one knot point and lane
+// c carries column c (and c + 32 when n > 32) through the bodies: every access to Minv[i + 5, :] and F[i][r, :] is one
+// contiguous row per knot point, the parent's F stays in registers along chains and is re-read (the lane's own store)
+// at branch points.  F keeps the reference's indexing: F[0] <- Minv[0:6, :] (:779), body i reads F[parent BODY index]
+// and writes F[i] (:771-781).
+template <typename T>
+__global__ void __launch_bounds__(kPassThreads)
+fbp_minv_fpass_col_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restrict__ q, T* __restrict__ Minv,
+                          T* __restrict__ F, const T* __restrict__ U, const T* __restrict__ Dinv) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NB = m.d.n, n = NB + 5, nq = NB + 6;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  T* sj = reinterpret_cast<T*>(smem_raw) + (size_t)warp * 2 * RBD_MAX_DOF;    // [NB][2]: (f1, f2) of every joint
+  for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
+    T* Mb = Minv + b * (int64_t)n * n;
+    T* Fb = F + b * (int64_t)n * 6 * n;
+    const T* Ub = U + b * (int64_t)n * 6;
+    const T* Db = Dinv + b * (int64_t)n;
+    __syncwarp();
+    if (lane >= 1 && lane < NB) {
+      T f1, f2;
+      joint_basis(m.d, lane, q[b * nq + lane + 6], f1, f2);
+      sj[2 * lane] = f1; sj[2 * lane + 1] = f2;
+    }
+    __syncwarp();
+    for (int col = lane; col < n; col += 32) {
+      T Fprev[6];                                          // F[i - 1][:, col]
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        Fprev[r] = Mb[r * n + col];
+        Fb[r * n + col] = Fprev[r];                                            // :779  F[0] = S Minv[0:6, :]
+      }
+      for (int i = 1; i < NB; ++i) {
+        const int mi = i + 5, p = m.d.parent[i];
+        T X[18], Ui[6], UX[6], Fp[6], XF[6];
+        build_X(m.d, i, sj[2 * i], sj[2 * i + 1], X);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) Ui[r] = Ub[mi * 6 + r];
+        XT_apply(X, Ui, UX);                                                   // (U^T X)^T = X^T U
+        const T invD = T(1) / Db[mi];
+        if (p == i - 1) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) Fp[r] = Fprev[r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) Fp[r] = Fb[(p * 6 + r) * n + col];       // written by this lane earlier
+        }
+        const T mij = Mb[mi * n + col] - invD * dot6(UX, Fp);                  // :771-773
+        Mb[mi * n + col] = mij;
+        X_apply(X, Fp, XF);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          Fprev[r] = fma_t(m.d.S[i][r], mij, XF[r]);                           // :774-776
+          Fb[(i * 6 + r) * n + col] = Fprev[r];
+        }
+      }
+    }
+  }
 }
 
 }  // namespace rbd

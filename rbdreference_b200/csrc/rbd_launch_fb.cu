@@ -207,6 +207,15 @@ template <typename T>
 int launch_fb_minv_fpass(const rbd_fb_model* m, int64_t B, const T* q, T* Minv, T* F, const T* U, const T* Dinv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && F && U && Dinv && B >= 0, "rbd_fb_minv_fpass: null argument or negative B");
   if (B == 0) return 0;
+  if (fb_variant_of(m) != 1) {
+    // one column per lane, a warp per knot point: coalesced rows of Minv and F (rbd_fb_pass_kernels.cuh)
+    const int warps = kPassThreads / 32;
+    int64_t blocks = (B + warps - 1) / warps;
+    if (blocks > grid_cap()) blocks = grid_cap();
+    fbp_minv_fpass_col_kernel<T><<<(unsigned)blocks, kPassThreads, (size_t)warps * 2 * RBD_MAX_DOF * sizeof(T), (cudaStream_t)stream>>>(
+        pick_fb<T>(m), B, q, Minv, F, U, Dinv);
+    return cuda_status("rbd_fb_minv_fpass(col)");
+  }
   fbp_minv_fpass_kernel<T><<<blocks_for(B, kFbPassThreads), kFbPassThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, Minv, F, U, Dinv);
   return cuda_status("rbd_fb_minv_fpass");
 }
