@@ -20,6 +20,7 @@
 #include "rbd_fb_kernels.cuh"
 #include "rbd_coop_pass_kernels.cuh"
 #include "rbd_pass_kernels.cuh"
+#include "rbd_coop_minv_kernels.cuh"
 
 namespace rbd {
 
@@ -834,6 +835,139 @@ fbp_minv_fpass_col_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const
           Fprev[r] = fma_t(m.d.S[i][r], mij, XF[r]);                           // :774-776
           Fb[(i * 6 + r) * n + col] = Fprev[r];
         }
+      }
+    }
+  }
+}
+
+// ---- minv_bpass, one COLUMN per lane (the scheme of minv_bpass_col_kernel, rbd_pass_kernels.cuh) -----------------------
+// A warp owns one knot point.  Phase 1: the articulated inertias leaf -> base (:694-733), shared by the lanes through
+// shared memory (lane c < 6 owns column c of IA_parent += X^T (IA - U U^T / D) X); every body's U and 1 / D stay in shared
+// memory, U and D also go to the caller's arrays, the base's U[0:6] = IA_0 and fb_Dinv = inv(IA_0) (:677-684).  Phase 2:
+// columns never mix in :700-726, so lane c carries matrix column c (and c + 32 when n > 32) from its body to the base with
+// a running F in six registers and writes every row of Minv and F once, contiguously across the lanes (zeros outside the
+// subtree; the reference's arrays start as zeros).  The reference's indexing is kept: rows / columns i + 5 for body i,
+// children of the base accumulate into F[5] (:724-726 with parent index 0 + 5), which is what the base step reads
+// (:687-691).
+__host__ __device__ inline int fbp_minv_bpass_warp_vals(int NB) { return (45 * NB + 36 + 3) & ~3; }   // IA | U | 1/D | (f1, f2) | fb_Dinv
+
+template <typename T>
+__global__ void __launch_bounds__(kPassThreads)
+fbp_minv_bpass_col_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* __restrict__ q, T* __restrict__ Minv,
+                          T* __restrict__ F, T* __restrict__ U, T* __restrict__ Dinv) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NB = m.d.n, n = NB + 5, nq = NB + 6;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  T* ws = reinterpret_cast<T*>(smem_raw) + (size_t)warp * fbp_minv_bpass_warp_vals(NB);
+  T* IA = ws;                    // [NB][36]
+  T* Us = IA + 36 * NB;          // [NB][6]
+  T* iD = Us + 6 * NB;           // [NB]
+  T* sj = iD + NB;               // [NB][2]
+  T* Di = sj + 2 * NB;           // [36]
+  for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < B; b += (int64_t)gridDim.x * nwarps) {
+    T* Mb = Minv + b * (int64_t)n * n;
+    T* Fb = F + b * (int64_t)n * 6 * n;                     // F[mi][r][col] = Fb[(mi * 6 + r) * n + col]
+    T* Ub = U + b * (int64_t)n * 6;
+    T* Db = Dinv + b * (int64_t)n;
+    __syncwarp();
+    for (int e = lane; e < NB * 36; e += 32) IA[e] = m.d.I[e / 36][e % 36];    // :662
+    if (lane >= 1 && lane < NB) {
+      T f1, f2;
+      joint_basis(m.d, lane, q[b * nq + lane + 6], f1, f2);
+      sj[2 * lane] = f1; sj[2 * lane + 1] = f2;
+    }
+    if (lane < 6) Db[lane] = T(0);
+    __syncwarp();
+    // ---------------------------------------------------------------- phase 1: articulated inertias
+    for (int i = NB - 1; i >= 1; --i) {
+      const int p = m.d.parent[i], mi = i + 5;
+      T X[18];
+      build_X(m.d, i, sj[2 * i], sj[2 * i + 1], X);
+      if (lane < 6) {                                       // U = IA_i S (:697): lane r computes U[r]
+        T acc = T(0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc = fma_t(IA[i * 36 + 6 * lane + k], m.d.S[i][k], acc);
+        Us[i * 6 + lane] = acc;
+      }
+      __syncwarp();
+      T Ui[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Ui[r] = Us[i * 6 + r];
+      const T D = dot6(m.d.S[i], Ui);                                          // :698
+      const T invD = T(1) / D;
+      if (lane < 6) Ub[mi * 6 + lane] = Ui[lane];
+      if (lane == 6) { Db[mi] = D; iD[i] = invD; }
+      if (lane < 6) {                                       // IA_p += X^T (IA_i - U U^T / D) X (:728-733), column `lane`
+        const int cc = lane < 3 ? lane : lane - 3;
+        T xk[6];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const T e = cc == 0 ? X[3 * r] : (cc == 1 ? X[3 * r + 1] : X[3 * r + 2]);
+          const T lo = cc == 0 ? X[9 + 3 * r] : (cc == 1 ? X[9 + 3 * r + 1] : X[9 + 3 * r + 2]);
+          xk[r] = lane < 3 ? e : T(0);
+          xk[3 + r] = lane < 3 ? lo : e;
+        }
+        const T ux = invD * dot6(Ui, xk);
+        T colv[6], t[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          T acc = T(0);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) acc = fma_t(IA[i * 36 + 6 * r + k], xk[k], acc);
+          colv[r] = acc - Ui[r] * ux;
+        }
+        XT_apply(X, colv, t);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) IA[p * 36 + 6 * r + lane] += t[r];
+      }
+      __syncwarp();
+    }
+    // the base (:677-684): U[0:6] = IA_0, fb_Dinv = inv(IA_0)
+    for (int e = lane; e < 36; e += 32) Ub[e] = IA[e];
+    if (lane == 0) {
+      T s[21];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = r; c < 6; ++c) s[sym6_idx(r, c)] = IA[6 * r + c];
+      sym6_invert(s);
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) Di[6 * r + c] = s[sym6_idx(r, c)];
+    }
+    __syncwarp();
+    // ---------------------------------------------------------------- phase 2: matrix column `col`, body col - 5
+    for (int col = lane; col < n; col += 32) {
+      const int jb = col - 5;
+      T Frun[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+      for (int i = NB - 1; i >= 1; --i) {
+        const int mi = i + 5;
+        const bool mine = jb >= 1 && ((m.d.sub_mask[i] >> jb) & 1u);
+        T mij = T(0), Fout[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+        if (mine) {
+          const T invD = iD[i];
+          mij = (jb == i ? invD : T(0)) - invD * dot6(m.d.S[i], Frun);         // :700-708
+          T X[18];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) Fout[r] = fma_t(Us[i * 6 + r], mij, Frun[r]);   // :721-723
+          build_X(m.d, i, sj[2 * i], sj[2 * i + 1], X);
+          XT_apply(X, Fout, Frun);                                             // now F[parent + 5][:, col] (:724-726)
+        }
+        Mb[mi * n + col] = mij;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) Fb[(mi * 6 + r) * n + col] = Fout[r];
+      }
+      // rows 0..5: F[0..4] = 0, F[5] = what the base's children left (:724-726), Minv[0:6, col] (:686-691)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+#pragma unroll
+        for (int mi = 0; mi < 5; ++mi) Fb[(mi * 6 + r) * n + col] = T(0);
+        Fb[(5 * 6 + r) * n + col] = Frun[r];
+        T acc = T(0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc = fma_t(Di[6 * r + k], Frun[k], acc);
+        Mb[r * n + col] = (col < 6 ? Di[6 * r + col] : T(0)) - acc;
       }
     }
   }

@@ -200,6 +200,19 @@ template <typename T>
 int launch_fb_minv_bpass(const rbd_fb_model* m, int64_t B, const T* q, T* Minv, T* F, T* U, T* Dinv, void* stream) {
   RBD_CHECK_ARGS(m && q && Minv && F && U && Dinv && B >= 0, "rbd_fb_minv_bpass: null argument or negative B");
   if (B == 0) return 0;
+  if (fb_variant_of(m) != 1) {
+    // articulated inertias shared through shared memory, then one column per lane (rbd_fb_pass_kernels.cuh)
+    const int warps = kPassThreads / 32;
+    const size_t smem = (size_t)warps * fbp_minv_bpass_warp_vals(m->d.d.n) * sizeof(T);
+    auto kern = fbp_minv_bpass_col_kernel<T>;
+    if (smem <= 48 * 1024 || cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+      int64_t blocks = (B + warps - 1) / warps;
+      if (blocks > grid_cap()) blocks = grid_cap();
+      kern<<<(unsigned)blocks, kPassThreads, smem, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, Minv, F, U, Dinv);
+      return cuda_status("rbd_fb_minv_bpass(col)");
+    }
+    cudaGetLastError();
+  }
   fbp_minv_bpass_kernel<T><<<blocks_for(B, kFbPassThreads), kFbPassThreads, 0, (cudaStream_t)stream>>>(pick_fb<T>(m), B, q, Minv, F, U, Dinv);
   return cuda_status("rbd_fb_minv_bpass");
 }

@@ -15,7 +15,7 @@ summ r02_prof_grad_fpass_level_iiwa14_f64 r02_grad_fpass_level_iiwa14_f64.txt
 summ r02_prof_grad_fpass_level_atlas_f64 r02_grad_fpass_level_atlas_f64.txt
 summ r02_prof_fb_grad_coop_hyq_f64 r02_fb_grad_coop_hyq_f64.txt
 summ r02_prof_fb_minv_coop_hyq_f64 r02_fb_minv_coop_hyq_f64.txt
-for f in r02_matrix.jsonl r02_passes.jsonl r02_sweep_f64.jsonl r02_ee_bench.jsonl r02_fb_bench.jsonl r02_sanitize.json r02_launches_bench_default.csv; do
+for f in r02_matrix.jsonl r02_passes.jsonl r02_fb_passes.jsonl r02_sweep_f64.jsonl r02_ee_bench.jsonl r02_fb_bench.jsonl r02_sanitize.json r02_launches_bench_default.csv; do
   [ -f $G/$f ] && cp $G/$f $P/$f
 done
 [ -f $G/r02_bench_default.json ] && tail -1 $G/r02_bench_default.json > $P/r02_bench_default.json

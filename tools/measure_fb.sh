@@ -21,5 +21,7 @@ for l in open('gpurun_out/r02_fb_bench.jsonl'):
     d=json.loads(l); c=d['config']; r=d['roofline']
     print('%-10s %-9s %s %.3e evals/s %.3f ms fma %.3f clk %s' % (c['robot'],c['op'],d['dtype'],d['value'],d['ms_per_step'],r['frac'] or 0,d['clocks']['samples']))
 PY
+: > $O/r02_fb_passes.jsonl
+for r in iiwa14_fb hyq_fb atlas_fb; do python tools/bench_passes.py --reps 5 --robot $r --batch 65536 >> $O/r02_fb_passes.jsonl 2>/dev/null; done
 cap regex:rnea_grad_coop r02_prof_fb_grad_coop_hyq_f64 python bench.py --robot hyq_fb --op rnea_grad --batch 262144 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $O/r02_ncu6.log 2>&1
 cap regex:minv_coop r02_prof_fb_minv_coop_hyq_f64 python bench.py --robot hyq_fb --op minv --batch 262144 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $O/r02_ncu7.log 2>&1
