@@ -228,9 +228,11 @@ int rbd_end_effector_pose_gradient_f32(const rbd_ee_model_t* m, int64_t B, const
  * finds the layout by probing the robot's own get_Xmat_Func_by_id(0).
  * Shapes: q (B, NB+6) with joint i at q[i+6]; qd, qdd, c (B, NB+5) with the base twist
  * [angular; linear] in base coordinates at [0:6] and joint i at [i+5]; v, a, f (B, 6, NB);
- * dc_du (B, NB+5, 2(NB+5)); Minv (B, NB+5, NB+5).  Reference behaviour kept: output_dense mirrors only
- * the leading NB x NB block (:799-804); velocity damping lands on [i, i] (body index) and on the
- * block [0:5, 0:5] for the base (:1336-1341). */
+ * dc_du (B, NB+5, 2(NB+5)); Minv (B, NB+5, NB+5).  Reference behaviour kept: velocity damping lands on
+ * [i, i] (body index) and on the block [0:5, 0:5] for the base (:1336-1341).  The reference fills BOTH triangles of a
+ * floating-base Minv (:761-781 work on whole rows) and output_dense only copies the upper triangle of the leading
+ * NB x NB block over the lower one (:799-804): either setting is the full symmetric matrix up to rounding.  The
+ * automatic (cooperative) kernel returns that matrix for both; kernel family 1 reproduces the two code paths. */
 typedef struct RbdFbModelDesc {
   RbdModelDesc bodies;
   int32_t pos_off, quat_off, w_first, transpose;
