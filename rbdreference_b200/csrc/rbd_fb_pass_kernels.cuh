@@ -398,14 +398,18 @@ fbp_grad_fpass_kernel(const __grid_constant__ FbModel<T> m, int64_t B, const T* 
 // Lane i of a group of G lanes is body i (body 0 = the base).  A body's non-zero columns are those of its joint ancestors
 // (column a + 5 for ancestor body a >= 1, itself included) and the base's six.  Round d handles the ancestor at distance d:
 //   * d < depth(i): one pair, the parent's pair of round d - 1 arrives by warp shuffle (as for a fixed base);
-//   * d = depth(i): the ancestor is the base - six pairs, column k = 0..5.  The base's own lane seeds them (:1175 /
-//     :1231-1243 with S = eye(6)); every other lane reads the parent's six results of the previous round from shared
-//     memory, where all results wait anyway.
+//   * the base's six columns (every body has them) are a second phase, level by level from the base: the 6 x (bodies of
+//     the level) pairs of a level are spread over the lanes of the group - a lane works for ANOTHER body there, whose
+//     X, I v and qd wait in shared memory next to the results, where the parent's pair of the previous level is read
+//     too.  The base's own pairs are the seeds (:1175 / :1231-1243 with S = eye(6)).  (First version: every lane ran the
+//     six pairs of its own body in the round in which its ancestor is the base - a six-fold serial loop in almost every
+//     round: Atlas + base 6.2 ms per 2^16.)
 // The three (6, n, NB) slabs then leave in one coalesced pass through a per-CTA map (structural zeros where it says -1).
-__host__ __device__ inline int fbp_level_knot_vals(int NB, int npairs) { return (12 * NB + 18 * npairs + 3) & ~3; }
+constexpr int kFbLvlBody = 37;          // per body and knot point: X (18) | I v (6) | qd | X_0 a_grav or qd[0:6] (base row only) ... odd stride
+__host__ __device__ inline int fbp_level_knot_vals(int NB, int npairs) { return (12 * NB + 18 * npairs + kFbLvlBody * NB + 3) & ~3; }
 __host__ __device__ inline size_t fbp_level_head_bytes(int NB, int G, size_t tsize) {
   const size_t slab = (size_t)6 * (NB + 5) * NB;
-  return (((size_t)NB * 4 * sizeof(int) + (size_t)(32 / G) * slab * sizeof(short) + 15) & ~(size_t)15) +
+  return (((size_t)NB * 6 * sizeof(int) + 64 * sizeof(int) + (size_t)(32 / G) * slab * sizeof(short) + 15) & ~(size_t)15) +
          (((size_t)NB * kCpLvlMdl + 3) & ~(size_t)3) * tsize;
 }
 
@@ -425,13 +429,16 @@ fbp_grad_fpass_level_kernel(const __grid_constant__ FbModel<T> m, int npairs, in
   const int gbase = g * G;
   const bool valid = i < NB;
   int* topo = reinterpret_cast<int*>(smem_raw);                            // [NB][4]: parent kind depth first-pair
-  short* pmap = reinterpret_cast<short*>(topo + 4 * NB);                    // [IPW][6][n][NB]: where the value waits, or -1
+  int* lvl_body = topo + 4 * NB;                                           // [NB]: bodies sorted by depth
+  int* lvl_begin = lvl_body + 2 * NB;                                      // [maxdepth + 2] (<= 34 entries of the 64)
+  short* pmap = reinterpret_cast<short*>(topo + 6 * NB + 64);               // [IPW][6][n][NB]: where the value waits, or -1
   T* mdl = reinterpret_cast<T*>(smem_raw + fbp_level_head_bytes(NB, G, 0)); // [NB][97]: XA XB XC S I
   const int knot_vals = fbp_level_knot_vals(NB, npairs);
   T* ws = mdl + (((size_t)NB * kCpLvlMdl + 3) & ~(size_t)3) + (size_t)warp * IPW * knot_vals;
   T* sv = ws + g * knot_vals;                              // [6][NB] of this lane's knot point
   T* sa = sv + 6 * NB;
   T* res = sa + 6 * NB;                                    // [3][6][npairs]
+  T* bd = res + 18 * npairs;                               // [NB][37]: X, I v, qd of every body of this knot point
   for (int k = threadIdx.x; k < NB * kCpLvlMdl; k += blockDim.x) {
     const int b = k / kCpLvlMdl, w = k - b * kCpLvlMdl;
     mdl[k] = w < 18 ? m.d.XA[b][w] : w < 36 ? m.d.XB[b][w - 18] : w < 54 ? m.d.XC[b][w - 36] : w < 60 ? m.d.S[b][w - 54] : w < 96 ? m.d.I[b][w - 60] : T(0);
@@ -449,6 +456,15 @@ fbp_grad_fpass_level_kernel(const __grid_constant__ FbModel<T> m, int npairs, in
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0) {                                   // bodies by depth
+    int pos = 0;
+    for (int L = 0; L <= maxdepth; ++L) {
+      lvl_begin[L] = pos;
+      for (int b = 0; b < NB; ++b)
+        if (topo[4 * b + 2] == L) lvl_body[pos++] = b;
+    }
+    lvl_begin[maxdepth + 1] = pos;
+  }
   if (threadIdx.x < NB) {
     const int b = threadIdx.x;
     int idx = topo[4 * b + 3];
@@ -468,7 +484,6 @@ fbp_grad_fpass_level_kernel(const __grid_constant__ FbModel<T> m, int npairs, in
   const int par = topo[4 * ib], kind = topo[4 * ib + 1];
   const int depth = valid ? topo[4 * ib + 2] : -1;
   const int pair0 = topo[4 * ib + 3];
-  const int ppair6 = par >= 0 ? topo[4 * par + 3] + topo[4 * par + 2] : 0;   // the parent's first base pair
   const T* mc = mdl + ib * kCpLvlMdl;
   T S[6], Im[36];                                          // lane = body for the whole kernel
 #pragma unroll
@@ -521,6 +536,14 @@ fbp_grad_fpass_level_kernel(const __grid_constant__ FbModel<T> m, int npairs, in
 #pragma unroll
     for (int r = 0; r < 6; ++r) vi[r] = sv[r * NB + ib];
     mat6_apply(Im, vi, Iv);                                                      // :1180 / :1248
+    if (valid) {                                            // what the second phase needs of this body
+      T* mybd = bd + i * kFbLvlBody;
+#pragma unroll
+      for (int k = 0; k < 18; ++k) mybd[k] = X[k];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) { mybd[18 + r] = Iv[r]; mybd[25 + r] = DQ ? xg[r] : qd0[r]; }
+      mybd[24] = qdi;
+    }
     T cdv[6], cda[6];                                       // dv / da of this lane's joint pair of the previous round
 #pragma unroll
     for (int r = 0; r < 6; ++r) { cdv[r] = T(0); cda[r] = T(0); }
@@ -571,49 +594,62 @@ fbp_grad_fpass_level_kernel(const __grid_constant__ FbModel<T> m, int npairs, in
           cdv[r] = dvc[r];
           cda[r] = dac[r];
         }
-      } else if (depth == d) {
-        // ---- the base's six columns
+      }
+    }
+    __syncwarp();
+    // ---- the base's six columns of every body, level by level: task t of a level = (body lvl[t / 6], column t % 6)
 #pragma unroll 1
-        for (int k = 0; k < 6; ++k) {
-          T dvc[6], dac[6];
-          if (i == 0) {
-            T e[6];
+    for (int L = 0; L <= maxdepth; ++L) {
+      const int l0 = lvl_begin[L], ntask = 6 * (lvl_begin[L + 1] - l0);
+#pragma unroll 1
+      for (int t = i; t < ntask; t += G) {
+        const int bb = lvl_body[l0 + t / 6], k = t - 6 * (t / 6);
+        const T* b2 = bd + bb * kFbLvlBody;
+        const T* mc2 = mdl + bb * kCpLvlMdl;
+        T dvc[6], dac[6], v2[6], Iv2[6];
 #pragma unroll
-            for (int r = 0; r < 6; ++r) { e[r] = r == k ? T(1) : T(0); dvc[r] = T(0); }
-            if (DQ) {
-              crm_mul(xg, e, dac);                                               // :1175 with S = eye(6); :1166-1168 adds zeros
-            } else {
-              T t1[6], t2[6];
+        for (int r = 0; r < 6; ++r) { v2[r] = sv[r * NB + bb]; Iv2[r] = b2[18 + r]; }
+        if (bb == 0) {
+          T e[6], x0[6];
 #pragma unroll
-              for (int r = 0; r < 6; ++r) dvc[r] = e[r];                         // :1231
-              crm_mul(e, qd0, t1);                                               // :1236-1238
-              crm_mul(vi, e, t2);                                                // :1243
-#pragma unroll
-              for (int r = 0; r < 6; ++r) dac[r] = t1[r] + t2[r];
-            }
+          for (int r = 0; r < 6; ++r) { e[r] = r == k ? T(1) : T(0); dvc[r] = T(0); x0[r] = b2[25 + r]; }
+          if (DQ) {
+            crm_mul(x0, e, dac);                                                 // :1175 with S = eye(6); :1166-1168 adds zeros
           } else {
-            T ppv[6], ppa[6], t[6];
-            const T* pr = res + ppair6 + k;                                      // the parent's pair of column k (previous round)
+            T t1[6], t2[6];
 #pragma unroll
-            for (int r = 0; r < 6; ++r) { ppv[r] = pr[r * npairs]; ppa[r] = pr[(6 + r) * npairs]; }
-            X_apply(X, ppv, dvc);
-            X_apply(X, ppa, dac);
-            crm_mul(dvc, S, t);
+            for (int r = 0; r < 6; ++r) dvc[r] = e[r];                           // :1231
+            crm_mul(e, x0, t1);                                                  // :1236-1238
+            crm_mul(v2, e, t2);                                                  // :1243
 #pragma unroll
-            for (int r = 0; r < 6; ++r) dac[r] = fma_t(qdi, t[r], dac[r]);
+            for (int r = 0; r < 6; ++r) dac[r] = t1[r] + t2[r];
           }
-          T dfc[6];
-          fbp_df(Im, vi, Iv, dvc, dac, dfc);
-          T* rp = res + pair0 + depth + k;
+        } else {
+          const int pb = topo[4 * bb];
+          const T* pr = res + topo[4 * pb + 3] + topo[4 * pb + 2] + k;           // the parent's pair of column k (previous level)
+          T X2[18], S2[6], ppv[6], ppa[6], tt[6];
 #pragma unroll
-          for (int r = 0; r < 6; ++r) {
-            rp[r * npairs] = dvc[r];
-            rp[(6 + r) * npairs] = dac[r];
-            rp[(12 + r) * npairs] = dfc[r];
-          }
+          for (int q2 = 0; q2 < 18; ++q2) X2[q2] = b2[q2];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) { S2[r] = mc2[54 + r]; ppv[r] = pr[r * npairs]; ppa[r] = pr[(6 + r) * npairs]; }
+          X_apply(X2, ppv, dvc);
+          X_apply(X2, ppa, dac);
+          crm_mul(dvc, S2, tt);
+          const T qd2 = b2[24];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) dac[r] = fma_t(qd2, tt[r], dac[r]);
+        }
+        T dfc[6];
+        fbp_df(mc2 + 60, v2, Iv2, dvc, dac, dfc);
+        T* rp = res + topo[4 * bb + 3] + topo[4 * bb + 2] + k;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          rp[r * npairs] = dvc[r];
+          rp[(6 + r) * npairs] = dac[r];
+          rp[(12 + r) * npairs] = dfc[r];
         }
       }
-      __syncwarp();                                         // the round's results are visible to the children's base round
+      __syncwarp();                                         // the level's results are visible to the next level
     }
     // ---- the warp's slabs of the three tensors (contiguous: consecutive knot points), every sector once
     const int total = nk * slab;
