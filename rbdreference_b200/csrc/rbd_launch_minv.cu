@@ -76,7 +76,6 @@ int launch_minv(const rbd_model* m, int64_t B, const T* q, int dense, T* Minv, v
     if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
     int nb = 0;
     cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem);
-    if (std::getenv("RBD_DEBUG")) std::fprintf(stderr, "[rbd] tile minv: gc %d warps %d smem %zu occupancy %d (%s)\n", tp.gc, warps, smem, nb, cudaGetErrorString(eo));
     if (eo == cudaSuccess && nb > 0) {
       const int64_t ntiles = (B + 31) / 32;
       int64_t blocks = (int64_t)sm_count() * nb;
